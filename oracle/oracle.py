@@ -1,0 +1,268 @@
+"""ctypes wrapper around the CPU oracle (oracle/liboracle.so).  TEST INFRASTRUCTURE ONLY:
+import this from tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs,
+never from the product package."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(os.path.dirname(_HERE), "hip-bvh-construction_b200"))
+from b2bvh import types as T  # noqa: E402
+
+_lib = None
+
+
+def build(verbose=False):
+    """Compile liboracle.so (and oracle/_ref when /root/reference exists)."""
+    r = subprocess.run(["make", "-C", _HERE, "all"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("oracle build failed:\n" + r.stdout + r.stderr)
+    if verbose:
+        print(r.stdout)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(path):
+            build()
+        _lib = C.CDLL(path)
+        _lib.orc_area.restype = C.c_float
+        _lib.orc_cost_bvh4.restype = C.c_float
+        _lib.orc_cost_lbvh.restype = C.c_float
+        _lib.orc_cost_bvh2_ploc.restype = C.c_float
+        _lib.orc_cost_binned_sah_quirk.restype = C.c_float
+        _lib.orc_cost_binned_sah_proper.restype = C.c_float
+        _lib.orc_ray_zdir.restype = C.c_float
+        _lib.orc_ray_zdir.argtypes = [C.c_float]
+        for f in ("orc_fnv1a_words", "orc_lbvh_apetrei", "orc_collapse4", "orc_bvh2_depth", "orc_traverse", "orc_binned_sah_build",
+                  "orc_morton_code_cfg"):
+            getattr(_lib, f).restype = C.c_uint32
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _u32(n):
+    return C.c_uint32(int(n))
+
+
+class MortonCfg(C.Structure):
+    _fields_ = [("axis", C.c_int * 3), ("pre", C.c_int * 2), ("swap", C.c_int), ("sum", C.c_int), ("nb", C.c_int * 3)]
+
+
+def fnv1a(keys, vals=None):
+    keys = np.ascontiguousarray(keys, dtype=np.uint32)
+    if vals is not None:
+        vals = np.ascontiguousarray(vals, dtype=np.uint32)
+    return int(lib().orc_fnv1a_words(_p(keys), _p(vals), C.c_uint64(keys.size)))
+
+
+def primrefs(tris):
+    n = tris.size
+    refs = np.zeros(n, dtype=T.PRIM_REF)
+    boxes = np.zeros(n, dtype=T.AABB)
+    scene = np.zeros(1, dtype=T.AABB)
+    lib().orc_primrefs(_p(tris), _u32(n), _p(refs), _p(boxes), _p(scene))
+    return refs, boxes, scene
+
+
+def morton_config(extent):
+    cfg = MortonCfg()
+    e = (C.c_float * 3)(*[float(x) for x in extent])
+    lib().orc_morton_config(e, C.byref(cfg))
+    return cfg
+
+
+def morton_code(p, cfg):
+    q = (C.c_float * 3)(*[float(x) for x in p])
+    return int(lib().orc_morton_code_cfg(q, C.byref(cfg)))
+
+
+def morton_codes(boxes, scene):
+    """boxes: AABB[n] or PRIM_REF[n]."""
+    n = boxes.size
+    keys = np.zeros(n, dtype=np.uint32)
+    vals = np.zeros(n, dtype=np.uint32)
+    if boxes.dtype == T.PRIM_REF:
+        base, stride = C.c_void_p(boxes.ctypes.data + 4), 28
+    else:
+        base, stride = C.c_void_p(boxes.ctypes.data), 24
+    lib().orc_morton_codes(base, _u32(stride), _p(scene), _u32(n), _p(keys), _p(vals))
+    return keys, vals
+
+
+def sort_kv(keys, vals):
+    n = keys.size
+    ko = np.zeros(n, dtype=np.uint32)
+    vo = np.zeros(n, dtype=np.uint32)
+    lib().orc_sort_kv(_p(keys), _p(vals), _u32(n), _p(ko), _p(vo))
+    return ko, vo
+
+
+def lbvh_karras(refs, skeys, svals):
+    n = skeys.size
+    nodes = np.zeros(2 * n - 1, dtype=T.BVH2_NODE)
+    parents = np.zeros(2 * n - 1, dtype=np.uint32)
+    lib().orc_lbvh_karras(_p(refs), _p(skeys), _p(svals), _u32(n), _p(nodes), _p(parents))
+    return nodes, parents
+
+
+def lbvh_apetrei(tris, skeys, svals):
+    n = skeys.size
+    nodes = np.zeros(2 * n - 1, dtype=T.BVH2_NODE)
+    root = lib().orc_lbvh_apetrei(_p(tris), _p(skeys), _p(svals), _u32(n), _p(nodes))
+    return nodes, int(root)
+
+
+def ploc(boxes, svals):
+    n = svals.size
+    nodes = np.zeros(n - 1, dtype=T.BVH2_NODE)
+    leaves = np.zeros(n, dtype=T.PRIM_REF)
+    stats = np.zeros(4, dtype=np.uint32)
+    lib().orc_ploc(_p(boxes), _p(svals), _u32(n), _p(nodes), _p(leaves), _p(stats))
+    return nodes, leaves, {"iterations": int(stats[0]), "global_iterations": int(stats[1]), "sum_clusters": int(stats[2]) | (int(stats[3]) << 32)}
+
+
+def hploc(boxes, skeys, svals):
+    n = svals.size
+    nodes = np.zeros(n - 1, dtype=T.BVH2_NODE)
+    leaves = np.zeros(n, dtype=T.PRIM_REF)
+    stats = np.zeros(2, dtype=np.uint32)
+    lib().orc_hploc(_p(boxes), _p(skeys), _p(svals), _u32(n), _p(nodes), _p(leaves), _p(stats))
+    return nodes, leaves, {"merge_calls": int(stats[0]), "allocated": int(stats[1])}
+
+
+def collapse4(nodes, leaves, root, n):
+    wide = np.zeros(max(n - 1, 1), dtype=T.BVH4_NODE)
+    wl = np.zeros(n, dtype=T.PRIM_NODE)
+    cnt = lib().orc_collapse4(_p(nodes), _p(leaves), _u32(root), _u32(n), _p(wide), _p(wl))
+    return wide[:cnt].copy(), wl, int(cnt)
+
+
+def cost_bvh4(wide, wl, prim_boxes, root, n):
+    return float(lib().orc_cost_bvh4(_p(wide), _p(wl), _p(prim_boxes), _u32(root), _u32(wide.size), _u32(n - 1)))
+
+
+def cost_lbvh(nodes, root, n):
+    return float(lib().orc_cost_lbvh(_p(nodes), _u32(root), _u32(n), _u32(n - 1)))
+
+
+def cost_bvh2_ploc(nodes, leaves, root, n):
+    return float(lib().orc_cost_bvh2_ploc(_p(nodes), _p(leaves), _u32(root), _u32(n)))
+
+
+def check_bvh2(nodes, leaves, root, n):
+    return bool(lib().orc_check_bvh2(_p(nodes), _p(leaves), _u32(root), _u32(n)))
+
+
+def check_bvh4(wide, wl, root, n):
+    return bool(lib().orc_check_bvh4(_p(wide), _p(wl), _u32(root), _u32(n - 1)))
+
+
+def check_root_aabb(nodes, root, n):
+    return bool(lib().orc_check_root_aabb(_p(nodes), _u32(root), _u32(n), _u32(n - 1)))
+
+
+def bvh2_depth(nodes, root, n):
+    return int(lib().orc_bvh2_depth(_p(nodes), _u32(root), _u32(n)))
+
+
+def qt_rotation(axis_angle):
+    a = (C.c_float * 4)(*[float(x) for x in axis_angle])
+    o = (C.c_float * 4)()
+    lib().orc_qt_rotation(a, o)
+    return np.array(list(o), dtype=np.float32)
+
+
+def ray_zdir(fov):
+    return float(lib().orc_ray_zdir(C.c_float(float(fov))))
+
+
+def generate_rays(cam, width, height):
+    rays = np.zeros(width * height, dtype=T.RAY)
+    lib().orc_generate_rays(_p(cam), _u32(width), _u32(height), _p(rays))
+    return rays
+
+
+def traverse(rays, nodes, leaves, tris, transform, root, n):
+    hits = np.zeros(rays.size, dtype=T.HIT)
+    cnt = lib().orc_traverse(_p(rays), _p(nodes), _p(leaves), _p(tris), _p(transform), _u32(root), _u32(n - 1), _u32(rays.size), _p(hits))
+    return hits, int(cnt)
+
+
+def binned_sah(tris):
+    n = tris.size
+    nodes = np.zeros(3 * n - 1, dtype=T.SAH_NODE)
+    cnt = int(lib().orc_binned_sah_build(_p(tris), _u32(n), _p(nodes)))
+    return nodes[:cnt], cnt
+
+
+def cost_binned_sah(nodes):
+    quirk = float(lib().orc_cost_binned_sah_quirk(_p(nodes), _u32(0), _u32(nodes.size)))
+    proper = float(lib().orc_cost_binned_sah_proper(_p(nodes), _u32(nodes.size)))
+    return quirk, proper
+
+
+def check_sah(nodes, n):
+    return bool(lib().orc_check_sah(_p(nodes), _u32(n)))
+
+
+def synth_half(n):
+    """half-size h = 1000 * N^(-1/3), rounded to float once on the host."""
+    return np.float32(1000.0 * float(n) ** (-1.0 / 3.0))
+
+
+def synth_uniform(n, seed, first=0, count=None, half=None):
+    count = n if count is None else count
+    out = np.zeros(count, dtype=T.TRIANGLE)
+    h = synth_half(n) if half is None else np.float32(half)
+    lib().orc_synth_uniform(C.c_uint64(first), _u32(count), _u32(seed), C.c_float(float(h)), _p(out))
+    return out
+
+
+def top_level(root_boxes):
+    g = root_boxes.size
+    nodes = np.zeros(2 * g - 1, dtype=T.BVH2_NODE)
+    lib().orc_top_level(_p(root_boxes), _u32(g), _p(nodes))
+    return nodes
+
+
+# ---- full pipelines (launch order of the reference builders) ----
+def build_lbvh(tris, single_pass=False):
+    """TwoPassLbvh::build (TwoPassLbvh.cpp:17-197) / SinglePassLbvh::build (SinglePassLbvh.cpp:17-188)."""
+    n = tris.size
+    refs, boxes, scene = primrefs(tris)
+    keys, vals = morton_codes(refs, scene)
+    sk, sv = sort_kv(keys, vals)
+    if single_pass:
+        nodes, root = lbvh_apetrei(tris, sk, sv)
+    else:
+        nodes, _ = lbvh_karras(refs, sk, sv)
+        root = 0
+    wide, wl, cnt = collapse4(nodes, None, root, n)
+    cost = cost_bvh4(wide, wl, boxes, 0, n)
+    return dict(scene=scene, keys=keys, vals=vals, skeys=sk, svals=sv, nodes=nodes, root=root, wide=wide, wide_leaves=wl,
+                wide_count=cnt, cost=cost, boxes=boxes, refs=refs)
+
+
+def build_ploc(tris, hierarchical=False):
+    """PLOCNew::build (PLOC++Bvh.cpp:16-196) / HPLOC::build (Hploc.cpp:16-165)."""
+    n = tris.size
+    refs, boxes, scene = primrefs(tris)
+    keys, vals = morton_codes(boxes, scene)
+    sk, sv = sort_kv(keys, vals)
+    if hierarchical:
+        nodes, leaves, stats = hploc(boxes, sk, sv)
+    else:
+        nodes, leaves, stats = ploc(boxes, sv)
+    wide, wl, cnt = collapse4(nodes, leaves, 0, n)
+    cost = cost_bvh4(wide, wl, boxes, 0, n)
+    return dict(scene=scene, keys=keys, vals=vals, skeys=sk, svals=sv, nodes=nodes, leaves=leaves, root=0, wide=wide,
+                wide_leaves=wl, wide_count=cnt, cost=cost, boxes=boxes, stats=stats)
