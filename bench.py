@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""bench.py — BVH build throughput (Mprims/s) of the B200-native builder, one JSON line on rank 0.
+
+Workload (config.workload): BASELINE.json configs[3]/[4] — synthetic `synth_uniform_v1` triangles,
+10 M per GPU, single-pass LBVH + 4-wide collapse; the input (640 MB/GPU) and every intermediate are larger than the 126 MB
+L2, so no L2 flush is needed between steps (config.l2).  N > 1: the stream is sharded by primitive range, one process per
+GPU; the shards agree on the global scene box with ONE NCCL all-reduce(MAX) of {-min,max} and exchange their root boxes with
+ONE all-gather for the top-level tree (weak scaling: 10 M per GPU).
+
+  value  = primitives built per second, whole job, inputs resident in HBM (device-timed, max over ranks)
+  e2e    = same through the public host API with HOST (pinned) triangles: H2D of the triangles + build + D2H of the
+           Bvh2 nodes, Bvh4 nodes and Bvh4 leaves every step (what TwoPassLbvh::build does, TwoPassLbvh.cpp:19,145,185-193)
+  roofline = dominant kernel: algorithmic bytes per launch / CUDA-event time per launch vs MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline = the reference's CPU builder (BinnedSahBvh, restated in oracle/) on a bounded sample, 1 thread
+
+`--impl reference` times that CPU builder alone (rank 0 only)."""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "hip-bvh-construction_b200"))
+
+PRIMS_PER_GPU = 10_000_000
+SEED = 0x00B20010
+REF_SAMPLE = 262_144       # --impl reference: triangles per step
+CPU_BASELINE_SAMPLE = 1_000_000
+
+# algorithmic bytes per primitive and launch (DESIGN.md "Kernels")
+ALGO_BYTES = {
+    "primref_extents": 64 + 24,
+    "morton30": 24 + 8,
+    "radix_hist": 4,
+    "onesweep_pass": 15,            # 8 B in + 8 B out per pair; pass 0 does not read values (iota): (12 + 3*16) / 4
+    "lbvh_fused_apetrei": 132,
+    "lbvh_fused_karras": 140,
+}
+
+
+def peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+        sm = [int(r[0]) for r in self.rows if r and r[0].isdigit()]
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for r in self.rows if len(r) >= 6 for k in range(4) if r[2 + k].lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def run_reference(args):
+    """The reference's own CPU implementation of the build (SahBvh::build, BinnedSahBvh.cpp:13-204; restated in oracle/ because the
+    reference's loop needs a live GPU context) on the host cores; bounded sample of the same synthetic stream."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as orc
+    orc.build()
+    tris = orc.synth_uniform(PRIMS_PER_GPU * args.gpus, SEED, first=0, count=REF_SAMPLE)
+    for _ in range(args.warmup):
+        orc.binned_sah(tris)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        nodes, cnt = orc.binned_sah(tris)
+    dt = (time.perf_counter() - t0) / args.steps
+    v = REF_SAMPLE / dt / 1e6
+    line = {"impl": "reference", "metric": "bvh_build_throughput", "value": v, "unit": "Mprims/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(args.gpus),
+            "cpu_baseline": {"value": v, "unit": "Mprims/s", "cores": 1, "kind": "port",
+                             "sample": f"first {REF_SAMPLE} triangles of the synth_uniform_v1 stream per step, binned-SAH CPU builder (BinnedSahBvh.cpp:13-204 restated), 1 thread of {os.cpu_count()}"},
+            "e2e": {"value": v, "unit": "Mprims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_config(gpus):
+    return {"workload": f"synth_uniform_v1 {PRIMS_PER_GPU // 1_000_000}M triangles per GPU (BASELINE configs[3]/[4]), single-pass LBVH + Bvh4 collapse",
+            "prims_per_gpu": PRIMS_PER_GPU, "total_prims": PRIMS_PER_GPU * gpus, "seed": hex(SEED), "builder": "SinglePassLbvh",
+            "parallelism": f"primitive-range shards x{gpus}" if gpus > 1 else "single GPU",
+            "l2": "inputs and intermediates (>=640 MB per GPU) exceed the 126 MB L2; no flush between steps"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b2bvh", choices=["b2bvh", "reference"])
+    ap.add_argument("--prims", type=int, default=PRIMS_PER_GPU, help="primitives per GPU (default: the benchmark config)")
+    ap.add_argument("--no-extras", action="store_true", help="skip e2e / cpu baseline / mesh extras (profiling runs)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b2bvh" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    from b2bvh import capi, types as T
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n = args.prims
+    n_total = n * world
+    stream = torch.cuda.current_stream()
+    ctx = capi.Context(local, stream=stream.cuda_stream)
+    d_tris = ctx.synth_uniform(n_total, SEED, first=rank * n, count=n)
+    ctx.sync()
+    algo = capi.SINGLE_PASS_LBVH
+
+    box6 = torch.zeros(6, dtype=torch.float32, device="cuda")
+    roots = torch.zeros(world * 6, dtype=torch.float32, device="cuda")
+    root_local = torch.zeros(6, dtype=torch.float32, device="cuda")
+    top_nodes = torch.zeros((2 * world - 1) * 8, dtype=torch.float32, device="cuda")
+    launches = [0]
+
+    def step(tris_ptr, on_device):
+        if world == 1:
+            tree = ctx.build(algo, tris_ptr, n=n, tris_on_device=on_device)
+            launches[0] += tree.n_launches
+            return tree
+        # sharded build: local boxes -> ONE all-reduce(MAX) of {-min,max} -> local build in the global frame -> ONE all-gather of roots
+        capi.check(ctx.lib.b2bvh_shard_extents(ctx.h, tris_ptr, n, 1 if on_device else 0, box6.data_ptr()), "b2bvh_shard_extents")
+        dist.all_reduce(box6, op=dist.ReduceOp.MAX)
+        b = box6.cpu().numpy()
+        tree = ctx.build(algo, tris_ptr, n=n, tris_on_device=on_device, scene_box=np.concatenate([-b[:3], b[3:]]))
+        node = ctx.download(tree.d_bvhNodes + 32 * tree.root, T.BVH2_NODE, 1)
+        root_local.copy_(torch.from_numpy(np.concatenate([node["mn"][0], node["mx"][0]])))
+        dist.all_gather_into_tensor(roots, root_local)
+        capi.check(ctx.lib.b2bvh_top_level(ctx.h, roots.data_ptr(), world, top_nodes.data_ptr()), "b2bvh_top_level")
+        launches[0] += tree.n_launches + 2
+        return tree
+
+    def barrier():
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if dist:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()) / steps
+
+    # ---- device-resident throughput (value) ----
+    for _ in range(args.warmup):
+        tree = step(d_tris, True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches[0] = 0
+    ms_step = timed(lambda: step(d_tris, True), args.steps)
+    gpu_launches = launches[0]
+    clocks = sampler.stop() if rank == 0 else None
+    value = n_total / (ms_step * 1e-3) / 1e6
+    stage_ms = {capi.STAGE_NAMES[k]: float(tree.stage_ms[k]) for k in (capi.T_EXTENTS, capi.T_MORTON, capi.T_SORT, capi.T_BUILD, capi.T_COLLAPSE)}
+
+    # ---- per-kernel CUDA-event times over a second run of the same steps (roofline) ----
+    per = {}
+    ctx.profile(True)
+    for _ in range(max(3, min(args.steps, 10))):
+        ctx.profile(True)
+        step(d_tris, True)
+        ctx.sync()
+        for name, ms in ctx.profile_entries():
+            per.setdefault(name, []).append(ms)
+    ctx.profile(False)
+    peak, peak_src = peak_hbm()
+    kernels = {}
+    for name, v in per.items():
+        avg = sum(v) / len(v)
+        k = {"launches_per_step": len(v) // max(3, min(args.steps, 10)), "avg_ms": avg, "total_ms_per_step": sum(v) / max(3, min(args.steps, 10))}
+        if name in ALGO_BYTES:
+            k["algorithmic_bytes_per_launch"] = ALGO_BYTES[name] * n
+            k["gbs"] = ALGO_BYTES[name] * n / (avg * 1e-3) / 1e9
+            k["frac"] = k["gbs"] / peak
+        kernels[name] = k
+    dom = max((nm for nm in kernels if "gbs" in kernels[nm]), key=lambda nm: kernels[nm]["total_ms_per_step"])
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s", "frac": kernels[dom]["frac"],
+                "traffic": None, "peak_source": peak_src, "avg_launch_ms": kernels[dom]["avg_ms"],
+                "algorithmic_bytes_per_launch": kernels[dom]["algorithmic_bytes_per_launch"]}
+    tr = os.path.join(ROOT, "profiles", "dram_traffic.json")  # ncu --set full capture of the dominant kernel (profiles/README.md)
+    if os.path.exists(tr):
+        try:
+            roofline["traffic"] = json.load(open(tr)).get(dom)
+        except Exception:
+            pass
+
+    line = {"metric": "bvh_build_throughput", "value": value, "unit": "Mprims/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(world), "clocks": clocks, "gpu_launches": gpu_launches, "stage_ms": stage_ms, "roofline": roofline,
+            "kernels": kernels, "n_wide": int(tree.n_wide)}
+
+    if not args.no_extras:
+        # ---- end to end through the public API with HOST triangles ----
+        nbytes = n * 64
+        h_tris = ctx.pinned(nbytes)
+        capi.check(ctx.lib.b2bvh_d2h(ctx.h, h_tris, d_tris, nbytes), "d2h")
+        out_bytes = (2 * n - 1) * 32 + n * 128 + n * 8
+        h_out = ctx.pinned(out_bytes)
+        d2h = [0]
+
+        def e2e_step():
+            t = step(h_tris, False)
+            b0, b1, b2 = (2 * n - 1) * 32, t.n_wide * 128, n * 8
+            capi.check(ctx.lib.b2bvh_d2h(ctx.h, h_out, t.d_bvhNodes, b0), "d2h nodes")
+            capi.check(ctx.lib.b2bvh_d2h(ctx.h, h_out + b0, t.d_wideBvhNodes, b1), "d2h wide")
+            capi.check(ctx.lib.b2bvh_d2h(ctx.h, h_out + b0 + b1, t.d_wideLeafNodes, b2), "d2h wide leaves")
+            d2h[0] = b0 + b1 + b2
+
+        for _ in range(2):
+            e2e_step()
+        e2e_steps = max(3, args.steps // 2)
+        ms_e2e = timed(e2e_step, e2e_steps)
+        line["e2e"] = {"value": n_total / (ms_e2e * 1e-3) / 1e6, "unit": "Mprims/s", "ms_per_step": ms_e2e, "steps": e2e_steps,
+                       "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": d2h[0],
+                       "api": "b2bvh_build(host triangles, pinned) + b2bvh_d2h of Bvh2 nodes, Bvh4 nodes, Bvh4 leaves"}
+
+        if rank == 0 and world == 1:
+            # ---- CPU baseline beside it: the reference's CPU builder on a bounded sample (oracle = checker/baseline only) ----
+            sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            import oracle as orc
+            orc.build()
+            sample = min(CPU_BASELINE_SAMPLE, n)
+            host = ctx.download(d_tris, T.TRIANGLE, sample)
+            t0 = time.perf_counter()
+            _, cnt = orc.binned_sah(host)
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": sample / dt / 1e6, "unit": "Mprims/s", "cores": 1, "kind": "port", "seconds": dt,
+                                    "sample": f"first {sample} triangles of the workload, one build, binned-SAH CPU builder (BinnedSahBvh.cpp:13-204 restated in oracle/), 1 thread of {os.cpu_count()} host cores"}
+            # ---- the reference's own scenes (BASELINE configs[1]/[2]), when staged ----
+            extras = {}
+            mesh_dir = os.path.join(ROOT, "oracle", "_ref", "meshes")
+            for mesh in ("bunny", "sponza"):
+                p = os.path.join(mesh_dir, mesh + ".tri")
+                if not os.path.exists(p):
+                    continue
+                mt = T.triangles_from_array(np.fromfile(p, dtype=np.float32).reshape(-1, 9))
+                dm = ctx.upload(mt)
+                res = {"n": int(mt.size)}
+                for nm, al in (("TwoPassLbvh", capi.TWO_PASS_LBVH), ("SinglePassLbvh", capi.SINGLE_PASS_LBVH), ("PLOC++", capi.PLOCPP), ("HPLOC", capi.HPLOC)):
+                    try:
+                        for _ in range(3):
+                            ctx.build(al, dm, n=mt.size, tris_on_device=True)
+                        best = None
+                        for _ in range(10):
+                            t = ctx.build(al, dm, n=mt.size, tris_on_device=True)
+                            tot = sum(t.stage_ms[k] for k in (capi.T_EXTENTS, capi.T_MORTON, capi.T_SORT, capi.T_BUILD))
+                            if best is None or tot < best[0]:
+                                best = (tot, [float(t.stage_ms[k]) for k in (capi.T_EXTENTS, capi.T_MORTON, capi.T_SORT, capi.T_BUILD, capi.T_COLLAPSE)])
+                        res[nm] = {"total_ms": best[0], "Mprims_s": mt.size / best[0] / 1e3, "extents_morton_sort_build_collapse_ms": best[1],
+                                   "bvh4_cost": ctx.tree_cost(t)}
+                    except capi.B2bvhError as e:
+                        res[nm] = {"error": str(e)[:80]}
+                ctx.free(dm)
+                extras[mesh] = res
+            line["reference_scenes"] = extras
+
+    if rank == 0:
+        print(json.dumps(line))
+    if dist:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

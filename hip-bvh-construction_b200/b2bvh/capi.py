@@ -1,0 +1,279 @@
+"""ctypes binding of include/b2bvh.h — the same symbols the C++ host classes bind with dlopen.
+No compute happens here; every call goes to libb2bvh.so (hand-written CUDA).  Missing library => ImportError-like
+RuntimeError at load(), never a silent fallback."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import types as T
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "libb2bvh.so")
+
+TWO_PASS_LBVH, SINGLE_PASS_LBVH, PLOCPP, HPLOC = 0, 1, 2, 3
+TRAVERSE_WHILE, TRAVERSE_SPECULATIVE_WHILE = 0, 1
+T_EXTENTS, T_MORTON, T_SORT, T_BUILD, T_TRAVERSAL, T_COLLAPSE, T_RAYGEN, T_COUNT = range(8)
+STAGE_NAMES = ["CalculateCentroidExtentsTime", "CalculateMortonCodesTime", "SortingTime", "BvhBuildTime", "TraversalTime",
+               "CollapseTime", "RayGenTime"]
+
+
+class Aabb(C.Structure):
+    _fields_ = [("mn", C.c_float * 3), ("mx", C.c_float * 3)]
+
+
+class BuildOpts(C.Structure):
+    _fields_ = [("collapse", C.c_uint32), ("tris_on_device", C.c_uint32), ("use_scene_box", C.c_uint32), ("scene_box", Aabb),
+                ("stage_timing", C.c_uint32), ("karras_two_kernel", C.c_uint32), ("reserved", C.c_uint32 * 4)]
+
+
+class Tree(C.Structure):
+    _fields_ = [("algo", C.c_uint32), ("n_prims", C.c_uint32), ("n_internal", C.c_uint32), ("root", C.c_uint32), ("n_wide", C.c_uint32),
+                ("leaves_separate", C.c_uint32),
+                ("d_triangleBuff", C.c_void_p), ("d_triangleAabb", C.c_void_p), ("d_sceneExtents", C.c_void_p),
+                ("d_mortonCodeKeys", C.c_void_p), ("d_mortonCodeValues", C.c_void_p), ("d_sortedMortonCodeKeys", C.c_void_p),
+                ("d_sortedMortonCodeValues", C.c_void_p), ("d_bvhNodes", C.c_void_p), ("d_parentIdxs", C.c_void_p),
+                ("d_leafNodes", C.c_void_p), ("d_wideBvhNodes", C.c_void_p), ("d_wideLeafNodes", C.c_void_p),
+                ("stage_ms", C.c_float * T_COUNT), ("build_ms", C.c_float), ("h2d_ms", C.c_float), ("n_iterations", C.c_uint32),
+                ("n_launches", C.c_uint32)]
+
+
+# every symbol include/b2bvh.h declares (tests check the library exports each of them)
+SYMBOLS = ["b2bvh_ctx_create", "b2bvh_ctx_destroy", "b2bvh_device_name", "b2bvh_device_sm_count", "b2bvh_alloc", "b2bvh_free",
+           "b2bvh_memset", "b2bvh_h2d", "b2bvh_d2h", "b2bvh_sync", "b2bvh_host_alloc_pinned", "b2bvh_host_free_pinned",
+           "b2bvh_last_error", "b2bvh_build", "b2bvh_scene_extents", "b2bvh_morton_codes", "b2bvh_sort_pairs", "b2bvh_generate_rays",
+           "b2bvh_traverse", "b2bvh_shard_extents", "b2bvh_top_level", "b2bvh_cost_bvh4", "b2bvh_cost_lbvh", "b2bvh_tree_cost",
+           "b2bvh_abi_version", "b2bvh_synth_uniform", "b2bvh_profile_enable", "b2bvh_profile_count", "b2bvh_profile_entry"]
+
+_lib = None
+
+
+class B2bvhError(RuntimeError):
+    pass
+
+
+def load():
+    """dlopen libb2bvh.so.  Fails loudly when the CUDA library has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise B2bvhError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                         f"(nvcc, sm_100a).  There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    vp, u32, sz, fp = C.c_void_p, C.c_uint32, C.c_size_t, C.POINTER(C.c_float)
+    sig = {
+        "b2bvh_ctx_create": [C.c_int, vp, C.POINTER(vp)], "b2bvh_ctx_destroy": [vp], "b2bvh_device_name": [vp, C.c_char_p, sz],
+        "b2bvh_device_sm_count": [vp, C.POINTER(C.c_int)], "b2bvh_alloc": [vp, sz, C.POINTER(vp)], "b2bvh_free": [vp, vp],
+        "b2bvh_memset": [vp, vp, C.c_int, sz], "b2bvh_h2d": [vp, vp, vp, sz], "b2bvh_d2h": [vp, vp, vp, sz], "b2bvh_sync": [vp],
+        "b2bvh_host_alloc_pinned": [sz, C.POINTER(vp)], "b2bvh_host_free_pinned": [vp],
+        "b2bvh_build": [vp, C.c_int, vp, u32, C.POINTER(BuildOpts), C.POINTER(Tree)],
+        "b2bvh_scene_extents": [vp, vp, u32, vp, vp], "b2bvh_morton_codes": [vp, vp, vp, u32, vp, vp],
+        "b2bvh_sort_pairs": [vp, vp, vp, vp, vp, u32, u32, u32],
+        "b2bvh_generate_rays": [vp, vp, u32, u32, vp, fp],
+        "b2bvh_traverse": [vp, C.POINTER(Tree), vp, u32, vp, C.c_int, vp, vp, fp],
+        "b2bvh_shard_extents": [vp, vp, u32, u32, vp], "b2bvh_top_level": [vp, vp, u32, vp],
+        "b2bvh_cost_bvh4": [vp, vp, vp, u32, u32, u32], "b2bvh_cost_lbvh": [vp, u32, u32, u32],
+        "b2bvh_tree_cost": [vp, C.POINTER(Tree), fp], "b2bvh_abi_version": [], "b2bvh_last_error": [],
+        "b2bvh_synth_uniform": [vp, C.c_uint64, u32, u32, C.c_float, vp], "b2bvh_profile_enable": [vp, C.c_int],
+        "b2bvh_profile_count": [vp, C.POINTER(C.c_int)], "b2bvh_profile_entry": [vp, C.c_int, C.c_char_p, sz, fp],
+    }
+    for name, args in sig.items():
+        f = getattr(lib, name)
+        f.argtypes = args
+        f.restype = C.c_int
+    lib.b2bvh_last_error.restype = C.c_char_p
+    lib.b2bvh_cost_bvh4.restype = C.c_float
+    lib.b2bvh_cost_lbvh.restype = C.c_float
+    lib.b2bvh_abi_version.restype = C.c_uint32
+    _lib = lib
+    return lib
+
+
+def check(status, what=""):
+    if status != 0:
+        raise B2bvhError(f"{what} failed with status {status}: {load().b2bvh_last_error().decode()}")
+
+
+def _hp(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """Replaces BvhConstruction::Context (src/Context.cpp:7-22): one device, one stream."""
+
+    def __init__(self, device=0, stream=None):
+        self.lib = load()
+        h = C.c_void_p()
+        check(self.lib.b2bvh_ctx_create(int(device), C.c_void_p(stream) if stream else None, C.byref(h)), "b2bvh_ctx_create")
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.b2bvh_ctx_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def name(self):
+        buf = C.create_string_buffer(256)
+        check(self.lib.b2bvh_device_name(self.h, buf, 256))
+        return buf.value.decode()
+
+    def sm_count(self):
+        v = C.c_int()
+        check(self.lib.b2bvh_device_sm_count(self.h, C.byref(v)))
+        return v.value
+
+    # GpuMemory<T> look-alike primitives
+    def alloc(self, nbytes):
+        p = C.c_void_p()
+        check(self.lib.b2bvh_alloc(self.h, nbytes, C.byref(p)), "b2bvh_alloc")
+        return p.value
+
+    def free(self, dptr):
+        check(self.lib.b2bvh_free(self.h, C.c_void_p(dptr)), "b2bvh_free")
+
+    def upload(self, arr):
+        arr = np.ascontiguousarray(arr)
+        d = self.alloc(arr.nbytes)
+        check(self.lib.b2bvh_h2d(self.h, C.c_void_p(d), _hp(arr), arr.nbytes), "b2bvh_h2d")
+        return d
+
+    def h2d(self, dptr, arr):
+        arr = np.ascontiguousarray(arr)
+        check(self.lib.b2bvh_h2d(self.h, C.c_void_p(dptr), _hp(arr), arr.nbytes), "b2bvh_h2d")
+
+    def download(self, dptr, dtype, count):
+        out = np.zeros(count, dtype=dtype)
+        if count:
+            check(self.lib.b2bvh_d2h(self.h, _hp(out), C.c_void_p(dptr), out.nbytes), "b2bvh_d2h")
+        return out
+
+    def sync(self):
+        check(self.lib.b2bvh_sync(self.h))
+
+    def pinned(self, nbytes):
+        p = C.c_void_p()
+        check(self.lib.b2bvh_host_alloc_pinned(nbytes, C.byref(p)), "b2bvh_host_alloc_pinned")
+        return p.value
+
+    # ---- stages ----
+    def build(self, algo, tris, n=None, collapse=True, tris_on_device=False, scene_box=None, karras_two_kernel=False):
+        """tris: TRIANGLE[n] numpy array (host) or an int device/pinned-host pointer (then pass n)."""
+        opts = BuildOpts()
+        opts.collapse = 1 if collapse else 0
+        opts.tris_on_device = 1 if tris_on_device else 0
+        opts.stage_timing = 1
+        opts.karras_two_kernel = 1 if karras_two_kernel else 0
+        if scene_box is not None:
+            opts.use_scene_box = 1
+            sb = np.asarray(scene_box, dtype=np.float32).reshape(6)
+            for k in range(3):
+                opts.scene_box.mn[k] = float(sb[k])
+                opts.scene_box.mx[k] = float(sb[3 + k])
+        if isinstance(tris, np.ndarray):
+            assert tris.dtype == T.TRIANGLE and tris.flags["C_CONTIGUOUS"]
+            n = tris.size
+            ptr = _hp(tris)
+            self._keepalive = tris
+        else:
+            ptr = C.c_void_p(int(tris))
+        tree = Tree()
+        check(self.lib.b2bvh_build(self.h, int(algo), ptr, int(n), C.byref(opts), C.byref(tree)), "b2bvh_build")
+        return tree
+
+    def tree_cost(self, tree):
+        c = C.c_float()
+        check(self.lib.b2bvh_tree_cost(self.h, C.byref(tree), C.byref(c)), "b2bvh_tree_cost")
+        return float(c.value)
+
+    def fetch(self, tree):
+        """D2H of everything a build produced (GpuMemory::getData on every member)."""
+        n = tree.n_prims
+        separate = bool(tree.leaves_separate)
+        r = dict(n=n, root=tree.root, n_wide=tree.n_wide)
+        r["boxes"] = self.download(tree.d_triangleAabb, T.AABB, n)
+        r["scene"] = self.download(tree.d_sceneExtents, T.AABB, 1)
+        r["keys"] = self.download(tree.d_mortonCodeKeys, np.uint32, n)
+        r["vals"] = self.download(tree.d_mortonCodeValues, np.uint32, n)
+        r["skeys"] = self.download(tree.d_sortedMortonCodeKeys, np.uint32, n)
+        r["svals"] = self.download(tree.d_sortedMortonCodeValues, np.uint32, n)
+        r["nodes"] = self.download(tree.d_bvhNodes, T.BVH2_NODE, n - 1 if separate else 2 * n - 1)
+        r["parents"] = self.download(tree.d_parentIdxs, np.uint32, 2 * n - 1) if tree.d_parentIdxs else None
+        r["leaves"] = self.download(tree.d_leafNodes, T.PRIM_REF, n) if separate else None
+        if tree.n_wide:
+            r["wide"] = self.download(tree.d_wideBvhNodes, T.BVH4_NODE, tree.n_wide)
+            r["wide_leaves"] = self.download(tree.d_wideLeafNodes, T.PRIM_NODE, n)
+        return r
+
+    def sort_pairs(self, keys, vals, start_bit=0, end_bit=32):
+        keys = np.ascontiguousarray(keys, dtype=np.uint32)
+        n = keys.size
+        dk = self.upload(keys)
+        dv = self.upload(np.ascontiguousarray(vals, dtype=np.uint32)) if vals is not None else None
+        ko, vo = self.alloc(4 * n), self.alloc(4 * n)
+        try:
+            check(self.lib.b2bvh_sort_pairs(self.h, C.c_void_p(dk), C.c_void_p(dv) if dv else None, C.c_void_p(ko), C.c_void_p(vo), n,
+                                            start_bit, end_bit), "b2bvh_sort_pairs")
+            return self.download(ko, np.uint32, n), self.download(vo, np.uint32, n)
+        finally:
+            for p in (dk, dv, ko, vo):
+                if p:
+                    self.free(p)
+
+    def synth_uniform(self, n_total, seed, first=0, count=None, half=None):
+        """synth_uniform_v1 triangles [first, first+count) generated on the device; returns the device pointer."""
+        count = n_total if count is None else count
+        h = np.float32(1000.0 * float(n_total) ** (-1.0 / 3.0)) if half is None else np.float32(half)
+        d = self.alloc(count * 64)
+        check(self.lib.b2bvh_synth_uniform(self.h, int(first), int(count), int(seed), C.c_float(float(h)), C.c_void_p(d)), "b2bvh_synth_uniform")
+        return d
+
+    def profile(self, on=True):
+        check(self.lib.b2bvh_profile_enable(self.h, 1 if on else 0))
+
+    def profile_entries(self):
+        n = C.c_int()
+        check(self.lib.b2bvh_profile_count(self.h, C.byref(n)))
+        out = []
+        buf = C.create_string_buffer(64)
+        ms = C.c_float()
+        for i in range(n.value):
+            check(self.lib.b2bvh_profile_entry(self.h, i, buf, 64, C.byref(ms)))
+            out.append((buf.value.decode(), float(ms.value)))
+        return out
+
+    def generate_rays(self, cam, width, height):
+        d_cam_host = np.ascontiguousarray(cam)
+        d_rays = self.alloc(width * height * 32)
+        ms = C.c_float()
+        check(self.lib.b2bvh_generate_rays(self.h, _hp(d_cam_host), width, height, C.c_void_p(d_rays), C.byref(ms)), "b2bvh_generate_rays")
+        return d_rays, float(ms.value)
+
+    def traverse(self, tree, d_rays, n_rays, transform, kernel=TRAVERSE_WHILE, want_rgba=False):
+        d_hits = self.alloc(n_rays * 32)
+        d_rgba = self.alloc(n_rays * 4) if want_rgba else None
+        ms = C.c_float()
+        tr = np.ascontiguousarray(transform)
+        try:
+            check(self.lib.b2bvh_traverse(self.h, C.byref(tree), C.c_void_p(d_rays), n_rays, _hp(tr), int(kernel), C.c_void_p(d_hits),
+                                          C.c_void_p(d_rgba) if d_rgba else None, C.byref(ms)), "b2bvh_traverse")
+            hits = self.download(d_hits, T.HIT, n_rays)
+            rgba = self.download(d_rgba, np.uint8, n_rays * 4).reshape(-1, 4) if d_rgba else None
+            return hits, rgba, float(ms.value)
+        finally:
+            self.free(d_hits)
+            if d_rgba:
+                self.free(d_rgba)
+
+
+def cost_bvh4(wide, wide_leaves, prim_boxes, n):
+    lib = load()
+    return float(lib.b2bvh_cost_bvh4(_hp(wide), _hp(wide_leaves), _hp(prim_boxes), 0, wide.size, n - 1))
+
+
+def cost_lbvh(nodes, root, n):
+    lib = load()
+    return float(lib.b2bvh_cost_lbvh(_hp(nodes), root, n, n - 1))

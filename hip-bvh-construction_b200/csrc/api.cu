@@ -1,0 +1,382 @@
+/*
+ * api.cu — the C ABI of libb2bvh.so (include/b2bvh.h): context, memory, the build orchestration that replaces the
+ * bodies of TwoPassLbvh::build / SinglePassLbvh::build / PLOCNew::build / HPLOC::build (src/*.cpp), and the host-side
+ * SAH cost reporting (Utility::calculatebvh4Cost / calculateLbvhCost, Utility.cpp:317-396).
+ *
+ * Differences from the reference's host flow that do not change results:
+ *   - kernels are compiled ahead of time for sm_100a (no RTC per launch, Kernel.cpp:52-122), the sort object and all
+ *     device buffers live in the context and are reused across builds (TwoPassLbvh.cpp:73 constructs RadixSort per build);
+ *   - no blocking event-sync after every launch (Timer.h:48-56): stage boundaries are CUDA events on one stream and
+ *     are read once at the end;
+ *   - primitive boxes are computed on the device (the reference's TwoPass path does it on the host in
+ *     doEarlySplitClipping with splitting disabled).
+ */
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+
+int b2_fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+int b2_check(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return 0;
+  return b2_fail(e == cudaErrorMemoryAllocation ? B2BVH_ERR_OOM : B2BVH_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+int b2_reserve(b2bvh_ctx* ctx, int slot, size_t bytes, void** out) {
+  b2bvh_ctx::Buf& b = ctx->bufs[slot];
+  if (bytes == 0) bytes = 16;
+  if (b.cap < bytes) {
+    if (b.p) { B2_CUDA(cudaStreamSynchronize(ctx->stream)); B2_CUDA(cudaFree(b.p)); b.p = nullptr; b.cap = 0; }
+    const size_t want = (bytes + 255) & ~(size_t)255;
+    B2_CUDA(cudaMalloc(&b.p, want));
+    b.cap = want;
+  }
+  *out = b.p;
+  return 0;
+}
+
+enum {
+  SLOT_TRIS = 0, SLOT_AABB, SLOT_CTL, SLOT_KEYS, SLOT_VALS, SLOT_SKEYS, SLOT_SVALS, SLOT_TKEYS, SLOT_TVALS, SLOT_SORT, SLOT_NODES,
+  SLOT_PARENTS, SLOT_LBVH, SLOT_WIDE, SLOT_WLEAVES, SLOT_COLLAPSE, SLOT_LEAVES, SLOT_PLOC, SLOT_HPLOC, SLOT_MISC, SLOT_COUNT
+};
+/* SLOT_CTL (256 B): [0..23] scene box, [32..63] extents scratch8, [64..87] {-min,max}, [96] root index, [128..] misc */
+
+extern "C" {
+
+uint32_t b2bvh_abi_version(void) { return 1; }
+const char* b2bvh_last_error(void) { return g_err; }
+
+int b2bvh_ctx_create(int device, void* cuda_stream, b2bvh_ctx** out) {
+  if (!out) return b2_fail(B2BVH_ERR_INVALID, "ctx_create: out is null");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return b2_fail(B2BVH_ERR_CUDA, "ctx_create: no CUDA device (%s); libb2bvh has no CPU fallback", e == cudaSuccess ? "count is 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= count) return b2_fail(B2BVH_ERR_INVALID, "ctx_create: device %d out of range [0,%d)", device, count);
+  B2_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  B2_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) return b2_fail(B2BVH_ERR_CUDA, "ctx_create: device '%s' is sm_%d%d; libb2bvh is built for sm_100a only", prop.name, prop.major, prop.minor);
+  b2bvh_ctx* c = new b2bvh_ctx();
+  memset(c, 0, sizeof(*c));
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  snprintf(c->name, sizeof(c->name), "%s", prop.name);
+  if (cuda_stream) { c->stream = (cudaStream_t)cuda_stream; c->own_stream = false; }
+  else { B2_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+  for (int i = 0; i < 16; i++) B2_CUDA(cudaEventCreate(&c->ev[i]));
+  void* ctl;
+  B2_TRY(b2_reserve(c, SLOT_CTL, 256, &ctl));
+  B2_CUDA(cudaMemsetAsync(ctl, 0, 256, c->stream));
+  B2_CUDA(cudaStreamSynchronize(c->stream));
+  *out = c;
+  return 0;
+}
+
+int b2bvh_ctx_destroy(b2bvh_ctx* ctx) {
+  if (!ctx) return 0;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (int i = 0; i < 32; i++) if (ctx->bufs[i].p) cudaFree(ctx->bufs[i].p);
+  for (int i = 0; i < 16; i++) cudaEventDestroy(ctx->ev[i]);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return 0;
+}
+
+int b2bvh_device_name(b2bvh_ctx* ctx, char* buf, size_t cap) {
+  if (!ctx || !buf || cap == 0) return b2_fail(B2BVH_ERR_INVALID, "device_name: bad argument");
+  snprintf(buf, cap, "%s", ctx->name);
+  return 0;
+}
+int b2bvh_device_sm_count(b2bvh_ctx* ctx, int* out) {
+  if (!ctx || !out) return b2_fail(B2BVH_ERR_INVALID, "device_sm_count: bad argument");
+  *out = ctx->sm_count;
+  return 0;
+}
+int b2bvh_alloc(b2bvh_ctx* ctx, size_t bytes, void** dptr) {
+  if (!ctx || !dptr) return b2_fail(B2BVH_ERR_INVALID, "alloc: bad argument");
+  B2_CUDA(cudaSetDevice(ctx->device));
+  B2_CUDA(cudaMalloc(dptr, bytes ? bytes : 16));
+  return 0;
+}
+int b2bvh_free(b2bvh_ctx* ctx, void* dptr) {
+  if (!ctx) return b2_fail(B2BVH_ERR_INVALID, "free: bad argument");
+  B2_CUDA(cudaStreamSynchronize(ctx->stream));
+  B2_CUDA(cudaFree(dptr));
+  return 0;
+}
+int b2bvh_memset(b2bvh_ctx* ctx, void* dptr, int value, size_t bytes) {
+  if (!ctx || !dptr) return b2_fail(B2BVH_ERR_INVALID, "memset: bad argument");
+  B2_CUDA(cudaMemsetAsync(dptr, value, bytes, ctx->stream));
+  return 0;
+}
+int b2bvh_h2d(b2bvh_ctx* ctx, void* dptr, const void* hptr, size_t bytes) {
+  if (!ctx || (bytes && (!dptr || !hptr))) return b2_fail(B2BVH_ERR_INVALID, "h2d: bad argument");
+  B2_CUDA(cudaMemcpyAsync(dptr, hptr, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  B2_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int b2bvh_d2h(b2bvh_ctx* ctx, void* hptr, const void* dptr, size_t bytes) {
+  if (!ctx || (bytes && (!dptr || !hptr))) return b2_fail(B2BVH_ERR_INVALID, "d2h: bad argument");
+  B2_CUDA(cudaMemcpyAsync(hptr, dptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  B2_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int b2bvh_sync(b2bvh_ctx* ctx) {
+  if (!ctx) return b2_fail(B2BVH_ERR_INVALID, "sync: bad argument");
+  B2_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int b2bvh_host_alloc_pinned(size_t bytes, void** hptr) {
+  if (!hptr) return b2_fail(B2BVH_ERR_INVALID, "host_alloc_pinned: bad argument");
+  B2_CUDA(cudaHostAlloc(hptr, bytes ? bytes : 16, cudaHostAllocDefault));
+  return 0;
+}
+int b2bvh_host_free_pinned(void* hptr) {
+  B2_CUDA(cudaFreeHost(hptr));
+  return 0;
+}
+
+/* ------------------------------------------------------------------ individually callable stages */
+int b2bvh_scene_extents(b2bvh_ctx* ctx, const b2bvh_triangle* d_tris, uint32_t n, b2bvh_aabb* d_triAabb, b2bvh_aabb* d_scene) {
+  if (!ctx || !d_tris || !d_triAabb || !d_scene || n == 0) return b2_fail(B2BVH_ERR_INVALID, "scene_extents: bad argument");
+  unsigned char* ctl = (unsigned char*)ctx->bufs[SLOT_CTL].p;
+  return b2_launch_extents(ctx, d_tris, n, d_triAabb, d_scene, (u32*)(ctl + 32), nullptr);
+}
+int b2bvh_morton_codes(b2bvh_ctx* ctx, const b2bvh_aabb* d_triAabb, const b2bvh_aabb* d_scene, uint32_t n, uint32_t* d_keys, uint32_t* d_vals) {
+  if (!ctx || !d_triAabb || !d_scene || !d_keys || !d_vals || n == 0) return b2_fail(B2BVH_ERR_INVALID, "morton_codes: bad argument");
+  return b2_launch_morton(ctx, d_triAabb, d_scene, n, d_keys, d_vals);
+}
+int b2bvh_sort_pairs(b2bvh_ctx* ctx, const uint32_t* d_keysIn, const uint32_t* d_valsIn, uint32_t* d_keysOut, uint32_t* d_valsOut, uint32_t n,
+                     uint32_t startBit, uint32_t endBit) {
+  if (!ctx || !d_keysIn || !d_keysOut || !d_valsOut) return b2_fail(B2BVH_ERR_INVALID, "sort_pairs: bad argument");
+  if (((uintptr_t)d_keysIn | (uintptr_t)d_valsIn) & 15) return b2_fail(B2BVH_ERR_INVALID, "sort_pairs: inputs must be 16-byte aligned");
+  void *tk, *tv, *sc;
+  B2_TRY(b2_reserve(ctx, SLOT_TKEYS, (size_t)n * 4, &tk));
+  B2_TRY(b2_reserve(ctx, SLOT_TVALS, (size_t)n * 4, &tv));
+  B2_TRY(b2_reserve(ctx, SLOT_SORT, b2_sort_scratch_bytes(n), &sc));
+  return b2_launch_sort(ctx, d_keysIn, d_valsIn, d_keysOut, d_valsOut, (u32*)tk, (u32*)tv, sc, n, startBit, endBit);
+}
+
+/* ------------------------------------------------------------------ the build */
+int b2bvh_build(b2bvh_ctx* ctx, int algo, const b2bvh_triangle* tris, uint32_t n, const b2bvh_build_opts* optsIn, b2bvh_tree* out) {
+  if (!ctx || !tris || !out) return b2_fail(B2BVH_ERR_INVALID, "build: null argument");
+  if (algo < B2BVH_TWO_PASS_LBVH || algo > B2BVH_HPLOC) return b2_fail(B2BVH_ERR_INVALID, "build: unknown algo %d", algo);
+  if (n < 2) return b2_fail(B2BVH_ERR_INVALID, "build: need at least 2 primitives, got %u", n);
+  if (n > 0x3FFFFFFFu) return b2_fail(B2BVH_ERR_INVALID, "build: n=%u exceeds 2^30-1", n);
+  b2bvh_build_opts opts;
+  memset(&opts, 0, sizeof(opts));
+  if (optsIn) opts = *optsIn; else opts.collapse = 1;
+  B2_CUDA(cudaSetDevice(ctx->device));
+  memset(out, 0, sizeof(*out));
+  const bool separate = (algo == B2BVH_PLOCPP || algo == B2BVH_HPLOC);
+  const u32 launches0 = ctx->launches;
+  cudaStream_t s = ctx->stream;
+
+  /* ---- buffers (grown on demand, reused) ---- */
+  void *dTris = nullptr, *dAabb, *dKeys, *dVals, *dSKeys, *dSVals, *dTKeys, *dTVals, *dSort, *dNodes, *dParents = nullptr, *dLbvh = nullptr,
+       *dWide = nullptr, *dWLeaves = nullptr, *dCollapse = nullptr, *dLeaves = nullptr, *dMerge = nullptr;
+  unsigned char* ctl = (unsigned char*)ctx->bufs[SLOT_CTL].p;
+  b2bvh_aabb* dScene = (b2bvh_aabb*)ctl;
+  u32* dScratch8 = (u32*)(ctl + 32);
+  u32* dRoot = (u32*)(ctl + 96);
+  if (!opts.tris_on_device) B2_TRY(b2_reserve(ctx, SLOT_TRIS, (size_t)n * sizeof(b2bvh_triangle), &dTris));
+  B2_TRY(b2_reserve(ctx, SLOT_AABB, (size_t)n * sizeof(b2bvh_aabb), &dAabb));
+  B2_TRY(b2_reserve(ctx, SLOT_KEYS, (size_t)n * 4, &dKeys));
+  B2_TRY(b2_reserve(ctx, SLOT_VALS, (size_t)n * 4, &dVals));
+  B2_TRY(b2_reserve(ctx, SLOT_SKEYS, (size_t)n * 4, &dSKeys));
+  B2_TRY(b2_reserve(ctx, SLOT_SVALS, (size_t)n * 4, &dSVals));
+  B2_TRY(b2_reserve(ctx, SLOT_TKEYS, (size_t)n * 4, &dTKeys));
+  B2_TRY(b2_reserve(ctx, SLOT_TVALS, (size_t)n * 4, &dTVals));
+  B2_TRY(b2_reserve(ctx, SLOT_SORT, b2_sort_scratch_bytes(n), &dSort));
+  B2_TRY(b2_reserve(ctx, SLOT_NODES, (size_t)(separate ? n - 1 : 2 * (size_t)n - 1) * sizeof(b2bvh_bvh2_node), &dNodes));
+  if (algo == B2BVH_TWO_PASS_LBVH) B2_TRY(b2_reserve(ctx, SLOT_PARENTS, (2 * (size_t)n - 1) * 4, &dParents));
+  if (!separate) B2_TRY(b2_reserve(ctx, SLOT_LBVH, (2 * (size_t)n - 1) * 4, &dLbvh));
+  if (separate) B2_TRY(b2_reserve(ctx, SLOT_LEAVES, (size_t)n * sizeof(b2bvh_prim_ref), &dLeaves));
+  if (algo == B2BVH_PLOCPP) B2_TRY(b2_reserve(ctx, SLOT_PLOC, b2_ploc_scratch_bytes(n), &dMerge));
+  if (algo == B2BVH_HPLOC) B2_TRY(b2_reserve(ctx, SLOT_HPLOC, b2_hploc_scratch_bytes(n), &dMerge));
+  if (opts.collapse) {
+    B2_TRY(b2_reserve(ctx, SLOT_WIDE, (size_t)n * sizeof(b2bvh_bvh4_node), &dWide));
+    B2_TRY(b2_reserve(ctx, SLOT_WLEAVES, (size_t)n * sizeof(b2bvh_prim_node), &dWLeaves));
+    B2_TRY(b2_reserve(ctx, SLOT_COLLAPSE, b2_collapse_scratch_bytes(n), &dCollapse));
+  }
+
+  /* ---- upload (TwoPassLbvh.cpp:19-20) ---- */
+  const b2bvh_triangle* dT = tris;
+  if (!opts.tris_on_device) {
+    B2_CUDA(cudaEventRecord(ctx->ev[8], s));
+    B2_CUDA(cudaMemcpyAsync(dTris, tris, (size_t)n * sizeof(b2bvh_triangle), cudaMemcpyHostToDevice, s));
+    B2_CUDA(cudaEventRecord(ctx->ev[9], s));
+    dT = (const b2bvh_triangle*)dTris;
+  }
+
+  /* ---- S1 extents ---- */
+  B2_CUDA(cudaEventRecord(ctx->ev[0], s));
+  B2_TRY(b2_launch_extents(ctx, dT, n, (b2bvh_aabb*)dAabb, dScene, dScratch8, nullptr));
+  if (opts.use_scene_box) B2_CUDA(cudaMemcpyAsync(dScene, &opts.scene_box, sizeof(b2bvh_aabb), cudaMemcpyHostToDevice, s));
+  B2_CUDA(cudaEventRecord(ctx->ev[1], s));
+  /* ---- S2 Morton (+ SetupClusters for PLOC/HPLOC is inside their launchers but is accounted under BUILD here) ---- */
+  B2_TRY(b2_launch_morton(ctx, (const b2bvh_aabb*)dAabb, dScene, n, (u32*)dKeys, (u32*)dVals));
+  B2_CUDA(cudaEventRecord(ctx->ev[2], s));
+  /* ---- S3 sort (values of pass 0 are the iota written by S2: not re-read) ---- */
+  B2_TRY(b2_launch_sort(ctx, (const u32*)dKeys, nullptr, (u32*)dSKeys, (u32*)dSVals, (u32*)dTKeys, (u32*)dTVals, dSort, n, 0, 32));
+  B2_CUDA(cudaEventRecord(ctx->ev[3], s));
+  /* ---- S4 / S6 / S7 hierarchy ---- */
+  u32 iterations = 0;
+  switch (algo) {
+    case B2BVH_TWO_PASS_LBVH:
+      if (opts.karras_two_kernel)
+        B2_TRY(b2_launch_lbvh_karras_two_kernel(ctx, (const u32*)dSKeys, (const u32*)dSVals, (const b2bvh_aabb*)dAabb, n, (b2bvh_bvh2_node*)dNodes,
+                                                (u32*)dParents, (u32*)dLbvh));
+      else
+        B2_TRY(b2_launch_lbvh_fused(ctx, (const u32*)dSKeys, (const u32*)dSVals, (const b2bvh_aabb*)dAabb, n, (b2bvh_bvh2_node*)dNodes,
+                                    (u32*)dParents, (u32*)dLbvh, dRoot, 1));
+      B2_CUDA(cudaMemsetAsync(dRoot, 0, 4, s));
+      break;
+    case B2BVH_SINGLE_PASS_LBVH:
+      B2_TRY(b2_launch_lbvh_fused(ctx, (const u32*)dSKeys, (const u32*)dSVals, (const b2bvh_aabb*)dAabb, n, (b2bvh_bvh2_node*)dNodes, nullptr,
+                                  (u32*)dLbvh, dRoot, 0));
+      break;
+    case B2BVH_PLOCPP:
+      B2_TRY(b2_launch_ploc(ctx, (const b2bvh_aabb*)dAabb, (const u32*)dSVals, n, (b2bvh_bvh2_node*)dNodes, (b2bvh_prim_ref*)dLeaves, dMerge,
+                            &iterations));
+      B2_CUDA(cudaMemsetAsync(dRoot, 0, 4, s));
+      break;
+    case B2BVH_HPLOC:
+      B2_TRY(b2_launch_hploc(ctx, (const b2bvh_aabb*)dAabb, (const u32*)dSKeys, (const u32*)dSVals, n, (b2bvh_bvh2_node*)dNodes,
+                             (b2bvh_prim_ref*)dLeaves, dMerge, &iterations));
+      B2_CUDA(cudaMemsetAsync(dRoot, 0, 4, s));
+      break;
+  }
+  B2_CUDA(cudaEventRecord(ctx->ev[4], s));
+  /* ---- S5 collapse ---- */
+  u32 nWide = 0;
+  if (opts.collapse)
+    B2_TRY(b2_launch_collapse(ctx, (const b2bvh_bvh2_node*)dNodes, (const b2bvh_prim_ref*)dLeaves, dRoot, n, (b2bvh_bvh4_node*)dWide,
+                              (b2bvh_prim_node*)dWLeaves, dCollapse, &nWide));
+  B2_CUDA(cudaEventRecord(ctx->ev[5], s));
+  u32 root = 0;
+  B2_CUDA(cudaMemcpyAsync(&root, dRoot, 4, cudaMemcpyDeviceToHost, s));
+  B2_CUDA(cudaStreamSynchronize(s));
+
+  out->algo = (u32)algo;
+  out->n_prims = n;
+  out->n_internal = n - 1;
+  out->root = root;
+  out->n_wide = nWide;
+  out->leaves_separate = separate ? 1u : 0u;
+  out->d_triangleBuff = dT;
+  out->d_triangleAabb = (const b2bvh_aabb*)dAabb;
+  out->d_sceneExtents = dScene;
+  out->d_mortonCodeKeys = (const u32*)dKeys;
+  out->d_mortonCodeValues = (const u32*)dVals;
+  out->d_sortedMortonCodeKeys = (const u32*)dSKeys;
+  out->d_sortedMortonCodeValues = (const u32*)dSVals;
+  out->d_bvhNodes = (const b2bvh_bvh2_node*)dNodes;
+  out->d_parentIdxs = (const u32*)dParents;
+  out->d_leafNodes = (const b2bvh_prim_ref*)dLeaves;
+  out->d_wideBvhNodes = (const b2bvh_bvh4_node*)dWide;
+  out->d_wideLeafNodes = (const b2bvh_prim_node*)dWLeaves;
+  float ms = 0;
+  B2_CUDA(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[5]));
+  out->build_ms = ms;
+  B2_CUDA(cudaEventElapsedTime(&out->stage_ms[B2BVH_T_EXTENTS], ctx->ev[0], ctx->ev[1]));
+  B2_CUDA(cudaEventElapsedTime(&out->stage_ms[B2BVH_T_MORTON], ctx->ev[1], ctx->ev[2]));
+  B2_CUDA(cudaEventElapsedTime(&out->stage_ms[B2BVH_T_SORT], ctx->ev[2], ctx->ev[3]));
+  B2_CUDA(cudaEventElapsedTime(&out->stage_ms[B2BVH_T_BUILD], ctx->ev[3], ctx->ev[4]));
+  B2_CUDA(cudaEventElapsedTime(&out->stage_ms[B2BVH_T_COLLAPSE], ctx->ev[4], ctx->ev[5]));
+  if (!opts.tris_on_device) B2_CUDA(cudaEventElapsedTime(&out->h2d_ms, ctx->ev[8], ctx->ev[9]));
+  out->n_iterations = iterations;
+  out->n_launches = ctx->launches - launches0;
+  return 0;
+}
+
+/* ------------------------------------------------------------------ sharded helpers */
+int b2bvh_shard_extents(b2bvh_ctx* ctx, const b2bvh_triangle* tris, uint32_t n, uint32_t tris_on_device, float* d_negmin_max6) {
+  if (!ctx || !tris || !d_negmin_max6 || n == 0) return b2_fail(B2BVH_ERR_INVALID, "shard_extents: bad argument");
+  B2_CUDA(cudaSetDevice(ctx->device));
+  void *dTris = nullptr, *dAabb;
+  const b2bvh_triangle* dT = tris;
+  if (!tris_on_device) {
+    B2_TRY(b2_reserve(ctx, SLOT_TRIS, (size_t)n * sizeof(b2bvh_triangle), &dTris));
+    B2_CUDA(cudaMemcpyAsync(dTris, tris, (size_t)n * sizeof(b2bvh_triangle), cudaMemcpyHostToDevice, ctx->stream));
+    dT = (const b2bvh_triangle*)dTris;
+  }
+  B2_TRY(b2_reserve(ctx, SLOT_AABB, (size_t)n * sizeof(b2bvh_aabb), &dAabb));
+  unsigned char* ctl = (unsigned char*)ctx->bufs[SLOT_CTL].p;
+  return b2_launch_extents(ctx, dT, n, (b2bvh_aabb*)dAabb, (b2bvh_aabb*)ctl, (u32*)(ctl + 32), d_negmin_max6);
+}
+
+/* ------------------------------------------------------------------ host-side SAH cost reporting */
+static inline float h_area(const b2bvh_aabb& b) {
+  const float ex = b.m_max.x - b.m_min.x, ey = b.m_max.y - b.m_min.y, ez = b.m_max.z - b.m_min.z;
+  const float xy = ex * ey, xz = ex * ez, yz = ey * ez;
+  float s = xy + xz;
+  s = s + yz;
+  return 2 * s;
+}
+static inline float h_min(float a, float b) { return (b < a) ? b : a; }
+static inline float h_max(float a, float b) { return (b > a) ? b : a; }
+
+/* Utility::calculatebvh4Cost (Utility.cpp:351-396): root box = union of the root's child boxes, then a float
+ * running sum in index order: 1 + sum over wide nodes of internal-child areas / rootArea + sum over leaf slots of
+ * primitive areas / rootArea. */
+float b2bvh_cost_bvh4(const b2bvh_bvh4_node* wide, const b2bvh_prim_node* wideLeaves, const b2bvh_aabb* primAabbs, uint32_t root, uint32_t n_wide,
+                      uint32_t n_internal) {
+  b2bvh_aabb rb = {{B2BVH_FLT_MAX, B2BVH_FLT_MAX, B2BVH_FLT_MAX}, {-B2BVH_FLT_MAX, -B2BVH_FLT_MAX, -B2BVH_FLT_MAX}};
+  for (int k = 0; k < 4; k++) {
+    if (wide[root].m_child[k] == B2BVH_INVALID) continue;
+    const b2bvh_aabb& c = wide[root].m_aabb[k];
+    rb.m_min.x = h_min(rb.m_min.x, c.m_min.x); rb.m_min.y = h_min(rb.m_min.y, c.m_min.y); rb.m_min.z = h_min(rb.m_min.z, c.m_min.z);
+    rb.m_max.x = h_max(rb.m_max.x, c.m_max.x); rb.m_max.y = h_max(rb.m_max.y, c.m_max.y); rb.m_max.z = h_max(rb.m_max.z, c.m_max.z);
+  }
+  const float inv = 1.0f / h_area(rb);
+  float cost = 1.0f;
+  for (uint32_t i = 0; i < n_wide; i++)
+    for (int k = 0; k < 4; k++) {
+      const uint32_t c = wide[i].m_child[k];
+      if (c != B2BVH_INVALID && c < n_internal) cost += h_area(wide[i].m_aabb[k]) * inv;
+    }
+  for (uint32_t i = 0; i < n_internal + 1; i++) cost += h_area(primAabbs[wideLeaves[i].m_primIdx]) * inv;
+  return cost;
+}
+
+/* Utility::calculateLbvhCost (Utility.cpp:317-349). */
+float b2bvh_cost_lbvh(const b2bvh_bvh2_node* nodes, uint32_t root, uint32_t n_leaf, uint32_t n_internal) {
+  const float inv = 1.0f / h_area(nodes[root].m_aabb);
+  float cost = 1.0f;
+  for (uint32_t i = 0; i < n_internal; i++) {
+    if (nodes[i].m_leftChildIdx != B2BVH_INVALID) cost += h_area(nodes[nodes[i].m_leftChildIdx].m_aabb) * inv;
+    if (nodes[i].m_rightChildIdx != B2BVH_INVALID) cost += h_area(nodes[nodes[i].m_rightChildIdx].m_aabb) * inv;
+  }
+  for (uint32_t i = n_internal; i < n_leaf + n_internal; i++)
+    if (nodes[i].m_leftChildIdx != B2BVH_INVALID) cost += h_area(nodes[i].m_aabb) * inv;
+  return cost;
+}
+
+int b2bvh_tree_cost(b2bvh_ctx* ctx, const b2bvh_tree* tree, float* cost) {
+  if (!ctx || !tree || !cost) return b2_fail(B2BVH_ERR_INVALID, "tree_cost: bad argument");
+  if (tree->n_wide == 0) return b2_fail(B2BVH_ERR_INVALID, "tree_cost: tree has no wide nodes (collapse was off)");
+  std::vector<b2bvh_bvh4_node> w(tree->n_wide);
+  std::vector<b2bvh_prim_node> wl(tree->n_prims);
+  std::vector<b2bvh_aabb> pb(tree->n_prims);
+  B2_TRY(b2bvh_d2h(ctx, w.data(), tree->d_wideBvhNodes, w.size() * sizeof(b2bvh_bvh4_node)));
+  B2_TRY(b2bvh_d2h(ctx, wl.data(), tree->d_wideLeafNodes, wl.size() * sizeof(b2bvh_prim_node)));
+  B2_TRY(b2bvh_d2h(ctx, pb.data(), tree->d_triangleAabb, pb.size() * sizeof(b2bvh_aabb)));
+  *cost = b2bvh_cost_bvh4(w.data(), wl.data(), pb.data(), 0, tree->n_wide, tree->n_internal);
+  return 0;
+}
+
+} /* extern "C" */

@@ -1,0 +1,195 @@
+/*
+ * common.cuh — device-side vocabulary shared by every kernel of libb2bvh: box math with a fixed
+ * floating-point contract, cache-hinted loads/stores, small warp helpers, and the context struct.
+ *
+ * Floating-point contract: every +,-,*,/ is rounded individually — no FMA
+ * contraction anywhere results are compared against the oracle.  The whole library is compiled
+ * with -fmad=false; the area formula additionally spells the roundings out so the contract
+ * survives a flag change.  Reference math being restated: src/Common.h:310-416 (Aabb).
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/b2bvh.h"
+
+typedef uint32_t u32;
+typedef uint64_t u64;
+
+#define B2_INVALID 0xFFFFFFFFu
+#define B2_FLT_MAX 3.402823466e+38f
+#define B2_FULL 0xFFFFFFFFu
+
+struct Box {
+  float lx, ly, lz, hx, hy, hz;
+};
+
+__device__ __forceinline__ Box box_empty() { return Box{B2_FLT_MAX, B2_FLT_MAX, B2_FLT_MAX, -B2_FLT_MAX, -B2_FLT_MAX, -B2_FLT_MAX}; }
+__device__ __forceinline__ Box box_union(const Box& a, const Box& b) {
+  return Box{fminf(a.lx, b.lx), fminf(a.ly, b.ly), fminf(a.lz, b.lz), fmaxf(a.hx, b.hx), fmaxf(a.hy, b.hy), fmaxf(a.hz, b.hz)};
+}
+/* Aabb::area(), Common.h:361-365: 2*(ex*ey + ex*ez + ey*ez), left to right, each op rounded. */
+__device__ __forceinline__ float box_area(const Box& b) {
+  const float ex = __fsub_rn(b.hx, b.lx), ey = __fsub_rn(b.hy, b.ly), ez = __fsub_rn(b.hz, b.lz);
+  const float xy = __fmul_rn(ex, ey), xz = __fmul_rn(ex, ez), yz = __fmul_rn(ey, ez);
+  return __fmul_rn(2.0f, __fadd_rn(__fadd_rn(xy, xz), yz));
+}
+
+/* 24-byte Aabb (align 4): three 8-byte loads when the address allows it (even element index), scalars otherwise. */
+__device__ __forceinline__ Box load_aabb(const b2bvh_aabb* p) {
+  const float* f = reinterpret_cast<const float*>(p);
+  return Box{__ldg(f), __ldg(f + 1), __ldg(f + 2), __ldg(f + 3), __ldg(f + 4), __ldg(f + 5)};
+}
+__device__ __forceinline__ void store_aabb(b2bvh_aabb* p, const Box& b) {
+  float* f = reinterpret_cast<float*>(p);
+  f[0] = b.lx; f[1] = b.ly; f[2] = b.lz; f[3] = b.hx; f[4] = b.hy; f[5] = b.hz;
+}
+
+/* 32-byte Bvh2Node as two 16-byte words: {left, right, lx, ly} {lz, hx, hy, hz}. */
+struct Node2 {
+  u32 left, right;
+  Box box;
+};
+__device__ __forceinline__ uint4 node2_lo(u32 l, u32 r, const Box& b) { return make_uint4(l, r, __float_as_uint(b.lx), __float_as_uint(b.ly)); }
+__device__ __forceinline__ uint4 node2_hi(const Box& b) {
+  return make_uint4(__float_as_uint(b.lz), __float_as_uint(b.hx), __float_as_uint(b.hy), __float_as_uint(b.hz));
+}
+__device__ __forceinline__ Node2 node2_unpack(uint4 a, uint4 c) {
+  Node2 n;
+  n.left = a.x; n.right = a.y;
+  n.box = Box{__uint_as_float(a.z), __uint_as_float(a.w), __uint_as_float(c.x), __uint_as_float(c.y), __uint_as_float(c.z), __uint_as_float(c.w)};
+  return n;
+}
+/* plain store (write-back in L2) */
+__device__ __forceinline__ void store_node2(b2bvh_bvh2_node* p, u32 l, u32 r, const Box& b) {
+  uint4* q = reinterpret_cast<uint4*>(p);
+  q[0] = node2_lo(l, r, b);
+  q[1] = node2_hi(b);
+}
+/* L2-coherent load (ld.global.cg): for nodes written by other CTAs during the same launch */
+__device__ __forceinline__ Node2 load_node2_cg(const b2bvh_bvh2_node* p) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  return node2_unpack(__ldcg(q), __ldcg(q + 1));
+}
+/* read-only path: for nodes produced by an earlier launch */
+__device__ __forceinline__ Node2 load_node2_ro(const b2bvh_bvh2_node* p) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  return node2_unpack(__ldg(q), __ldg(q + 1));
+}
+
+/* acq_rel / release / acquire primitives for the bottom-up passes (replace the reference's
+ * __threadfence() + atomicAdd pairs, TwoPassLbvhKernel.h:225-233, SinglePassLbvhKernel.h:100-124). */
+__device__ __forceinline__ u32 atom_add_acq_rel(u32* p, u32 v) {
+  u32 old;
+  asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+  return old;
+}
+__device__ __forceinline__ u32 atom_exch_acq_rel(u32* p, u32 v) {
+  u32 old;
+  asm volatile("atom.exch.acq_rel.gpu.global.b32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+  return old;
+}
+__device__ __forceinline__ u32 ld_acquire(const u32* p) {
+  u32 v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(u32* p, u32 v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ u64 ld_acquire64(const u64* p) {
+  u64 v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release64(u64* p, u64 v) { asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ u32 ld_relaxed(const u32* p) {
+  u32 v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed(u32* p, u32 v) { asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+/* order-preserving float <-> uint map: unsigned compare of the image == float compare (-0 < +0) */
+__device__ __forceinline__ u32 float_to_ordered(float f) {
+  const u32 b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float ordered_to_float(u32 k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k); }
+
+__device__ __forceinline__ u32 lane_id() { return threadIdx.x & 31u; }
+__device__ __forceinline__ u32 lanemask_lt() {
+  u32 m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+
+/* ------------------------------------------------------------------ host side */
+struct b2bvh_ctx {
+  int device;
+  int sm_count;
+  cudaStream_t stream;
+  bool own_stream;
+  cudaEvent_t ev[16];
+  char name[256];
+  /* build-owned device buffers, grown on demand and reused across builds */
+  struct Buf {
+    void* p;
+    size_t cap;
+  } bufs[32];
+  u32 launches;
+  /* optional per-launch profiler (b2bvh_profile_*): one CUDA event pair per kernel launch */
+  bool prof_on;
+  int prof_n;
+  struct Prof {
+    const char* name;
+    cudaEvent_t a, b;
+  } prof[512];
+  int prof_events; /* number of event pairs created so far */
+};
+
+int b2_fail(int code, const char* fmt, ...);
+int b2_check(cudaError_t e, const char* what);
+#define B2_CUDA(x)                                 \
+  do {                                             \
+    int _s = b2_check((x), #x);                    \
+    if (_s) return _s;                             \
+  } while (0)
+#define B2_TRY(x)              \
+  do {                         \
+    int _s = (x);              \
+    if (_s) return _s;         \
+  } while (0)
+int b2_prof_begin(b2bvh_ctx* ctx, const char* name);
+int b2_prof_end(b2bvh_ctx* ctx);
+/* bracket of every kernel launch: B2_KERNEL(ctx, "name"); kernel<<<...>>>(...); B2_LAUNCH_CHECK(ctx); */
+#define B2_KERNEL(ctx, name)                          \
+  do {                                                \
+    if ((ctx)->prof_on) B2_TRY(b2_prof_begin((ctx), (name))); \
+  } while (0)
+#define B2_LAUNCH_CHECK(ctx)                          \
+  do {                                                \
+    (ctx)->launches++;                                \
+    B2_CUDA(cudaGetLastError());                      \
+    if ((ctx)->prof_on) B2_TRY(b2_prof_end((ctx)));   \
+  } while (0)
+
+int b2_reserve(b2bvh_ctx* ctx, int slot, size_t bytes, void** out);
+
+/* stage launchers (one per .cu file) */
+int b2_launch_extents(b2bvh_ctx* ctx, const b2bvh_triangle* d_tris, u32 n, b2bvh_aabb* d_triAabb, b2bvh_aabb* d_scene, u32* d_scratch8,
+                      float* d_negmin_max6);
+int b2_launch_morton(b2bvh_ctx* ctx, const b2bvh_aabb* d_triAabb, const b2bvh_aabb* d_scene, u32 n, u32* d_keys, u32* d_vals);
+size_t b2_sort_scratch_bytes(u32 n);
+int b2_launch_sort(b2bvh_ctx* ctx, const u32* d_keysIn, const u32* d_valsIn, u32* d_keysOut, u32* d_valsOut, u32* d_keysTmp, u32* d_valsTmp,
+                   void* d_scratch, u32 n, u32 startBit, u32 endBit);
+int b2_launch_lbvh_fused(b2bvh_ctx* ctx, const u32* d_sortedKeys, const u32* d_sortedVals, const b2bvh_aabb* d_triAabb, u32 n,
+                         b2bvh_bvh2_node* d_nodes, u32* d_parents, u32* d_scratch /* 3n+1 u32 */, u32* d_root, int karrasNumbering);
+int b2_launch_lbvh_karras_two_kernel(b2bvh_ctx* ctx, const u32* d_sortedKeys, const u32* d_sortedVals, const b2bvh_aabb* d_triAabb, u32 n,
+                                     b2bvh_bvh2_node* d_nodes, u32* d_parents, u32* d_flags);
+size_t b2_collapse_scratch_bytes(u32 n);
+int b2_launch_collapse(b2bvh_ctx* ctx, const b2bvh_bvh2_node* d_nodes, const b2bvh_prim_ref* d_leaves, const u32* d_rootIdx, u32 n,
+                       b2bvh_bvh4_node* d_wide, b2bvh_prim_node* d_wideLeaves, void* d_scratch, u32* h_nWide);
+size_t b2_ploc_scratch_bytes(u32 n);
+int b2_launch_ploc(b2bvh_ctx* ctx, const b2bvh_aabb* d_triAabb, const u32* d_sortedVals, u32 n, b2bvh_bvh2_node* d_nodes,
+                   b2bvh_prim_ref* d_leaves, void* d_scratch, u32* h_iterations);
+size_t b2_hploc_scratch_bytes(u32 n);
+int b2_launch_hploc(b2bvh_ctx* ctx, const b2bvh_aabb* d_triAabb, const u32* d_sortedKeys, const u32* d_sortedVals, u32 n,
+                    b2bvh_bvh2_node* d_nodes, b2bvh_prim_ref* d_leaves, void* d_scratch, u32* h_mergeCalls);

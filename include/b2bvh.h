@@ -1,0 +1,152 @@
+/*
+ * b2bvh.h — C ABI of libb2bvh.so, the B200 (sm_100a) BVH-build hot path.
+ *
+ * This is the drop-in boundary.  The reference (Niravaana/HIP-BVH-Construction) has no FFI
+ * layer of its own: its builder classes talk to the GPU through Orochi (oro* calls, dlopen'd
+ * HIP or CUDA driver API).  Every entry point below names the reference interface it stands
+ * in for; the C++ builder classes in hip-bvh-construction_b200/host/ (same names and members as
+ * the reference's) and the Python mirror in hip-bvh-construction_b200/b2bvh/ bind exactly these
+ * symbols at run time (dlopen / ctypes), the way the reference binds Orochi.
+ *
+ * Conventions: extern "C", plain pointers and sizes, every call returns 0 on success and a
+ * non-zero b2bvh_status otherwise (b2bvh_last_error() holds the text); no exceptions cross
+ * the boundary; one context = one device + one stream; calls on one context are serialised
+ * by the caller (the reference is single-threaded, Timer.h:48-56).
+ * There is NO CPU fallback: without a CUDA device b2bvh_ctx_create fails with B2BVH_ERR_CUDA.
+ */
+#ifndef B2BVH_H
+#define B2BVH_H
+
+#include "b2bvh_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum b2bvh_status {
+  B2BVH_OK = 0,
+  B2BVH_ERR_INVALID = 1, /* bad argument (null pointer, n == 0, n too large, unknown enum) */
+  B2BVH_ERR_CUDA = 2,    /* CUDA runtime error, or no device */
+  B2BVH_ERR_OOM = 3,
+  B2BVH_ERR_INTERNAL = 4 /* device-side consistency check failed */
+} b2bvh_status;
+
+/* Which builder object of the reference the build reproduces. */
+typedef enum b2bvh_algo {
+  B2BVH_TWO_PASS_LBVH = 0,    /* TwoPassLbvh::build    src/TwoPassLbvh.cpp:17-197    (Karras numbering, root 0)        */
+  B2BVH_SINGLE_PASS_LBVH = 1, /* SinglePassLbvh::build src/SinglePassLbvh.cpp:17-188 (Apetrei numbering, root reported) */
+  B2BVH_PLOCPP = 2,           /* PLOCNew::build        src/PLOC++Bvh.cpp:16-196      (canonical numbering, root 0)     */
+  B2BVH_HPLOC = 3             /* HPLOC::build          src/Hploc.cpp:16-165          (canonical numbering, root 0)     */
+} b2bvh_algo;
+
+typedef enum b2bvh_traversal {
+  B2BVH_TRAVERSE_WHILE = 0,            /* BvhTraversalWhile            src/TraversalKernel.h:238 */
+  B2BVH_TRAVERSE_SPECULATIVE_WHILE = 1 /* BvhTraversalSpeculativeWhile src/TraversalKernel.h:337 */
+} b2bvh_traversal;
+
+typedef struct b2bvh_ctx b2bvh_ctx; /* opaque: device + stream + scratch arena; replaces Context (src/Context.cpp:7-15) */
+
+typedef struct b2bvh_build_opts {
+  uint32_t collapse;        /* 1: also build the 4-wide tree (CollapseToWide4Bvh, TwoPassLbvh.cpp:154-183)           */
+  uint32_t tris_on_device;  /* 0: `tris` is a host pointer (copied H2D like TwoPassLbvh.cpp:19-20); 1: device pointer */
+  uint32_t use_scene_box;   /* 1: use `scene_box` (global box of a sharded build) instead of the local union          */
+  b2bvh_aabb scene_box;
+  uint32_t stage_timing;    /* 1: CUDA-event time per stage (the reference's Timer tokens); 0: whole-build time only  */
+  uint32_t karras_two_kernel; /* TWO_PASS only. 1: emit (determineRange/findSplit) + separate refit kernel, as the
+                                 reference's launch order; 0: one fused bottom-up pass that yields the same numbering */
+  uint32_t reserved[4];
+} b2bvh_build_opts;
+
+/* Everything a build leaves on the device.  Pointers are DEVICE pointers owned by the context
+ * (valid until the next build on the same context or b2bvh_ctx_destroy).  Field names follow the
+ * public GpuMemory<> members of the reference builders (src/TwoPassLbvh.h:19-30, src/Hploc.h:19-32). */
+typedef struct b2bvh_tree {
+  uint32_t algo;
+  uint32_t n_prims;          /* N                                                     */
+  uint32_t n_internal;       /* m_nInternalNodes = N-1                                */
+  uint32_t root;             /* m_rootNodeIdx (Bvh2); the Bvh4 root is always 0       */
+  uint32_t n_wide;           /* wide-node count (internalNodeOffset, TwoPassLbvh.cpp:187); 0 when collapse == 0 */
+  uint32_t leaves_separate;  /* 0: LBVH layout, nodes[2N-1], leaf i = nodes[N-1+i]; 1: PLOC/HPLOC layout, nodes[N-1] + leaf_nodes[N] */
+  const b2bvh_triangle* d_triangleBuff;       /* N                  */
+  const b2bvh_aabb* d_triangleAabb;           /* N   primitive boxes */
+  const b2bvh_aabb* d_sceneExtents;           /* 1                  */
+  const uint32_t* d_mortonCodeKeys;           /* N                  */
+  const uint32_t* d_mortonCodeValues;         /* N                  */
+  const uint32_t* d_sortedMortonCodeKeys;     /* N                  */
+  const uint32_t* d_sortedMortonCodeValues;   /* N                  */
+  const b2bvh_bvh2_node* d_bvhNodes;          /* 2N-1 or N-1        */
+  const uint32_t* d_parentIdxs;               /* 2N-1, TWO_PASS only (TwoPassLbvh.cpp:96), else NULL */
+  const b2bvh_prim_ref* d_leafNodes;          /* N, PLOC/HPLOC only (PLOC++Bvh.h), else NULL         */
+  const b2bvh_bvh4_node* d_wideBvhNodes;      /* n_wide             */
+  const b2bvh_prim_node* d_wideLeafNodes;     /* N                  */
+  float stage_ms[B2BVH_T_COUNT];              /* indexed by b2bvh_stage == TimerCodes; filled when stage_timing */
+  float build_ms;                             /* device time of the whole build (extents..collapse), H2D excluded */
+  float h2d_ms;                               /* device time of the triangle upload when tris_on_device == 0      */
+  uint32_t n_iterations;                      /* PLOC++: iterations run; HPLOC: merge calls; else 0               */
+  uint32_t n_launches;                        /* kernels launched by this build                                   */
+} b2bvh_tree;
+
+/* ---- context / memory: replaces Context (src/Context.cpp:7-22) and OrochiUtils malloc/copy helpers
+ * (dependencies/Orochi/Orochi/OrochiUtils.h:84-161) that back GpuMemory<T>. ---- */
+int b2bvh_ctx_create(int device, void* cuda_stream /* cudaStream_t or NULL for a private stream */, b2bvh_ctx** out);
+int b2bvh_ctx_destroy(b2bvh_ctx* ctx);
+int b2bvh_device_name(b2bvh_ctx* ctx, char* buf, size_t cap);          /* "Executing on '<device>'", Context.cpp:14 */
+int b2bvh_device_sm_count(b2bvh_ctx* ctx, int* out);
+int b2bvh_alloc(b2bvh_ctx* ctx, size_t bytes, void** dptr);            /* oroMalloc                                  */
+int b2bvh_free(b2bvh_ctx* ctx, void* dptr);                            /* oroFree                                    */
+int b2bvh_memset(b2bvh_ctx* ctx, void* dptr, int value, size_t bytes); /* GpuMemory::reset                           */
+int b2bvh_h2d(b2bvh_ctx* ctx, void* dptr, const void* hptr, size_t bytes); /* OrochiUtils::copyHtoD                  */
+int b2bvh_d2h(b2bvh_ctx* ctx, void* hptr, const void* dptr, size_t bytes); /* GpuMemory::getData                     */
+int b2bvh_sync(b2bvh_ctx* ctx);                                        /* OrochiUtils::waitForCompletion             */
+int b2bvh_host_alloc_pinned(size_t bytes, void** hptr);
+int b2bvh_host_free_pinned(void* hptr);
+const char* b2bvh_last_error(void);
+
+/* ---- the build: replaces the body of <Builder>::build(Context&, std::vector<Triangle>&). ---- */
+int b2bvh_build(b2bvh_ctx* ctx, int algo, const b2bvh_triangle* tris, uint32_t n, const b2bvh_build_opts* opts, b2bvh_tree* out);
+
+/* Stages, individually callable (all pointers are device pointers).  Each names the reference kernel(s) it replaces. */
+int b2bvh_scene_extents(b2bvh_ctx* ctx, const b2bvh_triangle* d_tris, uint32_t n, b2bvh_aabb* d_triAabb,
+                        b2bvh_aabb* d_scene);             /* CalculateSceneExtents / CalculatePrimRefExtents, CommonBlocksKernel.h:92,116 */
+int b2bvh_morton_codes(b2bvh_ctx* ctx, const b2bvh_aabb* d_triAabb, const b2bvh_aabb* d_scene, uint32_t n, uint32_t* d_keys,
+                       uint32_t* d_vals);                 /* CalculateMortonCodes[PrimRef], CommonBlocksKernel.h:374,387                  */
+int b2bvh_sort_pairs(b2bvh_ctx* ctx, const uint32_t* d_keysIn, const uint32_t* d_valsIn, uint32_t* d_keysOut, uint32_t* d_valsOut,
+                     uint32_t n, uint32_t startBit, uint32_t endBit); /* Oro::RadixSort::sort(KeyValueSoA...), RadixSort.cpp:291-318   */
+
+/* ---- traversal: replaces the body of TwoPassLbvh::traverseBvh (src/TwoPassLbvh.cpp:199-311). ---- */
+int b2bvh_generate_rays(b2bvh_ctx* ctx, const b2bvh_camera* cam, uint32_t width, uint32_t height, b2bvh_ray* d_rays,
+                        float* ms);                       /* GenerateRays, CommonBlocksKernel.h:432-463 */
+int b2bvh_traverse(b2bvh_ctx* ctx, const b2bvh_tree* tree, const b2bvh_ray* d_rays, uint32_t n_rays, const b2bvh_transform* xform,
+                   int kernel, b2bvh_hit* d_hits /* may be NULL */, uint8_t* d_rgba /* may be NULL */, float* ms);
+
+/* ---- sharded (multi-GPU) build helpers; new work specified by the north star, no reference counterpart.
+ * rank-local steps only — the 6-float all-reduce and the root all-gather between them belong to the caller's
+ * communicator (torch.distributed / NCCL). ---- */
+int b2bvh_shard_extents(b2bvh_ctx* ctx, const b2bvh_triangle* tris, uint32_t n, uint32_t tris_on_device,
+                        float* d_negmin_max6 /* device, 6 floats: {-min.xyz, max.xyz}, ready for one all-reduce(MAX) */);
+int b2bvh_top_level(b2bvh_ctx* ctx, const b2bvh_aabb* d_rootBoxes, uint32_t g, b2bvh_bvh2_node* d_topNodes /* 2g-1 */);
+
+/* ---- SAH-cost reporting on the host (pure functions on host copies; Utility.cpp:317-396). ---- */
+float b2bvh_cost_bvh4(const b2bvh_bvh4_node* wide, const b2bvh_prim_node* wideLeaves, const b2bvh_aabb* primAabbs, uint32_t root,
+                      uint32_t n_wide, uint32_t n_internal);                     /* Utility::calculatebvh4Cost */
+float b2bvh_cost_lbvh(const b2bvh_bvh2_node* nodes, uint32_t root, uint32_t n_leaf, uint32_t n_internal); /* Utility::calculateLbvhCost */
+/* convenience: D2H the wide tree and return calculatebvh4Cost, i.e. the builders' m_cost (TwoPassLbvh.cpp:185-196) */
+int b2bvh_tree_cost(b2bvh_ctx* ctx, const b2bvh_tree* tree, float* cost);
+
+/* ---- synthetic input of the benchmark configs (BASELINE.json configs 4/5; definition synth_uniform_v1 in SURVEY.md §8d):
+ * triangles [first, first+count) of the stream with `seed`, written to DEVICE memory; RNG = the reference's tea<16>/lcg/randf
+ * (CommonBlocksKernel.h:401-430).  `half` = 1000 * Ntotal^(-1/3) rounded to float by the caller. ---- */
+int b2bvh_synth_uniform(b2bvh_ctx* ctx, uint64_t first, uint32_t count, uint32_t seed, float half, b2bvh_triangle* d_tris);
+
+/* ---- per-launch profiler: when enabled every kernel launch of the context is bracketed by a CUDA event pair; entries are
+ * read after a sync.  Replaces Timer::measure (src/Timer.h:31-73) at kernel granularity, without its per-launch host sync. ---- */
+int b2bvh_profile_enable(b2bvh_ctx* ctx, int on);  /* also clears the recorded entries */
+int b2bvh_profile_count(b2bvh_ctx* ctx, int* count);
+int b2bvh_profile_entry(b2bvh_ctx* ctx, int index, char* name, size_t cap, float* ms);
+
+uint32_t b2bvh_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2BVH_H */

@@ -25,7 +25,7 @@
 #if defined(__cplusplus)
 #define B2BVH_ALIGNAS(n) alignas(n)
 #else
-#define B2BVH_ALIGNAS(n) _Alignas(n)
+#define B2BVH_ALIGNAS(n) __attribute__((aligned(n))) /* C: attribute form is accepted after `struct` */
 #endif
 
 #define B2BVH_INVALID 0xFFFFFFFFu          /* INVALID_NODE_IDX / INVALID_PRIM_IDX, Common.h:90-92 */

@@ -150,16 +150,22 @@ struct MortonCfg {
   int nb[3];       /* numBits.x/y/z                                        */
 };
 
-/* (int)log2(a/b) as the kernel evaluates it (float log2, truncation), with the
- * out-of-range conversions pinned: NaN -> 0, +-inf/huge -> +-(1<<20).        */
+/* (int)log2(a/b) as the GPU evaluates it: float log2, then a float->int conversion that SATURATES
+ * (NaN -> 0, +inf/huge -> INT_MAX, -inf -> INT_MIN; cvt.rzi.s32.f32 on NVIDIA, v_cvt_i32_f32 on AMD),
+ * followed by two's-complement wrapping integer arithmetic.  This matters only for scenes with a zero
+ * extent (e2 == 0 -> ratio inf); there the x86 conversion of the emulated reference (INT_MIN) is not
+ * what the reference's GPU path computes, so the GPU semantic is the one pinned here.                */
 static int ilog2_ratio(float a, float b) {
   float r = a / b;
   float l = log2f(r);
   if (l != l) return 0;
-  if (l > 1048576.0f) return 1 << 20;
-  if (l < -1048576.0f) return -(1 << 20);
+  if (l >= 2147483648.0f) return 2147483647;
+  if (l <= -2147483648.0f) return (int)0x80000000u;
   return (int)l;
 }
+static inline int wadd(int a, int b) { return (int)((u32)a + (u32)b); }
+static inline int wsub(int a, int b) { return (int)((u32)a - (u32)b); }
+static inline int wmul2(int a) { return (int)((u32)a * 2u); }
 static inline u32 shl32(u32 v, int n) { return (n < 0 || n > 31) ? 0u : (v << n); }
 static inline u32 shr32(u32 v, int n) { return (n < 0 || n > 31) ? 0u : (v >> n); }
 static inline int imin(int a, int b) { return a < b ? a : b; }
@@ -176,15 +182,15 @@ void orc_morton_config(const float ext[3], MortonCfg* c) {
   for (int i = 0; i < 3; i++) c->axis[i] = order[k][i];
   float e0 = ext[c->axis[0]], e1 = ext[c->axis[1]], e2 = ext[c->axis[2]];
   int px = ilog2_ratio(e0, e1), py = ilog2_ratio(e1, e2), pz = ilog2_ratio(e0, e2);
-  int swap = pz - (px + py);                                   /* :252 */
+  int swap = wsub(pz, wadd(px, py));                           /* :252 */
   px = imin(px, 30);                                           /* :254 */
-  py = imin(py * 2, 30 - px) / 2;                              /* :255 */
-  int sum = px + py * 2;                                       /* :257 */
-  if (sum != 30) sum += swap; else swap = 0;                   /* :259-262 */
-  int nbz = (e2 != 0.0f) ? imax(0, (30 - sum) / 3) : 0;        /* :264 */
+  py = imin(wmul2(py), wsub(30, px)) / 2;                      /* :255 */
+  int sum = wadd(px, wmul2(py));                               /* :257 */
+  if (sum != 30) sum = wadd(sum, swap); else swap = 0;         /* :259-262 */
+  int nbz = (e2 != 0.0f) ? imax(0, wsub(30, sum) / 3) : 0;     /* :264 */
   int nbx, nby;
-  if (swap > 0) { nbx = imax(0, (30 - nbz - sum) / 2 + py + px + 1); nby = 30 - nbx - nbz; }  /* :266-270 */
-  else { nby = imax(0, (30 - nbz - sum) / 2 + py); nbx = 30 - nby - nbz; }                    /* :271-275 */
+  if (swap > 0) { nbx = imax(0, wadd(wadd(wadd(wsub(wsub(30, nbz), sum) / 2, py), px), 1)); nby = wsub(wsub(30, nbx), nbz); }  /* :266-270 */
+  else { nby = imax(0, wadd(wsub(wsub(30, nbz), sum) / 2, py)); nbx = wsub(wsub(30, nby), nbz); }                             /* :271-275 */
   c->pre[0] = px; c->pre[1] = py; c->swap = swap; c->sum = sum;
   c->nb[0] = nbx; c->nb[1] = nby; c->nb[2] = nbz;
 }

@@ -1,0 +1,155 @@
+"""GPU parity, LBVH builders: every buffer a build leaves on the device is compared byte for byte with the CPU oracle
+(integer stages bit-exact; AABBs are min/max only, so also bit-exact; SAH cost identical as float32).  All calls go
+through the C ABI (b2bvh.capi -> libb2bvh.so)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, load_mesh, random_tris
+from b2bvh import capi
+
+pytestmark = pytest.mark.gpu
+KA = json.load(open(os.path.join(GOLDEN, "known_answers.json")))
+
+
+def h32(orc, a):
+    return orc.fnv1a(np.ascontiguousarray(a).view(np.uint32).reshape(-1))
+
+
+def assert_same_struct(a, b, what):
+    assert a.dtype == b.dtype and a.shape == b.shape, what
+    if a.tobytes() != b.tobytes():
+        bad = np.nonzero(np.frombuffer(a.tobytes(), np.uint8).reshape(a.size, -1) != np.frombuffer(b.tobytes(), np.uint8).reshape(b.size, -1))[0]
+        raise AssertionError(f"{what}: first differing element {bad[0]} of {a.size}: gpu={a[bad[0]]} oracle={b[bad[0]]}")
+
+
+def check_lbvh(ctx, oracle, tris, algo, **kw):
+    n = tris.size
+    single = algo == capi.SINGLE_PASS_LBVH
+    tree = ctx.build(algo, tris, **kw)
+    g = ctx.fetch(tree)
+    o = oracle.build_lbvh(tris, single_pass=single)
+    assert_same_struct(g["boxes"], o["boxes"], "primitive boxes")
+    assert_same_struct(g["scene"], o["scene"], "scene box")
+    assert np.array_equal(g["keys"], o["keys"]), "morton keys"
+    assert np.array_equal(g["vals"], np.arange(n, dtype=np.uint32))
+    assert np.array_equal(g["skeys"], o["skeys"]) and np.array_equal(g["svals"], o["svals"]), "sorted pairs"
+    assert g["root"] == o["root"]
+    assert_same_struct(g["nodes"], o["nodes"], "bvh2 nodes")
+    if not single:
+        _, parents = oracle.lbvh_karras(o["refs"], o["skeys"], o["svals"])
+        assert np.array_equal(g["parents"], parents), "parent indices"
+    assert g["n_wide"] == o["wide_count"]
+    assert_same_struct(g["wide"], o["wide"], "bvh4 nodes")
+    assert_same_struct(g["wide_leaves"], o["wide_leaves"], "bvh4 leaves")
+    cost = ctx.tree_cost(tree)
+    assert np.float32(cost) == np.float32(o["cost"]), (cost, o["cost"])
+    return tree, g, o
+
+
+SYNTH = [("uniform", 2, 1), ("uniform", 3, 2), ("uniform", 33, 3), ("uniform", 1000, 4), ("uniform", 8192, 5), ("uniform", 8193, 6),
+         ("uniform", 100_003, 7), ("clustered", 20_000, 8), ("flat", 5000, 9), ("duplicate", 700, 10), ("anisotropic", 30_000, 11)]
+
+
+@pytest.mark.parametrize("algo", [capi.TWO_PASS_LBVH, capi.SINGLE_PASS_LBVH], ids=["twopass", "singlepass"])
+@pytest.mark.parametrize("kind,n,seed", SYNTH, ids=[f"{k}-{n}" for k, n, _ in SYNTH])
+def test_synthetic(ctx, oracle, algo, kind, n, seed):
+    check_lbvh(ctx, oracle, random_tris(n, seed, kind), algo)
+
+
+@pytest.mark.parametrize("kind,n,seed", [("uniform", 5000, 21), ("clustered", 40_000, 22)])
+def test_twopass_two_kernel_variant(ctx, oracle, kind, n, seed):
+    check_lbvh(ctx, oracle, random_tris(n, seed, kind), capi.TWO_PASS_LBVH, karras_two_kernel=True)
+
+
+@pytest.mark.parametrize("algo", [capi.TWO_PASS_LBVH, capi.SINGLE_PASS_LBVH], ids=["twopass", "singlepass"])
+@pytest.mark.parametrize("mesh", ["cornellbox", "bunny", "sponza"])
+def test_reference_meshes(ctx, oracle, algo, mesh):
+    tris = load_mesh(mesh)
+    if tris is None:
+        pytest.skip(f"{mesh} not staged")
+    tree, g, o = check_lbvh(ctx, oracle, tris, algo)
+    ka = KA[mesh]
+    assert oracle.fnv1a(g["skeys"], g["svals"]) == ka["sorted_kv_fnv"]
+    assert h32(oracle, g["wide"]) == ka["lbvh_wide_fnv"] and g["n_wide"] == ka["lbvh_wide_count"]
+    assert np.float32(ctx.tree_cost(tree)) == np.float32(ka["lbvh_cost"])
+    if "readme" in ka:
+        assert ctx.tree_cost(tree) == pytest.approx(ka["readme"]["lbvh"], rel=1e-5)
+
+
+def test_device_resident_input_and_repeatability(ctx, oracle):
+    tris = random_tris(50_000, 31)
+    d = ctx.upload(tris)
+    try:
+        t1 = ctx.build(capi.SINGLE_PASS_LBVH, d, n=tris.size, tris_on_device=True)
+        a = ctx.fetch(t1)
+        t2 = ctx.build(capi.SINGLE_PASS_LBVH, tris)
+        b = ctx.fetch(t2)
+        for k in ("nodes", "wide", "wide_leaves", "skeys", "svals"):
+            assert a[k].tobytes() == b[k].tobytes(), k
+    finally:
+        ctx.free(d)
+
+
+def test_large_synthetic_properties(ctx, oracle):
+    """Full-size properties (2M primitives of synth_uniform_v1): sortedness + stability, permutation, root box, tree validity, and
+    the Karras and Apetrei numberings describe the same ordered tree."""
+    n = 2_000_000
+    tris = oracle.synth_uniform(n, 0x00B20010)
+    tree = ctx.build(capi.TWO_PASS_LBVH, tris)
+    g = ctx.fetch(tree)
+    sk, sv = g["skeys"], g["svals"]
+    assert np.all(sk[1:] >= sk[:-1])
+    eq = sk[1:] == sk[:-1]
+    assert np.all(sv[1:][eq] > sv[:-1][eq]), "stable: equal keys keep index order"
+    assert np.array_equal(np.sort(sv), np.arange(n, dtype=np.uint32))
+    assert np.array_equal(g["keys"][sv], sk)
+    assert oracle.check_root_aabb(g["nodes"], 0, n) and oracle.check_bvh2(g["nodes"], None, 0, n)
+    assert oracle.check_bvh4(g["wide"], g["wide_leaves"], 0, n)
+    o_nodes, _ = oracle.lbvh_karras(oracle.primrefs(tris)[0], sk, sv)
+    assert g["nodes"].tobytes() == o_nodes.tobytes()
+    t2 = ctx.build(capi.SINGLE_PASS_LBVH, tris)
+    g2 = ctx.fetch(t2)
+    assert g2["wide"].tobytes() == g["wide"].tobytes() and g2["wide_leaves"].tobytes() == g["wide_leaves"].tobytes()
+    assert np.float32(ctx.tree_cost(t2)) == np.float32(ctx.tree_cost(tree))
+
+
+@pytest.mark.parametrize("n", [1, 5, 3071, 3072, 8191, 8192, 8193, 70_001, 1_000_000])
+@pytest.mark.parametrize("bits", [(0, 32), (0, 30), (4, 20), (0, 8)])
+def test_sort_pairs_is_stable_sort(ctx, n, bits):
+    """Oro::RadixSort contract (Orochi Test/RadixSort/main.cpp:130,239): equal to std::stable_sort on the selected bits."""
+    rng = np.random.default_rng(n * 31 + bits[1])
+    keys = rng.integers(0, 2 ** 32, size=n, dtype=np.uint64).astype(np.uint32)
+    if n > 100:
+        keys[rng.integers(0, n, size=n // 3)] = keys[0]  # heavy duplicates
+    vals = rng.integers(0, 2 ** 32, size=n, dtype=np.uint64).astype(np.uint32)
+    ko, vo = ctx.sort_pairs(keys, vals, *bits)
+    mask = np.uint32(((1 << (bits[1] - bits[0])) - 1) << bits[0])
+    order = np.argsort(keys & mask, kind="stable")
+    assert np.array_equal(ko, keys[order]) and np.array_equal(vo, vals[order])
+
+
+def test_device_synth_generator_matches_oracle(ctx, oracle):
+    from b2bvh import types as T
+    n_total, first, count = 10_000_000, 9_999_000, 1000
+    d = ctx.synth_uniform(n_total, 0x00B20010, first=first, count=count)
+    try:
+        g = ctx.download(d, T.TRIANGLE, count)
+    finally:
+        ctx.free(d)
+    assert g.tobytes() == oracle.synth_uniform(n_total, 0x00B20010, first=first, count=count).tobytes()
+
+
+def test_profiler_reports_every_launch(ctx):
+    tris = random_tris(10_000, 77)
+    ctx.profile(True)
+    tree = ctx.build(capi.SINGLE_PASS_LBVH, tris)
+    ctx.sync()
+    entries = ctx.profile_entries()
+    ctx.profile(False)
+    assert len(entries) == tree.n_launches
+    names = [e[0] for e in entries]
+    assert names[:3] == ["primref_extents", "morton30", "radix_hist"] and names.count("onesweep_pass") == 4
+    assert all(ms >= 0 for _, ms in entries)
