@@ -1,6 +1,4 @@
 #include "common.cuh"
-size_t b2_ploc_scratch_bytes(u32 n) { return 16; }
-int b2_launch_ploc(b2bvh_ctx*, const b2bvh_aabb*, const u32*, u32, b2bvh_bvh2_node*, b2bvh_prim_ref*, void*, u32*) { return b2_fail(B2BVH_ERR_INTERNAL, "ploc: not built yet"); }
 size_t b2_hploc_scratch_bytes(u32 n) { return 16; }
 int b2_launch_hploc(b2bvh_ctx*, const b2bvh_aabb*, const u32*, const u32*, u32, b2bvh_bvh2_node*, b2bvh_prim_ref*, void*, u32*) { return b2_fail(B2BVH_ERR_INTERNAL, "hploc: not built yet"); }
 extern "C" {

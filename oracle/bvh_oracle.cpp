@@ -446,20 +446,30 @@ void orc_ploc(const Box* triAabb, const u32* vals, u32 n, b2bvh_bvh2_node* nodes
  * (key<<32 | index); a hierarchy node whose range is larger than 16 leaves, or
  * the root, PLOC-merges the <=16 leading cluster ids of each child range inside
  * a 32-slot list.  The memory contents of nodeIndices are simulated literally.
- * CANONICAL numbering: hierarchy nodes are processed in post-order and node
- * ids are handed out in that order (the kernel's order is atomicAdd order, :165).
- * stats[0] = number of plocMerge calls.                                      */
+ *
+ * CANONICAL numbering.  The kernel hands out node indices from a global
+ * atomicAdd (:162-168), i.e. in warp-arrival order; topology and boxes do not
+ * depend on it.  The canonical order used here needs no global counter, so the
+ * GPU builder reproduces it without serialising: every cluster carries one
+ * FREE index; leaf g (g >= 1) starts with g-1, leaf 0 with none.  When lanes
+ * l < p merge, the new node takes the free index carried by p and the merged
+ * cluster keeps the one carried by l (the cluster without an index contains
+ * leaf 0, is always first in its list and therefore never a partner).  All
+ * N-1 indices are used exactly once.  Finally the root is exchanged with the
+ * node that received index 0, so that the root index is 0 as in the reference
+ * (the last allocation of :167 is index 0).
+ * stats[0] = number of plocMerge calls, stats[1] = nodes created.             */
 struct HplocState {
   const u32* keys; u32 n; b2bvh_bvh2_node* nodes; b2bvh_prim_ref* leaves;
-  std::vector<u32> nodeIdx; u32 allocated; u32 calls;
+  std::vector<u32> nodeIdx, freeIdx; u32 allocated; u32 calls;
 };
 static void hploc_merge(HplocState& S, u32 L, u32 R, u32 split, bool fin) {
   const u32 nInt = S.n - 1;
-  u32 cl[32]; Box bx[32]; u64 nn[32];
-  for (int i = 0; i < 32; i++) { cl[i] = INVALID; bx[i] = box_empty(); }
+  u32 cl[32], fr[32]; Box bx[32]; u64 nn[32];
+  for (int i = 0; i < 32; i++) { cl[i] = INVALID; fr[i] = INVALID; bx[i] = box_empty(); }
   auto load = [&](u32 start, u32 end, u32 offset) -> u32 {
     u32 cnt = std::min(end - start, 16u);
-    for (u32 l = 0; l < cnt; l++) cl[l + offset] = S.nodeIdx[start + l];
+    for (u32 l = 0; l < cnt; l++) { cl[l + offset] = S.nodeIdx[start + l]; fr[l + offset] = S.freeIdx[start + l]; }
     u32 valid = 0; for (int i = 0; i < 32; i++) valid += cl[i] != INVALID;
     return std::min(cnt, valid - offset);
   };
@@ -482,27 +492,25 @@ static void hploc_merge(HplocState& S, u32 L, u32 R, u32 split, bool fin) {
           nn[j] = std::min(nn[j], a | l);
         }
       }
-    bool mrg[32]; u32 total = 0;
-    for (u32 l = 0; l < np; l++) { u32 p = (u32)nn[l]; mrg[l] = ((u32)nn[p] == l) && l < p; total += mrg[l]; }
-    u32 base = nInt - S.allocated - total;            /* :167 */
-    S.allocated += total;
-    u32 ncl[32]; Box nbx[32]; u32 out = 0, rank = 0;
+    u32 ncl[32], nfr[32]; Box nbx[32]; u32 out = 0;
     for (u32 l = 0; l < np; l++) {
       u32 p = (u32)nn[l];
       bool mutual = ((u32)nn[p] == l);
       if (mutual && l > p) continue;
       if (mutual) {
-        u32 m = base + rank++;
+        u32 m = fr[p];                       /* canonical: the partner's free index */
+        S.allocated++;
         Box b = bx[l]; box_grow(b, bx[p]);
         S.nodes[m].m_leftChildIdx = cl[l]; S.nodes[m].m_rightChildIdx = cl[p]; S.nodes[m].m_aabb = b;
         ncl[out] = m; nbx[out] = b;
       } else { ncl[out] = cl[l]; nbx[out] = bx[l]; }
+      nfr[out] = fr[l];
       out++;
     }
-    for (u32 l = 0; l < np; l++) { cl[l] = l < out ? ncl[l] : INVALID; if (l < out) bx[l] = nbx[l]; }
+    for (u32 l = 0; l < np; l++) { cl[l] = l < out ? ncl[l] : INVALID; fr[l] = l < out ? nfr[l] : INVALID; if (l < out) bx[l] = nbx[l]; }
     np = out;
   }
-  for (u32 l = 0; l < stored; l++) S.nodeIdx[L + l] = cl[l];
+  for (u32 l = 0; l < stored; l++) { S.nodeIdx[L + l] = cl[l]; S.freeIdx[L + l] = fr[l]; }
   S.calls++;
 }
 static void hploc_visit(HplocState& S, u32 L, u32 R) {
@@ -526,9 +534,20 @@ static void hploc_visit(HplocState& S, u32 L, u32 R) {
 void orc_hploc(const Box* triAabb, const u32* keys, const u32* vals, u32 n, b2bvh_bvh2_node* nodes, b2bvh_prim_ref* leaves, u32* stats) {
   setup_clusters(triAabb, vals, n, nodes, leaves);
   HplocState S; S.keys = keys; S.n = n; S.nodes = nodes; S.leaves = leaves; S.allocated = 0; S.calls = 0;
-  S.nodeIdx.resize(n);
-  for (u32 g = 0; g < n; g++) S.nodeIdx[g] = g + (n - 1);
+  S.nodeIdx.resize(n); S.freeIdx.resize(n);
+  for (u32 g = 0; g < n; g++) { S.nodeIdx[g] = g + (n - 1); S.freeIdx[g] = g ? g - 1 : INVALID; }
   hploc_visit(S, 0, n - 1);
+  /* root -> index 0 */
+  u32 root = S.nodeIdx[0];
+  if (root != 0) {
+    std::swap(nodes[0], nodes[root]);       /* nodes[0] = root node, nodes[root] = the node that had index 0 */
+    for (u32 i = 0; i + 1 < n; i++) {       /* its parent (possibly the root itself) must point at the new place */
+      if (nodes[i].m_leftChildIdx == 0) nodes[i].m_leftChildIdx = root;
+      else if (nodes[i].m_rightChildIdx == 0) nodes[i].m_rightChildIdx = root;
+      else continue;
+      break;
+    }
+  }
   if (stats) { stats[0] = S.calls; stats[1] = S.allocated; }
 }
 
