@@ -15,6 +15,7 @@
  * 8 B per task record, 8 B per PrimNode.
  */
 #include "common.cuh"
+#include "lookback.cuh"
 
 #define COL_THREADS 256
 #define COL_MAX_LEVELS 4096 /* ranges recorded per level; deeper trees are handled by re-basing (see launcher) */
@@ -133,28 +134,20 @@ __global__ void __launch_bounds__(COL_THREADS) collapse4_level_kernel(const b2bv
     for (int k = 0; k < COL_THREADS / 32; k++) { const u32 t = sWarp[k]; if (k < (int)w) warpBase += t; tileTotal += t; }
     const u32 localExcl = warpBase + incl - nInternal;
 
-    /* decoupled look-back across the tiles of this level */
-    if (tid == 0) {
-      st_relaxed(st + tile, (tile == 0 ? COL_FLAG_INC : COL_FLAG_AGG) | tileTotal);
-      u32 excl = 0;
-      if (tile > 0) {
-        int t = (int)tile - 1;
-        while (true) {
-          u32 v;
-          do { v = ld_relaxed(st + t); } while ((v & (COL_FLAG_AGG | COL_FLAG_INC)) == 0);
-          excl += v & COL_VAL_MASK;
-          if (v & COL_FLAG_INC) break;
-          t--;
+    /* decoupled look-back across the tiles of this level, warp 0 reads 32 predecessors per round trip */
+    if (w == 0) {
+      if (l == 0) st_relaxed(st + tile, (tile == 0 ? LB_INC : LB_AGG) | tileTotal);
+      const u32 excl = warp_lookback_u32(st, tile);
+      if (l == 0) {
+        if (tile > 0) st_relaxed(st + tile, LB_INC | (excl + tileTotal));
+        sTileExcl = excl;
+        if (tile == nTiles - 1) {
+          /* last tile of the level: publish the next level's range for the next launch */
+          const u32 next = end + excl + tileTotal;
+          ctrl->range[(level + 1) & 1u] = make_uint2(end, next);
+          ctrl->nWide = next;
+          ctrl->lastLevelSize = next - end;
         }
-        st_relaxed(st + tile, COL_FLAG_INC | (excl + tileTotal));
-      }
-      sTileExcl = excl;
-      if (tile == nTiles - 1) {
-        /* last tile of the level: publish the next level's range for the next launch */
-        const u32 next = end + excl + tileTotal;
-        ctrl->range[(level + 1) & 1u] = make_uint2(end, next);
-        ctrl->nWide = next;
-        ctrl->lastLevelSize = next - end;
       }
     }
     __syncthreads();

@@ -23,6 +23,7 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "lookback.cuh"
 
 #define PLOC_R 8
 #define PLOC_THREADS 512
@@ -205,28 +206,20 @@ __global__ void __launch_bounds__(PLOC_THREADS) ploc_iter_kernel(const u32* __re
     const u32 localExcl = warpBase + incl - packed;
     const u32 tileKeep = total & 0xFFFFu, tileRemoved = total >> 16;
 
-    if (tid == 0) {
+    if (w == 0) { /* look-back: one word carries both prefix sums (merging clusters, removed clusters) */
       const u64 mine = ((u64)tileKeep << 31) | (u64)tileRemoved;
-      st_release64(statusCur + tile, (tile == 0 ? PL_FLAG_INC : PL_FLAG_AGG) | mine);
-      u64 excl = 0;
-      if (tile > 0) {
-        int t = (int)tile - 1;
-        while (true) {
-          u64 v;
-          do { v = ld_acquire64(statusCur + t); } while ((v & PL_FLAG_MASK) == 0);
-          excl += v & ~PL_FLAG_MASK;
-          if (v & PL_FLAG_INC) break;
-          t--;
+      if (l == 0) st_release64(statusCur + tile, (tile == 0 ? LB64_INC : LB64_AGG) | mine);
+      const u64 excl = warp_lookback_u64(statusCur, tile);
+      if (l == 0) {
+        if (tile > 0) st_release64(statusCur + tile, LB64_INC | (excl + mine));
+        S.exclKeep = (u32)(excl >> 31);
+        S.exclRemoved = (u32)(excl & 0x7FFFFFFFu);
+        if (tile == nTiles - 1) {
+          ctrl->count[(iter + 1) & 1u] = count - (S.exclRemoved + tileRemoved);
+          ctrl->ticket[(iter + 1) & 1u] = 0;
+          ctrl->itersRun = iter + 1;
+          ctrl->liveBuf = (iter + 1) & 1u;
         }
-        st_release64(statusCur + tile, PL_FLAG_INC | (excl + mine));
-      }
-      S.exclKeep = (u32)(excl >> 31);
-      S.exclRemoved = (u32)(excl & 0x7FFFFFFFu);
-      if (tile == nTiles - 1) {
-        ctrl->count[(iter + 1) & 1u] = count - (S.exclRemoved + tileRemoved);
-        ctrl->ticket[(iter + 1) & 1u] = 0;
-        ctrl->itersRun = iter + 1;
-        ctrl->liveBuf = (iter + 1) & 1u;
       }
     }
     __syncthreads();

@@ -31,9 +31,9 @@
 #define RS_TILE (RS_THREADS * RS_ITEMS)
 #define RS_MAX_PASSES 4
 
-#define RS_FLAG_AGG 0x40000000u
-#define RS_FLAG_INC 0x80000000u
-#define RS_VAL_MASK 0x3FFFFFFFu
+#define RS_FLAG_AGG 1u
+#define RS_FLAG_INC 2u
+#define RS_VAL_MASK 0x3FFFFFFFu /* n < 2^30 (historical limit of the flag|count word; kept as the documented maximum) */
 
 #define HIST_THREADS 512
 #define HIST_ITEMS 16
@@ -42,14 +42,18 @@
  *   [0, 1024)                 bins[pass][digit]  -> exclusive offsets after the histogram launch
  *   [1024, 1028)              tile tickets per pass
  *   [1028]                    finished-CTA counter of the histogram launch
- *   [1032 + pass*nTiles*256 ) status[pass][tile][digit]                                    */
+ *   [1032 + pass*nTilesPad)   flags[pass][tile]: 0 / RS_FLAG_AGG / RS_FLAG_INC, ONE word per tile        (zeroed per sort)
+ *   then counts[pass][tile][2][256]: the tile's digit aggregates and inclusive prefixes                  (never zeroed)
+ * A tile's 256 counts are published with plain stores followed by one release-store of its flag; a reader polls 32 flags
+ * per round trip (one warp load) and then sums the published rows with independent, pipelined loads. */
 #define RS_OFF_TICKET 1024
 #define RS_OFF_DONE 1028
-#define RS_OFF_STATUS 1032
+#define RS_OFF_FLAGS 1032
 
+static inline size_t rs_tiles(u32 n) { return ((size_t)n + RS_TILE - 1) / RS_TILE; }
+static inline size_t rs_tiles_pad(u32 n) { return (rs_tiles(n) + 31) & ~(size_t)31; }
 size_t b2_sort_scratch_bytes(u32 n) {
-  const size_t nTiles = ((size_t)n + RS_TILE - 1) / RS_TILE;
-  return (RS_OFF_STATUS + (size_t)RS_MAX_PASSES * nTiles * RS_RADIX) * sizeof(u32);
+  return (RS_OFF_FLAGS + (size_t)RS_MAX_PASSES * rs_tiles_pad(n) + (size_t)RS_MAX_PASSES * rs_tiles(n) * 2 * RS_RADIX) * sizeof(u32);
 }
 
 __global__ void __launch_bounds__(HIST_THREADS) radix_hist_kernel(const u32* __restrict__ keys, u32 n, u32* __restrict__ scratch, u32 startBit,
@@ -149,7 +153,7 @@ struct OnesweepSmem {
 template <bool IOTA_VALUES>
 __global__ void __launch_bounds__(RS_THREADS) onesweep_pass_kernel(const u32* __restrict__ keysIn, const u32* __restrict__ valsIn,
                                                                    u32* __restrict__ keysOut, u32* __restrict__ valsOut, u32* __restrict__ scratch,
-                                                                   u32 n, u32 nTiles, u32 pass, u32 shift, u32 mask) {
+                                                                   u32 n, u32 nTiles, u32 nTilesPad, u32 pass, u32 shift, u32 mask) {
   extern __shared__ __align__(128) unsigned char smemRaw[];
   OnesweepSmem& S = *reinterpret_cast<OnesweepSmem*>(smemRaw);
   const u32 tid = threadIdx.x, w = tid >> 5, l = tid & 31u;
@@ -164,6 +168,8 @@ __global__ void __launch_bounds__(RS_THREADS) onesweep_pass_kernel(const u32* __
   __syncthreads();
   const u32 tile = S.tile;
   const u32 tileBase = tile * RS_TILE;
+  u32* flags = scratch + RS_OFF_FLAGS + (size_t)pass * nTilesPad;
+  u32* counts = scratch + RS_OFF_FLAGS + (size_t)RS_MAX_PASSES * nTilesPad + (size_t)pass * nTiles * 2 * RS_RADIX; /* [tile][agg|inc][digit] */
   const u32 valid = min((u32)RS_TILE, n - tileBase);
   const bool full = (valid == RS_TILE);
 
@@ -211,9 +217,8 @@ __global__ void __launch_bounds__(RS_THREADS) onesweep_pass_kernel(const u32* __
   if (tid < RS_RADIX) {
 #pragma unroll
     for (int k = 0; k < RS_WARPS; k++) { const u32 t = S.warpHist[k][tid]; S.warpHist[k][tid] = count; count += t; }
-    /* publish this tile's digit count as early as possible */
-    u32* st = scratch + RS_OFF_STATUS + ((size_t)pass * nTiles + tile) * RS_RADIX + tid;
-    st_relaxed(st, (tile == 0 ? RS_FLAG_INC : RS_FLAG_AGG) | count);
+    /* publish this tile's digit counts as early as possible (tile 0: they are already inclusive) */
+    __stcg(counts + ((size_t)tile * 2 + (tile == 0 ? 1 : 0)) * RS_RADIX + tid, count);
     /* exclusive scan of count over the 256 digits */
     u32 incl = count;
     for (int o = 1; o < 32; o <<= 1) {
@@ -224,6 +229,7 @@ __global__ void __launch_bounds__(RS_THREADS) onesweep_pass_kernel(const u32* __
     S.digitStart[tid] = incl - count; /* completed below */
   }
   __syncthreads();
+  if (tid == 0) st_release(flags + tile, tile == 0 ? RS_FLAG_INC : RS_FLAG_AGG); /* orders the 256 count stores of the CTA before the flag */
   if (tid < RS_RADIX) {
     u32 add = 0;
     for (u32 k = 0; k < w; k++) add += S.warpTotals[k];
@@ -239,23 +245,36 @@ __global__ void __launch_bounds__(RS_THREADS) onesweep_pass_kernel(const u32* __
     S.keys[pos[i]] = key[i];
   }
 
-  /* ---- decoupled look-back, one thread per digit ---- */
+  /* ---- decoupled look-back: warps 0..7 (one lane per digit) poll 32 tile flags per round trip, then add up the rows ---- */
   if (tid < RS_RADIX) {
     u32 excl = 0;
-    if (tile > 0) {
-      const u32* st = scratch + RS_OFF_STATUS + ((size_t)pass * nTiles + tile - 1) * RS_RADIX + tid;
+    int t = (int)tile; /* exclusive end of the window */
+    while (t > 0) {
+      const int idx = t - 1 - (int)l;
+      u32 f, firstInc;
       while (true) {
-        u32 v;
-        do { v = ld_relaxed(st); } while ((v & (RS_FLAG_AGG | RS_FLAG_INC)) == 0);
-        excl += v & RS_VAL_MASK;
-        if (v & RS_FLAG_INC) break;
-        st -= RS_RADIX;
+        f = idx >= 0 ? ld_acquire(flags + idx) : RS_FLAG_INC; /* virtual tile -1 */
+        const u32 incM = __ballot_sync(B2_FULL, f == RS_FLAG_INC), zeroM = __ballot_sync(B2_FULL, f == 0u);
+        firstInc = incM ? (u32)__ffs(incM) - 1u : 32u;
+        const u32 firstZero = zeroM ? (u32)__ffs(zeroM) - 1u : 32u;
+        if (firstZero > min(firstInc, 31u)) break;
       }
-      st_relaxed(scratch + RS_OFF_STATUS + ((size_t)pass * nTiles + tile) * RS_RADIX + tid, RS_FLAG_INC | (excl + count));
+      const int last = (int)min(firstInc, 31u);
+      const u32 incBit = (firstInc < 32u) ? (1u << firstInc) : 0u;
+#pragma unroll 8
+      for (int k = 0; k <= last; k++) {
+        const int tt = t - 1 - k;
+        if (tt < 0) break;
+        excl += __ldcg(counts + ((size_t)tt * 2 + ((incBit >> k) & 1u)) * RS_RADIX + tid);
+      }
+      if (firstInc < 32u) break;
+      t -= 32;
     }
+    if (tile > 0) __stcg(counts + ((size_t)tile * 2 + 1) * RS_RADIX + tid, excl + count);
     S.globalBase[tid] = (int)(__ldg(scratch + pass * RS_RADIX + tid) + excl) - (int)S.digitStart[tid];
   }
   __syncthreads();
+  if (tid == 0 && tile > 0) st_release(flags + tile, RS_FLAG_INC);
 
   /* ---- keys out: element j of the digit-ordered tile goes to globalBase[digit] + j ---- */
   int dst[RS_ITEMS];
@@ -301,7 +320,8 @@ int b2_launch_sort(b2bvh_ctx* ctx, const u32* d_keysIn, const u32* d_valsIn, u32
   const u32 nPasses = (endBit - startBit + RS_RADIX_BITS - 1) / RS_RADIX_BITS;
   const u32 nTiles = (n + RS_TILE - 1) / RS_TILE;
   u32* scratch = reinterpret_cast<u32*>(d_scratch);
-  B2_CUDA(cudaMemsetAsync(scratch, 0, (RS_OFF_STATUS + (size_t)nPasses * nTiles * RS_RADIX) * sizeof(u32), ctx->stream));
+  const u32 nTilesPad = (u32)rs_tiles_pad(n);
+  B2_CUDA(cudaMemsetAsync(scratch, 0, (RS_OFF_FLAGS + (size_t)RS_MAX_PASSES * nTilesPad) * sizeof(u32), ctx->stream));
   {
     const u32 chunk = HIST_THREADS * HIST_ITEMS;
     u32 grid = (n + chunk - 1) / chunk;
@@ -330,9 +350,9 @@ int b2_launch_sort(b2bvh_ctx* ctx, const u32* d_keysIn, const u32* d_valsIn, u32
     const u32 mask = (1u << bits) - 1u;
     B2_KERNEL(ctx, "onesweep_pass");
     if (vin == nullptr)
-      onesweep_pass_kernel<true><<<nTiles, RS_THREADS, smem, ctx->stream>>>(kin, nullptr, kout, vout, scratch, n, nTiles, p, shift, mask);
+      onesweep_pass_kernel<true><<<nTiles, RS_THREADS, smem, ctx->stream>>>(kin, nullptr, kout, vout, scratch, n, nTiles, nTilesPad, p, shift, mask);
     else
-      onesweep_pass_kernel<false><<<nTiles, RS_THREADS, smem, ctx->stream>>>(kin, vin, kout, vout, scratch, n, nTiles, p, shift, mask);
+      onesweep_pass_kernel<false><<<nTiles, RS_THREADS, smem, ctx->stream>>>(kin, vin, kout, vout, scratch, n, nTiles, nTilesPad, p, shift, mask);
     B2_LAUNCH_CHECK(ctx);
     kin = kout;
     vin = vout;

@@ -1,0 +1,50 @@
+"""Per-kernel CUDA-event times of one build (development tool; not part of the bench contract).
+usage: python tools/kernel_bench.py [--n 10000000] [--algo singlepass|twopass|ploc|hploc] [--reps 5]
+B2BVH_LIB=/path/to/variant.so selects another build of the library."""
+import argparse
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "hip-bvh-construction_b200"))
+from b2bvh import capi  # noqa: E402
+
+if os.environ.get("B2BVH_LIB"):
+    capi.LIB_PATH = os.environ["B2BVH_LIB"]
+
+ALGOS = {"twopass": capi.TWO_PASS_LBVH, "singlepass": capi.SINGLE_PASS_LBVH, "ploc": capi.PLOCPP, "hploc": capi.HPLOC}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=10_000_000)
+    ap.add_argument("--algo", default="singlepass")
+    ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--two-kernel", action="store_true")
+    a = ap.parse_args()
+    ctx = capi.Context(0)
+    d = ctx.synth_uniform(a.n, 0x00B20010)
+    for _ in range(3):
+        tree = ctx.build(ALGOS[a.algo], d, n=a.n, tris_on_device=True, karras_two_kernel=a.two_kernel)
+    agg = {}
+    tot = []
+    for _ in range(a.reps):
+        ctx.profile(True)
+        tree = ctx.build(ALGOS[a.algo], d, n=a.n, tris_on_device=True, karras_two_kernel=a.two_kernel)
+        ctx.sync()
+        for name, ms in ctx.profile_entries():
+            agg.setdefault(name, []).append(ms)
+        ctx.profile(False)
+        tree = ctx.build(ALGOS[a.algo], d, n=a.n, tris_on_device=True, karras_two_kernel=a.two_kernel)
+        tot.append((tree.build_ms, [tree.stage_ms[k] for k in (0, 1, 2, 3, 5)]))
+    print(f"lib={os.path.basename(capi.LIB_PATH)} algo={a.algo} n={a.n} launches={tree.n_launches} iterations={tree.n_iterations} n_wide={tree.n_wide}")
+    best = min(tot)
+    print(f"  build_ms(best)={best[0]:.4f}  stages ext/morton/sort/build/collapse = " + " / ".join(f"{x:.4f}" for x in best[1]) +
+          f"  -> {a.n / best[0] / 1e3:.1f} Mprims/s")
+    for name, v in agg.items():
+        per = len(v) // a.reps
+        print(f"  {name:28s} launches/build={per:3d}  avg={sum(v) / len(v) * 1e3:9.2f} us  total/build={sum(v) / a.reps * 1e3:10.2f} us")
+
+
+if __name__ == "__main__":
+    main()
