@@ -35,8 +35,8 @@ CPU_BASELINE_SAMPLE = 1_000_000
 ALGO_BYTES = {
     "primref_extents": 64 + 24,
     "morton30": 24 + 8,
-    "radix_hist": 4,
-    "onesweep_pass": 15,            # 8 B in + 8 B out per pair; pass 0 does not read values (iota): (12 + 3*16) / 4
+    "radix_count": 4,
+    "radix_scatter": 15,            # 8 B in + 8 B out per pair; pass 0 does not read values (iota): (12 + 3*16) / 4
     "lbvh_fused_apetrei": 132,
     "lbvh_fused_karras": 140,
 }
@@ -143,7 +143,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n = args.prims
     n_total = n * world
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()  # one explicit stream shared by torch (events, NCCL) and the library
+    torch.cuda.set_stream(stream)
     ctx = capi.Context(local, stream=stream.cuda_stream)
     d_tris = ctx.synth_uniform(n_total, SEED, first=rank * n, count=n)
     ctx.sync()

@@ -1,0 +1,84 @@
+"""Primitive-range sharded build across the GPUs of one node (north star; no reference counterpart — the reference is
+single-device, Context.cpp:11).
+
+Rank r owns triangles [r*N/G, (r+1)*N/G).  Per build:
+  1. local primitive boxes + local scene box                       (b2bvh_shard_extents, on the GPU)
+  2. ONE all-reduce(MAX) of 6 floats {-min, max}  -> global scene box, so every shard codes Morton keys in the same frame
+  3. local Morton + sort + hierarchy + refit (+ collapse), unchanged single-GPU path with the global box
+  4. ONE all-gather of the G sub-tree root boxes (24 B each)
+  5. every rank builds the same top-level tree over the G roots     (b2bvh_top_level, on the GPU)
+The collectives carry bytes, not bandwidth; they ride on torch.distributed (NCCL over NVLink on the GPUs; gloo in the
+CPU tests, where the per-rank engine is a test double).  No other data-path exchange exists: the result is G sub-trees +
+a top tree (not node-identical to a single-GPU build of the whole input; parity is per shard and for the top tree)."""
+import numpy as np
+
+
+def shard_range(n_total, rank, world):
+    """[first, last) of rank's primitive range."""
+    return (n_total * rank) // world, (n_total * (rank + 1)) // world
+
+
+class ShardedBuild:
+    """engine: object with
+         shard_extents(tris) -> tensor[6] {-min.xyz, max.xyz} on the collective's device
+         build(tris, scene_box6) -> (root_box6 as numpy float32[6], tree)
+         top_level(root_boxes tensor[G*6]) -> top-level nodes
+         tensor(np_array) -> tensor on the collective's device
+       dist: torch.distributed (initialised) or None for world == 1."""
+
+    def __init__(self, engine, dist=None, rank=0, world=1):
+        self.engine, self.dist, self.rank, self.world = engine, dist, rank, world
+
+    def build(self, tris):
+        import torch
+        box6 = self.engine.shard_extents(tris)
+        if self.world > 1:
+            self.dist.all_reduce(box6, op=self.dist.ReduceOp.MAX)
+        b = box6.detach().cpu().numpy().astype(np.float32)
+        scene = np.concatenate([-b[:3], b[3:]]).astype(np.float32)
+        root_box, tree = self.engine.build(tris, scene)
+        mine = self.engine.tensor(np.asarray(root_box, dtype=np.float32))
+        if self.world > 1:
+            roots = torch.empty(self.world * 6, dtype=torch.float32, device=mine.device)
+            self.dist.all_gather_into_tensor(roots, mine)
+        else:
+            roots = mine
+        top = self.engine.top_level(roots)
+        return dict(scene=scene, tree=tree, roots=roots, top=top)
+
+
+class GpuEngine:
+    """The real engine: one b2bvh Context on this rank's GPU (stream shared with torch so NCCL and the kernels are ordered)."""
+
+    def __init__(self, ctx, algo, collapse=True):
+        import torch
+        from . import capi, types as T
+        self.ctx, self.algo, self.collapse, self.capi, self.T, self.torch = ctx, algo, collapse, capi, T, torch
+        self.box6 = torch.zeros(6, dtype=torch.float32, device="cuda")
+        self.top_nodes = None
+
+    def tensor(self, a):
+        return self.torch.from_numpy(a).cuda()
+
+    def _ptr_n(self, tris):
+        if isinstance(tris, tuple):  # (device pointer, n)
+            return tris[0], tris[1], 1
+        return tris.ctypes.data, tris.size, 0
+
+    def shard_extents(self, tris):
+        p, n, on_dev = self._ptr_n(tris)
+        self.capi.check(self.ctx.lib.b2bvh_shard_extents(self.ctx.h, p, n, on_dev, self.box6.data_ptr()), "b2bvh_shard_extents")
+        return self.box6
+
+    def build(self, tris, scene):
+        p, n, on_dev = self._ptr_n(tris)
+        tree = self.ctx.build(self.algo, p, n=n, tris_on_device=bool(on_dev), scene_box=scene, collapse=self.collapse)
+        node = self.ctx.download(tree.d_bvhNodes + 32 * tree.root, self.T.BVH2_NODE, 1)
+        return np.concatenate([node["mn"][0], node["mx"][0]]), tree
+
+    def top_level(self, roots):
+        g = roots.numel() // 6
+        if self.top_nodes is None or self.top_nodes.numel() < (2 * g - 1) * 8:
+            self.top_nodes = self.torch.zeros((2 * g - 1) * 8, dtype=self.torch.float32, device="cuda")
+        self.capi.check(self.ctx.lib.b2bvh_top_level(self.ctx.h, roots.data_ptr(), g, self.top_nodes.data_ptr()), "b2bvh_top_level")
+        return self.top_nodes

@@ -1,0 +1,82 @@
+/*
+ * demo_main.cpp — the reference's driver (src/main.cpp:26-85) against the B200 library: pick a builder, load triangles,
+ * build(), traverseBvh().  The reference chooses the builder with #defines (main.cpp:18-22) and hard-codes an OBJ path; here
+ * both are command-line arguments and the mesh is a raw triangle file (float32 x 9 per triangle, the format written by
+ * oracle/stage_meshes.py with the reference's own OBJ loader) or a synthetic stream.
+ *
+ *   b2bvh_demo <twopass|singlepass|ploc|hploc> <mesh.tri | synth:N> [expected_cost]
+ * exits 0 when the build succeeded (and the cost matches expected_cost to 1e-5 relative, when given).
+ */
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+
+#include "BvhConstruction.h"
+
+using namespace BvhConstruction;
+
+static std::vector<Triangle> loadTriangles(Context& ctx, const std::string& arg) {
+  std::vector<Triangle> tris;
+  if (arg.rfind("synth:", 0) == 0) {
+    const u32 n = (u32)atoll(arg.c_str() + 6);
+    void* d = nullptr;
+    checkStatus(Api::get().b2bvh_alloc(ctx.m_ctx, (size_t)n * sizeof(Triangle), &d), "b2bvh_alloc");
+    const float half = (float)(1000.0 * pow((double)n, -1.0 / 3.0));
+    checkStatus(Api::get().b2bvh_synth_uniform(ctx.m_ctx, 0, n, 0x00B20010u, half, (Triangle*)d), "b2bvh_synth_uniform");
+    tris.resize(n);
+    checkStatus(Api::get().b2bvh_d2h(ctx.m_ctx, tris.data(), d, (size_t)n * sizeof(Triangle)), "b2bvh_d2h");
+    Api::get().b2bvh_free(ctx.m_ctx, d);
+    return tris;
+  }
+  std::ifstream f(arg, std::ios::binary | std::ios::ate);
+  if (!f) throw std::runtime_error("cannot open " + arg);
+  const size_t bytes = (size_t)f.tellg();
+  f.seekg(0);
+  std::vector<float> raw(bytes / 4);
+  f.read(reinterpret_cast<char*>(raw.data()), (std::streamsize)bytes);
+  tris.resize(raw.size() / 9);
+  for (size_t i = 0; i < tris.size(); i++) {
+    memset(&tris[i], 0, sizeof(Triangle));
+    tris[i].v1 = float3{raw[9 * i + 0], raw[9 * i + 1], raw[9 * i + 2]};
+    tris[i].v2 = float3{raw[9 * i + 3], raw[9 * i + 4], raw[9 * i + 5]};
+    tris[i].v3 = float3{raw[9 * i + 6], raw[9 * i + 7], raw[9 * i + 8]};
+  }
+  return tris;
+}
+
+template <class Builder>
+static float run(Context& ctx, std::vector<Triangle>& tris) {
+  Builder bvh;
+  bvh.build(ctx, tris);
+  bvh.traverseBvh(ctx);
+  std::cout << "wide nodes : " << bvh.m_wideNodeCount << "  root : " << bvh.m_rootNodeIdx << "  internal nodes : " << bvh.m_nInternalNodes << std::endl;
+  size_t hits = 0;
+  for (const HitInfo& h : bvh.m_hits) hits += h.m_primIdx != INVALID_NODE_IDX;
+  if (!bvh.m_hits.empty()) std::cout << "primary rays : " << bvh.m_hits.size() << "  hits : " << hits << std::endl;
+  return bvh.m_cost;
+}
+
+int main(int argc, char* argv[]) {
+  try {
+    if (argc < 3) { fprintf(stderr, "usage: %s <twopass|singlepass|ploc|hploc> <mesh.tri | synth:N> [expected_cost]\n", argv[0]); return 2; }
+    Context context;
+    std::vector<Triangle> triangles = loadTriangles(context, argv[2]);
+    std::cout << "triangles : " << triangles.size() << std::endl;
+    const std::string which = argv[1];
+    float cost;
+    if (which == "twopass") cost = run<TwoPassLbvh>(context, triangles);
+    else if (which == "singlepass") cost = run<SinglePassLbvh>(context, triangles);
+    else if (which == "ploc") cost = run<PLOCNew>(context, triangles);
+    else if (which == "hploc") cost = run<HPLOC>(context, triangles);
+    else throw std::runtime_error("unknown builder " + which);
+    if (argc > 3) {
+      const float want = (float)atof(argv[3]);
+      if (fabsf(cost - want) > 1e-5f * fabsf(want)) { fprintf(stderr, "cost %.7g differs from expected %.7g\n", cost, want); return 1; }
+    }
+  } catch (std::exception& e) { /* main.cpp:80-84 */
+    std::cerr << e.what();
+    return -1;
+  }
+  return 0;
+}

@@ -235,10 +235,13 @@ def top_level(root_boxes):
 
 
 # ---- full pipelines (launch order of the reference builders) ----
-def build_lbvh(tris, single_pass=False):
-    """TwoPassLbvh::build (TwoPassLbvh.cpp:17-197) / SinglePassLbvh::build (SinglePassLbvh.cpp:17-188)."""
+def build_lbvh(tris, single_pass=False, scene_override=None):
+    """TwoPassLbvh::build (TwoPassLbvh.cpp:17-197) / SinglePassLbvh::build (SinglePassLbvh.cpp:17-188).
+    scene_override: AABB[1] global scene box of a sharded build (replaces the local union for Morton coding)."""
     n = tris.size
     refs, boxes, scene = primrefs(tris)
+    if scene_override is not None:
+        scene = scene_override
     keys, vals = morton_codes(refs, scene)
     sk, sv = sort_kv(keys, vals)
     if single_pass:
@@ -252,10 +255,12 @@ def build_lbvh(tris, single_pass=False):
                 wide_count=cnt, cost=cost, boxes=boxes, refs=refs)
 
 
-def build_ploc(tris, hierarchical=False):
+def build_ploc(tris, hierarchical=False, scene_override=None):
     """PLOCNew::build (PLOC++Bvh.cpp:16-196) / HPLOC::build (Hploc.cpp:16-165)."""
     n = tris.size
     refs, boxes, scene = primrefs(tris)
+    if scene_override is not None:
+        scene = scene_override
     keys, vals = morton_codes(boxes, scene)
     sk, sv = sort_kv(keys, vals)
     if hierarchical:
@@ -266,3 +271,18 @@ def build_ploc(tris, hierarchical=False):
     cost = cost_bvh4(wide, wl, boxes, 0, n)
     return dict(scene=scene, keys=keys, vals=vals, skeys=sk, svals=sv, nodes=nodes, leaves=leaves, root=0, wide=wide,
                 wide_leaves=wl, wide_count=cnt, cost=cost, boxes=boxes, stats=stats)
+
+
+def build_sharded(tris, world, single_pass=True):
+    """The sharded procedure of b2bvh/sharded.py restated sequentially: per-shard boxes, global box = union, per-shard LBVH in the
+    global frame, top-level tree over the shard roots.  Returns (global scene AABB[1], [per-shard build dicts], top-level nodes)."""
+    n = tris.size
+    ranges = [((n * r) // world, (n * (r + 1)) // world) for r in range(world)]
+    scene = np.zeros(1, dtype=T.AABB)
+    scene["mn"] = np.min([primrefs(tris[a:b])[2]["mn"][0] for a, b in ranges], axis=0)
+    scene["mx"] = np.max([primrefs(tris[a:b])[2]["mx"][0] for a, b in ranges], axis=0)
+    shards = [build_lbvh(np.ascontiguousarray(tris[a:b]), single_pass=single_pass, scene_override=scene) for a, b in ranges]
+    roots = np.zeros(world, dtype=T.AABB)
+    for r, s in enumerate(shards):
+        roots[r]["mn"] = s["nodes"][s["root"]]["mn"]; roots[r]["mx"] = s["nodes"][s["root"]]["mx"]
+    return scene, shards, top_level(roots)

@@ -53,3 +53,17 @@ def test_product_does_not_touch_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp")):
                 text = open(os.path.join(d, f)).read()
                 assert "import oracle" not in text and "liboracle" not in text and "oracle/" not in text.replace("as in oracle", ""), os.path.join(d, f)
+
+
+def test_cpp_host_layer_builds_and_fails_loudly_without_gpu():
+    """The reference-compatible C++ classes (host/BvhConstruction.h) compile, bind libb2bvh.so with dlopen, and refuse to run
+    without a CUDA device (no CPU fallback)."""
+    import torch
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "hip-bvh-construction_b200", "host"), "all"], stdout=subprocess.DEVNULL)
+    exe = os.path.join(ROOT, "hip-bvh-construction_b200", "b2bvh_demo")
+    assert os.path.exists(exe)
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    env = dict(os.environ, B2BVH_LIB=capi.LIB_PATH)
+    r = subprocess.run([exe, "twopass", "synth:100"], env=env, capture_output=True, text=True)
+    assert r.returncode != 0 and "no CUDA device" in r.stderr

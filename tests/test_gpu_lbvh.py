@@ -151,5 +151,5 @@ def test_profiler_reports_every_launch(ctx):
     ctx.profile(False)
     assert len(entries) == tree.n_launches
     names = [e[0] for e in entries]
-    assert names[:3] == ["primref_extents", "morton30", "radix_hist"] and names.count("onesweep_pass") == 4
+    assert names[:3] == ["primref_extents", "morton30", "radix_count"] and names.count("radix_scatter") == 4
     assert all(ms >= 0 for _, ms in entries)

@@ -21,10 +21,11 @@ def main():
     ap.add_argument("--algo", default="singlepass")
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--two-kernel", action="store_true")
+    ap.add_argument("--warmup", type=int, default=3)
     a = ap.parse_args()
     ctx = capi.Context(0)
     d = ctx.synth_uniform(a.n, 0x00B20010)
-    for _ in range(3):
+    for _ in range(a.warmup):
         tree = ctx.build(ALGOS[a.algo], d, n=a.n, tris_on_device=True, karras_two_kernel=a.two_kernel)
     agg = {}
     tot = []
