@@ -20,6 +20,8 @@
  * Traffic per primitive: sorted value 4 + sorted key 4 (+ neighbours from L1/L2) + gathered box 24 + leaf node 32 written
  *   + internal node 32 written + sibling node 32 re-read + 4 (exchange word)  ~ 132 B (+8 when the parent array is written).
  */
+#include <stdlib.h>
+
 #include "common.cuh"
 
 #define LBVH_THREADS 256
@@ -38,22 +40,13 @@ __device__ __forceinline__ u32 choose_parent(const u32* __restrict__ keys, u32 n
   return isLeft ? hi - 1 : lo - 1;
 }
 
+/* The climb through GLOBAL memory, starting from a finished node `self` covering [lo, hi) with box `box` whose parent has
+ * split `p` (this node being its left child iff isLeft).  Returns when the node is the first to arrive at some parent
+ * (the sibling's thread takes over) or when the root has been written. */
 template <bool KARRAS>
-__global__ void __launch_bounds__(LBVH_THREADS) lbvh_fused_kernel(const u32* __restrict__ keys, const u32* __restrict__ vals,
-                                                                  const b2bvh_aabb* __restrict__ triAabb, u32 n, b2bvh_bvh2_node* nodes,
-                                                                  u32* parents, u32* meet /* n-1 words, 0xFFFFFFFF */, u32* rootOut) {
-  const u32 g = blockIdx.x * LBVH_THREADS + threadIdx.x;
-  if (g >= n) return;
+__device__ __forceinline__ void climb_global(const u32* __restrict__ keys, u32 n, b2bvh_bvh2_node* nodes, u32* parents, u32* meet, u32* rootOut,
+                                             u32 self, u32 lo, u32 hi, Box box, u32 p, bool isLeft) {
   const u32 nInt = n - 1;
-  const u32 prim = __ldg(vals + g);
-  Box box = load_aabb(triAabb + prim);
-  store_node2(nodes + nInt + g, prim, B2_INVALID, box);
-  if (n == 1) { if (rootOut) *rootOut = 0; return; }
-
-  u32 lo = g, hi = g + 1;
-  u32 self = nInt + g; /* index of the node this thread currently stands on (already written) */
-  bool isLeft;
-  u32 p = choose_parent(keys, n, lo, hi, isLeft);
   while (true) {
     if (!KARRAS) {
       /* Apetrei numbering: hand our index to the parent slot (the sibling cannot derive it) */
@@ -81,6 +74,119 @@ __global__ void __launch_bounds__(LBVH_THREADS) lbvh_fused_kernel(const u32* __r
     if (parents) { parents[left] = id; parents[right] = id; if (isRoot) parents[id] = B2_INVALID; }
     if (isRoot) { if (rootOut) *rootOut = id; return; }
     self = id;
+  }
+}
+
+template <bool KARRAS>
+__global__ void __launch_bounds__(LBVH_THREADS) lbvh_fused_kernel(const u32* __restrict__ keys, const u32* __restrict__ vals,
+                                                                  const b2bvh_aabb* __restrict__ triAabb, u32 n, b2bvh_bvh2_node* nodes,
+                                                                  u32* parents, u32* meet /* n-1 words, 0xFFFFFFFF */, u32* rootOut) {
+  const u32 g = blockIdx.x * LBVH_THREADS + threadIdx.x;
+  if (g >= n) return;
+  const u32 nInt = n - 1;
+  const u32 prim = __ldg(vals + g);
+  const Box box = load_aabb(triAabb + prim);
+  store_node2(nodes + nInt + g, prim, B2_INVALID, box);
+  if (n == 1) { if (rootOut) *rootOut = 0; return; }
+  bool isLeft;
+  const u32 p = choose_parent(keys, n, g, g + 1, isLeft);
+  climb_global<KARRAS>(keys, n, nodes, parents, meet, rootOut, nInt + g, g, g + 1, box, p, isLeft);
+}
+
+/* ---------------------------------------------------------------- CTA-local climb in shared memory, then the global climb
+ * A CTA owns BL consecutive leaves [b0, b1).  Every internal node whose range lies inside [b0, b1) is finished by one of the
+ * CTA's own threads, and when BOTH children of a node lie inside, the two arrivals can meet in shared memory: the
+ * exchange word, the first arriver's box and its index are shared-memory traffic, and no fence or L2 round trip is paid.
+ * That covers all but O(log BL) nodes per CTA.  A finished node whose sibling does NOT lie inside the CTA (its parent
+ * straddles a CTA boundary) is left "stranded" in its slot; after a CTA barrier the stranded nodes, and the nodes that
+ * reached the CTA boundary directly, continue through the global protocol above.  Every finished node is written to global
+ * memory exactly once, with two 16-byte stores, as before; results are identical to lbvh_fused_kernel. */
+#define LBVH_BL 512
+#define LBVH_CONSUMED 0xFFFFFFFEu
+
+struct LbvhBlockSmem {
+  u32 key[LBVH_BL + 2];          /* keys of leaves b0-1 .. b1 */
+  u32 meet[LBVH_BL];             /* exchange word of split p (between leaves p and p+1), index p - b0 */
+  u32 sibId[LBVH_BL][2];         /* [split][side]: index of the child that arrived from that side (0 = left child) */
+  float sibBox[LBVH_BL][2][6];
+};
+
+__device__ __forceinline__ u32 choose_parent_smem(const u32* sk, u32 kb /* leaf index of sk[0] */, u32 n, u32 lo, u32 hi, bool& isLeft) {
+  if (lo == 0) { isLeft = true; return hi - 1; }
+  if (hi == n) { isLeft = false; return lo - 1; }
+  const u64 a = ((u64)sk[hi - 1 - kb] << 32) | (hi - 1), b = ((u64)sk[hi - kb] << 32) | hi;
+  const u64 c = ((u64)sk[lo - 1 - kb] << 32) | (lo - 1), d = ((u64)sk[lo - kb] << 32) | lo;
+  isLeft = (a ^ b) < (c ^ d);
+  return isLeft ? hi - 1 : lo - 1;
+}
+
+template <bool KARRAS>
+__global__ void __launch_bounds__(LBVH_BL) lbvh_block_kernel(const u32* __restrict__ keys, const u32* __restrict__ vals,
+                                                             const b2bvh_aabb* __restrict__ triAabb, u32 n, b2bvh_bvh2_node* nodes, u32* parents,
+                                                             u32* meet, u32* rootOut) {
+  __shared__ LbvhBlockSmem S;
+  const u32 t = threadIdx.x;
+  const u32 b0 = blockIdx.x * LBVH_BL, b1 = min(n, b0 + LBVH_BL);
+  const u32 g = b0 + t;
+  const u32 nInt = n - 1;
+  const u32 kb = b0 - 1; /* leaf index of S.key[0] (wraps for b0 == 0; slot 0 is then unused) */
+  S.meet[t] = B2_INVALID;
+  S.sibId[t][0] = B2_INVALID; S.sibId[t][1] = B2_INVALID;
+  if (g < n) S.key[t + 1] = __ldg(keys + g);
+  if (t == 0 && b0 > 0) S.key[0] = __ldg(keys + b0 - 1);
+  if (t == 0 && b1 < n) S.key[b1 - b0 + 1] = __ldg(keys + b1);
+  Box box = box_empty();
+  u32 self = B2_INVALID, lo = 0, hi = 0, p = 0;
+  bool isLeft = false, goGlobal = false;
+  if (g < n) {
+    const u32 prim = __ldg(vals + g);
+    box = load_aabb(triAabb + prim);
+    store_node2(nodes + nInt + g, prim, B2_INVALID, box);
+  }
+  __syncthreads();
+  if (n == 1) { if (g == 0 && rootOut) *rootOut = 0; return; }
+
+  if (g < n) {
+    lo = g; hi = g + 1; self = nInt + g;
+    p = choose_parent_smem(S.key, kb, n, lo, hi, isLeft);
+    while (true) {
+      if (p < b0 || p + 1 >= b1) { goGlobal = true; break; } /* the parent straddles the CTA boundary */
+      const u32 slot = p - b0;
+      const int side = isLeft ? 0 : 1;
+      float* sb = S.sibBox[slot][side];
+      sb[0] = box.lx; sb[1] = box.ly; sb[2] = box.lz; sb[3] = box.hx; sb[4] = box.hy; sb[5] = box.hz;
+      S.sibId[slot][side] = self;
+      __threadfence_block();
+      const u32 other = atomicExch(&S.meet[slot], isLeft ? lo : hi);
+      if (other == B2_INVALID) break; /* first arriver: waits in its slot for the sibling (or for the escalation below) */
+      __threadfence_block();
+      S.meet[slot] = LBVH_CONSUMED;
+      if (isLeft) hi = other; else lo = other;
+      const float* ob = S.sibBox[slot][side ^ 1];
+      const u32 sib = S.sibId[slot][side ^ 1];
+      box = box_union(box, Box{ob[0], ob[1], ob[2], ob[3], ob[4], ob[5]});
+      const u32 left = isLeft ? self : sib, right = isLeft ? sib : self;
+      const bool isRoot = (lo == 0 && hi == n);
+      const u32 split = p;
+      if (!isRoot) p = choose_parent_smem(S.key, kb, n, lo, hi, isLeft);
+      const u32 id = KARRAS ? (isRoot ? 0u : (isLeft ? hi - 1 : lo)) : split;
+      store_node2(nodes + id, left, right, box);
+      if (parents) { parents[left] = id; parents[right] = id; if (isRoot) parents[id] = B2_INVALID; }
+      if (isRoot) { if (rootOut) *rootOut = id; break; }
+      self = id;
+    }
+  }
+  __syncthreads();
+  /* ---- global climb: (1) this thread's own node if it reached the CTA boundary, (2) the stranded node of slot t ---- */
+  if (goGlobal) climb_global<KARRAS>(keys, n, nodes, parents, meet, rootOut, self, lo, hi, box, p, isLeft);
+  const u32 m = S.meet[t];
+  if (m != B2_INVALID && m != LBVH_CONSUMED) {
+    const u32 sp = b0 + t; /* split of the stranded node's parent */
+    const int side = (S.sibId[t][0] != B2_INVALID) ? 0 : 1;
+    const float* ob = S.sibBox[t][side];
+    const Box sbox = Box{ob[0], ob[1], ob[2], ob[3], ob[4], ob[5]};
+    const u32 slo = side == 0 ? m : sp + 1, shi = side == 0 ? sp + 1 : m;
+    climb_global<KARRAS>(keys, n, nodes, parents, meet, rootOut, S.sibId[t][side], slo, shi, sbox, sp, side == 0);
   }
 }
 
@@ -153,12 +259,21 @@ __global__ void __launch_bounds__(LBVH_THREADS) lbvh_refit_kernel(b2bvh_bvh2_nod
 int b2_launch_lbvh_fused(b2bvh_ctx* ctx, const u32* d_sortedKeys, const u32* d_sortedVals, const b2bvh_aabb* d_triAabb, u32 n,
                          b2bvh_bvh2_node* d_nodes, u32* d_parents, u32* d_scratch, u32* d_root, int karrasNumbering) {
   if (n > 1) B2_CUDA(cudaMemsetAsync(d_scratch, 0xFF, (size_t)(n - 1) * sizeof(u32), ctx->stream));
-  const u32 grid = (n + LBVH_THREADS - 1) / LBVH_THREADS;
   B2_KERNEL(ctx, karrasNumbering ? "lbvh_fused_karras" : "lbvh_fused_apetrei");
-  if (karrasNumbering)
-    lbvh_fused_kernel<true><<<grid, LBVH_THREADS, 0, ctx->stream>>>(d_sortedKeys, d_sortedVals, d_triAabb, n, d_nodes, d_parents, d_scratch, d_root);
-  else
-    lbvh_fused_kernel<false><<<grid, LBVH_THREADS, 0, ctx->stream>>>(d_sortedKeys, d_sortedVals, d_triAabb, n, d_nodes, d_parents, d_scratch, d_root);
+  static const bool globalOnly = getenv("B2BVH_LBVH_GLOBAL_ONLY") != nullptr; /* development switch: the all-global-memory variant */
+  if (globalOnly) {
+    const u32 grid = (n + LBVH_THREADS - 1) / LBVH_THREADS;
+    if (karrasNumbering)
+      lbvh_fused_kernel<true><<<grid, LBVH_THREADS, 0, ctx->stream>>>(d_sortedKeys, d_sortedVals, d_triAabb, n, d_nodes, d_parents, d_scratch, d_root);
+    else
+      lbvh_fused_kernel<false><<<grid, LBVH_THREADS, 0, ctx->stream>>>(d_sortedKeys, d_sortedVals, d_triAabb, n, d_nodes, d_parents, d_scratch, d_root);
+  } else {
+    const u32 grid = (n + LBVH_BL - 1) / LBVH_BL;
+    if (karrasNumbering)
+      lbvh_block_kernel<true><<<grid, LBVH_BL, 0, ctx->stream>>>(d_sortedKeys, d_sortedVals, d_triAabb, n, d_nodes, d_parents, d_scratch, d_root);
+    else
+      lbvh_block_kernel<false><<<grid, LBVH_BL, 0, ctx->stream>>>(d_sortedKeys, d_sortedVals, d_triAabb, n, d_nodes, d_parents, d_scratch, d_root);
+  }
   B2_LAUNCH_CHECK(ctx);
   return 0;
 }

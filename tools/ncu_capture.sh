@@ -14,7 +14,8 @@ for K in "$@"; do
     *) ALGO=singlepass;;
   esac
   case $K in
-    collapse4_level) CNT="-s 4 -c 12";;
+    collapse_number) CNT="-s 6 -c 10";;
+    radix_scatter|radix_count) CNT="-c 4";;
     ploc_iter) CNT="-c 5";;
     onesweep_pass) CNT="-c 4";;
     *) CNT="-c 1";;
