@@ -203,7 +203,7 @@ int b2bvh_build(b2bvh_ctx* ctx, int algo, const b2bvh_triangle* tris, uint32_t n
   B2_TRY(b2_reserve(ctx, SLOT_SORT, b2_sort_scratch_bytes(n), &dSort));
   B2_TRY(b2_reserve(ctx, SLOT_NODES, (size_t)(separate ? n - 1 : 2 * (size_t)n - 1) * sizeof(b2bvh_bvh2_node), &dNodes));
   if (algo == B2BVH_TWO_PASS_LBVH) B2_TRY(b2_reserve(ctx, SLOT_PARENTS, (2 * (size_t)n - 1) * 4, &dParents));
-  if (!separate) B2_TRY(b2_reserve(ctx, SLOT_LBVH, (2 * (size_t)n - 1) * 4, &dLbvh));
+  if (!separate) B2_TRY(b2_reserve(ctx, SLOT_LBVH, b2_lbvh_scratch_bytes(n), &dLbvh));
   if (separate) B2_TRY(b2_reserve(ctx, SLOT_LEAVES, (size_t)n * sizeof(b2bvh_prim_ref), &dLeaves));
   if (algo == B2BVH_PLOCPP) B2_TRY(b2_reserve(ctx, SLOT_PLOC, b2_ploc_scratch_bytes(n), &dMerge));
   if (algo == B2BVH_HPLOC) B2_TRY(b2_reserve(ctx, SLOT_HPLOC, b2_hploc_scratch_bytes(n), &dMerge));
@@ -264,7 +264,7 @@ int b2bvh_build(b2bvh_ctx* ctx, int algo, const b2bvh_triangle* tris, uint32_t n
   /* ---- S5 collapse ---- */
   u32 nWide = 0;
   if (opts.collapse)
-    B2_TRY(b2_launch_collapse(ctx, (const b2bvh_bvh2_node*)dNodes, (const b2bvh_prim_ref*)dLeaves, dRoot, n, (b2bvh_bvh4_node*)dWide,
+    B2_TRY(b2_launch_collapse(ctx, (const b2bvh_bvh2_node*)dNodes, (const b2bvh_prim_ref*)dLeaves, (const u32*)dSVals, dRoot, n, (b2bvh_bvh4_node*)dWide,
                               (b2bvh_prim_node*)dWLeaves, dCollapse, &nWide));
   B2_CUDA(cudaEventRecord(ctx->ev[5], s));
   u32 root = 0;

@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(COL_THREADS) collapse_number_kernel(const uint
 
 /* ---- 3. wide nodes + leaf records ---- */
 template <bool SEPARATE_LEAVES>
-__global__ void __launch_bounds__(COL_THREADS) collapse_emit_kernel(const b2bvh_bvh2_node* __restrict__ nodes, const b2bvh_prim_ref* __restrict__ leaves,
+__global__ void __launch_bounds__(COL_THREADS) collapse_emit_kernel(const b2bvh_bvh2_node* __restrict__ nodes, const u32* __restrict__ sortedVals,
                                                                    u32 nInt, const uint4* __restrict__ expansion, const uint2* __restrict__ tasks,
                                                                    const u32* __restrict__ firstChild, const CollapseCtrl* __restrict__ ctrl,
                                                                    b2bvh_bvh4_node* __restrict__ wide, b2bvh_prim_node* __restrict__ wideLeaves) {
@@ -198,8 +198,9 @@ __global__ void __launch_bounds__(COL_THREADS) collapse_emit_kernel(const b2bvh_
         } else {
           outChild[k] = ch[k];
           const u32 slot = ch[k] - nInt;
-          const u32 prim = SEPARATE_LEAVES ? __ldg(&leaves[slot].m_primIdx) : __ldg(&nodes[ch[k]].m_leftChildIdx);
-          reinterpret_cast<uint2*>(wideLeaves)[slot] = make_uint2(prim, g);
+          /* leaf slot s holds primitive sortedVals[s] in both layouts (Bvh2 leaf m_leftChildIdx / PrimRef m_primIdx): read the
+           * dense 4-byte array instead of one 32-byte node or 28-byte PrimRef per leaf */
+          reinterpret_cast<uint2*>(wideLeaves)[slot] = make_uint2(__ldg(sortedVals + slot), g);
         }
       }
     }
@@ -217,7 +218,7 @@ __global__ void __launch_bounds__(COL_THREADS) collapse_emit_kernel(const b2bvh_
   }
 }
 
-int b2_launch_collapse(b2bvh_ctx* ctx, const b2bvh_bvh2_node* d_nodes, const b2bvh_prim_ref* d_leaves, const u32* d_rootIdx, u32 n,
+int b2_launch_collapse(b2bvh_ctx* ctx, const b2bvh_bvh2_node* d_nodes, const b2bvh_prim_ref* d_leaves, const u32* d_sortedVals, const u32* d_rootIdx, u32 n,
                        b2bvh_bvh4_node* d_wide, b2bvh_prim_node* d_wideLeaves, void* d_scratch, u32* h_nWide) {
   if (n < 2) return b2_fail(B2BVH_ERR_INVALID, "collapse needs at least 2 primitives");
   unsigned char* base = reinterpret_cast<unsigned char*>(d_scratch);
@@ -252,9 +253,9 @@ int b2_launch_collapse(b2bvh_ctx* ctx, const b2bvh_bvh2_node* d_nodes, const b2b
   if (grid > cap * 2) grid = cap * 2;
   B2_KERNEL(ctx, "collapse_emit");
   if (d_leaves)
-    collapse_emit_kernel<true><<<grid, COL_THREADS, 0, ctx->stream>>>(d_nodes, d_leaves, nInt, expansion, tasks, firstChild, ctrl, d_wide, d_wideLeaves);
+    collapse_emit_kernel<true><<<grid, COL_THREADS, 0, ctx->stream>>>(d_nodes, d_sortedVals, nInt, expansion, tasks, firstChild, ctrl, d_wide, d_wideLeaves);
   else
-    collapse_emit_kernel<false><<<grid, COL_THREADS, 0, ctx->stream>>>(d_nodes, d_leaves, nInt, expansion, tasks, firstChild, ctrl, d_wide, d_wideLeaves);
+    collapse_emit_kernel<false><<<grid, COL_THREADS, 0, ctx->stream>>>(d_nodes, d_sortedVals, nInt, expansion, tasks, firstChild, ctrl, d_wide, d_wideLeaves);
   B2_LAUNCH_CHECK(ctx);
   *h_nWide = h.nWide;
   return 0;

@@ -180,12 +180,14 @@ int b2_launch_morton(b2bvh_ctx* ctx, const b2bvh_aabb* d_triAabb, const b2bvh_aa
 size_t b2_sort_scratch_bytes(u32 n);
 int b2_launch_sort(b2bvh_ctx* ctx, const u32* d_keysIn, const u32* d_valsIn, u32* d_keysOut, u32* d_valsOut, u32* d_keysTmp, u32* d_valsTmp,
                    void* d_scratch, u32 n, u32 startBit, u32 endBit);
+size_t b2_lbvh_scratch_bytes(u32 n);
 int b2_launch_lbvh_fused(b2bvh_ctx* ctx, const u32* d_sortedKeys, const u32* d_sortedVals, const b2bvh_aabb* d_triAabb, u32 n,
-                         b2bvh_bvh2_node* d_nodes, u32* d_parents, u32* d_scratch /* 3n+1 u32 */, u32* d_root, int karrasNumbering);
+                         b2bvh_bvh2_node* d_nodes, u32* d_parents, u32* d_scratch /* b2_lbvh_scratch_bytes(n) */, u32* d_root, int karrasNumbering);
 int b2_launch_lbvh_karras_two_kernel(b2bvh_ctx* ctx, const u32* d_sortedKeys, const u32* d_sortedVals, const b2bvh_aabb* d_triAabb, u32 n,
                                      b2bvh_bvh2_node* d_nodes, u32* d_parents, u32* d_flags);
 size_t b2_collapse_scratch_bytes(u32 n);
-int b2_launch_collapse(b2bvh_ctx* ctx, const b2bvh_bvh2_node* d_nodes, const b2bvh_prim_ref* d_leaves, const u32* d_rootIdx, u32 n,
+int b2_launch_collapse(b2bvh_ctx* ctx, const b2bvh_bvh2_node* d_nodes, const b2bvh_prim_ref* d_leaves, const u32* d_sortedVals, const u32* d_rootIdx,
+                       u32 n,
                        b2bvh_bvh4_node* d_wide, b2bvh_prim_node* d_wideLeaves, void* d_scratch, u32* h_nWide);
 size_t b2_ploc_scratch_bytes(u32 n);
 int b2_launch_ploc(b2bvh_ctx* ctx, const b2bvh_aabb* d_triAabb, const u32* d_sortedVals, u32 n, b2bvh_bvh2_node* d_nodes,

@@ -104,7 +104,16 @@ __global__ void __launch_bounds__(LBVH_THREADS) lbvh_fused_kernel(const u32* __r
 #define LBVH_BL 512
 #define LBVH_CONSUMED 0xFFFFFFFEu
 
+/* A finished node that must continue through global memory: 48 bytes, written by lbvh_block_kernel, consumed by lbvh_climb_kernel */
+struct LbvhPending {
+  u32 self, lo, hi, pSide; /* pSide = parent split | (isLeft << 31) */
+  float box[6];
+  u32 pad[2];
+};
+static_assert(sizeof(LbvhPending) == 48, "LbvhPending layout");
+
 struct LbvhBlockSmem {
+  u32 pendCount, pendBase;
   u32 key[LBVH_BL + 2];          /* keys of leaves b0-1 .. b1 */
   u32 meet[LBVH_BL];             /* exchange word of split p (between leaves p and p+1), index p - b0 */
   u32 sibId[LBVH_BL][2];         /* [split][side]: index of the child that arrived from that side (0 = left child) */
@@ -123,7 +132,7 @@ __device__ __forceinline__ u32 choose_parent_smem(const u32* sk, u32 kb /* leaf 
 template <bool KARRAS>
 __global__ void __launch_bounds__(LBVH_BL) lbvh_block_kernel(const u32* __restrict__ keys, const u32* __restrict__ vals,
                                                              const b2bvh_aabb* __restrict__ triAabb, u32 n, b2bvh_bvh2_node* nodes, u32* parents,
-                                                             u32* meet, u32* rootOut) {
+                                                             u32* meet, u32* rootOut, u32* pendingCount, LbvhPending* pending, u32 pendingCap) {
   __shared__ LbvhBlockSmem S;
   const u32 t = threadIdx.x;
   const u32 b0 = blockIdx.x * LBVH_BL, b1 = min(n, b0 + LBVH_BL);
@@ -132,6 +141,7 @@ __global__ void __launch_bounds__(LBVH_BL) lbvh_block_kernel(const u32* __restri
   const u32 kb = b0 - 1; /* leaf index of S.key[0] (wraps for b0 == 0; slot 0 is then unused) */
   S.meet[t] = B2_INVALID;
   S.sibId[t][0] = B2_INVALID; S.sibId[t][1] = B2_INVALID;
+  if (t == 0) S.pendCount = 0;
   if (g < n) S.key[t + 1] = __ldg(keys + g);
   if (t == 0 && b0 > 0) S.key[0] = __ldg(keys + b0 - 1);
   if (t == 0 && b1 < n) S.key[b1 - b0 + 1] = __ldg(keys + b1);
@@ -177,16 +187,54 @@ __global__ void __launch_bounds__(LBVH_BL) lbvh_block_kernel(const u32* __restri
     }
   }
   __syncthreads();
-  /* ---- global climb: (1) this thread's own node if it reached the CTA boundary, (2) the stranded node of slot t ---- */
-  if (goGlobal) climb_global<KARRAS>(keys, n, nodes, parents, meet, rootOut, self, lo, hi, box, p, isLeft);
+  /* ---- hand over to the global climb (separate launch, so this CTA retires as soon as its shared-memory work is done):
+   * (1) this thread's own node if it reached the CTA boundary, (2) the stranded node of slot t ---- */
   const u32 m = S.meet[t];
-  if (m != B2_INVALID && m != LBVH_CONSUMED) {
+  const bool stranded = (m != B2_INVALID && m != LBVH_CONSUMED);
+  u32 myIdx = 0;
+  const u32 mine = (goGlobal ? 1u : 0u) + (stranded ? 1u : 0u);
+  if (mine) myIdx = atomicAdd(&S.pendCount, mine);
+  __syncthreads();
+  if (t == 0 && S.pendCount) S.pendBase = atomicAdd(pendingCount, S.pendCount);
+  __syncthreads();
+  u32 slotOut = S.pendBase + myIdx;
+  if (goGlobal) {
+    if (slotOut < pendingCap) {
+      uint4* q = reinterpret_cast<uint4*>(pending + slotOut);
+      q[0] = make_uint4(self, lo, hi, p | (isLeft ? 0x80000000u : 0u));
+      q[1] = make_uint4(__float_as_uint(box.lx), __float_as_uint(box.ly), __float_as_uint(box.lz), __float_as_uint(box.hx));
+      q[2] = make_uint4(__float_as_uint(box.hy), __float_as_uint(box.hz), 0u, 0u);
+    } else {
+      climb_global<KARRAS>(keys, n, nodes, parents, meet, rootOut, self, lo, hi, box, p, isLeft); /* overflow of the hand-over list */
+    }
+    slotOut++;
+  }
+  if (stranded) {
     const u32 sp = b0 + t; /* split of the stranded node's parent */
     const int side = (S.sibId[t][0] != B2_INVALID) ? 0 : 1;
     const float* ob = S.sibBox[t][side];
-    const Box sbox = Box{ob[0], ob[1], ob[2], ob[3], ob[4], ob[5]};
     const u32 slo = side == 0 ? m : sp + 1, shi = side == 0 ? sp + 1 : m;
-    climb_global<KARRAS>(keys, n, nodes, parents, meet, rootOut, S.sibId[t][side], slo, shi, sbox, sp, side == 0);
+    if (slotOut < pendingCap) {
+      uint4* q = reinterpret_cast<uint4*>(pending + slotOut);
+      q[0] = make_uint4(S.sibId[t][side], slo, shi, sp | (side == 0 ? 0x80000000u : 0u));
+      q[1] = make_uint4(__float_as_uint(ob[0]), __float_as_uint(ob[1]), __float_as_uint(ob[2]), __float_as_uint(ob[3]));
+      q[2] = make_uint4(__float_as_uint(ob[4]), __float_as_uint(ob[5]), 0u, 0u);
+    } else {
+      climb_global<KARRAS>(keys, n, nodes, parents, meet, rootOut, S.sibId[t][side], slo, shi, Box{ob[0], ob[1], ob[2], ob[3], ob[4], ob[5]}, sp, side == 0);
+    }
+  }
+}
+
+template <bool KARRAS>
+__global__ void __launch_bounds__(LBVH_THREADS) lbvh_climb_kernel(const u32* __restrict__ keys, u32 n, b2bvh_bvh2_node* nodes, u32* parents, u32* meet,
+                                                                  u32* rootOut, const u32* __restrict__ pendingCount,
+                                                                  const LbvhPending* __restrict__ pending, u32 pendingCap) {
+  const u32 count = min(*pendingCount, pendingCap);
+  for (u32 i = blockIdx.x * LBVH_THREADS + threadIdx.x; i < count; i += gridDim.x * LBVH_THREADS) {
+    const uint4* q = reinterpret_cast<const uint4*>(pending + i);
+    const uint4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+    const Box box = Box{__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z), __uint_as_float(b.w), __uint_as_float(c.x), __uint_as_float(c.y)};
+    climb_global<KARRAS>(keys, n, nodes, parents, meet, rootOut, a.x, a.y, a.z, box, a.w & 0x7FFFFFFFu, (a.w >> 31) != 0u);
   }
 }
 
@@ -256,6 +304,13 @@ __global__ void __launch_bounds__(LBVH_THREADS) lbvh_refit_kernel(b2bvh_bvh2_nod
   }
 }
 
+size_t b2_lbvh_scratch_bytes(u32 n) {
+  /* the larger of: fused path (meet words + hand-over list) and two-kernel path (2n-1 flags) */
+  const size_t fused = (((size_t)n * 4 + 15) & ~(size_t)15) + 16 + ((size_t)n / 8 + 1024) * sizeof(LbvhPending);
+  const size_t two = (2 * (size_t)n - 1) * 4;
+  return fused > two ? fused : two;
+}
+
 int b2_launch_lbvh_fused(b2bvh_ctx* ctx, const u32* d_sortedKeys, const u32* d_sortedVals, const b2bvh_aabb* d_triAabb, u32 n,
                          b2bvh_bvh2_node* d_nodes, u32* d_parents, u32* d_scratch, u32* d_root, int karrasNumbering) {
   if (n > 1) B2_CUDA(cudaMemsetAsync(d_scratch, 0xFF, (size_t)(n - 1) * sizeof(u32), ctx->stream));
@@ -268,11 +323,26 @@ int b2_launch_lbvh_fused(b2bvh_ctx* ctx, const u32* d_sortedKeys, const u32* d_s
     else
       lbvh_fused_kernel<false><<<grid, LBVH_THREADS, 0, ctx->stream>>>(d_sortedKeys, d_sortedVals, d_triAabb, n, d_nodes, d_parents, d_scratch, d_root);
   } else {
+    /* scratch: meet[n-1] | (16-byte aligned) pendingCount | pending[cap] */
+    const size_t off = (((size_t)n * 4 + 15) & ~(size_t)15);
+    u32* pendingCount = reinterpret_cast<u32*>(reinterpret_cast<unsigned char*>(d_scratch) + off);
+    LbvhPending* pending = reinterpret_cast<LbvhPending*>(reinterpret_cast<unsigned char*>(d_scratch) + off + 16);
+    const u32 cap = n / 8 + 1024;
+    B2_CUDA(cudaMemsetAsync(pendingCount, 0, 4, ctx->stream));
     const u32 grid = (n + LBVH_BL - 1) / LBVH_BL;
     if (karrasNumbering)
-      lbvh_block_kernel<true><<<grid, LBVH_BL, 0, ctx->stream>>>(d_sortedKeys, d_sortedVals, d_triAabb, n, d_nodes, d_parents, d_scratch, d_root);
+      lbvh_block_kernel<true><<<grid, LBVH_BL, 0, ctx->stream>>>(d_sortedKeys, d_sortedVals, d_triAabb, n, d_nodes, d_parents, d_scratch, d_root, pendingCount, pending, cap);
     else
-      lbvh_block_kernel<false><<<grid, LBVH_BL, 0, ctx->stream>>>(d_sortedKeys, d_sortedVals, d_triAabb, n, d_nodes, d_parents, d_scratch, d_root);
+      lbvh_block_kernel<false><<<grid, LBVH_BL, 0, ctx->stream>>>(d_sortedKeys, d_sortedVals, d_triAabb, n, d_nodes, d_parents, d_scratch, d_root, pendingCount, pending, cap);
+    B2_LAUNCH_CHECK(ctx);
+    u32 grid2 = (cap + LBVH_THREADS - 1) / LBVH_THREADS;
+    const u32 cap2 = (u32)ctx->sm_count * 8u;
+    if (grid2 > cap2) grid2 = cap2;
+    B2_KERNEL(ctx, "lbvh_climb");
+    if (karrasNumbering)
+      lbvh_climb_kernel<true><<<grid2, LBVH_THREADS, 0, ctx->stream>>>(d_sortedKeys, n, d_nodes, d_parents, d_scratch, d_root, pendingCount, pending, cap);
+    else
+      lbvh_climb_kernel<false><<<grid2, LBVH_THREADS, 0, ctx->stream>>>(d_sortedKeys, n, d_nodes, d_parents, d_scratch, d_root, pendingCount, pending, cap);
   }
   B2_LAUNCH_CHECK(ctx);
   return 0;
