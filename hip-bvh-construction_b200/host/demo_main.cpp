@@ -2,7 +2,7 @@
  * demo_main.cpp — the reference's driver (src/main.cpp:26-85) against the B200 library: pick a builder, load triangles,
  * build(), traverseBvh().  The reference chooses the builder with #defines (main.cpp:18-22) and hard-codes an OBJ path; here
  * both are command-line arguments and the mesh is a raw triangle file (float32 x 9 per triangle, the format written by
- * oracle/stage_meshes.py with the reference's own OBJ loader) or a synthetic stream.
+ * the mesh staging script of the test infrastructure with the reference's own OBJ loader) or a synthetic stream.
  *
  *   b2bvh_demo <twopass|singlepass|ploc|hploc> <mesh.tri | synth:N> [expected_cost]
  * exits 0 when the build succeeded (and the cost matches expected_cost to 1e-5 relative, when given).
