@@ -3,59 +3,77 @@
  *
  * Replaces CollapseToWide4Bvh (TwoPassLbvhKernel.h:237-337 for the LBVH layout, Ploc++Kernel.h:364-465 for the
  * separate-leaf layout; host setup TwoPassLbvh.cpp:154-183).  The reference runs ONE persistent launch whose threads
- * spin on a task queue and allocate wide nodes with a global atomicAdd: node numbering is timing dependent and the
- * launch needs every thread resident.  Here the work is split so that the expensive, latency-bound part is fully
- * parallel and only a light numbering pass is level-synchronous:
- *   1. collapse_expand_kernel   for EVERY internal Bvh2 node, the (up to 4) children it would have as a wide node: twice,
- *                               the internal child with the largest area is replaced by its two children (strict '>' so the
- *                               first of equals wins, areas without FMA).  One thread per node, no synchronisation, 16 B out.
- *   2. collapse_number_kernel   one launch per level of the wide tree: the tasks of a level are a contiguous index range;
- *                               the number of internal children is prefix-summed across the level (CTA scan + warp-window
- *                               look-back between ticketed tiles) and the children get consecutive indices in (task, slot)
- *                               order.  That is breadth-first numbering — what a sequential execution of the reference's
- *                               task loop produces — so the output is deterministic and comparable with memcmp.  Per task:
- *                               8 B task + 16 B expansion read, 4 B + 8 B per child written.
- *   3. collapse_emit_kernel     one thread per wide node: child boxes gathered, the 128-byte node written with eight
- *                               16-byte stores, PrimNode records for leaf children.
+ * spin on a task queue and allocate wide nodes with a global atomicAdd: node numbering is timing dependent.  Here the
+ * wide tree is numbered breadth-first — what a sequential execution of the reference's task loop produces — so the output
+ * is deterministic and comparable with memcmp (canonical numbering of the oracle).  Two launches:
+ *
+ *   1. collapse_expand_kernel      for EVERY internal Bvh2 node, the (up to 4) children it would have as a wide node: twice,
+ *                                  the internal child with the largest area is replaced by its two children (strict '>' so
+ *                                  the first of equals wins, areas without FMA).  One thread per node, no synchronisation,
+ *                                  16 B out.  Keeps the dependent node reads out of the level-synchronous part.
+ *   2. collapse_persistent_kernel  one cooperative launch, every CTA resident, levels separated by a grid barrier (one atomic
+ *                                  counter).  One task = one wide node = one thread: task (8 B) -> expansion (16 B) -> boxes
+ *                                  of the internal children (32 B each).  Numbering: the tasks of a level are a contiguous
+ *                                  index range cut into tiles of 256; tile (wave k, CTA c) is tile k*G + c.  A tile posts its
+ *                                  number of internal children in counts[k][c] (tagged with the level, so the array is
+ *                                  never reset) and sums the words of wave k-1 (complete by then) and of its predecessors
+ *                                  in wave k (being computed at the same moment by the other resident CTAs): no chain of
+ *                                  dependent look-backs, one spin on words that are all due at the same time.  The children
+ *                                  get consecutive indices in (task, slot) order, their tasks are appended, and the 128-byte
+ *                                  node goes out through a swizzled shared-memory transpose as full, contiguous lines:
+ *                                  half-written 32-byte sectors make the B200 L2 fetch the other half from DRAM (measured:
+ *                                  the former one-thread-per-node emit read 1.14 GB to write 0.6 GB,
+ *                                  profiles/r01c_ncu_summary.txt).  Runs of levels that fit one tile (the top of the tree
+ *                                  and the tail of a deep one) are processed by CTA 0 alone between two barriers.
+ *
+ * Traffic per primitive (10 M uniform): expansion 32 r + 16 w; ~0.47 wide nodes x (8 task + 32 expansion sector + ~32 child
+ * boxes read, 128 node + 8 task written) + 8 PrimNode + 4 sorted value  ~ 160 B, of which ~133 B are compulsory.
  */
 #include "common.cuh"
-#include "lookback.cuh"
 
 #define COL_THREADS 256
-#define COL_MAX_LEVELS 4096 /* ranges recorded per level; deeper trees are handled by re-basing (see launcher) */
-#define COL_BATCH 24
+#define COL_TAG_SHIFT 11u
+#define COL_COUNT_MASK 0x7FFu
 
-#define COL_FLAG_AGG 0x40000000u
-#define COL_FLAG_INC 0x80000000u
-#define COL_VAL_MASK 0x3FFFFFFFu
-
-/* scratch layout: CollapseCtrl (256 B) | uint4 expansion[n] | uint2 tasks[n] | u32 firstChild[n] | u32 status[n/256 + COL_MAX_LEVELS + 2] */
+/* scratch layout: CollapseCtrl (256 B) | uint4 expansion[n] | uint2 tasks[n] | u32 counts[(n/256/G + 3) * G] */
 struct CollapseCtrl {
-  u32 nWide;
-  u32 lastLevelSize;
-  u32 pad[2];
-  uint2 range[2];  /* range[level & 1] = {start,end} wide-index range of `level` */
-  u32 ticket[COL_BATCH];
+  u32 bar;        /* grid barrier: arrivals so far */
+  u32 pad[3];
+  uint4 next[2];  /* {level, start, end, -}: the level to process after barrier b is published in next[b & 1] (a CTA that
+                     leaves barrier b early may publish the level after it before a late CTA has read this one) */
 };
 
+static inline size_t col_count_words(u32 n, u32 g) { return ((size_t)(n / COL_THREADS) / g + 3) * g; }
 size_t b2_collapse_scratch_bytes(u32 n) {
-  return 256 + (size_t)n * (sizeof(uint4) + sizeof(uint2) + sizeof(u32)) + ((size_t)n / COL_THREADS + COL_MAX_LEVELS + 2) * sizeof(u32);
+  /* the counts array is largest for the largest grid: waves*G <= n/256 + 3*G, G <= 16 CTAs x 1024 SMs */
+  return 256 + (size_t)n * (sizeof(uint4) + sizeof(uint2)) + ((size_t)n / COL_THREADS + 3 * 16384) * sizeof(u32);
 }
 
-template <bool SEPARATE_LEAVES>
-__device__ __forceinline__ Box col_child_box(const b2bvh_bvh2_node* __restrict__ nodes, u32 id) { return load_node2_ro(nodes + id).box; }
+struct ColSmem {
+  uint4 stage[COL_THREADS * 8]; /* 256 wide nodes, 16-byte pieces, piece p of node t at t*8 + (p ^ (t & 7)) */
+  u32 warpSum[3][COL_THREADS / 32];
+  u32 bcast[4];
+};
 
-/* ---- 1. expansion of every internal node (also resets the level control block) ---- */
-__global__ void __launch_bounds__(COL_THREADS) collapse_expand_kernel(const b2bvh_bvh2_node* __restrict__ nodes, u32 nInt, uint4* __restrict__ expansion,
-                                                                     CollapseCtrl* ctrl, uint2* tasks, const u32* __restrict__ rootIdx) {
-  const u32 i = blockIdx.x * COL_THREADS + threadIdx.x;
-  if (i == 0) {
-    ctrl->nWide = 1; ctrl->lastLevelSize = 1; ctrl->pad[0] = ctrl->pad[1] = 0;
-    ctrl->range[0] = make_uint2(0, 1);
-    ctrl->range[1] = make_uint2(1, 1);
-    for (int k = 0; k < COL_BATCH; k++) ctrl->ticket[k] = 0;
-    tasks[0] = make_uint2(*rootIdx, B2_INVALID);
+__device__ __forceinline__ void grid_barrier(u32* bar, u32 target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1u);
+    while (ld_acquire(bar) < target) {}
   }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void publish_level(CollapseCtrl* ctrl, u32 barrier, u32 level, u32 start, u32 end) {
+  u32* nx = reinterpret_cast<u32*>(&ctrl->next[barrier & 1u]);
+  st_relaxed(nx, level); st_relaxed(nx + 1, start); st_relaxed(nx + 2, end);
+}
+
+/* ---- 1. expansion of every internal node: CollapseToWide4Bvh, TwoPassLbvhKernel.h:262-296 — two rounds of "replace the
+ * internal child with the largest area by its two children" (the new right child is appended) ---- */
+__global__ void __launch_bounds__(COL_THREADS) collapse_expand_kernel(const b2bvh_bvh2_node* __restrict__ nodes, u32 nInt, uint4* __restrict__ expansion) {
+  const u32 i = blockIdx.x * COL_THREADS + threadIdx.x;
   if (i >= nInt) return;
   const uint2 top = __ldg(reinterpret_cast<const uint2*>(nodes + i));
   u32 ch[4] = {top.x, top.y, B2_INVALID, B2_INVALID};
@@ -99,164 +117,205 @@ __global__ void __launch_bounds__(COL_THREADS) collapse_expand_kernel(const b2bv
   expansion[i] = make_uint4(ch[0], ch[1], ch[2], ch[3]);
 }
 
-/* ---- 2. breadth-first numbering, one launch per level ---- */
-__global__ void __launch_bounds__(COL_THREADS) collapse_number_kernel(const uint4* __restrict__ expansion, u32 nInt, CollapseCtrl* ctrl, uint2* tasks,
-                                                                     u32* __restrict__ firstChild, u32* status, u32 level, u32 launchInBatch) {
-  __shared__ u32 sTile, sTileExcl;
-  __shared__ u32 sWarp[COL_THREADS / 32];
-  /* range[level & 1] was published by the previous launch and is not written during this one */
-  const uint2 range = ctrl->range[level & 1u];
-  const u32 start = range.x, end = range.y;
-  if (start >= end) { /* tree finished: keep every later level empty */
-    if (blockIdx.x == 0 && threadIdx.x == 0) { ctrl->range[(level + 1) & 1u] = make_uint2(end, end); ctrl->lastLevelSize = 0; }
-    return;
-  }
-  const u32 nTiles = (end - start + COL_THREADS - 1) / COL_THREADS;
-  /* status words of this level: disjoint from every other level's (floor(start/256) + level is strictly increasing
-   * by at least the level's tile count) */
-  u32* st = status + (start / COL_THREADS) + level;
+/* One tile of 256 tasks [tileStart, min(tileStart + 256, end)): expansion, numbering of the children from
+ * childBase + (exclusive count inside the tile), child tasks, wide nodes, leaf records.  `prefixFn` supplies childBase once
+ * the tile's own count is known.  Returns the tile's number of internal children (same value in every thread). */
+template <typename PrefixFn>
+__device__ __forceinline__ u32 collapse_tile(const b2bvh_bvh2_node* __restrict__ nodes, const uint4* __restrict__ expansion,
+                                             const u32* __restrict__ sortedVals, u32 nInt, uint2* tasks,
+                                             b2bvh_bvh4_node* wide, b2bvh_prim_node* wideLeaves, ColSmem& S, u32 tileStart, u32 end, PrefixFn prefixFn) {
   const u32 tid = threadIdx.x, w = tid >> 5, l = tid & 31u;
-
-  while (true) {
-    if (tid == 0) sTile = atomicAdd(&ctrl->ticket[launchInBatch], 1u);
-    __syncthreads();
-    const u32 tile = sTile;
-    if (tile >= nTiles) return;
-    const u32 g = start + tile * COL_THREADS + tid;
-    const bool active = g < end;
-    uint4 ex = make_uint4(B2_INVALID, B2_INVALID, B2_INVALID, B2_INVALID);
-    if (active) ex = __ldg(expansion + tasks[g].x);
-    const u32 nInternal = (ex.x < nInt ? 1u : 0u) + (ex.y < nInt ? 1u : 0u) + (ex.z < nInt ? 1u : 0u) + (ex.w < nInt ? 1u : 0u);
-
-    /* CTA exclusive scan of nInternal */
-    u32 incl = nInternal;
+  const u32 g = tileStart + tid;
+  const bool active = g < end;
+  u32 ch[4] = {B2_INVALID, B2_INVALID, B2_INVALID, B2_INVALID};
+  u32 parent = B2_INVALID;
+  if (active) {
+    const uint2 task = __ldcg(tasks + g); /* written by another CTA one level earlier */
+    parent = task.y;
+    const uint4 ex = __ldg(expansion + task.x);
+    ch[0] = ex.x; ch[1] = ex.y; ch[2] = ex.z; ch[3] = ex.w;
+  }
+  const u32 nInternal = (ch[0] < nInt ? 1u : 0u) + (ch[1] < nInt ? 1u : 0u) + (ch[2] < nInt ? 1u : 0u) + (ch[3] < nInt ? 1u : 0u);
+  const u32 cc = (ch[0] != B2_INVALID ? 1u : 0u) + (ch[1] != B2_INVALID ? 1u : 0u) + (ch[2] != B2_INVALID ? 1u : 0u) + (ch[3] != B2_INVALID ? 1u : 0u);
+  /* boxes of the internal children: in flight while the tile waits for its prefix (leaf slots keep the empty box,
+   * TwoPassLbvhKernel.h:320-325) */
+  Box box[4];
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const u32 t = __shfl_up_sync(B2_FULL, incl, o);
-      if ((int)l >= o) incl += t;
-    }
-    if (l == 31) sWarp[w] = incl;
-    __syncthreads();
-    u32 warpBase = 0, tileTotal = 0;
+  for (int k = 0; k < 4; k++) {
+    box[k] = box_empty();
+    if (ch[k] < nInt) box[k] = load_node2_ro(nodes + ch[k]).box;
+  }
+  /* CTA exclusive scan */
+  u32 incl = nInternal;
 #pragma unroll
-    for (int k = 0; k < COL_THREADS / 32; k++) { const u32 t = sWarp[k]; if (k < (int)w) warpBase += t; tileTotal += t; }
-    const u32 localExcl = warpBase + incl - nInternal;
+  for (int o = 1; o < 32; o <<= 1) {
+    const u32 v = __shfl_up_sync(B2_FULL, incl, o);
+    if ((int)l >= o) incl += v;
+  }
+  if (l == 31) S.warpSum[0][w] = incl;
+  __syncthreads();
+  u32 warpBase = 0, tileTotal = 0;
+#pragma unroll
+  for (int k = 0; k < COL_THREADS / 32; k++) { const u32 v = S.warpSum[0][k]; if (k < (int)w) warpBase += v; tileTotal += v; }
+  const u32 childBase = prefixFn(tileTotal); /* contains CTA barriers */
+  u32 nextId = childBase + warpBase + incl - nInternal;
 
-    /* decoupled look-back across the tiles of this level, warp 0 reads 32 predecessors per round trip */
-    if (w == 0) {
-      if (l == 0) st_relaxed(st + tile, (tile == 0 ? LB_INC : LB_AGG) | tileTotal);
-      const u32 excl = warp_lookback_u32(st, tile);
-      if (l == 0) {
-        if (tile > 0) st_relaxed(st + tile, LB_INC | (excl + tileTotal));
-        sTileExcl = excl;
-        if (tile == nTiles - 1) {
-          /* last tile of the level: publish the next level's range for the next launch */
-          const u32 next = end + excl + tileTotal;
-          ctrl->range[(level + 1) & 1u] = make_uint2(end, next);
-          ctrl->nWide = next;
-          ctrl->lastLevelSize = next - end;
-        }
+  /* ---- children: tasks for the internal ones, leaf records for the others; the node into the transpose buffer ---- */
+  u32 outChild[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    outChild[k] = ch[k];
+    if (ch[k] != B2_INVALID) {
+      if (ch[k] < nInt) {
+        outChild[k] = nextId;
+        tasks[nextId] = make_uint2(ch[k], g);
+        nextId++;
+      } else {
+        const u32 slot = ch[k] - nInt;
+        /* leaf slot s holds primitive sortedVals[s] in both layouts (Bvh2 leaf m_leftChildIdx / PrimRef m_primIdx) */
+        reinterpret_cast<uint2*>(wideLeaves)[slot] = make_uint2(__ldg(sortedVals + slot), g);
       }
     }
-    __syncthreads();
-    if (active) {
-      u32 nextId = end + sTileExcl + localExcl;
-      firstChild[g] = nextId;
-      if (ex.x < nInt) tasks[nextId++] = make_uint2(ex.x, g);
-      if (ex.y < nInt) tasks[nextId++] = make_uint2(ex.y, g);
-      if (ex.z < nInt) tasks[nextId++] = make_uint2(ex.z, g);
-      if (ex.w < nInt) tasks[nextId++] = make_uint2(ex.w, g);
-    }
-    __syncthreads(); /* sTile / sWarp are reused by the next tile */
   }
+  {
+    const u32 sw = tid & 7u;
+    uint4* row = S.stage + tid * 8;
+    const Box &b0 = box[0], &b1 = box[1], &b2 = box[2], &b3 = box[3];
+#define FU(x) __float_as_uint(x)
+    row[0 ^ sw] = make_uint4(FU(b0.lx), FU(b0.ly), FU(b0.lz), FU(b0.hx));
+    row[1 ^ sw] = make_uint4(FU(b0.hy), FU(b0.hz), FU(b1.lx), FU(b1.ly));
+    row[2 ^ sw] = make_uint4(FU(b1.lz), FU(b1.hx), FU(b1.hy), FU(b1.hz));
+    row[3 ^ sw] = make_uint4(FU(b2.lx), FU(b2.ly), FU(b2.lz), FU(b2.hx));
+    row[4 ^ sw] = make_uint4(FU(b2.hy), FU(b2.hz), FU(b3.lx), FU(b3.ly));
+    row[5 ^ sw] = make_uint4(FU(b3.lz), FU(b3.hx), FU(b3.hy), FU(b3.hz));
+    row[6 ^ sw] = make_uint4(outChild[0], outChild[1], outChild[2], outChild[3]);
+    row[7 ^ sw] = make_uint4(parent, cc, 0u, 0u);
+#undef FU
+  }
+  __syncthreads();
+  /* ---- 256 nodes x 128 B leave as contiguous 16-byte pieces: every warp store covers whole lines ---- */
+  {
+    const u32 valid = min((u32)COL_THREADS, end - tileStart) * 8u;
+    uint4* out = reinterpret_cast<uint4*>(wide + tileStart);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const u32 q = (u32)i * COL_THREADS + tid;
+      const u32 node = q >> 3, part = q & 7u;
+      if (q < valid) out[q] = S.stage[node * 8 + (part ^ (node & 7u))];
+    }
+  }
+  __syncthreads(); /* stage / warpSum are reused by the next tile */
+  return tileTotal;
 }
 
-/* ---- 3. wide nodes + leaf records ---- */
-template <bool SEPARATE_LEAVES>
-__global__ void __launch_bounds__(COL_THREADS) collapse_emit_kernel(const b2bvh_bvh2_node* __restrict__ nodes, const u32* __restrict__ sortedVals,
-                                                                   u32 nInt, const uint4* __restrict__ expansion, const uint2* __restrict__ tasks,
-                                                                   const u32* __restrict__ firstChild, const CollapseCtrl* __restrict__ ctrl,
-                                                                   b2bvh_bvh4_node* __restrict__ wide, b2bvh_prim_node* __restrict__ wideLeaves) {
-  const u32 nWide = ctrl->nWide;
-  for (u32 g = blockIdx.x * COL_THREADS + threadIdx.x; g < nWide; g += gridDim.x * COL_THREADS) {
-    const uint2 task = __ldg(tasks + g);
-    const uint4 ex = __ldg(expansion + task.x);
-    const u32 ch[4] = {ex.x, ex.y, ex.z, ex.w};
-    u32 nextId = __ldg(firstChild + g);
-    u32 outChild[4];
-    Box outBox[4];
-    u32 cc = 0;
+__global__ void __launch_bounds__(COL_THREADS, 5) collapse_persistent_kernel(const b2bvh_bvh2_node* __restrict__ nodes, const uint4* __restrict__ expansion,
+                                                                            const u32* __restrict__ sortedVals, u32 nInt, const u32* __restrict__ rootIdx, uint2* tasks,
+                                                                            b2bvh_bvh4_node* wide, b2bvh_prim_node* wideLeaves, CollapseCtrl* ctrl,
+                                                                            u32* counts) {
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  ColSmem& S = *reinterpret_cast<ColSmem*>(smemRaw);
+  const u32 G = gridDim.x, c = blockIdx.x, tid = threadIdx.x, w = tid >> 5, l = tid & 31u;
+  u32 level = 0, start = 0, end = 1, barriers = 0;
+  if (c == 0 && tid == 0) tasks[0] = make_uint2(*rootIdx, B2_INVALID);
+  __syncthreads();
+
+  while (true) {
+    const u32 size = end - start;
+    if (size == 0) break;
+    if (size <= COL_THREADS) {
+      /* ---- a run of one-tile levels: CTA 0 alone, no grid barrier in between ---- */
+      if (c == 0) {
+        do {
+          const u32 e = end;
+          const u32 total = collapse_tile(nodes, expansion, sortedVals, nInt, tasks, wide, wideLeaves, S, start, end, [e](u32) { return e; });
+          start = end; end += total; level++;
+        } while (end - start <= COL_THREADS && end != start);
+        if (tid == 0) publish_level(ctrl, barriers + 1u, level, start, end);
+      }
+    } else {
+      /* ---- a level of many tiles: tile (wave k, CTA c) = k*G + c ---- */
+      const u32 nTiles = (size + COL_THREADS - 1) / COL_THREADS;
+      const u32 tag = level + 1u;
+      u32 waveBase = 0; /* children of all complete waves before the current one */
+      for (u32 k = 0; k * G + c < nTiles; k++) {
+        const u32 tile = k * G + c;
+        u32* row = counts + (size_t)k * G;
+        const u32 lvlEnd = end;
+        auto prefix = [&](u32 tileTotal) -> u32 {
+          if (tid == 0) st_relaxed(row + c, (tag << COL_TAG_SHIFT) | tileTotal);
+          /* wave k-1 (every word is due: the wave before the last one is always full) and the predecessors in wave k */
+          u32 sumPrev = 0, sumSame = 0;
+          if (k > 0)
+            for (u32 i = tid; i < G; i += COL_THREADS) {
+              u32 v;
+              do { v = ld_relaxed(row - G + i); } while ((v >> COL_TAG_SHIFT) != tag);
+              sumPrev += v & COL_COUNT_MASK;
+            }
+          for (u32 i = tid; i < c; i += COL_THREADS) {
+            u32 v;
+            do { v = ld_relaxed(row + i); } while ((v >> COL_TAG_SHIFT) != tag);
+            sumSame += v & COL_COUNT_MASK;
+          }
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-      outChild[k] = B2_INVALID;
-      outBox[k] = box_empty();
-      if (ch[k] != B2_INVALID) {
-        cc++;
-        if (ch[k] < nInt) {
-          outChild[k] = nextId++;
-          outBox[k] = load_node2_ro(nodes + ch[k]).box;
-        } else {
-          outChild[k] = ch[k];
-          const u32 slot = ch[k] - nInt;
-          /* leaf slot s holds primitive sortedVals[s] in both layouts (Bvh2 leaf m_leftChildIdx / PrimRef m_primIdx): read the
-           * dense 4-byte array instead of one 32-byte node or 28-byte PrimRef per leaf */
-          reinterpret_cast<uint2*>(wideLeaves)[slot] = make_uint2(__ldg(sortedVals + slot), g);
-        }
+          for (int o = 16; o > 0; o >>= 1) { sumPrev += __shfl_xor_sync(B2_FULL, sumPrev, o); sumSame += __shfl_xor_sync(B2_FULL, sumSame, o); }
+          if (l == 0) { S.warpSum[1][w] = sumPrev; S.warpSum[2][w] = sumSame; }
+          __syncthreads();
+          u32 p = 0, s = 0;
+#pragma unroll
+          for (int q = 0; q < COL_THREADS / 32; q++) { p += S.warpSum[1][q]; s += S.warpSum[2][q]; }
+          waveBase += p;
+          const u32 base = lvlEnd + waveBase + s;
+          if (tile == nTiles - 1 && tid == 0) publish_level(ctrl, barriers + 1u, level + 1u, lvlEnd, base + tileTotal); /* last tile of the level */
+          return base;
+        };
+        collapse_tile(nodes, expansion, sortedVals, nInt, tasks, wide, wideLeaves, S, start + tile * COL_THREADS, end, prefix);
       }
     }
-    /* 128 bytes: 4 boxes (24 floats), 4 children, parent, childCount, 2 zero pad words */
-    uint4* out = reinterpret_cast<uint4*>(wide + g);
-    const float* f0 = &outBox[0].lx; const float* f1 = &outBox[1].lx; const float* f2 = &outBox[2].lx; const float* f3 = &outBox[3].lx;
-    out[0] = make_uint4(__float_as_uint(f0[0]), __float_as_uint(f0[1]), __float_as_uint(f0[2]), __float_as_uint(f0[3]));
-    out[1] = make_uint4(__float_as_uint(f0[4]), __float_as_uint(f0[5]), __float_as_uint(f1[0]), __float_as_uint(f1[1]));
-    out[2] = make_uint4(__float_as_uint(f1[2]), __float_as_uint(f1[3]), __float_as_uint(f1[4]), __float_as_uint(f1[5]));
-    out[3] = make_uint4(__float_as_uint(f2[0]), __float_as_uint(f2[1]), __float_as_uint(f2[2]), __float_as_uint(f2[3]));
-    out[4] = make_uint4(__float_as_uint(f2[4]), __float_as_uint(f2[5]), __float_as_uint(f3[0]), __float_as_uint(f3[1]));
-    out[5] = make_uint4(__float_as_uint(f3[2]), __float_as_uint(f3[3]), __float_as_uint(f3[4]), __float_as_uint(f3[5]));
-    out[6] = make_uint4(outChild[0], outChild[1], outChild[2], outChild[3]);
-    out[7] = make_uint4(task.y, cc, 0u, 0u);
+    barriers++;
+    grid_barrier(&ctrl->bar, barriers * G);
+    {
+      const u32* nx = reinterpret_cast<const u32*>(&ctrl->next[barriers & 1u]);
+      level = ld_relaxed(nx); start = ld_relaxed(nx + 1); end = ld_relaxed(nx + 2);
+    }
   }
 }
 
 int b2_launch_collapse(b2bvh_ctx* ctx, const b2bvh_bvh2_node* d_nodes, const b2bvh_prim_ref* d_leaves, const u32* d_sortedVals, const u32* d_rootIdx, u32 n,
                        b2bvh_bvh4_node* d_wide, b2bvh_prim_node* d_wideLeaves, void* d_scratch, u32* h_nWide) {
+  (void)d_leaves; /* both layouts name leaves by slot; the primitive index comes from the sorted value array */
   if (n < 2) return b2_fail(B2BVH_ERR_INVALID, "collapse needs at least 2 primitives");
+  static int occ = 0;
+  const size_t smem = sizeof(ColSmem);
+  if (!occ) {
+    B2_CUDA(cudaFuncSetAttribute(collapse_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, collapse_persistent_kernel, COL_THREADS, smem));
+    if (occ < 1) return b2_fail(B2BVH_ERR_INTERNAL, "collapse: kernel does not fit on an SM");
+  }
+  /* every CTA must be resident (grid barrier): at most SMs x occupancy; small inputs use fewer CTAs (cheaper barriers) */
+  u32 grid = (u32)ctx->sm_count * (u32)occ;
+  const u32 want = (n + 1023u) / 1024u;
+  if (grid > want) grid = want;
+  if (grid < 1) grid = 1;
   unsigned char* base = reinterpret_cast<unsigned char*>(d_scratch);
   CollapseCtrl* ctrl = reinterpret_cast<CollapseCtrl*>(base);
   uint4* expansion = reinterpret_cast<uint4*>(base + 256);
   uint2* tasks = reinterpret_cast<uint2*>(base + 256 + (size_t)n * sizeof(uint4));
-  u32* firstChild = reinterpret_cast<u32*>(base + 256 + (size_t)n * (sizeof(uint4) + sizeof(uint2)));
-  u32* status = firstChild + n;
-  const size_t statusWords = (size_t)n / COL_THREADS + COL_MAX_LEVELS + 2;
-  const u32 nInt = n - 1;
-  B2_CUDA(cudaMemsetAsync(status, 0, statusWords * sizeof(u32), ctx->stream));
+  u32* counts = reinterpret_cast<u32*>(base + 256 + (size_t)n * (sizeof(uint4) + sizeof(uint2)));
+  u32 nInt = n - 1;
+  B2_CUDA(cudaMemsetAsync(ctrl, 0, 256, ctx->stream));
+  B2_CUDA(cudaMemsetAsync(counts, 0, col_count_words(n, grid) * sizeof(u32), ctx->stream));
   B2_KERNEL(ctx, "collapse_expand");
-  collapse_expand_kernel<<<(nInt + COL_THREADS - 1) / COL_THREADS, COL_THREADS, 0, ctx->stream>>>(d_nodes, nInt, expansion, ctrl, tasks, d_rootIdx);
+  collapse_expand_kernel<<<(nInt + COL_THREADS - 1) / COL_THREADS, COL_THREADS, 0, ctx->stream>>>(d_nodes, nInt, expansion);
   B2_LAUNCH_CHECK(ctx);
-  const u32 cap = (u32)ctx->sm_count * 8u;
-  u32 levels = 0;
+  B2_KERNEL(ctx, "collapse_levels");
+  void* args[] = {(void*)&d_nodes, (void*)&expansion, (void*)&d_sortedVals, (void*)&nInt, (void*)&d_rootIdx, (void*)&tasks, (void*)&d_wide, (void*)&d_wideLeaves, (void*)&ctrl, (void*)&counts};
+  B2_CUDA(cudaLaunchCooperativeKernel((const void*)collapse_persistent_kernel, dim3(grid), dim3(COL_THREADS), args, smem, ctx->stream));
+  B2_LAUNCH_CHECK(ctx);
   CollapseCtrl h;
-  while (true) {
-    for (u32 k = 0; k < COL_BATCH; k++) {
-      B2_KERNEL(ctx, "collapse_number");
-      collapse_number_kernel<<<cap, COL_THREADS, 0, ctx->stream>>>(expansion, nInt, ctrl, tasks, firstChild, status, levels + k, k);
-      B2_LAUNCH_CHECK(ctx);
-    }
-    levels += COL_BATCH;
-    B2_CUDA(cudaMemcpyAsync(&h, ctrl, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
-    B2_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (h.lastLevelSize == 0) break;
-    if (levels + COL_BATCH > COL_MAX_LEVELS) return b2_fail(B2BVH_ERR_INTERNAL, "collapse: wide tree deeper than %d levels", COL_MAX_LEVELS);
-    B2_CUDA(cudaMemsetAsync(ctrl->ticket, 0, sizeof(u32) * COL_BATCH, ctx->stream));
-  }
-  u32 grid = (h.nWide + COL_THREADS - 1) / COL_THREADS;
-  if (grid > cap * 2) grid = cap * 2;
-  B2_KERNEL(ctx, "collapse_emit");
-  if (d_leaves)
-    collapse_emit_kernel<true><<<grid, COL_THREADS, 0, ctx->stream>>>(d_nodes, d_sortedVals, nInt, expansion, tasks, firstChild, ctrl, d_wide, d_wideLeaves);
-  else
-    collapse_emit_kernel<false><<<grid, COL_THREADS, 0, ctx->stream>>>(d_nodes, d_sortedVals, nInt, expansion, tasks, firstChild, ctrl, d_wide, d_wideLeaves);
-  B2_LAUNCH_CHECK(ctx);
-  *h_nWide = h.nWide;
+  B2_CUDA(cudaMemcpyAsync(&h, ctrl, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  B2_CUDA(cudaStreamSynchronize(ctx->stream));
+  /* the loop ends after reading an empty level from next[b & 1]: its start == end == number of wide nodes (both slots agree on it
+     only by accident, so take the larger end) */
+  *h_nWide = h.next[0].z > h.next[1].z ? h.next[0].z : h.next[1].z;
   return 0;
 }

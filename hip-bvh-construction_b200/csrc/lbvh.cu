@@ -93,18 +93,31 @@ __global__ void __launch_bounds__(LBVH_THREADS) lbvh_fused_kernel(const u32* __r
   climb_global<KARRAS>(keys, n, nodes, parents, meet, rootOut, nInt + g, g, g + 1, box, p, isLeft);
 }
 
-/* ---------------------------------------------------------------- CTA-local climb in shared memory, then the global climb
- * A CTA owns BL consecutive leaves [b0, b1).  Every internal node whose range lies inside [b0, b1) is finished by one of the
- * CTA's own threads, and when BOTH children of a node lie inside, the two arrivals can meet in shared memory: the
- * exchange word, the first arriver's box and its index are shared-memory traffic, and no fence or L2 round trip is paid.
- * That covers all but O(log BL) nodes per CTA.  A finished node whose sibling does NOT lie inside the CTA (its parent
- * straddles a CTA boundary) is left "stranded" in its slot; after a CTA barrier the stranded nodes, and the nodes that
- * reached the CTA boundary directly, continue through the global protocol above.  Every finished node is written to global
- * memory exactly once, with two 16-byte stores, as before; results are identical to lbvh_fused_kernel. */
-#define LBVH_BL 512
-#define LBVH_CONSUMED 0xFFFFFFFEu
+/* ---------------------------------------------------------------- CTA-local tile build in shared memory, then the global climb
+ * A CTA owns TILE consecutive leaves [b0, b1) and keeps an ordered list of CLUSTERS (finished subtrees): range start, root
+ * node index and the depth d of the boundary to the right neighbour (d = length of the common prefix of the two augmented
+ * keys that meet there; -1 outside the key array).  A cluster picks the deeper of its two boundaries as its parent's split
+ * (findParent, SinglePassLbvhKernel.h:64-86), so two neighbours form a node exactly when the boundary between them is
+ * deeper than both boundaries next to it — a local maximum of d.  All such pairs merge in the same ROUND (no two
+ * adjacent boundaries can both be maxima), the list is compacted with ballots and one shared-memory scan, and the next
+ * round starts: about a third of the clusters disappear per round, every lane of a live warp holds a live cluster, and no
+ * atomics or fences are involved.  (The former version climbed leaf by leaf with one shared-memory exchange per node:
+ * 32 warp-instructions per leaf, half of them in warps with one live lane, profiles/r01c_ncu_summary.txt.)
+ * Finished nodes are staged in shared memory — Apetrei and Karras indices of nodes finished inside a tile both lie in
+ * [b0, b1) — and leave as whole 32-byte sectors: half-written sectors make the B200 L2 read the other half from DRAM.
+ * Clusters left when no boundary inside the tile is a maximum (their parents straddle the tile) are handed to
+ * lbvh_climb_kernel, which finishes the top of the tree with the global exchange protocol above. */
+#define LBVH_TILE 512
+#define LBVH_TILE_THREADS 512
+#define LBVH_PAR_UNSET 0xFFFFFFFEu
+/* one cluster = one 32-bit word: [27:21] d + 1 (0 = outside the key array), [20:10] local index of the root node in the
+ * staging buffer, [9:0] range start - b0 */
+#define LW_D_SHIFT 21
+#define LW_ID_SHIFT 10
+#define LW_ID_MASK 0x7FFu
+#define LW_LO_MASK 0x3FFu
 
-/* A finished node that must continue through global memory: 48 bytes, written by lbvh_block_kernel, consumed by lbvh_climb_kernel */
+/* A finished node that must continue through global memory: 48 bytes, written by lbvh_tile_kernel, consumed by lbvh_climb_kernel */
 struct LbvhPending {
   u32 self, lo, hi, pSide; /* pSide = parent split | (isLeft << 31) */
   float box[6];
@@ -112,115 +125,170 @@ struct LbvhPending {
 };
 static_assert(sizeof(LbvhPending) == 48, "LbvhPending layout");
 
-struct LbvhBlockSmem {
-  u32 pendCount, pendBase;
-  u32 key[LBVH_BL + 2];          /* keys of leaves b0-1 .. b1 */
-  u32 meet[LBVH_BL];             /* exchange word of split p (between leaves p and p+1), index p - b0 */
-  u32 sibId[LBVH_BL][2];         /* [split][side]: index of the child that arrived from that side (0 = left child) */
-  float sibBox[LBVH_BL][2][6];
+template <bool PARENTS>
+struct LbvhTileSmem {
+  uint4 stage[4 * LBVH_TILE];     /* node with local index i at stage[2i], stage[2i+1]; internal nodes [0,TILE), leaves [TILE,2*TILE) */
+  u32 w[2][LBVH_TILE + 4];        /* w[b][j+2] = cluster j; w[b][1] = left sentinel (d of the boundary left of the tile);
+                                     w[b][count+2] = right sentinel (range start = b1 - b0) */
+  alignas(8) unsigned char chunkMerges[16]; /* merges per warp (32 clusters) */
+  u32 finalCur, finalCount, pendBase;
+  u32 par[PARENTS ? 2 * LBVH_TILE : 1];
 };
 
-__device__ __forceinline__ u32 choose_parent_smem(const u32* sk, u32 kb /* leaf index of sk[0] */, u32 n, u32 lo, u32 hi, bool& isLeft) {
-  if (lo == 0) { isLeft = true; return hi - 1; }
-  if (hi == n) { isLeft = false; return lo - 1; }
-  const u64 a = ((u64)sk[hi - 1 - kb] << 32) | (hi - 1), b = ((u64)sk[hi - kb] << 32) | hi;
-  const u64 c = ((u64)sk[lo - 1 - kb] << 32) | (lo - 1), d = ((u64)sk[lo - kb] << 32) | lo;
-  isLeft = (a ^ b) < (c ^ d);
-  return isLeft ? hi - 1 : lo - 1;
+__device__ __forceinline__ int boundary_depth(u32 keyA, u32 keyB, u32 a /* b = a + 1 */) {
+  return __clzll((long long)(((u64)(keyA ^ keyB) << 32) | (u64)(a ^ (a + 1u))));
 }
+__device__ __forceinline__ void named_barrier(u32 id, u32 threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
 template <bool KARRAS>
-__global__ void __launch_bounds__(LBVH_BL) lbvh_block_kernel(const u32* __restrict__ keys, const u32* __restrict__ vals,
-                                                             const b2bvh_aabb* __restrict__ triAabb, u32 n, b2bvh_bvh2_node* nodes, u32* parents,
-                                                             u32* meet, u32* rootOut, u32* pendingCount, LbvhPending* pending, u32 pendingCap) {
-  __shared__ LbvhBlockSmem S;
-  const u32 t = threadIdx.x;
-  const u32 b0 = blockIdx.x * LBVH_BL, b1 = min(n, b0 + LBVH_BL);
-  const u32 g = b0 + t;
+__global__ void __launch_bounds__(LBVH_TILE_THREADS, 4) lbvh_tile_kernel(const u32* __restrict__ keys, const u32* __restrict__ vals,
+                                                                      const b2bvh_aabb* __restrict__ triAabb, u32 n, b2bvh_bvh2_node* nodes, u32* parents,
+                                                                      u32* meet, u32* rootOut, u32* pendingCount, LbvhPending* pending, u32 pendingCap) {
+  constexpr bool PARENTS = KARRAS; /* only TwoPassLbvh publishes d_parentIdxs */
+  constexpr u32 T = LBVH_TILE;
+  static_assert(LBVH_TILE == LBVH_TILE_THREADS, "one leaf per thread");
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  LbvhTileSmem<PARENTS>& S = *reinterpret_cast<LbvhTileSmem<PARENTS>*>(smemRaw);
+  const u32 tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+  const u32 b0 = blockIdx.x * T, b1 = min(n, b0 + T), cnt0 = b1 - b0;
   const u32 nInt = n - 1;
-  const u32 kb = b0 - 1; /* leaf index of S.key[0] (wraps for b0 == 0; slot 0 is then unused) */
-  S.meet[t] = B2_INVALID;
-  S.sibId[t][0] = B2_INVALID; S.sibId[t][1] = B2_INVALID;
-  if (t == 0) S.pendCount = 0;
-  if (g < n) S.key[t + 1] = __ldg(keys + g);
-  if (t == 0 && b0 > 0) S.key[0] = __ldg(keys + b0 - 1);
-  if (t == 0 && b1 < n) S.key[b1 - b0 + 1] = __ldg(keys + b1);
-  Box box = box_empty();
-  u32 self = B2_INVALID, lo = 0, hi = 0, p = 0;
-  bool isLeft = false, goGlobal = false;
-  if (g < n) {
+  const bool single = gridDim.x == 1;
+  auto globalId = [&](u32 local) -> u32 { return local < T ? b0 + local : nInt + b0 + (local - T); };
+
+  /* ---- leaves: sorted value -> primitive box (gather), leaf node staged, boundary depths ---- */
+  S.stage[2 * tid].x = B2_INVALID; /* internal node tid: not finished */
+  if (PARENTS) { S.par[tid] = LBVH_PAR_UNSET; S.par[T + tid] = LBVH_PAR_UNSET; }
+  if (tid < cnt0) {
+    const u32 g = b0 + tid;
     const u32 prim = __ldg(vals + g);
-    box = load_aabb(triAabb + prim);
-    store_node2(nodes + nInt + g, prim, B2_INVALID, box);
+    const u32 k0 = __ldg(keys + g);
+    const float2* bp = reinterpret_cast<const float2*>(triAabb + prim); /* 24-byte boxes: 8-byte aligned */
+    const float2 q0 = __ldg(bp), q1 = __ldg(bp + 1), q2 = __ldg(bp + 2);
+    int d = -1;
+    if (g + 1 < n) d = boundary_depth(k0, __ldg(keys + g + 1), g);
+    S.stage[2 * (T + tid)] = make_uint4(prim, B2_INVALID, __float_as_uint(q0.x), __float_as_uint(q0.y));
+    S.stage[2 * (T + tid) + 1] = make_uint4(__float_as_uint(q1.x), __float_as_uint(q1.y), __float_as_uint(q2.x), __float_as_uint(q2.y));
+    S.w[0][tid + 2] = ((u32)(d + 1) << LW_D_SHIFT) | ((T + tid) << LW_ID_SHIFT) | tid;
+  }
+  if (tid == 0) {
+    const int dl = b0 > 0 ? boundary_depth(__ldg(keys + b0 - 1), __ldg(keys + b0), b0 - 1) : -1;
+    S.w[0][1] = (u32)(dl + 1) << LW_D_SHIFT;
+    S.w[0][cnt0 + 2] = cnt0;
   }
   __syncthreads();
-  if (n == 1) { if (g == 0 && rootOut) *rootOut = 0; return; }
+  {
+    uint4* out = reinterpret_cast<uint4*>(nodes + nInt + b0);
+    for (u32 q = tid; q < 2 * cnt0; q += LBVH_TILE_THREADS) out[q] = S.stage[2 * T + q];
+  }
+  if (n == 1) { if (tid == 0 && rootOut) *rootOut = 0; return; }
 
-  if (g < n) {
-    lo = g; hi = g + 1; self = nInt + g;
-    p = choose_parent_smem(S.key, kb, n, lo, hi, isLeft);
-    while (true) {
-      if (p < b0 || p + 1 >= b1) { goGlobal = true; break; } /* the parent straddles the CTA boundary */
-      const u32 slot = p - b0;
-      const int side = isLeft ? 0 : 1;
-      float* sb = S.sibBox[slot][side];
-      sb[0] = box.lx; sb[1] = box.ly; sb[2] = box.lz; sb[3] = box.hx; sb[4] = box.hy; sb[5] = box.hz;
-      S.sibId[slot][side] = self;
-      __threadfence_block();
-      const u32 other = atomicExch(&S.meet[slot], isLeft ? lo : hi);
-      if (other == B2_INVALID) break; /* first arriver: waits in its slot for the sibling (or for the escalation below) */
-      __threadfence_block();
-      S.meet[slot] = LBVH_CONSUMED;
-      if (isLeft) hi = other; else lo = other;
-      const float* ob = S.sibBox[slot][side ^ 1];
-      const u32 sib = S.sibId[slot][side ^ 1];
-      box = box_union(box, Box{ob[0], ob[1], ob[2], ob[3], ob[4], ob[5]});
-      const u32 left = isLeft ? self : sib, right = isLeft ? sib : self;
-      const bool isRoot = (lo == 0 && hi == n);
-      const u32 split = p;
-      if (!isRoot) p = choose_parent_smem(S.key, kb, n, lo, hi, isLeft);
-      const u32 id = KARRAS ? (isRoot ? 0u : (isLeft ? hi - 1 : lo)) : split;
-      store_node2(nodes + id, left, right, box);
-      if (parents) { parents[left] = id; parents[right] = id; if (isRoot) parents[id] = B2_INVALID; }
-      if (isRoot) { if (rootOut) *rootOut = id; break; }
-      self = id;
+  /* ---- rounds: only the warps that still hold clusters take part (named barrier over nW warps); the others wait below ---- */
+  u32 cur = 0, count = cnt0;
+  bool rootDone = false;
+  while (true) {
+    const u32 nW = (count + 31u) >> 5;
+    if (warp >= nW) break; /* the list only shrinks: this warp is done for good */
+    const u32* W = S.w[cur];
+    u32 xm1 = 0, x0 = 0, xp1 = 0;
+    bool mrg = false, absorbed = false;
+    if (tid < count) {
+      const u32 xm2 = W[tid];
+      xm1 = W[tid + 1]; x0 = W[tid + 2]; xp1 = W[tid + 3];
+      const u32 dLL = xm2 >> LW_D_SHIFT, dL = xm1 >> LW_D_SHIFT, d0 = x0 >> LW_D_SHIFT, dR = xp1 >> LW_D_SHIFT;
+      mrg = (tid + 1 < count) && d0 > dL && d0 > dR;   /* boundary tid is deeper than both boundaries next to it */
+      absorbed = (tid >= 1) && dL > dLL && dL > d0;    /* ... and so is boundary tid-1: this cluster joins its left neighbour */
+    }
+    const u32 bal = __ballot_sync(B2_FULL, mrg);
+    if (lane == 0) S.chunkMerges[warp] = (unsigned char)__popc(bal);
+    named_barrier(1, nW * 32u);
+    /* exclusive prefix of the per-warp merge counts: byte-wise prefix sums by one multiplication (sums <= 128 per half) */
+    u32 before, total;
+    {
+      const u64 ones = 0x0101010101010101ull;
+      u64 lo8 = *reinterpret_cast<const u64*>(S.chunkMerges);
+      if (nW < 8u) lo8 &= (1ull << (8u * nW)) - 1ull;
+      const u64 preLo = lo8 * ones;
+      const u32 totLo = (u32)(preLo >> 56);
+      before = warp == 0 ? 0u : (u32)(preLo >> (8u * ((warp - 1u) & 7u))) & 0xFFu;
+      total = totLo;
+      if (nW > 8u) {
+        u64 hi8 = *reinterpret_cast<const u64*>(S.chunkMerges + 8);
+        if (nW < 16u) hi8 &= (1ull << (8u * (nW - 8u))) - 1ull;
+        const u64 preHi = hi8 * ones;
+        total += (u32)(preHi >> 56);
+        if (warp >= 8u) before = totLo + (warp == 8u ? 0u : (u32)(preHi >> (8u * (warp - 9u))) & 0xFFu);
+      }
+    }
+    if (total == 0) break;
+    u32* Wn = S.w[cur ^ 1u];
+    if (tid < count && !absorbed) {
+      const u32 k = tid - before - __popc(bal & lanemask_lt());
+      u32 outw = x0;
+      if (mrg) {
+        const u32 lL = (x0 >> LW_ID_SHIFT) & LW_ID_MASK, lR = (xp1 >> LW_ID_SHIFT) & LW_ID_MASK;
+        const uint4 a0 = S.stage[2 * lL], a1 = S.stage[2 * lL + 1], c0 = S.stage[2 * lR], c1 = S.stage[2 * lR + 1];
+        const Box box = box_union(Box{__uint_as_float(a0.z), __uint_as_float(a0.w), __uint_as_float(a1.x), __uint_as_float(a1.y), __uint_as_float(a1.z), __uint_as_float(a1.w)},
+                                  Box{__uint_as_float(c0.z), __uint_as_float(c0.w), __uint_as_float(c1.x), __uint_as_float(c1.y), __uint_as_float(c1.z), __uint_as_float(c1.w)});
+        const bool isRoot = single && count == 2u;
+        u32 idLocal;
+        if (KARRAS) {
+          /* the merged cluster's own choice (its boundaries are tid-1 and tid+1) fixes its Karras index */
+          const u32 hiRel = W[tid + 4] & LW_LO_MASK;
+          idLocal = isRoot ? 0u : ((xp1 >> LW_D_SHIFT) > (xm1 >> LW_D_SHIFT) ? hiRel - 1u : (x0 & LW_LO_MASK));
+        } else {
+          idLocal = (xp1 & LW_LO_MASK) - 1u; /* Apetrei: the split position */
+        }
+        S.stage[2 * idLocal] = node2_lo(globalId(lL), globalId(lR), box);
+        S.stage[2 * idLocal + 1] = node2_hi(box);
+        if (PARENTS) { S.par[lL] = b0 + idLocal; S.par[lR] = b0 + idLocal; if (isRoot) S.par[idLocal] = B2_INVALID; }
+        if (isRoot) { rootDone = true; if (rootOut) *rootOut = b0 + idLocal; }
+        outw = (xp1 & ~((1u << LW_D_SHIFT) - 1u)) | (idLocal << LW_ID_SHIFT) | (x0 & LW_LO_MASK);
+      }
+      Wn[k + 2] = outw;
+    }
+    if (tid == 0) { Wn[1] = W[1]; Wn[count - total + 2] = W[count + 2]; }
+    named_barrier(1, nW * 32u);
+    cur ^= 1u;
+    count -= total;
+  }
+  if (tid == 0) { S.finalCur = cur; S.finalCount = count; } /* warp 0 takes part in every round */
+  rootDone = __syncthreads_or(rootDone);
+  cur = S.finalCur; count = S.finalCount;
+
+  /* ---- finished nodes (and parent indices) leave as whole sectors ---- */
+  {
+    uint4* out = reinterpret_cast<uint4*>(nodes + b0);
+    for (u32 q = tid; q < 2 * cnt0; q += LBVH_TILE_THREADS)
+      if (S.stage[q & ~1u].x != B2_INVALID) out[q] = S.stage[q];
+    if (PARENTS && parents) {
+      if (tid < cnt0) {
+        const u32 a = S.par[tid], b = S.par[T + tid];
+        if (a != LBVH_PAR_UNSET) parents[b0 + tid] = a;
+        if (b != LBVH_PAR_UNSET) parents[nInt + b0 + tid] = b;
+      }
     }
   }
+  if (rootDone) return; /* single tile: the whole tree was built here */
+
+  /* ---- hand the remaining clusters to the global climb ---- */
+  if (tid == 0) S.pendBase = atomicAdd(pendingCount, count);
   __syncthreads();
-  /* ---- hand over to the global climb (separate launch, so this CTA retires as soon as its shared-memory work is done):
-   * (1) this thread's own node if it reached the CTA boundary, (2) the stranded node of slot t ---- */
-  const u32 m = S.meet[t];
-  const bool stranded = (m != B2_INVALID && m != LBVH_CONSUMED);
-  u32 myIdx = 0;
-  const u32 mine = (goGlobal ? 1u : 0u) + (stranded ? 1u : 0u);
-  if (mine) myIdx = atomicAdd(&S.pendCount, mine);
-  __syncthreads();
-  if (t == 0 && S.pendCount) S.pendBase = atomicAdd(pendingCount, S.pendCount);
-  __syncthreads();
-  u32 slotOut = S.pendBase + myIdx;
-  if (goGlobal) {
+  if (tid < count) {
+    const u32* W = S.w[cur];
+    const u32 xm1 = W[tid + 1], x0 = W[tid + 2], xp1 = W[tid + 3];
+    const u32 slotOut = S.pendBase + tid;
+    const u32 l = (x0 >> LW_ID_SHIFT) & LW_ID_MASK;
+    const u32 self = globalId(l), lo = b0 + (x0 & LW_LO_MASK), hi = b0 + (xp1 & LW_LO_MASK);
+    const bool isLeft = (x0 >> LW_D_SHIFT) > (xm1 >> LW_D_SHIFT);
+    const u32 p = isLeft ? hi - 1 : lo - 1;
+    const Node2 me = node2_unpack(S.stage[2 * l], S.stage[2 * l + 1]);
     if (slotOut < pendingCap) {
       uint4* q = reinterpret_cast<uint4*>(pending + slotOut);
       q[0] = make_uint4(self, lo, hi, p | (isLeft ? 0x80000000u : 0u));
-      q[1] = make_uint4(__float_as_uint(box.lx), __float_as_uint(box.ly), __float_as_uint(box.lz), __float_as_uint(box.hx));
-      q[2] = make_uint4(__float_as_uint(box.hy), __float_as_uint(box.hz), 0u, 0u);
+      q[1] = make_uint4(__float_as_uint(me.box.lx), __float_as_uint(me.box.ly), __float_as_uint(me.box.lz), __float_as_uint(me.box.hx));
+      q[2] = make_uint4(__float_as_uint(me.box.hy), __float_as_uint(me.box.hz), 0u, 0u);
     } else {
-      climb_global<KARRAS>(keys, n, nodes, parents, meet, rootOut, self, lo, hi, box, p, isLeft); /* overflow of the hand-over list */
-    }
-    slotOut++;
-  }
-  if (stranded) {
-    const u32 sp = b0 + t; /* split of the stranded node's parent */
-    const int side = (S.sibId[t][0] != B2_INVALID) ? 0 : 1;
-    const float* ob = S.sibBox[t][side];
-    const u32 slo = side == 0 ? m : sp + 1, shi = side == 0 ? sp + 1 : m;
-    if (slotOut < pendingCap) {
-      uint4* q = reinterpret_cast<uint4*>(pending + slotOut);
-      q[0] = make_uint4(S.sibId[t][side], slo, shi, sp | (side == 0 ? 0x80000000u : 0u));
-      q[1] = make_uint4(__float_as_uint(ob[0]), __float_as_uint(ob[1]), __float_as_uint(ob[2]), __float_as_uint(ob[3]));
-      q[2] = make_uint4(__float_as_uint(ob[4]), __float_as_uint(ob[5]), 0u, 0u);
-    } else {
-      climb_global<KARRAS>(keys, n, nodes, parents, meet, rootOut, S.sibId[t][side], slo, shi, Box{ob[0], ob[1], ob[2], ob[3], ob[4], ob[5]}, sp, side == 0);
+      climb_global<KARRAS>(keys, n, nodes, parents, meet, rootOut, self, lo, hi, me.box, p, isLeft); /* overflow of the hand-over list */
     }
   }
 }
@@ -329,11 +397,17 @@ int b2_launch_lbvh_fused(b2bvh_ctx* ctx, const u32* d_sortedKeys, const u32* d_s
     LbvhPending* pending = reinterpret_cast<LbvhPending*>(reinterpret_cast<unsigned char*>(d_scratch) + off + 16);
     const u32 cap = n / 8 + 1024;
     B2_CUDA(cudaMemsetAsync(pendingCount, 0, 4, ctx->stream));
-    const u32 grid = (n + LBVH_BL - 1) / LBVH_BL;
+    const u32 grid = (n + LBVH_TILE - 1) / LBVH_TILE;
+    static bool attrSet = false;
+    if (!attrSet) {
+      B2_CUDA(cudaFuncSetAttribute(lbvh_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LbvhTileSmem<true>)));
+      B2_CUDA(cudaFuncSetAttribute(lbvh_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LbvhTileSmem<false>)));
+      attrSet = true;
+    }
     if (karrasNumbering)
-      lbvh_block_kernel<true><<<grid, LBVH_BL, 0, ctx->stream>>>(d_sortedKeys, d_sortedVals, d_triAabb, n, d_nodes, d_parents, d_scratch, d_root, pendingCount, pending, cap);
+      lbvh_tile_kernel<true><<<grid, LBVH_TILE_THREADS, sizeof(LbvhTileSmem<true>), ctx->stream>>>(d_sortedKeys, d_sortedVals, d_triAabb, n, d_nodes, d_parents, d_scratch, d_root, pendingCount, pending, cap);
     else
-      lbvh_block_kernel<false><<<grid, LBVH_BL, 0, ctx->stream>>>(d_sortedKeys, d_sortedVals, d_triAabb, n, d_nodes, d_parents, d_scratch, d_root, pendingCount, pending, cap);
+      lbvh_tile_kernel<false><<<grid, LBVH_TILE_THREADS, sizeof(LbvhTileSmem<false>), ctx->stream>>>(d_sortedKeys, d_sortedVals, d_triAabb, n, d_nodes, d_parents, d_scratch, d_root, pendingCount, pending, cap);
     B2_LAUNCH_CHECK(ctx);
     u32 grid2 = (cap + LBVH_THREADS - 1) / LBVH_THREADS;
     const u32 cap2 = (u32)ctx->sm_count * 8u;
