@@ -32,10 +32,8 @@
 #include "common.cuh"
 
 #define COL_THREADS 256
-#define COL_TAG_SHIFT 11u
-#define COL_COUNT_MASK 0x7FFu
 
-/* scratch layout: CollapseCtrl (256 B) | uint4 expansion[n] | uint2 tasks[n] | u32 counts[(n/256/G + 3) * G] */
+/* scratch layout: CollapseCtrl (256 B) | uint4 expansion[n] | uint4 taskCh[n] | u32 taskParent[n] | u64 counts[G] */
 struct CollapseCtrl {
   u32 bar;        /* grid barrier: arrivals so far */
   u32 pad[3];
@@ -43,10 +41,9 @@ struct CollapseCtrl {
                      leaves barrier b early may publish the level after it before a late CTA has read this one) */
 };
 
-static inline size_t col_count_words(u32 n, u32 g) { return ((size_t)(n / COL_THREADS) / g + 3) * g; }
 size_t b2_collapse_scratch_bytes(u32 n) {
-  /* the counts array is largest for the largest grid: waves*G <= n/256 + 3*G, G <= 16 CTAs x 1024 SMs */
-  return 256 + (size_t)n * (sizeof(uint4) + sizeof(uint2)) + ((size_t)n / COL_THREADS + 3 * 16384) * sizeof(u32);
+  /* one tagged count word per CTA, G <= 16 CTAs x 1024 SMs */
+  return 256 + (size_t)n * (2 * sizeof(uint4) + sizeof(u32)) + 8 + 16384 * sizeof(u64);
 }
 
 struct ColSmem {
@@ -122,7 +119,7 @@ __global__ void __launch_bounds__(COL_THREADS) collapse_expand_kernel(const b2bv
  * the tile's own count is known.  Returns the tile's number of internal children (same value in every thread). */
 template <typename PrefixFn>
 __device__ __forceinline__ u32 collapse_tile(const b2bvh_bvh2_node* __restrict__ nodes, const uint4* __restrict__ expansion,
-                                             const u32* __restrict__ sortedVals, u32 nInt, uint2* tasks,
+                                             const u32* __restrict__ sortedVals, u32 nInt, uint4* taskCh, u32* taskParent,
                                              b2bvh_bvh4_node* wide, b2bvh_prim_node* wideLeaves, ColSmem& S, u32 tileStart, u32 end, PrefixFn prefixFn) {
   const u32 tid = threadIdx.x, w = tid >> 5, l = tid & 31u;
   const u32 g = tileStart + tid;
@@ -130,20 +127,21 @@ __device__ __forceinline__ u32 collapse_tile(const b2bvh_bvh2_node* __restrict__
   u32 ch[4] = {B2_INVALID, B2_INVALID, B2_INVALID, B2_INVALID};
   u32 parent = B2_INVALID;
   if (active) {
-    const uint2 task = __ldcg(tasks + g); /* written by another CTA one level earlier */
-    parent = task.y;
-    const uint4 ex = __ldg(expansion + task.x);
-    ch[0] = ex.x; ch[1] = ex.y; ch[2] = ex.z; ch[3] = ex.w;
+    const uint4 t = __ldcg(taskCh + g); /* written by another CTA one level earlier */
+    parent = __ldcg(taskParent + g);
+    ch[0] = t.x; ch[1] = t.y; ch[2] = t.z; ch[3] = t.w;
   }
   const u32 nInternal = (ch[0] < nInt ? 1u : 0u) + (ch[1] < nInt ? 1u : 0u) + (ch[2] < nInt ? 1u : 0u) + (ch[3] < nInt ? 1u : 0u);
   const u32 cc = (ch[0] != B2_INVALID ? 1u : 0u) + (ch[1] != B2_INVALID ? 1u : 0u) + (ch[2] != B2_INVALID ? 1u : 0u) + (ch[3] != B2_INVALID ? 1u : 0u);
-  /* boxes of the internal children: in flight while the tile waits for its prefix (leaf slots keep the empty box,
-   * TwoPassLbvhKernel.h:320-325) */
+  /* internal children: their boxes (for this node) and their expansions (for their tasks) are gathered while the tile
+   * waits for its prefix; leaf slots keep the empty box (TwoPassLbvhKernel.h:320-325) */
   Box box[4];
+  uint4 childEx[4];
 #pragma unroll
   for (int k = 0; k < 4; k++) {
     box[k] = box_empty();
-    if (ch[k] < nInt) box[k] = load_node2_ro(nodes + ch[k]).box;
+    childEx[k] = make_uint4(0u, 0u, 0u, 0u);
+    if (ch[k] < nInt) { box[k] = load_node2_gather(nodes + ch[k]).box; childEx[k] = ldg_gather_u4(expansion + ch[k]); }
   }
   /* CTA exclusive scan */
   u32 incl = nInternal;
@@ -168,12 +166,13 @@ __device__ __forceinline__ u32 collapse_tile(const b2bvh_bvh2_node* __restrict__
     if (ch[k] != B2_INVALID) {
       if (ch[k] < nInt) {
         outChild[k] = nextId;
-        tasks[nextId] = make_uint2(ch[k], g);
+        taskCh[nextId] = childEx[k];
+        taskParent[nextId] = g;
         nextId++;
       } else {
         const u32 slot = ch[k] - nInt;
         /* leaf slot s holds primitive sortedVals[s] in both layouts (Bvh2 leaf m_leftChildIdx / PrimRef m_primIdx) */
-        reinterpret_cast<uint2*>(wideLeaves)[slot] = make_uint2(__ldg(sortedVals + slot), g);
+        reinterpret_cast<uint2*>(wideLeaves)[slot] = make_uint2(ldg_gather_u32(sortedVals + slot), g);
       }
     }
   }
@@ -208,15 +207,15 @@ __device__ __forceinline__ u32 collapse_tile(const b2bvh_bvh2_node* __restrict__
   return tileTotal;
 }
 
-__global__ void __launch_bounds__(COL_THREADS, 5) collapse_persistent_kernel(const b2bvh_bvh2_node* __restrict__ nodes, const uint4* __restrict__ expansion,
-                                                                            const u32* __restrict__ sortedVals, u32 nInt, const u32* __restrict__ rootIdx, uint2* tasks,
+__global__ void __launch_bounds__(COL_THREADS, 4) collapse_persistent_kernel(const b2bvh_bvh2_node* __restrict__ nodes, const uint4* __restrict__ expansion,
+                                                                            const u32* __restrict__ sortedVals, u32 nInt, const u32* __restrict__ rootIdx, uint4* taskCh, u32* taskParent,
                                                                             b2bvh_bvh4_node* wide, b2bvh_prim_node* wideLeaves, CollapseCtrl* ctrl,
-                                                                            u32* counts) {
+                                                                            u64* counts) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
   ColSmem& S = *reinterpret_cast<ColSmem*>(smemRaw);
   const u32 G = gridDim.x, c = blockIdx.x, tid = threadIdx.x, w = tid >> 5, l = tid & 31u;
   u32 level = 0, start = 0, end = 1, barriers = 0;
-  if (c == 0 && tid == 0) tasks[0] = make_uint2(*rootIdx, B2_INVALID);
+  if (c == 0 && tid == 0) { taskCh[0] = __ldg(expansion + *rootIdx); taskParent[0] = B2_INVALID; }
   __syncthreads();
 
   while (true) {
@@ -227,48 +226,51 @@ __global__ void __launch_bounds__(COL_THREADS, 5) collapse_persistent_kernel(con
       if (c == 0) {
         do {
           const u32 e = end;
-          const u32 total = collapse_tile(nodes, expansion, sortedVals, nInt, tasks, wide, wideLeaves, S, start, end, [e](u32) { return e; });
+          const u32 total = collapse_tile(nodes, expansion, sortedVals, nInt, taskCh, taskParent, wide, wideLeaves, S, start, end, [e](u32) { return e; });
           start = end; end += total; level++;
         } while (end - start <= COL_THREADS && end != start);
         if (tid == 0) publish_level(ctrl, barriers + 1u, level, start, end);
       }
     } else {
-      /* ---- a level of many tiles: tile (wave k, CTA c) = k*G + c ---- */
-      const u32 nTiles = (size + COL_THREADS - 1) / COL_THREADS;
-      const u32 tag = level + 1u;
-      u32 waveBase = 0; /* children of all complete waves before the current one */
-      for (u32 k = 0; k * G + c < nTiles; k++) {
-        const u32 tile = k * G + c;
-        u32* row = counts + (size_t)k * G;
-        const u32 lvlEnd = end;
-        auto prefix = [&](u32 tileTotal) -> u32 {
-          if (tid == 0) st_relaxed(row + c, (tag << COL_TAG_SHIFT) | tileTotal);
-          /* wave k-1 (every word is due: the wave before the last one is always full) and the predecessors in wave k */
-          u32 sumPrev = 0, sumSame = 0;
-          if (k > 0)
-            for (u32 i = tid; i < G; i += COL_THREADS) {
-              u32 v;
-              do { v = ld_relaxed(row - G + i); } while ((v >> COL_TAG_SHIFT) != tag);
-              sumPrev += v & COL_COUNT_MASK;
-            }
-          for (u32 i = tid; i < c; i += COL_THREADS) {
-            u32 v;
-            do { v = ld_relaxed(row + i); } while ((v >> COL_TAG_SHIFT) != tag);
-            sumSame += v & COL_COUNT_MASK;
-          }
+      /* ---- a level of many tiles: CTA c owns the contiguous chunk c of the level ---- */
+      const u32 chunk = ((size + G - 1) / G + COL_THREADS - 1) / COL_THREADS * COL_THREADS;
+      const u32 nActive = (size + chunk - 1) / chunk;
+      if (c < nActive) {
+        const u32 cStart = start + c * chunk, cEnd = min(end, cStart + chunk);
+        /* A. internal children of the whole chunk (16 B per task, coalesced, L2-resident: written one level earlier) */
+        u32 cnt = 0;
+        for (u32 g = cStart + tid; g < cEnd; g += COL_THREADS) {
+          const uint4 t = __ldcg(taskCh + g);
+          cnt += (t.x < nInt ? 1u : 0u) + (t.y < nInt ? 1u : 0u) + (t.z < nInt ? 1u : 0u) + (t.w < nInt ? 1u : 0u);
+        }
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) { sumPrev += __shfl_xor_sync(B2_FULL, sumPrev, o); sumSame += __shfl_xor_sync(B2_FULL, sumSame, o); }
-          if (l == 0) { S.warpSum[1][w] = sumPrev; S.warpSum[2][w] = sumSame; }
-          __syncthreads();
-          u32 p = 0, s = 0;
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(B2_FULL, cnt, o);
+        if (l == 0) S.warpSum[1][w] = cnt;
+        __syncthreads();
+        u32 chunkTotal = 0;
 #pragma unroll
-          for (int q = 0; q < COL_THREADS / 32; q++) { p += S.warpSum[1][q]; s += S.warpSum[2][q]; }
-          waveBase += p;
-          const u32 base = lvlEnd + waveBase + s;
-          if (tile == nTiles - 1 && tid == 0) publish_level(ctrl, barriers + 1u, level + 1u, lvlEnd, base + tileTotal); /* last tile of the level */
-          return base;
-        };
-        collapse_tile(nodes, expansion, sortedVals, nInt, tasks, wide, wideLeaves, S, start + tile * COL_THREADS, end, prefix);
+        for (int q = 0; q < COL_THREADS / 32; q++) chunkTotal += S.warpSum[1][q];
+        const u64 tag = (u64)(level + 1u) << 32;
+        if (tid == 0) st_relaxed64(counts + c, tag | chunkTotal);
+        /* B. children of the chunks before this one: every CTA posts after the same short pass, so the spin is short */
+        u32 before = 0;
+        for (u32 i = tid; i < c; i += COL_THREADS) {
+          u64 v;
+          do { v = ld_relaxed64(counts + i); } while ((v >> 32) != (tag >> 32));
+          before += (u32)v;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(B2_FULL, before, o);
+        if (l == 0) S.warpSum[2][w] = before;
+        __syncthreads();
+        u32 running = end;
+#pragma unroll
+        for (int q = 0; q < COL_THREADS / 32; q++) running += S.warpSum[2][q];
+        if (c == nActive - 1 && tid == 0) publish_level(ctrl, barriers + 1u, level + 1u, end, running + chunkTotal); /* last chunk of the level */
+        /* C. the chunk tile by tile: no CTA waits for another one here */
+        for (u32 tileStart = cStart; tileStart < cEnd; tileStart += COL_THREADS)
+          collapse_tile(nodes, expansion, sortedVals, nInt, taskCh, taskParent, wide, wideLeaves, S, tileStart, cEnd,
+                        [&running](u32 tileTotal) { const u32 b = running; running += tileTotal; return b; });
       }
     }
     barriers++;
@@ -299,16 +301,17 @@ int b2_launch_collapse(b2bvh_ctx* ctx, const b2bvh_bvh2_node* d_nodes, const b2b
   unsigned char* base = reinterpret_cast<unsigned char*>(d_scratch);
   CollapseCtrl* ctrl = reinterpret_cast<CollapseCtrl*>(base);
   uint4* expansion = reinterpret_cast<uint4*>(base + 256);
-  uint2* tasks = reinterpret_cast<uint2*>(base + 256 + (size_t)n * sizeof(uint4));
-  u32* counts = reinterpret_cast<u32*>(base + 256 + (size_t)n * (sizeof(uint4) + sizeof(uint2)));
+  uint4* taskCh = reinterpret_cast<uint4*>(base + 256 + (size_t)n * sizeof(uint4));
+  u32* taskParent = reinterpret_cast<u32*>(base + 256 + (size_t)n * 2 * sizeof(uint4));
+  u64* counts = reinterpret_cast<u64*>(taskParent + ((n + 1u) & ~1u)); /* one tagged word per CTA */
   u32 nInt = n - 1;
   B2_CUDA(cudaMemsetAsync(ctrl, 0, 256, ctx->stream));
-  B2_CUDA(cudaMemsetAsync(counts, 0, col_count_words(n, grid) * sizeof(u32), ctx->stream));
+  B2_CUDA(cudaMemsetAsync(counts, 0, (size_t)grid * sizeof(u64), ctx->stream));
   B2_KERNEL(ctx, "collapse_expand");
   collapse_expand_kernel<<<(nInt + COL_THREADS - 1) / COL_THREADS, COL_THREADS, 0, ctx->stream>>>(d_nodes, nInt, expansion);
   B2_LAUNCH_CHECK(ctx);
   B2_KERNEL(ctx, "collapse_levels");
-  void* args[] = {(void*)&d_nodes, (void*)&expansion, (void*)&d_sortedVals, (void*)&nInt, (void*)&d_rootIdx, (void*)&tasks, (void*)&d_wide, (void*)&d_wideLeaves, (void*)&ctrl, (void*)&counts};
+  void* args[] = {(void*)&d_nodes, (void*)&expansion, (void*)&d_sortedVals, (void*)&nInt, (void*)&d_rootIdx, (void*)&taskCh, (void*)&taskParent, (void*)&d_wide, (void*)&d_wideLeaves, (void*)&ctrl, (void*)&counts};
   B2_CUDA(cudaLaunchCooperativeKernel((const void*)collapse_persistent_kernel, dim3(grid), dim3(COL_THREADS), args, smem, ctx->stream));
   B2_LAUNCH_CHECK(ctx);
   CollapseCtrl h;

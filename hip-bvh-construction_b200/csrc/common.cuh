@@ -70,10 +70,31 @@ __device__ __forceinline__ Node2 load_node2_cg(const b2bvh_bvh2_node* p) {
   const uint4* q = reinterpret_cast<const uint4*>(p);
   return node2_unpack(__ldcg(q), __ldcg(q + 1));
 }
+/* Random gathers: a plain load miss makes the B200 L2 fetch the whole 128-byte line from DRAM (measured: 118 B of DRAM
+ * traffic per random 32-byte read, tools/micro/mem_micro.cu); the L2::64B qualifier halves that. */
+__device__ __forceinline__ uint4 ldg_gather_u4(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L2::64B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float2 ldg_gather_f2(const float2* p) {
+  float2 v;
+  asm volatile("ld.global.nc.L2::64B.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ u32 ldg_gather_u32(const u32* p) {
+  u32 v;
+  asm volatile("ld.global.nc.L2::64B.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
 /* read-only path: for nodes produced by an earlier launch */
 __device__ __forceinline__ Node2 load_node2_ro(const b2bvh_bvh2_node* p) {
   const uint4* q = reinterpret_cast<const uint4*>(p);
   return node2_unpack(__ldg(q), __ldg(q + 1));
+}
+__device__ __forceinline__ Node2 load_node2_gather(const b2bvh_bvh2_node* p) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  return node2_unpack(ldg_gather_u4(q), ldg_gather_u4(q + 1));
 }
 
 /* acq_rel / release / acquire primitives for the bottom-up passes (replace the reference's
@@ -105,6 +126,12 @@ __device__ __forceinline__ u32 ld_relaxed(const u32* p) {
   asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ u64 ld_relaxed64(const u64* p) {
+  u64 v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed64(u64* p, u64 v) { asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
 __device__ __forceinline__ void st_relaxed(u32* p, u32 v) { asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
 /* order-preserving float <-> uint map: unsigned compare of the image == float compare (-0 < +0) */

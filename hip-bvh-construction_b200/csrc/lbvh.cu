@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(LBVH_TILE_THREADS, 4) lbvh_tile_kernel(const u
     const u32 prim = __ldg(vals + g);
     const u32 k0 = __ldg(keys + g);
     const float2* bp = reinterpret_cast<const float2*>(triAabb + prim); /* 24-byte boxes: 8-byte aligned */
-    const float2 q0 = __ldg(bp), q1 = __ldg(bp + 1), q2 = __ldg(bp + 2);
+    const float2 q0 = ldg_gather_f2(bp), q1 = ldg_gather_f2(bp + 1), q2 = ldg_gather_f2(bp + 2);
     int d = -1;
     if (g + 1 < n) d = boundary_depth(k0, __ldg(keys + g + 1), g);
     S.stage[2 * (T + tid)] = make_uint4(prim, B2_INVALID, __float_as_uint(q0.x), __float_as_uint(q0.y));

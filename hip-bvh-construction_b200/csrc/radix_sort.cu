@@ -14,8 +14,9 @@
  *                         chunk offsets + digit totals
  *   radix_scatter_kernel  the CTA walks its chunk tile by tile (8192 pairs): keys and values arrive by TMA bulk copy
  *                         (cp.async.bulk + mbarrier, nothing staged in registers; the value tile is in flight while the
- *                         keys are ranked), warp-striped match.any ranking (stable), digit offsets carried in shared memory
- *                         from tile to tile, shared-memory reorder, digit-contiguous stores.
+ *                         keys are ranked), warp-striped ranking with shared-memory atomics + a neighbour fix-up that
+ *                         restores stability (see the kernel), digit offsets carried in shared memory from tile to tile,
+ *                         keys reordered in shared memory, values gathered through the tags, digit-contiguous stores.
  * No inter-CTA communication inside a launch: an earlier single-launch "onesweep" version with decoupled look-back spent
  * most of its time walking look-back chains as long as the number of resident CTAs (profiles/README.md, r01a) — on a
  * 148-SM part whose 126 MB L2 holds the whole key array of the 10 M benchmark, re-reading keys for the count costs far less
@@ -124,15 +125,24 @@ template <int ITEMS>
 struct ScatterSmem {
   static constexpr int TILE = RS_THREADS * ITEMS;
   u32 keys[TILE];                 /* raw key tile (TMA destination), then the digit-ordered keys      */
-  u32 vals[TILE];                 /* raw value tile (TMA destination), then the digit-ordered values  */
-  u32 warpHist[RS_WARPS][RS_RADIX];
+  u32 vals[TILE];                 /* raw value tile (TMA destination), read through the tags           */
+  u32 tagsRaw[TILE + 8];          /* per digit-ordered key: digit << 13 | position in the raw tile; 4 guard words (no group) on either side */
+  u32 warpHist[RS_WARPS][RS_RADIX]; /* per-warp digit counters, then the tile-local start of (warp, digit) */
   u32 digitBase[RS_RADIX];        /* global index where the next key of each digit goes (carried from tile to tile) */
   int globalBase[RS_RADIX];       /* digitBase - tile-local start of the digit                        */
-  u32 digitStart[RS_RADIX];
   u32 warpTotals[8];
   alignas(8) u64 bar[2];
 };
 
+/* Ranking.  A warp owns 32*ITEMS consecutive keys of the tile, lane l taking keys l, l+32, ... (warp-striped), and counts
+ * them with shared-memory atomics on its private 256 counters: ATOMS.ADD returns the rank of the key among the keys of
+ * its digit seen by the warp so far.  That costs 4 SM-cycles per warp instruction where match.any on 8 random bits costs
+ * 61 and eight ballots cost 26 (tools/micro/rank_micro.cu), but the lanes of ONE instruction that hold the same digit
+ * are served in an order the hardware does not promise.  They do receive consecutive ranks, so after the keys have been
+ * placed in digit order (with a tag = digit, warp, item, lane) every key looks at its direct neighbours: neighbours with
+ * the same (digit, warp, item) are exactly the keys it may have been swapped with, and its stable position inside that
+ * group is the number of members with a smaller lane.  Groups of more than one key are rare (11 % of the keys for random
+ * digits) and short, so the fix-up is two extra shared-memory reads per key. */
 template <int ITEMS, bool IOTA_VALUES>
 __global__ void __launch_bounds__(RS_THREADS, 2) radix_scatter_kernel(const u32* __restrict__ keysIn, const u32* __restrict__ valsIn,
                                                                       u32* __restrict__ keysOut, u32* __restrict__ valsOut,
@@ -140,9 +150,12 @@ __global__ void __launch_bounds__(RS_THREADS, 2) radix_scatter_kernel(const u32*
                                                                       u32 chunk, u32 shift, u32 mask, u32 gpad) {
   using Smem = ScatterSmem<ITEMS>;
   constexpr u32 TILE = Smem::TILE;
+  static_assert(TILE <= 8192, "tags hold a 13-bit tile position");
   extern __shared__ __align__(128) unsigned char smemRaw[];
   Smem& S = *reinterpret_cast<Smem*>(smemRaw);
+  u32* const tags = S.tagsRaw + 4;
   const u32 tid = threadIdx.x, w = tid >> 5, l = tid & 31u;
+  if (tid < 8) S.tagsRaw[tid < 4 ? tid : TILE + tid] = 0xFFFFFFFFu; /* guards: a group id no key can have */
 
   if (tid == 0) {
     mbar_init(&S.bar[0], 1);
@@ -159,13 +172,13 @@ __global__ void __launch_bounds__(RS_THREADS, 2) radix_scatter_kernel(const u32*
       if ((int)l >= o) incl += t;
     }
     if (l == 31) S.warpTotals[w] = incl;
-    S.digitStart[tid] = incl - tot;
+    S.globalBase[tid] = (int)(incl - tot);
   }
   __syncthreads();
   if (tid < RS_RADIX) {
     u32 add = 0;
     for (u32 k = 0; k < w; k++) add += S.warpTotals[k];
-    S.digitBase[tid] = S.digitStart[tid] + add + __ldg(counts + (size_t)tid * gpad + blockIdx.x);
+    S.digitBase[tid] = (u32)S.globalBase[tid] + add + __ldg(counts + (size_t)tid * gpad + blockIdx.x);
   }
   const u32 begin = blockIdx.x * chunk, end = min(n, begin + chunk);
   u32 phase = 0;
@@ -183,7 +196,8 @@ __global__ void __launch_bounds__(RS_THREADS, 2) radix_scatter_kernel(const u32*
         tma_load_1d(S.vals, valsIn + tileBase, TILE * 4, &S.bar[1]);
       }
     }
-    for (u32 k = l; k < RS_RADIX; k += 32) S.warpHist[w][k] = 0;
+#pragma unroll
+    for (u32 k = 0; k < RS_RADIX / 32; k++) S.warpHist[w][l + 32 * k] = 0;
 
     /* ---- keys, warp-striped: item i of lane l of warp w is tile element w*32*ITEMS + i*32 + l ---- */
     u32 key[ITEMS];
@@ -196,31 +210,22 @@ __global__ void __launch_bounds__(RS_THREADS, 2) radix_scatter_kernel(const u32*
 #pragma unroll
       for (int i = 0; i < ITEMS; i++) {
         const u32 e = stripe + i * 32;
-        key[i] = e < valid ? __ldg(keysIn + tileBase + e) : 0xFFFFFFFFu;
+        key[i] = e < valid ? __ldg(keysIn + tileBase + e) : 0xFFFFFFFFu; /* padding: last digit, last positions */
+        if (!IOTA_VALUES && e < valid) S.vals[e] = __ldg(valsIn + tileBase + e);
       }
     }
     __syncwarp();
-
-    /* ---- stable rank inside the warp: match-any on the digit, per-warp running digit counters ---- */
-    u32 pos[ITEMS];
+    /* ---- rank among the warp's keys of the same digit (order inside one instruction fixed up below) ---- */
+    u32 rank[ITEMS];
 #pragma unroll
-    for (int i = 0; i < ITEMS; i++) {
-      const u32 d = (key[i] >> shift) & mask;
-      const u32 peers = __match_any_sync(B2_FULL, d);
-      const u32 leader = __ffs(peers) - 1;
-      u32 old = 0;
-      if (l == leader) { old = S.warpHist[w][d]; S.warpHist[w][d] = old + __popc(peers); }
-      old = __shfl_sync(B2_FULL, old, leader);
-      pos[i] = old + __popc(peers & lanemask_lt());
-      __syncwarp();
-    }
+    for (int i = 0; i < ITEMS; i++) rank[i] = atomicAdd(&S.warpHist[w][(key[i] >> shift) & mask], 1u);
     __syncthreads(); /* all raw keys are in registers, all warp histograms complete */
 
     /* ---- per digit: exclusive prefix over warps, tile count, tile-local start ---- */
     u32 count = 0;
     if (tid < RS_RADIX) {
 #pragma unroll
-      for (int k = 0; k < RS_WARPS; k++) { const u32 t = S.warpHist[k][tid]; S.warpHist[k][tid] = count; count += t; }
+      for (int k = 0; k < RS_WARPS; k++) count += S.warpHist[k][tid];
       u32 incl = count;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
@@ -228,57 +233,57 @@ __global__ void __launch_bounds__(RS_THREADS, 2) radix_scatter_kernel(const u32*
         if ((int)l >= o) incl += t;
       }
       if (l == 31) S.warpTotals[w] = incl;
-      S.digitStart[tid] = incl - count;
+      count = incl - count; /* exclusive inside the warp's 32 digits (the per-digit total is re-read below) */
     }
     __syncthreads();
     if (tid < RS_RADIX) {
-      u32 add = 0;
-      for (u32 k = 0; k < w; k++) add += S.warpTotals[k];
-      const u32 start = S.digitStart[tid] + add;
-      S.digitStart[tid] = start;
+      u32 start = count;
+      for (u32 k = 0; k < w; k++) start += S.warpTotals[k];
       const u32 base = S.digitBase[tid];
       S.globalBase[tid] = (int)base - (int)start;
-      S.digitBase[tid] = base + count; /* padding keys of a ragged last tile only inflate the last digit of the last tile */
+      u32 run = start;
+#pragma unroll
+      for (int k = 0; k < RS_WARPS; k++) { const u32 t = S.warpHist[k][tid]; S.warpHist[k][tid] = run; run += t; }
+      S.digitBase[tid] = base + (run - start); /* padding keys of a ragged last tile only inflate the last digit of the last tile */
     }
     __syncthreads();
 
-    /* ---- keys into digit order in shared memory (overwrites the raw tile) ---- */
+    /* ---- keys into digit order in shared memory (overwrites the raw tile), tagged with where they came from ---- */
 #pragma unroll
     for (int i = 0; i < ITEMS; i++) {
       const u32 d = (key[i] >> shift) & mask;
-      pos[i] += S.digitStart[d] + S.warpHist[w][d];
-      S.keys[pos[i]] = key[i];
+      const u32 pos = S.warpHist[w][d] + rank[i];
+      S.keys[pos] = key[i];
+      tags[pos] = (d << 13) | (stripe + i * 32);
     }
-    /* ---- raw values into registers (the value tile landed while the keys were ranked) ---- */
-    u32 val[ITEMS];
-    if (IOTA_VALUES) {
-#pragma unroll
-      for (int i = 0; i < ITEMS; i++) val[i] = tileBase + stripe + i * 32;
-    } else if (full) {
-      mbar_wait(&S.bar[1], phase);
-#pragma unroll
-      for (int i = 0; i < ITEMS; i++) val[i] = S.vals[stripe + i * 32];
-    } else {
-#pragma unroll
-      for (int i = 0; i < ITEMS; i++) {
-        const u32 e = stripe + i * 32;
-        val[i] = e < valid ? __ldg(valsIn + tileBase + e) : 0u;
-      }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < ITEMS; i++) S.vals[pos[i]] = val[i];
+    if (!IOTA_VALUES && full) mbar_wait(&S.bar[1], phase); /* the value tile landed long ago */
     __syncthreads();
 
-    /* ---- out: element j of the digit-ordered tile goes to globalBase[digit] + j ---- */
+    /* ---- out: element j of the digit-ordered tile goes to globalBase[digit] + (j corrected inside its group) ---- */
 #pragma unroll
     for (int i = 0; i < ITEMS; i++) {
       const u32 j = tid + i * RS_THREADS;
-      if (j < valid) {
-        const u32 k = S.keys[j];
-        const int dst = S.globalBase[(k >> shift) & mask] + (int)j;
-        keysOut[dst] = k;
-        valsOut[dst] = S.vals[j];
+      const u32 t = tags[j];
+      const u32 grp = t >> 5, ln = t & 31u;
+      /* neighbours at distance 1 and 2 without branches (tags[] has two guard words on either side); a group that
+       * reaches further on one side takes the loop */
+      const u32 l1 = tags[j - 1], l2 = tags[j - 2], r1 = tags[j + 1], r2 = tags[j + 2];
+      const bool sl1 = (l1 >> 5) == grp, sl2 = sl1 && (l2 >> 5) == grp, sr1 = (r1 >> 5) == grp, sr2 = sr1 && (r2 >> 5) == grp;
+      u32 jj = j - ((sl1 && (l1 & 31u) > ln) ? 1u : 0u) - ((sl2 && (l2 & 31u) > ln) ? 1u : 0u) + ((sr1 && (r1 & 31u) < ln) ? 1u : 0u) +
+               ((sr2 && (r2 & 31u) < ln) ? 1u : 0u);
+      if (sl2 || sr2) {
+        if (sl2)
+          for (u32 q = j - 3; (tags[q] >> 5) == grp; q--) /* members before j: each one with a larger lane moves j one step left */
+            if ((tags[q] & 31u) > ln) jj--;
+        if (sr2)
+          for (u32 q = j + 3; (tags[q] >> 5) == grp; q++) /* members after j: each one with a smaller lane moves j one step right */
+            if ((tags[q] & 31u) < ln) jj++;
+      }
+      const u32 origin = t & 0x1FFFu;
+      if (origin < valid) {
+        const int dst = S.globalBase[t >> 13] + (int)jj;
+        keysOut[dst] = S.keys[j];
+        valsOut[dst] = IOTA_VALUES ? tileBase + origin : S.vals[origin];
       }
     }
     if (full) phase ^= 1u;
@@ -311,7 +316,7 @@ int b2_launch_sort(b2bvh_ctx* ctx, const u32* d_keysIn, const u32* d_valsIn, u32
   const u32 nPasses = (endBit - startBit + RS_RADIX_BITS - 1) / RS_RADIX_BITS;
   /* small inputs use 2048-pair tiles so that more SMs take part */
   const bool small = n < (1u << 20);
-  const u32 tile = RS_THREADS * (small ? 4u : 16u);
+  const u32 tile = RS_THREADS * (small ? 4u : 15u); /* 15: two CTAs of 3 x 30 KB tile buffers + counters fit one SM */
   const u32 grid = rs_grid(ctx, n, tile);
   const u32 gpad = rs_gpad(grid);
   u32 chunk = (n + grid - 1) / grid;
@@ -335,7 +340,7 @@ int b2_launch_sort(b2bvh_ctx* ctx, const u32* d_keysIn, const u32* d_valsIn, u32
     radix_scan_kernel<<<RS_RADIX / RS_SCAN_WARPS, RS_SCAN_WARPS * 32, 0, ctx->stream>>>(counts, totals, grid, gpad);
     B2_LAUNCH_CHECK(ctx);
     if (small) B2_TRY(launch_scatter<4>(ctx, grid, kin, vin, kout, vout, counts, totals, n, chunk, shift, mask, gpad));
-    else B2_TRY(launch_scatter<16>(ctx, grid, kin, vin, kout, vout, counts, totals, n, chunk, shift, mask, gpad));
+    else B2_TRY(launch_scatter<15>(ctx, grid, kin, vin, kout, vout, counts, totals, n, chunk, shift, mask, gpad));
     kin = kout;
     vin = vout;
   }
