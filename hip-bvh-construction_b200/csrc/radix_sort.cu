@@ -14,8 +14,8 @@
  *                         chunk offsets + digit totals
  *   radix_scatter_kernel  the CTA walks its chunk tile by tile (8192 pairs): keys and values arrive by TMA bulk copy
  *                         (cp.async.bulk + mbarrier, nothing staged in registers; the value tile is in flight while the
- *                         keys are ranked), warp-striped ranking with shared-memory atomics + a neighbour fix-up that
- *                         restores stability (see the kernel), digit offsets carried in shared memory from tile to tile,
+ *                         keys are ranked), warp-striped stable ranking with shared-memory atomics (see the kernel),
+ *                         digit offsets carried in shared memory from tile to tile,
  *                         keys reordered in shared memory, values gathered through the tags, digit-contiguous stores.
  * No inter-CTA communication inside a launch: an earlier single-launch "onesweep" version with decoupled look-back spent
  * most of its time walking look-back chains as long as the number of resident CTAs (profiles/README.md, r01a) — on a
@@ -126,7 +126,7 @@ struct ScatterSmem {
   static constexpr int TILE = RS_THREADS * ITEMS;
   u32 keys[TILE];                 /* raw key tile (TMA destination), then the digit-ordered keys      */
   u32 vals[TILE];                 /* raw value tile (TMA destination), read through the tags           */
-  u32 tagsRaw[TILE + 8];          /* per digit-ordered key: digit << 13 | position in the raw tile; 4 guard words (no group) on either side */
+  u32 tags[TILE];                 /* per digit-ordered key: its position in the raw tile               */
   u32 warpHist[RS_WARPS][RS_RADIX]; /* per-warp digit counters, then the tile-local start of (warp, digit) */
   u32 digitBase[RS_RADIX];        /* global index where the next key of each digit goes (carried from tile to tile) */
   int globalBase[RS_RADIX];       /* digitBase - tile-local start of the digit                        */
@@ -135,14 +135,13 @@ struct ScatterSmem {
 };
 
 /* Ranking.  A warp owns 32*ITEMS consecutive keys of the tile, lane l taking keys l, l+32, ... (warp-striped), and counts
- * them with shared-memory atomics on its private 256 counters: ATOMS.ADD returns the rank of the key among the keys of
- * its digit seen by the warp so far.  That costs 4 SM-cycles per warp instruction where match.any on 8 random bits costs
- * 61 and eight ballots cost 26 (tools/micro/rank_micro.cu), but the lanes of ONE instruction that hold the same digit
- * are served in an order the hardware does not promise.  They do receive consecutive ranks, so after the keys have been
- * placed in digit order (with a tag = digit, warp, item, lane) every key looks at its direct neighbours: neighbours with
- * the same (digit, warp, item) are exactly the keys it may have been swapped with, and its stable position inside that
- * group is the number of members with a smaller lane.  Groups of more than one key are rare (11 % of the keys for random
- * digits) and short, so the fix-up is two extra shared-memory reads per key. */
+ * them on its private 256 counters in shared memory.  match.any on the 8-bit digit — the textbook way to learn which lanes
+ * of an instruction share a digit — costs ~2 SM-cycles per DISTINCT value, 61 cycles for 8 random bits; eight ballots cost 26;
+ * a shared-memory atomic add costs 4 (tools/micro/rank_micro.cu).  So every lane reads its counter, adds 1 atomically and
+ * reads it again: the difference is the number of lanes of this instruction holding its digit.  A lane that is alone
+ * (89 % of the lanes for random digits) has its rank — the first read.  The others run match.any among themselves only
+ * (a couple of distinct values, a few cycles) and order themselves by lane: stable, whatever order the hardware served
+ * the atomics in. */
 template <int ITEMS, bool IOTA_VALUES>
 __global__ void __launch_bounds__(RS_THREADS, 2) radix_scatter_kernel(const u32* __restrict__ keysIn, const u32* __restrict__ valsIn,
                                                                       u32* __restrict__ keysOut, u32* __restrict__ valsOut,
@@ -150,12 +149,9 @@ __global__ void __launch_bounds__(RS_THREADS, 2) radix_scatter_kernel(const u32*
                                                                       u32 chunk, u32 shift, u32 mask, u32 gpad) {
   using Smem = ScatterSmem<ITEMS>;
   constexpr u32 TILE = Smem::TILE;
-  static_assert(TILE <= 8192, "tags hold a 13-bit tile position");
   extern __shared__ __align__(128) unsigned char smemRaw[];
   Smem& S = *reinterpret_cast<Smem*>(smemRaw);
-  u32* const tags = S.tagsRaw + 4;
   const u32 tid = threadIdx.x, w = tid >> 5, l = tid & 31u;
-  if (tid < 8) S.tagsRaw[tid < 4 ? tid : TILE + tid] = 0xFFFFFFFFu; /* guards: a group id no key can have */
 
   if (tid == 0) {
     mbar_init(&S.bar[0], 1);
@@ -215,10 +211,22 @@ __global__ void __launch_bounds__(RS_THREADS, 2) radix_scatter_kernel(const u32*
       }
     }
     __syncwarp();
-    /* ---- rank among the warp's keys of the same digit (order inside one instruction fixed up below) ---- */
+    /* ---- stable rank among the warp's keys of the same digit ---- */
     u32 rank[ITEMS];
 #pragma unroll
-    for (int i = 0; i < ITEMS; i++) rank[i] = atomicAdd(&S.warpHist[w][(key[i] >> shift) & mask], 1u);
+    for (int i = 0; i < ITEMS; i++) {
+      const u32 d = (key[i] >> shift) & mask;
+      volatile u32* h = &S.warpHist[w][d];
+      const u32 old = *h;
+      __syncwarp();
+      atomicAdd(const_cast<u32*>(h), 1u);
+      __syncwarp();
+      const bool shared = (*h - old) > 1u; /* other lanes of this instruction hold the same digit */
+      const u32 sm = __ballot_sync(B2_FULL, shared);
+      u32 r = old;
+      if (shared) r += __popc(__match_any_sync(sm, d) & lanemask_lt());
+      rank[i] = r;
+    }
     __syncthreads(); /* all raw keys are in registers, all warp histograms complete */
 
     /* ---- per digit: exclusive prefix over warps, tile count, tile-local start ---- */
@@ -254,7 +262,7 @@ __global__ void __launch_bounds__(RS_THREADS, 2) radix_scatter_kernel(const u32*
       const u32 d = (key[i] >> shift) & mask;
       const u32 pos = S.warpHist[w][d] + rank[i];
       S.keys[pos] = key[i];
-      tags[pos] = (d << 13) | (stripe + i * 32);
+      S.tags[pos] = stripe + i * 32;
     }
     if (!IOTA_VALUES && full) mbar_wait(&S.bar[1], phase); /* the value tile landed long ago */
     __syncthreads();
@@ -263,26 +271,11 @@ __global__ void __launch_bounds__(RS_THREADS, 2) radix_scatter_kernel(const u32*
 #pragma unroll
     for (int i = 0; i < ITEMS; i++) {
       const u32 j = tid + i * RS_THREADS;
-      const u32 t = tags[j];
-      const u32 grp = t >> 5, ln = t & 31u;
-      /* neighbours at distance 1 and 2 without branches (tags[] has two guard words on either side); a group that
-       * reaches further on one side takes the loop */
-      const u32 l1 = tags[j - 1], l2 = tags[j - 2], r1 = tags[j + 1], r2 = tags[j + 2];
-      const bool sl1 = (l1 >> 5) == grp, sl2 = sl1 && (l2 >> 5) == grp, sr1 = (r1 >> 5) == grp, sr2 = sr1 && (r2 >> 5) == grp;
-      u32 jj = j - ((sl1 && (l1 & 31u) > ln) ? 1u : 0u) - ((sl2 && (l2 & 31u) > ln) ? 1u : 0u) + ((sr1 && (r1 & 31u) < ln) ? 1u : 0u) +
-               ((sr2 && (r2 & 31u) < ln) ? 1u : 0u);
-      if (sl2 || sr2) {
-        if (sl2)
-          for (u32 q = j - 3; (tags[q] >> 5) == grp; q--) /* members before j: each one with a larger lane moves j one step left */
-            if ((tags[q] & 31u) > ln) jj--;
-        if (sr2)
-          for (u32 q = j + 3; (tags[q] >> 5) == grp; q++) /* members after j: each one with a smaller lane moves j one step right */
-            if ((tags[q] & 31u) < ln) jj++;
-      }
-      const u32 origin = t & 0x1FFFu;
+      const u32 origin = S.tags[j];
       if (origin < valid) {
-        const int dst = S.globalBase[t >> 13] + (int)jj;
-        keysOut[dst] = S.keys[j];
+        const u32 k = S.keys[j];
+        const int dst = S.globalBase[(k >> shift) & mask] + (int)j;
+        keysOut[dst] = k;
         valsOut[dst] = IOTA_VALUES ? tileBase + origin : S.vals[origin];
       }
     }
