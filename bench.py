@@ -37,8 +37,10 @@ ALGO_BYTES = {
     "morton30": 24 + 8,
     "radix_count": 4,
     "radix_scatter": 15,            # 8 B in + 8 B out per pair; pass 0 does not read values (iota): (12 + 3*16) / 4
-    "lbvh_fused_apetrei": 132,
-    "lbvh_fused_karras": 140,
+    "lbvh_fused_apetrei": 132,      # 4 value + 4 key + 28 gathered box (24 B payload) + 32 leaf node + 32 internal node + ~32 hand-over/climb
+    "lbvh_fused_karras": 140,       # + 8 parent indices
+    "collapse_expand": 48,          # 32 node read + 16 expansion written, per internal Bvh2 node
+    "collapse_levels": 113,         # 0.466 wide nodes/prim x (20 task r + 16 expansion + 32 box gathered + 128 node w + 20 task w) + 8 PrimNode + 4 value
 }
 
 
