@@ -5,51 +5,51 @@
  * separate-leaf layout; host setup TwoPassLbvh.cpp:154-183).  The reference runs ONE persistent launch whose threads
  * spin on a task queue and allocate wide nodes with a global atomicAdd: node numbering is timing dependent.  Here the
  * wide tree is numbered breadth-first — what a sequential execution of the reference's task loop produces — so the output
- * is deterministic and comparable with memcmp (canonical numbering of the oracle).  Two launches:
+ * is deterministic and comparable with memcmp (canonical numbering of the oracle).  Three launches:
  *
  *   1. collapse_expand_kernel      for EVERY internal Bvh2 node, the (up to 4) children it would have as a wide node: twice,
  *                                  the internal child with the largest area is replaced by its two children (strict '>' so
  *                                  the first of equals wins, areas without FMA).  One thread per node, no synchronisation,
  *                                  16 B out.  Keeps the dependent node reads out of the level-synchronous part.
- *   2. collapse_persistent_kernel  one cooperative launch, every CTA resident, levels separated by a grid barrier (one atomic
- *                                  counter).  One task = one wide node = one thread: task (8 B) -> expansion (16 B) -> boxes
- *                                  of the internal children (32 B each).  Numbering: the tasks of a level are a contiguous
- *                                  index range cut into tiles of 256; tile (wave k, CTA c) is tile k*G + c.  A tile posts its
- *                                  number of internal children in counts[k][c] (tagged with the level, so the array is
- *                                  never reset) and sums the words of wave k-1 (complete by then) and of its predecessors
- *                                  in wave k (being computed at the same moment by the other resident CTAs): no chain of
- *                                  dependent look-backs, one spin on words that are all due at the same time.  The children
- *                                  get consecutive indices in (task, slot) order, their tasks are appended, and the 128-byte
- *                                  node goes out through a swizzled shared-memory transpose as full, contiguous lines:
- *                                  half-written 32-byte sectors make the B200 L2 fetch the other half from DRAM (measured:
- *                                  the former one-thread-per-node emit read 1.14 GB to write 0.6 GB,
- *                                  profiles/r01c_ncu_summary.txt).  Runs of levels that fit one tile (the top of the tree
- *                                  and the tail of a deep one) are processed by CTA 0 alone between two barriers.
+ *   2. collapse_number_kernel      one cooperative launch, every CTA resident, levels separated by a grid barrier (one atomic
+ *                                  counter).  One task = one wide node = one thread; a task record is the expansion of its
+ *                                  Bvh2 node (16 B) + the wide parent (4 B).  The tasks of a level are a contiguous index
+ *                                  range; CTA c owns chunk c of it.  It counts the internal children of its chunk (one
+ *                                  coalesced pass over records that are still in L2), posts the count in counts[c] (tagged
+ *                                  with the level, never reset), sums the counts of the chunks before it — all due at the
+ *                                  same moment: no chain of dependent look-backs — and then numbers its children
+ *                                  consecutively in (task, slot) order, appending their records (their expansions are
+ *                                  gathered meanwhile) and noting each task's first child index.  Runs of levels that fit one
+ *                                  tile (the top of the tree, the tail of a deep one) are processed by CTA 0 alone between
+ *                                  two barriers.
+ *   3. collapse_emit_kernel        one thread per wide node, no synchronisation: boxes of the internal children gathered
+ *                                  with L2::64B loads, the 128-byte node written through a swizzled shared-memory transpose
+ *                                  as full contiguous lines, PrimNode records for the leaf children.
  *
- * Traffic per primitive (10 M uniform): expansion 32 r + 16 w; ~0.47 wide nodes x (8 task + 32 expansion sector + ~32 child
- * boxes read, 128 node + 8 task written) + 8 PrimNode + 4 sorted value  ~ 160 B, of which ~133 B are compulsory.
+ * Traffic per primitive (10 M uniform): expansion 32 r + 16 w; ~0.47 wide nodes x (numbering: 2 x 16 record r + 16 expansion
+ * gathered + 24 record/first-child w; emit: 24 record r + 32 child box gathered + 128 node w) + 8 PrimNode + 4 sorted value
+ * ~ 180 B, of which ~133 B are compulsory; a gather moves 64 B of DRAM whatever it asks for.
  */
 #include "common.cuh"
 
 #define COL_THREADS 256
 
-/* scratch layout: CollapseCtrl (256 B) | uint4 expansion[n] | uint4 taskCh[n] | u32 taskParent[n] | u64 counts[G] */
+/* scratch layout: CollapseCtrl (256 B) | uint4 expansion[n] | uint4 taskCh[n] | u32 taskParent[n] | u32 firstChild[n] | u64 counts[G] */
 struct CollapseCtrl {
   u32 bar;        /* grid barrier: arrivals so far */
-  u32 pad[3];
+  u32 nWide;      /* result: number of wide nodes */
+  u32 pad[2];
   uint4 next[2];  /* {level, start, end, -}: the level to process after barrier b is published in next[b & 1] (a CTA that
                      leaves barrier b early may publish the level after it before a late CTA has read this one) */
 };
 
 size_t b2_collapse_scratch_bytes(u32 n) {
   /* one tagged count word per CTA, G <= 16 CTAs x 1024 SMs */
-  return 256 + (size_t)n * (2 * sizeof(uint4) + sizeof(u32)) + 8 + 16384 * sizeof(u64);
+  return 256 + (size_t)n * (2 * sizeof(uint4) + 2 * sizeof(u32)) + 16 + 16384 * sizeof(u64);
 }
 
 struct ColSmem {
-  uint4 stage[COL_THREADS * 8]; /* 256 wide nodes, 16-byte pieces, piece p of node t at t*8 + (p ^ (t & 7)) */
   u32 warpSum[3][COL_THREADS / 32];
-  u32 bcast[4];
 };
 
 __device__ __forceinline__ void grid_barrier(u32* bar, u32 target) {
@@ -114,36 +114,28 @@ __global__ void __launch_bounds__(COL_THREADS) collapse_expand_kernel(const b2bv
   expansion[i] = make_uint4(ch[0], ch[1], ch[2], ch[3]);
 }
 
-/* One tile of 256 tasks [tileStart, min(tileStart + 256, end)): expansion, numbering of the children from
- * childBase + (exclusive count inside the tile), child tasks, wide nodes, leaf records.  `prefixFn` supplies childBase once
- * the tile's own count is known.  Returns the tile's number of internal children (same value in every thread). */
+/* ---- 2. numbering.  One tile of 256 tasks [tileStart, min(tileStart + 256, end)): count the internal children, number them
+ * from childBase + (exclusive count inside the tile) in (task, slot) order and append their tasks (the children's expansions
+ * are gathered while the scan runs).  `prefixFn` supplies childBase once the tile's own count is known.  Returns the tile's
+ * number of internal children (same value in every thread). ---- */
 template <typename PrefixFn>
-__device__ __forceinline__ u32 collapse_tile(const b2bvh_bvh2_node* __restrict__ nodes, const uint4* __restrict__ expansion,
-                                             const u32* __restrict__ sortedVals, u32 nInt, uint4* taskCh, u32* taskParent,
-                                             b2bvh_bvh4_node* wide, b2bvh_prim_node* wideLeaves, ColSmem& S, u32 tileStart, u32 end, PrefixFn prefixFn) {
+__device__ __forceinline__ u32 number_tile(const uint4* __restrict__ expansion, u32 nInt, uint4* taskCh, u32* taskParent, u32* firstChild,
+                                           ColSmem& S, u32 tileStart, u32 end, PrefixFn prefixFn) {
   const u32 tid = threadIdx.x, w = tid >> 5, l = tid & 31u;
   const u32 g = tileStart + tid;
   const bool active = g < end;
   u32 ch[4] = {B2_INVALID, B2_INVALID, B2_INVALID, B2_INVALID};
-  u32 parent = B2_INVALID;
   if (active) {
     const uint4 t = __ldcg(taskCh + g); /* written by another CTA one level earlier */
-    parent = __ldcg(taskParent + g);
     ch[0] = t.x; ch[1] = t.y; ch[2] = t.z; ch[3] = t.w;
   }
-  const u32 nInternal = (ch[0] < nInt ? 1u : 0u) + (ch[1] < nInt ? 1u : 0u) + (ch[2] < nInt ? 1u : 0u) + (ch[3] < nInt ? 1u : 0u);
-  const u32 cc = (ch[0] != B2_INVALID ? 1u : 0u) + (ch[1] != B2_INVALID ? 1u : 0u) + (ch[2] != B2_INVALID ? 1u : 0u) + (ch[3] != B2_INVALID ? 1u : 0u);
-  /* internal children: their boxes (for this node) and their expansions (for their tasks) are gathered while the tile
-   * waits for its prefix; leaf slots keep the empty box (TwoPassLbvhKernel.h:320-325) */
-  Box box[4];
   uint4 childEx[4];
 #pragma unroll
   for (int k = 0; k < 4; k++) {
-    box[k] = box_empty();
     childEx[k] = make_uint4(0u, 0u, 0u, 0u);
-    if (ch[k] < nInt) { box[k] = load_node2_gather(nodes + ch[k]).box; childEx[k] = ldg_gather_u4(expansion + ch[k]); }
+    if (ch[k] < nInt) childEx[k] = ldg_gather_u4(expansion + ch[k]);
   }
-  /* CTA exclusive scan */
+  const u32 nInternal = (ch[0] < nInt ? 1u : 0u) + (ch[1] < nInt ? 1u : 0u) + (ch[2] < nInt ? 1u : 0u) + (ch[3] < nInt ? 1u : 0u);
   u32 incl = nInternal;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -155,64 +147,23 @@ __device__ __forceinline__ u32 collapse_tile(const b2bvh_bvh2_node* __restrict__
   u32 warpBase = 0, tileTotal = 0;
 #pragma unroll
   for (int k = 0; k < COL_THREADS / 32; k++) { const u32 v = S.warpSum[0][k]; if (k < (int)w) warpBase += v; tileTotal += v; }
-  const u32 childBase = prefixFn(tileTotal); /* contains CTA barriers */
+  const u32 childBase = prefixFn(tileTotal);
   u32 nextId = childBase + warpBase + incl - nInternal;
-
-  /* ---- children: tasks for the internal ones, leaf records for the others; the node into the transpose buffer ---- */
-  u32 outChild[4];
+  if (active) firstChild[g] = nextId;
 #pragma unroll
-  for (int k = 0; k < 4; k++) {
-    outChild[k] = ch[k];
-    if (ch[k] != B2_INVALID) {
-      if (ch[k] < nInt) {
-        outChild[k] = nextId;
-        taskCh[nextId] = childEx[k];
-        taskParent[nextId] = g;
-        nextId++;
-      } else {
-        const u32 slot = ch[k] - nInt;
-        /* leaf slot s holds primitive sortedVals[s] in both layouts (Bvh2 leaf m_leftChildIdx / PrimRef m_primIdx) */
-        reinterpret_cast<uint2*>(wideLeaves)[slot] = make_uint2(ldg_gather_u32(sortedVals + slot), g);
-      }
+  for (int k = 0; k < 4; k++)
+    if (ch[k] < nInt) {
+      taskCh[nextId] = childEx[k];
+      taskParent[nextId] = g;
+      nextId++;
     }
-  }
-  {
-    const u32 sw = tid & 7u;
-    uint4* row = S.stage + tid * 8;
-    const Box &b0 = box[0], &b1 = box[1], &b2 = box[2], &b3 = box[3];
-#define FU(x) __float_as_uint(x)
-    row[0 ^ sw] = make_uint4(FU(b0.lx), FU(b0.ly), FU(b0.lz), FU(b0.hx));
-    row[1 ^ sw] = make_uint4(FU(b0.hy), FU(b0.hz), FU(b1.lx), FU(b1.ly));
-    row[2 ^ sw] = make_uint4(FU(b1.lz), FU(b1.hx), FU(b1.hy), FU(b1.hz));
-    row[3 ^ sw] = make_uint4(FU(b2.lx), FU(b2.ly), FU(b2.lz), FU(b2.hx));
-    row[4 ^ sw] = make_uint4(FU(b2.hy), FU(b2.hz), FU(b3.lx), FU(b3.ly));
-    row[5 ^ sw] = make_uint4(FU(b3.lz), FU(b3.hx), FU(b3.hy), FU(b3.hz));
-    row[6 ^ sw] = make_uint4(outChild[0], outChild[1], outChild[2], outChild[3]);
-    row[7 ^ sw] = make_uint4(parent, cc, 0u, 0u);
-#undef FU
-  }
-  __syncthreads();
-  /* ---- 256 nodes x 128 B leave as contiguous 16-byte pieces: every warp store covers whole lines ---- */
-  {
-    const u32 valid = min((u32)COL_THREADS, end - tileStart) * 8u;
-    uint4* out = reinterpret_cast<uint4*>(wide + tileStart);
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-      const u32 q = (u32)i * COL_THREADS + tid;
-      const u32 node = q >> 3, part = q & 7u;
-      if (q < valid) out[q] = S.stage[node * 8 + (part ^ (node & 7u))];
-    }
-  }
-  __syncthreads(); /* stage / warpSum are reused by the next tile */
+  __syncthreads(); /* warpSum is reused by the next tile */
   return tileTotal;
 }
 
-__global__ void __launch_bounds__(COL_THREADS, 4) collapse_persistent_kernel(const b2bvh_bvh2_node* __restrict__ nodes, const uint4* __restrict__ expansion,
-                                                                            const u32* __restrict__ sortedVals, u32 nInt, const u32* __restrict__ rootIdx, uint4* taskCh, u32* taskParent,
-                                                                            b2bvh_bvh4_node* wide, b2bvh_prim_node* wideLeaves, CollapseCtrl* ctrl,
-                                                                            u64* counts) {
-  extern __shared__ __align__(16) unsigned char smemRaw[];
-  ColSmem& S = *reinterpret_cast<ColSmem*>(smemRaw);
+__global__ void __launch_bounds__(COL_THREADS, 6) collapse_number_kernel(const uint4* __restrict__ expansion, u32 nInt, const u32* __restrict__ rootIdx,
+                                                                        uint4* taskCh, u32* taskParent, u32* firstChild, CollapseCtrl* ctrl, u64* counts) {
+  __shared__ ColSmem S;
   const u32 G = gridDim.x, c = blockIdx.x, tid = threadIdx.x, w = tid >> 5, l = tid & 31u;
   u32 level = 0, start = 0, end = 1, barriers = 0;
   if (c == 0 && tid == 0) { taskCh[0] = __ldg(expansion + *rootIdx); taskParent[0] = B2_INVALID; }
@@ -226,7 +177,7 @@ __global__ void __launch_bounds__(COL_THREADS, 4) collapse_persistent_kernel(con
       if (c == 0) {
         do {
           const u32 e = end;
-          const u32 total = collapse_tile(nodes, expansion, sortedVals, nInt, taskCh, taskParent, wide, wideLeaves, S, start, end, [e](u32) { return e; });
+          const u32 total = number_tile(expansion, nInt, taskCh, taskParent, firstChild, S, start, end, [e](u32) { return e; });
           start = end; end += total; level++;
         } while (end - start <= COL_THREADS && end != start);
         if (tid == 0) publish_level(ctrl, barriers + 1u, level, start, end);
@@ -269,8 +220,8 @@ __global__ void __launch_bounds__(COL_THREADS, 4) collapse_persistent_kernel(con
         if (c == nActive - 1 && tid == 0) publish_level(ctrl, barriers + 1u, level + 1u, end, running + chunkTotal); /* last chunk of the level */
         /* C. the chunk tile by tile: no CTA waits for another one here */
         for (u32 tileStart = cStart; tileStart < cEnd; tileStart += COL_THREADS)
-          collapse_tile(nodes, expansion, sortedVals, nInt, taskCh, taskParent, wide, wideLeaves, S, tileStart, cEnd,
-                        [&running](u32 tileTotal) { const u32 b = running; running += tileTotal; return b; });
+          number_tile(expansion, nInt, taskCh, taskParent, firstChild, S, tileStart, cEnd,
+                      [&running](u32 tileTotal) { const u32 b = running; running += tileTotal; return b; });
       }
     }
     barriers++;
@@ -280,6 +231,82 @@ __global__ void __launch_bounds__(COL_THREADS, 4) collapse_persistent_kernel(con
       level = ld_relaxed(nx); start = ld_relaxed(nx + 1); end = ld_relaxed(nx + 2);
     }
   }
+  if (c == 0 && tid == 0) ctrl->nWide = end;
+}
+
+/* ---- 3. wide nodes + leaf records: one thread per wide node, no synchronisation between CTAs.  Boxes of the internal
+ * children are gathered (leaf slots keep the empty box, TwoPassLbvhKernel.h:320-325); the 128-byte node goes out through a
+ * swizzled shared-memory transpose as full, contiguous lines (eight 16-byte stores per thread at a 128-byte stride run at a
+ * third of the speed, tools/micro/mem_micro.cu). ---- */
+struct EmitSmem {
+  uint4 stage[COL_THREADS * 8]; /* 256 wide nodes, 16-byte pieces, piece p of node t at t*8 + (p ^ (t & 7)) */
+};
+
+__global__ void __launch_bounds__(COL_THREADS, 5) collapse_emit_kernel(const b2bvh_bvh2_node* __restrict__ nodes, const u32* __restrict__ sortedVals, u32 nInt,
+                                                                      const uint4* __restrict__ taskCh, const u32* __restrict__ taskParent,
+                                                                      const u32* __restrict__ firstChild, const CollapseCtrl* __restrict__ ctrl,
+                                                                      b2bvh_bvh4_node* __restrict__ wide, b2bvh_prim_node* __restrict__ wideLeaves) {
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  EmitSmem& S = *reinterpret_cast<EmitSmem*>(smemRaw);
+  const u32 nWide = ctrl->nWide, tid = threadIdx.x;
+  for (u32 tileStart = blockIdx.x * COL_THREADS; tileStart < nWide; tileStart += gridDim.x * COL_THREADS) {
+    const u32 g = tileStart + tid;
+    u32 ch[4] = {B2_INVALID, B2_INVALID, B2_INVALID, B2_INVALID};
+    u32 parent = B2_INVALID, nextId = 0;
+    if (g < nWide) {
+      const uint4 t = __ldg(taskCh + g);
+      parent = __ldg(taskParent + g);
+      nextId = __ldg(firstChild + g);
+      ch[0] = t.x; ch[1] = t.y; ch[2] = t.z; ch[3] = t.w;
+    }
+    Box box[4];
+    u32 prim[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      box[k] = box_empty();
+      prim[k] = 0;
+      if (ch[k] < nInt) box[k] = load_node2_gather(nodes + ch[k]).box;
+      /* leaf slot s holds primitive sortedVals[s] in both layouts (Bvh2 leaf m_leftChildIdx / PrimRef m_primIdx) */
+      else if (ch[k] != B2_INVALID) prim[k] = ldg_gather_u32(sortedVals + (ch[k] - nInt));
+    }
+    u32 outChild[4], cc = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      outChild[k] = ch[k];
+      if (ch[k] != B2_INVALID) {
+        cc++;
+        if (ch[k] < nInt) outChild[k] = nextId++;
+        else reinterpret_cast<uint2*>(wideLeaves)[ch[k] - nInt] = make_uint2(prim[k], g);
+      }
+    }
+    {
+      const u32 sw = tid & 7u;
+      uint4* row = S.stage + tid * 8;
+      const Box &b0 = box[0], &b1 = box[1], &b2 = box[2], &b3 = box[3];
+#define FU(x) __float_as_uint(x)
+      row[0 ^ sw] = make_uint4(FU(b0.lx), FU(b0.ly), FU(b0.lz), FU(b0.hx));
+      row[1 ^ sw] = make_uint4(FU(b0.hy), FU(b0.hz), FU(b1.lx), FU(b1.ly));
+      row[2 ^ sw] = make_uint4(FU(b1.lz), FU(b1.hx), FU(b1.hy), FU(b1.hz));
+      row[3 ^ sw] = make_uint4(FU(b2.lx), FU(b2.ly), FU(b2.lz), FU(b2.hx));
+      row[4 ^ sw] = make_uint4(FU(b2.hy), FU(b2.hz), FU(b3.lx), FU(b3.ly));
+      row[5 ^ sw] = make_uint4(FU(b3.lz), FU(b3.hx), FU(b3.hy), FU(b3.hz));
+      row[6 ^ sw] = make_uint4(outChild[0], outChild[1], outChild[2], outChild[3]);
+      row[7 ^ sw] = make_uint4(parent, cc, 0u, 0u);
+#undef FU
+    }
+    __syncthreads();
+    {
+      const u32 valid = min((u32)COL_THREADS, nWide - tileStart) * 8u;
+      uint4* out = reinterpret_cast<uint4*>(wide + tileStart);
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const u32 q = (u32)i * COL_THREADS + tid;
+        const u32 node = q >> 3, part = q & 7u;
+        if (q < valid) out[q] = S.stage[node * 8 + (part ^ (node & 7u))];
+      }
+    }
+    __syncthreads(); /* the transpose buffer is reused by the next tile */
+  }
 }
 
 int b2_launch_collapse(b2bvh_ctx* ctx, const b2bvh_bvh2_node* d_nodes, const b2bvh_prim_ref* d_leaves, const u32* d_sortedVals, const u32* d_rootIdx, u32 n,
@@ -287,10 +314,10 @@ int b2_launch_collapse(b2bvh_ctx* ctx, const b2bvh_bvh2_node* d_nodes, const b2b
   (void)d_leaves; /* both layouts name leaves by slot; the primitive index comes from the sorted value array */
   if (n < 2) return b2_fail(B2BVH_ERR_INVALID, "collapse needs at least 2 primitives");
   static int occ = 0;
-  const size_t smem = sizeof(ColSmem);
+  const size_t emitSmem = sizeof(EmitSmem);
   if (!occ) {
-    B2_CUDA(cudaFuncSetAttribute(collapse_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, collapse_persistent_kernel, COL_THREADS, smem));
+    B2_CUDA(cudaFuncSetAttribute(collapse_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emitSmem));
+    B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, collapse_number_kernel, COL_THREADS, 0));
     if (occ < 1) return b2_fail(B2BVH_ERR_INTERNAL, "collapse: kernel does not fit on an SM");
   }
   /* every CTA must be resident (grid barrier): at most SMs x occupancy; small inputs use fewer CTAs (cheaper barriers) */
@@ -303,22 +330,28 @@ int b2_launch_collapse(b2bvh_ctx* ctx, const b2bvh_bvh2_node* d_nodes, const b2b
   uint4* expansion = reinterpret_cast<uint4*>(base + 256);
   uint4* taskCh = reinterpret_cast<uint4*>(base + 256 + (size_t)n * sizeof(uint4));
   u32* taskParent = reinterpret_cast<u32*>(base + 256 + (size_t)n * 2 * sizeof(uint4));
-  u64* counts = reinterpret_cast<u64*>(taskParent + ((n + 1u) & ~1u)); /* one tagged word per CTA */
+  u32* firstChild = taskParent + n;
+  u64* counts = reinterpret_cast<u64*>(firstChild + n); /* one tagged word per CTA; 2n words after a 16-byte aligned start */
   u32 nInt = n - 1;
   B2_CUDA(cudaMemsetAsync(ctrl, 0, 256, ctx->stream));
   B2_CUDA(cudaMemsetAsync(counts, 0, (size_t)grid * sizeof(u64), ctx->stream));
   B2_KERNEL(ctx, "collapse_expand");
   collapse_expand_kernel<<<(nInt + COL_THREADS - 1) / COL_THREADS, COL_THREADS, 0, ctx->stream>>>(d_nodes, nInt, expansion);
   B2_LAUNCH_CHECK(ctx);
-  B2_KERNEL(ctx, "collapse_levels");
-  void* args[] = {(void*)&d_nodes, (void*)&expansion, (void*)&d_sortedVals, (void*)&nInt, (void*)&d_rootIdx, (void*)&taskCh, (void*)&taskParent, (void*)&d_wide, (void*)&d_wideLeaves, (void*)&ctrl, (void*)&counts};
-  B2_CUDA(cudaLaunchCooperativeKernel((const void*)collapse_persistent_kernel, dim3(grid), dim3(COL_THREADS), args, smem, ctx->stream));
+  B2_KERNEL(ctx, "collapse_number");
+  void* args[] = {(void*)&expansion, (void*)&nInt, (void*)&d_rootIdx, (void*)&taskCh, (void*)&taskParent, (void*)&firstChild, (void*)&ctrl, (void*)&counts};
+  B2_CUDA(cudaLaunchCooperativeKernel((const void*)collapse_number_kernel, dim3(grid), dim3(COL_THREADS), args, 0, ctx->stream));
+  B2_LAUNCH_CHECK(ctx);
+  /* the number of wide nodes stays on the device: the emit grid is sized for the worst case and strides over ctrl->nWide */
+  u32 egrid = (nInt + COL_THREADS - 1) / COL_THREADS;
+  const u32 ecap = (u32)ctx->sm_count * 10u;
+  if (egrid > ecap) egrid = ecap;
+  B2_KERNEL(ctx, "collapse_emit");
+  collapse_emit_kernel<<<egrid, COL_THREADS, emitSmem, ctx->stream>>>(d_nodes, d_sortedVals, nInt, taskCh, taskParent, firstChild, ctrl, d_wide, d_wideLeaves);
   B2_LAUNCH_CHECK(ctx);
   CollapseCtrl h;
   B2_CUDA(cudaMemcpyAsync(&h, ctrl, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
   B2_CUDA(cudaStreamSynchronize(ctx->stream));
-  /* the loop ends after reading an empty level from next[b & 1]: its start == end == number of wide nodes (both slots agree on it
-     only by accident, so take the larger end) */
-  *h_nWide = h.next[0].z > h.next[1].z ? h.next[0].z : h.next[1].z;
+  *h_nWide = h.nWide;
   return 0;
 }

@@ -148,6 +148,17 @@ __device__ __forceinline__ u32 lanemask_lt() {
   return m;
 }
 
+/* A CTA's contiguous output staged as 32-bit words in shared memory leaves as 16-byte stores covering whole sectors
+ * (records of 24 or 28 bytes written field by field from one thread each cost one partial-sector store per field).
+ * `dst` must be 16-byte aligned; all threads of the CTA call it after a __syncthreads(). */
+__device__ __forceinline__ void cta_store_words(u32* dst, const u32* smemWords, u32 nWords) {
+  const u32 n4 = nWords >> 2;
+  uint4* d4 = reinterpret_cast<uint4*>(dst);
+  const uint4* s4 = reinterpret_cast<const uint4*>(smemWords);
+  for (u32 q = threadIdx.x; q < n4; q += blockDim.x) d4[q] = s4[q];
+  for (u32 q = (n4 << 2) + threadIdx.x; q < nWords; q += blockDim.x) dst[q] = smemWords[q];
+}
+
 /* ------------------------------------------------------------------ host side */
 struct b2bvh_ctx {
   int device;

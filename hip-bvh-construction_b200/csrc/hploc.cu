@@ -33,16 +33,22 @@ size_t b2_hploc_scratch_bytes(u32 n) { return 256 + 3 * (size_t)n * 4; }
 __global__ void __launch_bounds__(256) hploc_setup_kernel(const b2bvh_aabb* __restrict__ triAabb, const u32* __restrict__ sortedVals, u32 n,
                                                           b2bvh_prim_ref* __restrict__ leaves, u32* __restrict__ nodeIdx, u32* __restrict__ freeIdx,
                                                           u32* __restrict__ meet, u32* ctrl) {
-  const u32 g = blockIdx.x * 256 + threadIdx.x;
+  __shared__ __align__(16) u32 sLeaf[256 * 7];
+  const u32 t = threadIdx.x, g0 = blockIdx.x * 256, g = g0 + t;
   if (g < 8) ctrl[g] = (g == 1) ? B2_INVALID : 0u;
-  if (g >= n) return;
-  const u32 prim = __ldg(sortedVals + g);
-  const Box b = load_aabb(triAabb + prim);
-  float* l = reinterpret_cast<float*>(leaves + g);
-  l[0] = __uint_as_float(prim); l[1] = b.lx; l[2] = b.ly; l[3] = b.lz; l[4] = b.hx; l[5] = b.hy; l[6] = b.hz;
-  nodeIdx[g] = g + (n - 1);
-  freeIdx[g] = g ? g - 1 : B2_INVALID;
-  meet[g] = B2_INVALID;
+  if (g < n) {
+    const u32 prim = __ldg(sortedVals + g);
+    const float2* bp = reinterpret_cast<const float2*>(triAabb + prim); /* 24-byte boxes: 8-byte aligned */
+    const float2 q0 = ldg_gather_f2(bp), q1 = ldg_gather_f2(bp + 1), q2 = ldg_gather_f2(bp + 2);
+    u32* l = sLeaf + t * 7;
+    l[0] = prim; l[1] = __float_as_uint(q0.x); l[2] = __float_as_uint(q0.y); l[3] = __float_as_uint(q1.x); l[4] = __float_as_uint(q1.y);
+    l[5] = __float_as_uint(q2.x); l[6] = __float_as_uint(q2.y);
+    nodeIdx[g] = g + (n - 1);
+    freeIdx[g] = g ? g - 1 : B2_INVALID;
+    meet[g] = B2_INVALID;
+  }
+  __syncthreads();
+  cta_store_words(reinterpret_cast<u32*>(leaves + g0), sLeaf, min(256u, n - g0) * 7); /* 256 x 28 B = 7168 B per CTA: 16-byte aligned */
 }
 
 __device__ __forceinline__ Box shfl_box(const Box& b, int src) {

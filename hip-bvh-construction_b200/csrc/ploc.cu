@@ -57,15 +57,25 @@ size_t b2_ploc_scratch_bytes(u32 n) {
 __global__ void __launch_bounds__(256) ploc_setup_kernel(const b2bvh_aabb* __restrict__ triAabb, const u32* __restrict__ sortedVals, u32 n,
                                                          b2bvh_prim_ref* __restrict__ leaves, u32* __restrict__ ids, b2bvh_aabb* __restrict__ boxes,
                                                          PlocCtrl* ctrl) {
-  const u32 g = blockIdx.x * 256 + threadIdx.x;
+  __shared__ __align__(16) u32 sLeaf[256 * 7];
+  __shared__ __align__(16) u32 sBox[256 * 6];
+  const u32 t = threadIdx.x, g0 = blockIdx.x * 256, g = g0 + t;
   if (g == 0) { ctrl->count[0] = n; ctrl->count[1] = n; ctrl->ticket[0] = ctrl->ticket[1] = 0; ctrl->itersRun = 0; ctrl->liveBuf = 0; }
-  if (g >= n) return;
-  const u32 prim = __ldg(sortedVals + g);
-  const Box b = load_aabb(triAabb + prim);
-  float* l = reinterpret_cast<float*>(leaves + g);
-  l[0] = __uint_as_float(prim); l[1] = b.lx; l[2] = b.ly; l[3] = b.lz; l[4] = b.hx; l[5] = b.hy; l[6] = b.hz;
-  ids[g] = g + (n - 1);
-  store_aabb(boxes + g, b);
+  if (g < n) {
+    const u32 prim = __ldg(sortedVals + g);
+    const float2* bp = reinterpret_cast<const float2*>(triAabb + prim); /* 24-byte boxes: 8-byte aligned */
+    const float2 q0 = ldg_gather_f2(bp), q1 = ldg_gather_f2(bp + 1), q2 = ldg_gather_f2(bp + 2);
+    u32* l = sLeaf + t * 7;
+    l[0] = prim; l[1] = __float_as_uint(q0.x); l[2] = __float_as_uint(q0.y); l[3] = __float_as_uint(q1.x); l[4] = __float_as_uint(q1.y);
+    l[5] = __float_as_uint(q2.x); l[6] = __float_as_uint(q2.y);
+    u32* bx = sBox + t * 6;
+    bx[0] = l[1]; bx[1] = l[2]; bx[2] = l[3]; bx[3] = l[4]; bx[4] = l[5]; bx[5] = l[6];
+    ids[g] = g + (n - 1);
+  }
+  __syncthreads();
+  const u32 cnt = min(256u, n - g0);
+  cta_store_words(reinterpret_cast<u32*>(leaves + g0), sLeaf, cnt * 7); /* 256 x 28 B = 7168 B per CTA: 16-byte aligned */
+  cta_store_words(reinterpret_cast<u32*>(boxes + g0), sBox, cnt * 6);
 }
 
 /* ---- TMA bulk copy helpers (same PTX as radix_sort.cu) ---- */

@@ -14,7 +14,7 @@ for K in "$@"; do
     *) ALGO=singlepass;;
   esac
   case $K in
-    collapse_number) CNT="-s 6 -c 10";;
+    collapse_number) CNT="-c 1";;
     radix_scatter|radix_count) CNT="-c 4";;
     ploc_iter) CNT="-c 5";;
     onesweep_pass) CNT="-c 4";;
