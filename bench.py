@@ -40,7 +40,7 @@ ALGO_BYTES = {
     "lbvh_fused_apetrei": 132,      # 4 value + 4 key + 28 gathered box (24 B payload) + 32 leaf node + 32 internal node + ~32 hand-over/climb
     "lbvh_fused_karras": 140,       # + 8 parent indices
     "collapse_expand": 48,          # 32 node read + 16 expansion written, per internal Bvh2 node
-    "collapse_number": 34,          # 0.466 wide nodes/prim x (2 x 16 task record r + 16 expansion gathered + 24 record/first child w)
+    "collapse_number": 32,          # 0.466 wide nodes/prim x (8 task r + 16 expansion gathered + 16 record w + 16 record r + 12 task/first child w)
     "collapse_emit": 98,            # 0.466 x (24 record r + 32 box gathered + 128 node w) + 8 PrimNode + 4 value
 }
 

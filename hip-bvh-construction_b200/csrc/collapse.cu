@@ -12,29 +12,29 @@
  *                                  the first of equals wins, areas without FMA).  One thread per node, no synchronisation,
  *                                  16 B out.  Keeps the dependent node reads out of the level-synchronous part.
  *   2. collapse_number_kernel      one cooperative launch, every CTA resident, levels separated by a grid barrier (one atomic
- *                                  counter).  One task = one wide node = one thread; a task record is the expansion of its
- *                                  Bvh2 node (16 B) + the wide parent (4 B).  The tasks of a level are a contiguous index
- *                                  range; CTA c owns chunk c of it.  It counts the internal children of its chunk (one
- *                                  coalesced pass over records that are still in L2), posts the count in counts[c] (tagged
- *                                  with the level, never reset), sums the counts of the chunks before it — all due at the
- *                                  same moment: no chain of dependent look-backs — and then numbers its children
- *                                  consecutively in (task, slot) order, appending their records (their expansions are
- *                                  gathered meanwhile) and noting each task's first child index.  Runs of levels that fit one
- *                                  tile (the top of the tree, the tail of a deep one) are processed by CTA 0 alone between
- *                                  two barriers.
+ *                                  counter).  One task = one wide node = one thread; a task is (Bvh2 node, wide parent).
+ *                                  The tasks of a level are a contiguous index range; CTA c owns chunk c of it.  Pass A
+ *                                  copies the expansion of every task's node into the task's record (the gathers of the
+ *                                  whole chunk are independent and overlap) and counts the internal children; the CTA posts
+ *                                  the count in counts[c] (tagged with the level, never reset) and sums the counts of the
+ *                                  chunks before it — all due at the same moment: no chain of dependent look-backs.  Pass C
+ *                                  numbers the children consecutively in (task, slot) order, appends their tasks and notes
+ *                                  each task's first child index.  Runs of levels that fit one tile (the top of the tree,
+ *                                  the tail of a deep one) are processed by CTA 0 alone between two barriers.
  *   3. collapse_emit_kernel        one thread per wide node, no synchronisation: boxes of the internal children gathered
  *                                  with L2::64B loads, the 128-byte node written through a swizzled shared-memory transpose
  *                                  as full contiguous lines, PrimNode records for the leaf children.
  *
- * Traffic per primitive (10 M uniform): expansion 32 r + 16 w; ~0.47 wide nodes x (numbering: 2 x 16 record r + 16 expansion
- * gathered + 24 record/first-child w; emit: 24 record r + 32 child box gathered + 128 node w) + 8 PrimNode + 4 sorted value
- * ~ 180 B, of which ~133 B are compulsory; a gather moves 64 B of DRAM whatever it asks for.
+ * Traffic per primitive (10 M uniform): expansion 32 r + 16 w; ~0.47 wide nodes x (numbering: 8 task r + 16 expansion gathered
+ * + 16 record w + 16 record r + 12 task/first-child w; emit: 24 record r + 32 child box gathered + 128 node w) + 8 PrimNode
+ * + 4 sorted value ~ 180 B, of which ~133 B are compulsory; a gather moves 64 B of DRAM whatever it asks for.
  */
 #include "common.cuh"
 
 #define COL_THREADS 256
+#define NUM_THREADS 256  /* numbering kernel (1024-thread CTAs make the grid barrier cheaper but the tile loop slower: measured a wash) */
 
-/* scratch layout: CollapseCtrl (256 B) | uint4 expansion[n] | uint4 taskCh[n] | u32 taskParent[n] | u32 firstChild[n] | u64 counts[G] */
+/* scratch layout: CollapseCtrl (256 B) | uint4 expansion[n] | uint4 taskCh[n] | u32 taskParent[n] | u32 firstChild[n] | u32 taskNode[n] | u64 counts[G] */
 struct CollapseCtrl {
   u32 bar;        /* grid barrier: arrivals so far */
   u32 nWide;      /* result: number of wide nodes */
@@ -45,11 +45,11 @@ struct CollapseCtrl {
 
 size_t b2_collapse_scratch_bytes(u32 n) {
   /* one tagged count word per CTA, G <= 16 CTAs x 1024 SMs */
-  return 256 + (size_t)n * (2 * sizeof(uint4) + 2 * sizeof(u32)) + 16 + 16384 * sizeof(u64);
+  return 256 + (size_t)n * (2 * sizeof(uint4) + 3 * sizeof(u32)) + 16 + 16384 * sizeof(u64);
 }
 
 struct ColSmem {
-  u32 warpSum[3][COL_THREADS / 32];
+  u32 warpSum[3][NUM_THREADS / 32];
 };
 
 __device__ __forceinline__ void grid_barrier(u32* bar, u32 target) {
@@ -114,28 +114,45 @@ __global__ void __launch_bounds__(COL_THREADS) collapse_expand_kernel(const b2bv
   expansion[i] = make_uint4(ch[0], ch[1], ch[2], ch[3]);
 }
 
-/* ---- 2. numbering.  One tile of 256 tasks [tileStart, min(tileStart + 256, end)): count the internal children, number them
- * from childBase + (exclusive count inside the tile) in (task, slot) order and append their tasks (the children's expansions
- * are gathered while the scan runs).  `prefixFn` supplies childBase once the tile's own count is known.  Returns the tile's
- * number of internal children (same value in every thread). ---- */
-template <typename PrefixFn>
-__device__ __forceinline__ u32 number_tile(const uint4* __restrict__ expansion, u32 nInt, uint4* taskCh, u32* taskParent, u32* firstChild,
-                                           ColSmem& S, u32 tileStart, u32 end, PrefixFn prefixFn) {
+/* ---- 2. numbering ---- */
+__device__ __forceinline__ u32 count_internal(const uint4& t, u32 nInt) {
+  return (t.x < nInt ? 1u : 0u) + (t.y < nInt ? 1u : 0u) + (t.z < nInt ? 1u : 0u) + (t.w < nInt ? 1u : 0u);
+}
+
+/* A. tasks [a, b): fetch the expansion of each task's Bvh2 node into its record and count the internal children.  The
+ * iterations are independent, so the gathers of several tiles are in flight together (four per thread). */
+__device__ __forceinline__ u32 number_fetch(const uint4* __restrict__ expansion, u32 nInt, const u32* taskNode, uint4* taskCh, u32 a, u32 b) {
+  u32 cnt = 0;
+  u32 g = a + threadIdx.x;
+  for (; g + 3 * NUM_THREADS < b; g += 4 * NUM_THREADS) {
+    u32 nd[4];
+    uint4 ex[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) nd[k] = __ldcg(taskNode + g + k * NUM_THREADS); /* written by another CTA one level earlier */
+#pragma unroll
+    for (int k = 0; k < 4; k++) ex[k] = ldg_gather_u4(expansion + nd[k]);
+#pragma unroll
+    for (int k = 0; k < 4; k++) { taskCh[g + k * NUM_THREADS] = ex[k]; cnt += count_internal(ex[k], nInt); }
+  }
+  for (; g < b; g += NUM_THREADS) {
+    const uint4 ex = ldg_gather_u4(expansion + __ldcg(taskNode + g));
+    taskCh[g] = ex;
+    cnt += count_internal(ex, nInt);
+  }
+  return cnt;
+}
+
+/* C. one tile of NUM_THREADS tasks [tileStart, min(tileStart + NUM_THREADS, end)): number the internal children from
+ * childBase + (exclusive count inside the tile) in (task, slot) order and append their tasks.  The records were written by
+ * the same threads in number_fetch.  Returns the tile's number of internal children (same value in every thread). */
+__device__ __forceinline__ u32 number_tile(u32 nInt, u32* taskNode, const uint4* taskCh, u32* taskParent, u32* firstChild, ColSmem& S, u32 tileStart,
+                                           u32 end, u32 childBase) {
   const u32 tid = threadIdx.x, w = tid >> 5, l = tid & 31u;
   const u32 g = tileStart + tid;
   const bool active = g < end;
-  u32 ch[4] = {B2_INVALID, B2_INVALID, B2_INVALID, B2_INVALID};
-  if (active) {
-    const uint4 t = __ldcg(taskCh + g); /* written by another CTA one level earlier */
-    ch[0] = t.x; ch[1] = t.y; ch[2] = t.z; ch[3] = t.w;
-  }
-  uint4 childEx[4];
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    childEx[k] = make_uint4(0u, 0u, 0u, 0u);
-    if (ch[k] < nInt) childEx[k] = ldg_gather_u4(expansion + ch[k]);
-  }
-  const u32 nInternal = (ch[0] < nInt ? 1u : 0u) + (ch[1] < nInt ? 1u : 0u) + (ch[2] < nInt ? 1u : 0u) + (ch[3] < nInt ? 1u : 0u);
+  uint4 t = make_uint4(B2_INVALID, B2_INVALID, B2_INVALID, B2_INVALID);
+  if (active) t = taskCh[g];
+  const u32 nInternal = count_internal(t, nInt);
   u32 incl = nInternal;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -146,14 +163,14 @@ __device__ __forceinline__ u32 number_tile(const uint4* __restrict__ expansion, 
   __syncthreads();
   u32 warpBase = 0, tileTotal = 0;
 #pragma unroll
-  for (int k = 0; k < COL_THREADS / 32; k++) { const u32 v = S.warpSum[0][k]; if (k < (int)w) warpBase += v; tileTotal += v; }
-  const u32 childBase = prefixFn(tileTotal);
+  for (int k = 0; k < NUM_THREADS / 32; k++) { const u32 v = S.warpSum[0][k]; if (k < (int)w) warpBase += v; tileTotal += v; }
   u32 nextId = childBase + warpBase + incl - nInternal;
   if (active) firstChild[g] = nextId;
+  const u32 ch[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
   for (int k = 0; k < 4; k++)
     if (ch[k] < nInt) {
-      taskCh[nextId] = childEx[k];
+      taskNode[nextId] = ch[k];
       taskParent[nextId] = g;
       nextId++;
     }
@@ -161,51 +178,48 @@ __device__ __forceinline__ u32 number_tile(const uint4* __restrict__ expansion, 
   return tileTotal;
 }
 
-__global__ void __launch_bounds__(COL_THREADS, 6) collapse_number_kernel(const uint4* __restrict__ expansion, u32 nInt, const u32* __restrict__ rootIdx,
-                                                                        uint4* taskCh, u32* taskParent, u32* firstChild, CollapseCtrl* ctrl, u64* counts) {
+__global__ void __launch_bounds__(NUM_THREADS, 6) collapse_number_kernel(const uint4* __restrict__ expansion, u32 nInt, const u32* __restrict__ rootIdx,
+                                                                        u32* taskNode, uint4* taskCh, u32* taskParent, u32* firstChild,
+                                                                        CollapseCtrl* ctrl, u64* counts) {
   __shared__ ColSmem S;
   const u32 G = gridDim.x, c = blockIdx.x, tid = threadIdx.x, w = tid >> 5, l = tid & 31u;
   u32 level = 0, start = 0, end = 1, barriers = 0;
-  if (c == 0 && tid == 0) { taskCh[0] = __ldg(expansion + *rootIdx); taskParent[0] = B2_INVALID; }
+  if (c == 0 && tid == 0) { taskNode[0] = *rootIdx; taskParent[0] = B2_INVALID; }
   __syncthreads();
 
   while (true) {
     const u32 size = end - start;
     if (size == 0) break;
-    if (size <= COL_THREADS) {
+    if (size <= NUM_THREADS) {
       /* ---- a run of one-tile levels: CTA 0 alone, no grid barrier in between ---- */
       if (c == 0) {
         do {
-          const u32 e = end;
-          const u32 total = number_tile(expansion, nInt, taskCh, taskParent, firstChild, S, start, end, [e](u32) { return e; });
+          number_fetch(expansion, nInt, taskNode, taskCh, start, end);
+          const u32 total = number_tile(nInt, taskNode, taskCh, taskParent, firstChild, S, start, end, end);
           start = end; end += total; level++;
-        } while (end - start <= COL_THREADS && end != start);
+        } while (end - start <= NUM_THREADS && end != start);
         if (tid == 0) publish_level(ctrl, barriers + 1u, level, start, end);
       }
     } else {
       /* ---- a level of many tiles: CTA c owns the contiguous chunk c of the level ---- */
-      const u32 chunk = ((size + G - 1) / G + COL_THREADS - 1) / COL_THREADS * COL_THREADS;
+      const u32 chunk = ((size + G - 1) / G + NUM_THREADS - 1) / NUM_THREADS * NUM_THREADS;
       const u32 nActive = (size + chunk - 1) / chunk;
       if (c < nActive) {
         const u32 cStart = start + c * chunk, cEnd = min(end, cStart + chunk);
-        /* A. internal children of the whole chunk (16 B per task, coalesced, L2-resident: written one level earlier) */
-        u32 cnt = 0;
-        for (u32 g = cStart + tid; g < cEnd; g += COL_THREADS) {
-          const uint4 t = __ldcg(taskCh + g);
-          cnt += (t.x < nInt ? 1u : 0u) + (t.y < nInt ? 1u : 0u) + (t.z < nInt ? 1u : 0u) + (t.w < nInt ? 1u : 0u);
-        }
+        /* A. records + internal children of the whole chunk */
+        u32 cnt = number_fetch(expansion, nInt, taskNode, taskCh, cStart, cEnd);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(B2_FULL, cnt, o);
         if (l == 0) S.warpSum[1][w] = cnt;
         __syncthreads();
         u32 chunkTotal = 0;
 #pragma unroll
-        for (int q = 0; q < COL_THREADS / 32; q++) chunkTotal += S.warpSum[1][q];
+        for (int q = 0; q < NUM_THREADS / 32; q++) chunkTotal += S.warpSum[1][q];
         const u64 tag = (u64)(level + 1u) << 32;
         if (tid == 0) st_relaxed64(counts + c, tag | chunkTotal);
-        /* B. children of the chunks before this one: every CTA posts after the same short pass, so the spin is short */
+        /* B. children of the chunks before this one: every CTA posts after the same pass, so the spin is short */
         u32 before = 0;
-        for (u32 i = tid; i < c; i += COL_THREADS) {
+        for (u32 i = tid; i < c; i += NUM_THREADS) {
           u64 v;
           do { v = ld_relaxed64(counts + i); } while ((v >> 32) != (tag >> 32));
           before += (u32)v;
@@ -216,12 +230,11 @@ __global__ void __launch_bounds__(COL_THREADS, 6) collapse_number_kernel(const u
         __syncthreads();
         u32 running = end;
 #pragma unroll
-        for (int q = 0; q < COL_THREADS / 32; q++) running += S.warpSum[2][q];
+        for (int q = 0; q < NUM_THREADS / 32; q++) running += S.warpSum[2][q];
         if (c == nActive - 1 && tid == 0) publish_level(ctrl, barriers + 1u, level + 1u, end, running + chunkTotal); /* last chunk of the level */
         /* C. the chunk tile by tile: no CTA waits for another one here */
-        for (u32 tileStart = cStart; tileStart < cEnd; tileStart += COL_THREADS)
-          number_tile(expansion, nInt, taskCh, taskParent, firstChild, S, tileStart, cEnd,
-                      [&running](u32 tileTotal) { const u32 b = running; running += tileTotal; return b; });
+        for (u32 tileStart = cStart; tileStart < cEnd; tileStart += NUM_THREADS)
+          running += number_tile(nInt, taskNode, taskCh, taskParent, firstChild, S, tileStart, cEnd, running);
       }
     }
     barriers++;
@@ -317,7 +330,7 @@ int b2_launch_collapse(b2bvh_ctx* ctx, const b2bvh_bvh2_node* d_nodes, const b2b
   const size_t emitSmem = sizeof(EmitSmem);
   if (!occ) {
     B2_CUDA(cudaFuncSetAttribute(collapse_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emitSmem));
-    B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, collapse_number_kernel, COL_THREADS, 0));
+    B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, collapse_number_kernel, NUM_THREADS, 0));
     if (occ < 1) return b2_fail(B2BVH_ERR_INTERNAL, "collapse: kernel does not fit on an SM");
   }
   /* every CTA must be resident (grid barrier): at most SMs x occupancy; small inputs use fewer CTAs (cheaper barriers) */
@@ -331,7 +344,8 @@ int b2_launch_collapse(b2bvh_ctx* ctx, const b2bvh_bvh2_node* d_nodes, const b2b
   uint4* taskCh = reinterpret_cast<uint4*>(base + 256 + (size_t)n * sizeof(uint4));
   u32* taskParent = reinterpret_cast<u32*>(base + 256 + (size_t)n * 2 * sizeof(uint4));
   u32* firstChild = taskParent + n;
-  u64* counts = reinterpret_cast<u64*>(firstChild + n); /* one tagged word per CTA; 2n words after a 16-byte aligned start */
+  u32* taskNode = firstChild + n;
+  u64* counts = reinterpret_cast<u64*>(taskNode + n + (n & 1u)); /* one tagged word per CTA; 3n (+1) words after a 16-byte aligned start */
   u32 nInt = n - 1;
   B2_CUDA(cudaMemsetAsync(ctrl, 0, 256, ctx->stream));
   B2_CUDA(cudaMemsetAsync(counts, 0, (size_t)grid * sizeof(u64), ctx->stream));
@@ -339,8 +353,8 @@ int b2_launch_collapse(b2bvh_ctx* ctx, const b2bvh_bvh2_node* d_nodes, const b2b
   collapse_expand_kernel<<<(nInt + COL_THREADS - 1) / COL_THREADS, COL_THREADS, 0, ctx->stream>>>(d_nodes, nInt, expansion);
   B2_LAUNCH_CHECK(ctx);
   B2_KERNEL(ctx, "collapse_number");
-  void* args[] = {(void*)&expansion, (void*)&nInt, (void*)&d_rootIdx, (void*)&taskCh, (void*)&taskParent, (void*)&firstChild, (void*)&ctrl, (void*)&counts};
-  B2_CUDA(cudaLaunchCooperativeKernel((const void*)collapse_number_kernel, dim3(grid), dim3(COL_THREADS), args, 0, ctx->stream));
+  void* args[] = {(void*)&expansion, (void*)&nInt, (void*)&d_rootIdx, (void*)&taskNode, (void*)&taskCh, (void*)&taskParent, (void*)&firstChild, (void*)&ctrl, (void*)&counts};
+  B2_CUDA(cudaLaunchCooperativeKernel((const void*)collapse_number_kernel, dim3(grid), dim3(NUM_THREADS), args, 0, ctx->stream));
   B2_LAUNCH_CHECK(ctx);
   /* the number of wide nodes stays on the device: the emit grid is sized for the worst case and strides over ctrl->nWide */
   u32 egrid = (nInt + COL_THREADS - 1) / COL_THREADS;

@@ -177,8 +177,10 @@ __global__ void __launch_bounds__(LBVH_TILE_THREADS, 4) lbvh_tile_kernel(const u
   }
   __syncthreads();
   {
+    /* two 16-byte pieces per leaf, 512 threads: exactly two steps (a strided loop here is unrolled into 150 instructions) */
     uint4* out = reinterpret_cast<uint4*>(nodes + nInt + b0);
-    for (u32 q = tid; q < 2 * cnt0; q += LBVH_TILE_THREADS) out[q] = S.stage[2 * T + q];
+    if (tid < 2 * cnt0) out[tid] = S.stage[2 * T + tid];
+    if (tid + LBVH_TILE_THREADS < 2 * cnt0) out[tid + LBVH_TILE_THREADS] = S.stage[2 * T + tid + LBVH_TILE_THREADS];
   }
   if (n == 1) { if (tid == 0 && rootOut) *rootOut = 0; return; }
 
@@ -258,8 +260,11 @@ __global__ void __launch_bounds__(LBVH_TILE_THREADS, 4) lbvh_tile_kernel(const u
   /* ---- finished nodes (and parent indices) leave as whole sectors ---- */
   {
     uint4* out = reinterpret_cast<uint4*>(nodes + b0);
-    for (u32 q = tid; q < 2 * cnt0; q += LBVH_TILE_THREADS)
-      if (S.stage[q & ~1u].x != B2_INVALID) out[q] = S.stage[q];
+#pragma unroll
+    for (u32 i = 0; i < 2; i++) {
+      const u32 q = tid + i * LBVH_TILE_THREADS;
+      if (q < 2 * cnt0 && S.stage[q & ~1u].x != B2_INVALID) out[q] = S.stage[q];
+    }
     if (PARENTS && parents) {
       if (tid < cnt0) {
         const u32 a = S.par[tid], b = S.par[T + tid];
