@@ -112,6 +112,22 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+# camera / object presets of the reference (Common.h:26-77): translation, scale, object rotation (axis, angle), eye, camera rotation
+TRACE_PRESETS = {
+    "bunny": dict(t=[0.0, 0.0, -3.0], s=[3.0, 3.0, 3.0], q=None, eye=[0.0, 2.5, 5.8, 0.0], cq=[0.0, 0.0, 1.0, -1.57]),
+    "sponza": dict(t=[0.0, 0.0, -3.0], s=[1.0, 1.0, 1.0], q=[1.0, 0.0, 0.0, 1.57], eye=[-20.0, 18.5, 10.8, 0.0], cq=[0.0, 1.0, 0.0, -1.57]),
+}
+
+
+def qt_rotation(axis_angle):
+    """qtRotation (Common.h:461-472): unit axis * sin(angle/2), cos(angle/2), float32."""
+    import numpy as np
+    a = np.asarray(axis_angle, dtype=np.float32)
+    ax = a[:3] / np.sqrt(np.float32((a[:3] * a[:3]).sum(dtype=np.float32)))
+    h = np.float32(a[3] / np.float32(2.0))
+    return np.array([ax[0] * np.sin(h), ax[1] * np.sin(h), ax[2] * np.sin(h), np.cos(h)], dtype=np.float32)
+
+
 def workload_config(gpus):
     return {"workload": f"synth_uniform_v1 {PRIMS_PER_GPU // 1_000_000}M triangles per GPU (BASELINE configs[3]/[4]), single-pass LBVH + Bvh4 collapse",
             "prims_per_gpu": PRIMS_PER_GPU, "total_prims": PRIMS_PER_GPU * gpus, "seed": hex(SEED), "builder": "SinglePassLbvh",
@@ -302,6 +318,17 @@ def main():
                                 best = (tot, [float(t.stage_ms[k]) for k in (capi.T_EXTENTS, capi.T_MORTON, capi.T_SORT, capi.T_BUILD, capi.T_COLLAPSE)])
                         res[nm] = {"total_ms": best[0], "Mprims_s": mt.size / best[0] / 1e3, "extents_morton_sort_build_collapse_ms": best[1],
                                    "bvh4_cost": ctx.tree_cost(t)}
+                        # primary rays on the built Bvh2 (TwoPassLbvh::traverseBvh, 512 x 512, while-while and speculative-while)
+                        pr = TRACE_PRESETS[mesh]
+                        tr = T.make_transform(pr["t"], pr["s"], [0.0, 0.0, 0.0, 1.0] if pr["q"] is None else qt_rotation(pr["q"]))
+                        cam = T.make_camera(pr["eye"], qt_rotation(pr["cq"]), np.float32(45.0) * np.float32(np.pi) / np.float32(180.0))
+                        d_rays, ray_ms = ctx.generate_rays(cam, 512, 512)
+                        trace = {"ray_gen_ms": ray_ms}
+                        for knm, kk in (("while_while", capi.TRAVERSE_WHILE), ("speculative_while", capi.TRAVERSE_SPECULATIVE_WHILE)):
+                            tms = min(ctx.traverse(t, d_rays, 512 * 512, tr, kernel=kk)[2] for _ in range(5))
+                            trace[knm] = {"ms": tms, "Mray_s": 512 * 512 / tms / 1e3}
+                        ctx.free(d_rays)
+                        res[nm]["primary_rays_512x512"] = trace
                     except capi.B2bvhError as e:
                         res[nm] = {"error": str(e)[:80]}
                 ctx.free(dm)
