@@ -180,13 +180,12 @@ def main():
             tree = ctx.build(algo, tris_ptr, n=n, tris_on_device=on_device)
             launches[0] += tree.n_launches
             return tree
-        # sharded build: local boxes -> ONE all-reduce(MAX) of {-min,max} -> local build in the global frame -> ONE all-gather of roots
+        # sharded build: local boxes -> ONE all-reduce(MAX) of {-min,max} -> local build in the global frame (the reduced vector never
+        # leaves the device, the boxes of the first pass are reused) -> ONE all-gather of roots -> top-level tree on every rank
         capi.check(ctx.lib.b2bvh_shard_extents(ctx.h, tris_ptr, n, 1 if on_device else 0, box6.data_ptr()), "b2bvh_shard_extents")
         dist.all_reduce(box6, op=dist.ReduceOp.MAX)
-        b = box6.cpu().numpy()
-        tree = ctx.build(algo, tris_ptr, n=n, tris_on_device=on_device, scene_box=np.concatenate([-b[:3], b[3:]]))
-        node = ctx.download(tree.d_bvhNodes + 32 * tree.root, T.BVH2_NODE, 1)
-        root_local.copy_(torch.from_numpy(np.concatenate([node["mn"][0], node["mx"][0]])))
+        tree = ctx.build(algo, tris_ptr, n=n, tris_on_device=on_device, boxes_ready=True, d_scene_negmin_max=box6.data_ptr())
+        capi.check(ctx.lib.b2bvh_d2d(ctx.h, root_local.data_ptr(), tree.d_bvhNodes + 32 * tree.root + 8, 24), "b2bvh_d2d")
         dist.all_gather_into_tensor(roots, root_local)
         capi.check(ctx.lib.b2bvh_top_level(ctx.h, roots.data_ptr(), world, top_nodes.data_ptr()), "b2bvh_top_level")
         launches[0] += tree.n_launches + 2

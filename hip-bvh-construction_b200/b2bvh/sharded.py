@@ -21,7 +21,8 @@ def shard_range(n_total, rank, world):
 class ShardedBuild:
     """engine: object with
          shard_extents(tris) -> tensor[6] {-min.xyz, max.xyz} on the collective's device
-         build(tris, scene_box6) -> (root_box6 as numpy float32[6], tree)
+         build(tris, scene_box6) -> (root_box6 as numpy float32[6], tree); an engine with device_scene = True takes the
+                                    reduced {-min, max} tensor itself and returns the root box as a tensor on the same device
          top_level(root_boxes tensor[G*6]) -> top-level nodes
          tensor(np_array) -> tensor on the collective's device
        dist: torch.distributed (initialised) or None for world == 1."""
@@ -34,10 +35,15 @@ class ShardedBuild:
         box6 = self.engine.shard_extents(tris)
         if self.world > 1:
             self.dist.all_reduce(box6, op=self.dist.ReduceOp.MAX)
-        b = box6.detach().cpu().numpy().astype(np.float32)
-        scene = np.concatenate([-b[:3], b[3:]]).astype(np.float32)
-        root_box, tree = self.engine.build(tris, scene)
-        mine = self.engine.tensor(np.asarray(root_box, dtype=np.float32))
+        if getattr(self.engine, "device_scene", False):
+            # the reduced vector stays on the device: no host round trip between the collective and the build
+            scene = box6
+            mine, tree = self.engine.build(tris, box6)
+        else:
+            b = box6.detach().cpu().numpy().astype(np.float32)
+            scene = np.concatenate([-b[:3], b[3:]]).astype(np.float32)
+            root_box, tree = self.engine.build(tris, scene)
+            mine = self.engine.tensor(np.asarray(root_box, dtype=np.float32))
         if self.world > 1:
             roots = torch.empty(self.world * 6, dtype=torch.float32, device=mine.device)
             self.dist.all_gather_into_tensor(roots, mine)
@@ -55,7 +61,9 @@ class GpuEngine:
         from . import capi, types as T
         self.ctx, self.algo, self.collapse, self.capi, self.T, self.torch = ctx, algo, collapse, capi, T, torch
         self.box6 = torch.zeros(6, dtype=torch.float32, device="cuda")
+        self.root6 = torch.zeros(6, dtype=torch.float32, device="cuda")
         self.top_nodes = None
+        self.device_scene = True
 
     def tensor(self, a):
         return self.torch.from_numpy(a).cuda()
@@ -70,11 +78,14 @@ class GpuEngine:
         self.capi.check(self.ctx.lib.b2bvh_shard_extents(self.ctx.h, p, n, on_dev, self.box6.data_ptr()), "b2bvh_shard_extents")
         return self.box6
 
-    def build(self, tris, scene):
+    def build(self, tris, box6):
+        """box6: the all-reduced {-min, max} tensor (device).  The primitive boxes computed by shard_extents are reused."""
         p, n, on_dev = self._ptr_n(tris)
-        tree = self.ctx.build(self.algo, p, n=n, tris_on_device=bool(on_dev), scene_box=scene, collapse=self.collapse)
-        node = self.ctx.download(tree.d_bvhNodes + 32 * tree.root, self.T.BVH2_NODE, 1)
-        return np.concatenate([node["mn"][0], node["mx"][0]]), tree
+        tree = self.ctx.build(self.algo, p, n=n, tris_on_device=bool(on_dev), collapse=self.collapse, boxes_ready=True,
+                              d_scene_negmin_max=box6.data_ptr())
+        # root box = bytes 8..32 of the root node, device to device (stream-ordered)
+        self.capi.check(self.ctx.lib.b2bvh_d2d(self.ctx.h, self.root6.data_ptr(), tree.d_bvhNodes + 32 * tree.root + 8, 24), "b2bvh_d2d")
+        return self.root6, tree
 
     def top_level(self, roots):
         g = roots.numel() // 6

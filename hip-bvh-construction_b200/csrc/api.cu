@@ -54,7 +54,7 @@ enum {
 
 extern "C" {
 
-uint32_t b2bvh_abi_version(void) { return 1; }
+uint32_t b2bvh_abi_version(void) { return 2; }
 const char* b2bvh_last_error(void) { return g_err; }
 
 int b2bvh_ctx_create(int device, void* cuda_stream, b2bvh_ctx** out) {
@@ -132,6 +132,11 @@ int b2bvh_d2h(b2bvh_ctx* ctx, void* hptr, const void* dptr, size_t bytes) {
   if (!ctx || (bytes && (!dptr || !hptr))) return b2_fail(B2BVH_ERR_INVALID, "d2h: bad argument");
   B2_CUDA(cudaMemcpyAsync(hptr, dptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   B2_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int b2bvh_d2d(b2bvh_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  if (!ctx || (bytes && (!dst || !src))) return b2_fail(B2BVH_ERR_INVALID, "d2d: bad argument");
+  B2_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
   return 0;
 }
 int b2bvh_sync(b2bvh_ctx* ctx) {
@@ -217,15 +222,17 @@ int b2bvh_build(b2bvh_ctx* ctx, int algo, const b2bvh_triangle* tris, uint32_t n
   const b2bvh_triangle* dT = tris;
   if (!opts.tris_on_device) {
     B2_CUDA(cudaEventRecord(ctx->ev[8], s));
-    B2_CUDA(cudaMemcpyAsync(dTris, tris, (size_t)n * sizeof(b2bvh_triangle), cudaMemcpyHostToDevice, s));
+    /* boxes_ready: b2bvh_shard_extents already uploaded these triangles into the same buffer */
+    if (!opts.boxes_ready) B2_CUDA(cudaMemcpyAsync(dTris, tris, (size_t)n * sizeof(b2bvh_triangle), cudaMemcpyHostToDevice, s));
     B2_CUDA(cudaEventRecord(ctx->ev[9], s));
     dT = (const b2bvh_triangle*)dTris;
   }
 
   /* ---- S1 extents ---- */
   B2_CUDA(cudaEventRecord(ctx->ev[0], s));
-  B2_TRY(b2_launch_extents(ctx, dT, n, (b2bvh_aabb*)dAabb, dScene, dScratch8, nullptr));
-  if (opts.use_scene_box) B2_CUDA(cudaMemcpyAsync(dScene, &opts.scene_box, sizeof(b2bvh_aabb), cudaMemcpyHostToDevice, s));
+  if (!opts.boxes_ready) B2_TRY(b2_launch_extents(ctx, dT, n, (b2bvh_aabb*)dAabb, dScene, dScratch8, nullptr));
+  if (opts.d_scene_negmin_max) B2_TRY(b2_launch_scene_from_negmin_max(ctx, opts.d_scene_negmin_max, dScene));
+  else if (opts.use_scene_box) B2_CUDA(cudaMemcpyAsync(dScene, &opts.scene_box, sizeof(b2bvh_aabb), cudaMemcpyHostToDevice, s));
   B2_CUDA(cudaEventRecord(ctx->ev[1], s));
   /* ---- S2 Morton (+ SetupClusters for PLOC/HPLOC is inside their launchers but is accounted under BUILD here) ---- */
   B2_TRY(b2_launch_morton(ctx, (const b2bvh_aabb*)dAabb, dScene, n, (u32*)dKeys, (u32*)dVals));

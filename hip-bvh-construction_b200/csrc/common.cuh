@@ -214,6 +214,7 @@ int b2_reserve(b2bvh_ctx* ctx, int slot, size_t bytes, void** out);
 /* stage launchers (one per .cu file) */
 int b2_launch_extents(b2bvh_ctx* ctx, const b2bvh_triangle* d_tris, u32 n, b2bvh_aabb* d_triAabb, b2bvh_aabb* d_scene, u32* d_scratch8,
                       float* d_negmin_max6);
+int b2_launch_scene_from_negmin_max(b2bvh_ctx* ctx, const float* d_negmin_max6, b2bvh_aabb* d_scene);
 int b2_launch_morton(b2bvh_ctx* ctx, const b2bvh_aabb* d_triAabb, const b2bvh_aabb* d_scene, u32 n, u32* d_keys, u32* d_vals);
 size_t b2_sort_scratch_bytes(u32 n);
 int b2_launch_sort(b2bvh_ctx* ctx, const u32* d_keysIn, const u32* d_valsIn, u32* d_keysOut, u32* d_valsOut, u32* d_keysTmp, u32* d_valsTmp,

@@ -129,3 +129,17 @@ int b2_launch_morton(b2bvh_ctx* ctx, const b2bvh_aabb* d_triAabb, const b2bvh_aa
   B2_LAUNCH_CHECK(ctx);
   return 0;
 }
+
+/* global scene box of a sharded build: the all-reduced {-min, max} vector (b2bvh_shard_extents) back into an Aabb, on the device */
+__global__ void scene_from_negmin_max_kernel(const float* __restrict__ v, b2bvh_aabb* scene) {
+  if (threadIdx.x == 0) {
+    scene->m_min.x = -v[0]; scene->m_min.y = -v[1]; scene->m_min.z = -v[2];
+    scene->m_max.x = v[3]; scene->m_max.y = v[4]; scene->m_max.z = v[5];
+  }
+}
+int b2_launch_scene_from_negmin_max(b2bvh_ctx* ctx, const float* d_negmin_max6, b2bvh_aabb* d_scene) {
+  B2_KERNEL(ctx, "scene_from_negmin_max");
+  scene_from_negmin_max_kernel<<<1, 32, 0, ctx->stream>>>(d_negmin_max6, d_scene);
+  B2_LAUNCH_CHECK(ctx);
+  return 0;
+}

@@ -54,7 +54,10 @@ typedef struct b2bvh_build_opts {
   uint32_t stage_timing;    /* 1: CUDA-event time per stage (the reference's Timer tokens); 0: whole-build time only  */
   uint32_t karras_two_kernel; /* TWO_PASS only. 1: emit (determineRange/findSplit) + separate refit kernel, as the
                                  reference's launch order; 0: one fused bottom-up pass that yields the same numbering */
-  uint32_t reserved[4];
+  uint32_t boxes_ready;     /* 1: b2bvh_shard_extents ran on the same context and triangles: primitive boxes are in place, skip S1 */
+  const float* d_scene_negmin_max; /* device, 6 floats {-min.xyz, max.xyz} (the all-reduced output of b2bvh_shard_extents): the
+                                      global scene box without a host round trip; overrides scene_box when not NULL     */
+  uint32_t reserved[2];
 } b2bvh_build_opts;
 
 /* Everything a build leaves on the device.  Pointers are DEVICE pointers owned by the context
@@ -97,6 +100,7 @@ int b2bvh_free(b2bvh_ctx* ctx, void* dptr);                            /* oroFre
 int b2bvh_memset(b2bvh_ctx* ctx, void* dptr, int value, size_t bytes); /* GpuMemory::reset                           */
 int b2bvh_h2d(b2bvh_ctx* ctx, void* dptr, const void* hptr, size_t bytes); /* OrochiUtils::copyHtoD                  */
 int b2bvh_d2h(b2bvh_ctx* ctx, void* hptr, const void* dptr, size_t bytes); /* GpuMemory::getData                     */
+int b2bvh_d2d(b2bvh_ctx* ctx, void* dst, const void* src, size_t bytes); /* OrochiUtils::copyDtoDAsync (stream-ordered)  */
 int b2bvh_sync(b2bvh_ctx* ctx);                                        /* OrochiUtils::waitForCompletion             */
 int b2bvh_host_alloc_pinned(size_t bytes, void** hptr);
 int b2bvh_host_free_pinned(void* hptr);
