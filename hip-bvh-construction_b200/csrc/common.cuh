@@ -173,6 +173,7 @@ struct b2bvh_ctx {
     size_t cap;
   } bufs[32];
   u32 launches;
+  u32 lbvh_second_level; /* b2bvh_build_opts.lbvh_second_level of the running build */
   /* optional per-launch profiler (b2bvh_profile_*): one CUDA event pair per kernel launch */
   bool prof_on;
   int prof_n;

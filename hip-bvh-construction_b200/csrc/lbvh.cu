@@ -107,8 +107,12 @@ __global__ void __launch_bounds__(LBVH_THREADS) lbvh_fused_kernel(const u32* __r
  * [b0, b1) — and leave as whole 32-byte sectors: half-written sectors make the B200 L2 read the other half from DRAM.
  * Clusters left when no boundary inside the tile is a maximum (their parents straddle the tile) are handed to
  * lbvh_climb_kernel, which finishes the top of the tree with the global exchange protocol above. */
-#define LBVH_TILE 512
-#define LBVH_TILE_THREADS 512
+#define LBVH_TILE 256
+#define LBVH_TILE_THREADS 256
+#define LBVH_GROUP 32        /* tiles whose left-over clusters are merged further by one CTA of lbvh_group_kernel */
+#define LBVH_TILE_CAP 32     /* left-over clusters a tile may park in its slot (typically ~14; at most 124: two monotone depth runs) */
+#define LBVH_GROUP_CAP (LBVH_GROUP * LBVH_TILE_CAP)
+#define LBVH_OVERFLOW 0xFFFFFFFFu
 #define LBVH_PAR_UNSET 0xFFFFFFFEu
 /* one cluster = one 32-bit word: [27:21] d + 1 (0 = outside the key array), [20:10] local index of the root node in the
  * staging buffer, [9:0] range start - b0 */
@@ -121,7 +125,8 @@ __global__ void __launch_bounds__(LBVH_THREADS) lbvh_fused_kernel(const u32* __r
 struct LbvhPending {
   u32 self, lo, hi, pSide; /* pSide = parent split | (isLeft << 31) */
   float box[6];
-  u32 pad[2];
+  u32 depthRight;          /* d + 1 of the boundary right of the cluster (lbvh_group_kernel) */
+  u32 pad;
 };
 static_assert(sizeof(LbvhPending) == 48, "LbvhPending layout");
 
@@ -141,9 +146,10 @@ __device__ __forceinline__ int boundary_depth(u32 keyA, u32 keyB, u32 a /* b = a
 __device__ __forceinline__ void named_barrier(u32 id, u32 threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
 template <bool KARRAS>
-__global__ void __launch_bounds__(LBVH_TILE_THREADS, 4) lbvh_tile_kernel(const u32* __restrict__ keys, const u32* __restrict__ vals,
+__global__ void __launch_bounds__(LBVH_TILE_THREADS, 8) lbvh_tile_kernel(const u32* __restrict__ keys, const u32* __restrict__ vals,
                                                                       const b2bvh_aabb* __restrict__ triAabb, u32 n, b2bvh_bvh2_node* nodes, u32* parents,
-                                                                      u32* meet, u32* rootOut, u32* pendingCount, LbvhPending* pending, u32 pendingCap) {
+                                                                      u32* meet, u32* rootOut, u32* pendingCount, LbvhPending* pending, u32 pendingCap,
+                                                                      uint2* tileInfo, LbvhPending* tileBuf) {
   constexpr bool PARENTS = KARRAS; /* only TwoPassLbvh publishes d_parentIdxs */
   constexpr u32 T = LBVH_TILE;
   static_assert(LBVH_TILE == LBVH_TILE_THREADS, "one leaf per thread");
@@ -182,7 +188,7 @@ __global__ void __launch_bounds__(LBVH_TILE_THREADS, 4) lbvh_tile_kernel(const u
     if (tid < 2 * cnt0) out[tid] = S.stage[2 * T + tid];
     if (tid + LBVH_TILE_THREADS < 2 * cnt0) out[tid + LBVH_TILE_THREADS] = S.stage[2 * T + tid + LBVH_TILE_THREADS];
   }
-  if (n == 1) { if (tid == 0 && rootOut) *rootOut = 0; return; }
+  if (n == 1) { if (tid == 0) { if (rootOut) *rootOut = 0; if (tileBuf) tileInfo[0] = make_uint2(0u, 0u); } return; }
 
   /* ---- rounds: only the warps that still hold clusters take part (named barrier over nW warps); the others wait below ---- */
   u32 cur = 0, count = cnt0;
@@ -273,27 +279,202 @@ __global__ void __launch_bounds__(LBVH_TILE_THREADS, 4) lbvh_tile_kernel(const u
       }
     }
   }
-  if (rootDone) return; /* single tile: the whole tree was built here */
+  if (rootDone) { if (tid == 0 && tileBuf) tileInfo[blockIdx.x] = make_uint2(0u, 0u); return; } /* single tile: the whole tree was built here */
 
-  /* ---- hand the remaining clusters to the global climb ---- */
-  if (tid == 0) S.pendBase = atomicAdd(pendingCount, count);
+  /* ---- park the remaining clusters in the tile's slot for lbvh_group_kernel (or, if they do not fit, hand them to the global
+   * climb directly) ---- */
+  const bool parked = tileBuf != nullptr && count <= LBVH_TILE_CAP; /* tileBuf == nullptr: small input, no second level */
+  if (tid == 0) {
+    if (tileBuf) tileInfo[blockIdx.x] = make_uint2(parked ? count : LBVH_OVERFLOW, S.w[cur][1] >> LW_D_SHIFT);
+    if (!parked) S.pendBase = atomicAdd(pendingCount, count);
+  }
   __syncthreads();
   if (tid < count) {
     const u32* W = S.w[cur];
     const u32 xm1 = W[tid + 1], x0 = W[tid + 2], xp1 = W[tid + 3];
-    const u32 slotOut = S.pendBase + tid;
     const u32 l = (x0 >> LW_ID_SHIFT) & LW_ID_MASK;
     const u32 self = globalId(l), lo = b0 + (x0 & LW_LO_MASK), hi = b0 + (xp1 & LW_LO_MASK);
     const bool isLeft = (x0 >> LW_D_SHIFT) > (xm1 >> LW_D_SHIFT);
     const u32 p = isLeft ? hi - 1 : lo - 1;
     const Node2 me = node2_unpack(S.stage[2 * l], S.stage[2 * l + 1]);
+    const u32 slotOut = parked ? blockIdx.x * LBVH_TILE_CAP + tid : S.pendBase + tid;
+    if (parked || slotOut < pendingCap) {
+      uint4* q = reinterpret_cast<uint4*>((parked ? tileBuf : pending) + slotOut);
+      q[0] = make_uint4(self, lo, hi, p | (isLeft ? 0x80000000u : 0u));
+      q[1] = make_uint4(__float_as_uint(me.box.lx), __float_as_uint(me.box.ly), __float_as_uint(me.box.lz), __float_as_uint(me.box.hx));
+      q[2] = make_uint4(__float_as_uint(me.box.hy), __float_as_uint(me.box.hz), x0 >> LW_D_SHIFT, 0u);
+    } else {
+      climb_global<KARRAS>(keys, n, nodes, parents, meet, rootOut, self, lo, hi, me.box, p, isLeft); /* overflow of the hand-over list */
+    }
+  }
+}
+
+/* ---------------------------------------------------------------- second level: the left-over clusters of LBVH_GROUP adjacent tiles
+ * The clusters a tile could not merge (their parents straddle the tile) are, tile after tile, again an ordered list of
+ * clusters with known boundary depths, so the same rounds apply; one CTA takes the ~450 clusters of 32 tiles (8192 leaves)
+ * and leaves ~26.  Nodes finished here are stored directly (3 % of all nodes).  What is left goes to lbvh_climb_kernel.  A
+ * group that holds a tile whose clusters did not fit its slot is forwarded unchanged. */
+struct LbvhGroupSmem {
+  u32 w[2][LBVH_GROUP_CAP + 4];   /* [27:21] d + 1, [10:0] slot; same sentinels as in the tile kernel */
+  u32 lo[LBVH_GROUP_CAP + 1];     /* per slot: range start; slot LBVH_GROUP_CAP = end of the group's last cluster */
+  u32 id[LBVH_GROUP_CAP];         /* per slot: root node */
+  float box[LBVH_GROUP_CAP][6];
+  u32 tileOff[LBVH_GROUP + 1];
+  u32 chunkMerges[LBVH_GROUP_CAP / 32], chunkBefore[LBVH_GROUP_CAP / 32];
+  u32 total, pendBase, forward;
+};
+
+template <bool KARRAS>
+__global__ void __launch_bounds__(256) lbvh_group_kernel(const u32* __restrict__ keys, u32 n, b2bvh_bvh2_node* nodes, u32* parents, u32* meet, u32* rootOut,
+                                                         u32* pendingCount, LbvhPending* pending, u32 pendingCap, const uint2* __restrict__ tileInfo,
+                                                         const LbvhPending* __restrict__ tileBuf, u32 nTiles) {
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  LbvhGroupSmem& S = *reinterpret_cast<LbvhGroupSmem*>(smemRaw);
+  constexpr u32 SLOT_MASK = 0x7FFu, P = LBVH_GROUP_CAP / 256;
+  const u32 tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+  const u32 t0 = blockIdx.x * LBVH_GROUP, t1 = min(nTiles, t0 + LBVH_GROUP);
+  if (warp == 0) {
+    const u32 t = t0 + lane;
+    const u32 c = t < t1 ? __ldg(&tileInfo[t].x) : 0u;
+    const bool over = __any_sync(B2_FULL, c == LBVH_OVERFLOW);
+    u32 incl = over ? 0u : c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const u32 v = __shfl_up_sync(B2_FULL, incl, o);
+      if ((int)lane >= o) incl += v;
+    }
+    S.tileOff[lane] = incl - (over ? 0u : c);
+    if (lane == 31) { S.tileOff[32] = incl; S.forward = over ? 1u : 0u; }
+  }
+  __syncthreads();
+  u32 count = S.tileOff[LBVH_GROUP];
+  if (S.forward) {
+    /* some tile of the group went to the climb on its own: its neighbours cannot merge across it here, send them after it */
+    for (u32 t = t0 + warp; t < t1; t += 8) {
+      const u32 c = __ldg(&tileInfo[t].x);
+      if (c == LBVH_OVERFLOW || c == 0) continue;
+      u32 base = 0;
+      if (lane == 0) base = atomicAdd(pendingCount, c);
+      base = __shfl_sync(B2_FULL, base, 0);
+      if (lane < c) {
+        const uint4* q = reinterpret_cast<const uint4*>(tileBuf + (size_t)t * LBVH_TILE_CAP + lane);
+        const uint4 a = __ldg(q), b = __ldg(q + 1), cc = __ldg(q + 2);
+        if (base + lane < pendingCap) {
+          uint4* o = reinterpret_cast<uint4*>(pending + base + lane);
+          o[0] = a; o[1] = b; o[2] = cc;
+        } else {
+          const Box box = Box{__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z), __uint_as_float(b.w), __uint_as_float(cc.x), __uint_as_float(cc.y)};
+          climb_global<KARRAS>(keys, n, nodes, parents, meet, rootOut, a.x, a.y, a.z, box, a.w & 0x7FFFFFFFu, (a.w >> 31) != 0u);
+        }
+      }
+    }
+    return;
+  }
+  if (count == 0) return;
+  /* ---- gather the clusters in position order: warp per tile ---- */
+  for (u32 t = t0 + warp; t < t1; t += 8) {
+    const u32 off = S.tileOff[t - t0], c = S.tileOff[t - t0 + 1] - off;
+    if (lane < c) {
+      const uint4* q = reinterpret_cast<const uint4*>(tileBuf + (size_t)t * LBVH_TILE_CAP + lane);
+      const uint4 a = __ldg(q), b = __ldg(q + 1), cc = __ldg(q + 2);
+      const u32 s = off + lane;
+      S.lo[s] = a.y; S.id[s] = a.x;
+      float* bx = S.box[s];
+      bx[0] = __uint_as_float(b.x); bx[1] = __uint_as_float(b.y); bx[2] = __uint_as_float(b.z); bx[3] = __uint_as_float(b.w);
+      bx[4] = __uint_as_float(cc.x); bx[5] = __uint_as_float(cc.y);
+      S.w[0][s + 2] = (cc.z << LW_D_SHIFT) | s;
+      if (s + 1 == count) { S.lo[LBVH_GROUP_CAP] = a.z; S.w[0][count + 2] = LBVH_GROUP_CAP; }
+    }
+  }
+  if (tid == 0) S.w[0][1] = __ldg(&tileInfo[t0].y) << LW_D_SHIFT;
+  __syncthreads();
+
+  u32 cur = 0;
+  while (true) {
+    const u32* W = S.w[cur];
+    u32 xm1[P], x0[P], xp1[P], bal[P];
+    bool mrg[P], absorbed[P];
+#pragma unroll
+    for (u32 i = 0; i < P; i++) {
+      const u32 j = i * 256 + tid;
+      mrg[i] = false; absorbed[i] = false; xm1[i] = x0[i] = xp1[i] = 0;
+      if (j < count) {
+        const u32 xm2 = W[j];
+        xm1[i] = W[j + 1]; x0[i] = W[j + 2]; xp1[i] = W[j + 3];
+        const u32 dLL = xm2 >> LW_D_SHIFT, dL = xm1[i] >> LW_D_SHIFT, d0 = x0[i] >> LW_D_SHIFT, dR = xp1[i] >> LW_D_SHIFT;
+        mrg[i] = (j + 1 < count) && d0 > dL && d0 > dR;
+        absorbed[i] = (j >= 1) && dL > dLL && dL > d0;
+      }
+      bal[i] = __ballot_sync(B2_FULL, mrg[i]);
+      if (lane == 0) S.chunkMerges[i * 8 + warp] = __popc(bal[i]);
+    }
+    __syncthreads();
+    if (warp == 0) {
+      const u32 v = S.chunkMerges[lane]; /* chunks past the live clusters hold 0 */
+      u32 incl = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const u32 u = __shfl_up_sync(B2_FULL, incl, o);
+        if ((int)lane >= o) incl += u;
+      }
+      S.chunkBefore[lane] = incl - v;
+      if (lane == 31) S.total = incl;
+    }
+    __syncthreads();
+    const u32 total = S.total;
+    if (total == 0) break;
+    u32* Wn = S.w[cur ^ 1u];
+#pragma unroll
+    for (u32 i = 0; i < P; i++) {
+      const u32 j = i * 256 + tid;
+      if (j < count && !absorbed[i]) {
+        const u32 k = j - S.chunkBefore[i * 8 + warp] - __popc(bal[i] & lanemask_lt());
+        u32 outw = x0[i];
+        if (mrg[i]) {
+          const u32 sL = x0[i] & SLOT_MASK, sR = xp1[i] & SLOT_MASK;
+          float* bl = S.box[sL];
+          const float* br = S.box[sR];
+          const Box box = box_union(Box{bl[0], bl[1], bl[2], bl[3], bl[4], bl[5]}, Box{br[0], br[1], br[2], br[3], br[4], br[5]});
+          const u32 loL = S.lo[sL], mid = S.lo[sR], hi = S.lo[W[j + 4] & SLOT_MASK];
+          const bool isRoot = (loL == 0 && hi == n);
+          /* the merged cluster's own choice (its boundaries are j-1 and j+1) fixes its Karras index; Apetrei: the split position */
+          const u32 id = KARRAS ? (isRoot ? 0u : ((xp1[i] >> LW_D_SHIFT) > (xm1[i] >> LW_D_SHIFT) ? hi - 1u : loL)) : mid - 1u;
+          const u32 idL = S.id[sL], idR = S.id[sR];
+          store_node2(nodes + id, idL, idR, box);
+          if (parents) { parents[idL] = id; parents[idR] = id; if (isRoot) parents[id] = B2_INVALID; }
+          if (isRoot && rootOut) *rootOut = id;
+          bl[0] = box.lx; bl[1] = box.ly; bl[2] = box.lz; bl[3] = box.hx; bl[4] = box.hy; bl[5] = box.hz;
+          S.id[sL] = id;
+          outw = (xp1[i] & ~((1u << LW_D_SHIFT) - 1u)) | sL;
+        }
+        Wn[k + 2] = outw;
+      }
+    }
+    if (tid == 0) { Wn[1] = W[1]; Wn[count - total + 2] = W[count + 2]; }
+    __syncthreads();
+    cur ^= 1u;
+    count -= total;
+  }
+  /* ---- what is left goes to the global climb ---- */
+  const u32* W = S.w[cur];
+  if (count == 1 && S.lo[W[2] & SLOT_MASK] == 0 && S.lo[LBVH_GROUP_CAP] == n) return; /* the root was finished here */
+  if (tid == 0) S.pendBase = atomicAdd(pendingCount, count);
+  __syncthreads();
+  for (u32 j = tid; j < count; j += 256) {
+    const u32 xm1 = W[j + 1], x0 = W[j + 2], xp1 = W[j + 3];
+    const u32 s = x0 & SLOT_MASK;
+    const u32 self = S.id[s], lo = S.lo[s], hi = S.lo[xp1 & SLOT_MASK];
+    const bool isLeft = (x0 >> LW_D_SHIFT) > (xm1 >> LW_D_SHIFT);
+    const u32 p = isLeft ? hi - 1 : lo - 1;
+    const float* bx = S.box[s];
+    const u32 slotOut = S.pendBase + j;
     if (slotOut < pendingCap) {
       uint4* q = reinterpret_cast<uint4*>(pending + slotOut);
       q[0] = make_uint4(self, lo, hi, p | (isLeft ? 0x80000000u : 0u));
-      q[1] = make_uint4(__float_as_uint(me.box.lx), __float_as_uint(me.box.ly), __float_as_uint(me.box.lz), __float_as_uint(me.box.hx));
-      q[2] = make_uint4(__float_as_uint(me.box.hy), __float_as_uint(me.box.hz), 0u, 0u);
+      q[1] = make_uint4(__float_as_uint(bx[0]), __float_as_uint(bx[1]), __float_as_uint(bx[2]), __float_as_uint(bx[3]));
+      q[2] = make_uint4(__float_as_uint(bx[4]), __float_as_uint(bx[5]), x0 >> LW_D_SHIFT, 0u);
     } else {
-      climb_global<KARRAS>(keys, n, nodes, parents, meet, rootOut, self, lo, hi, me.box, p, isLeft); /* overflow of the hand-over list */
+      climb_global<KARRAS>(keys, n, nodes, parents, meet, rootOut, self, lo, hi, Box{bx[0], bx[1], bx[2], bx[3], bx[4], bx[5]}, p, isLeft);
     }
   }
 }
@@ -379,7 +560,9 @@ __global__ void __launch_bounds__(LBVH_THREADS) lbvh_refit_kernel(b2bvh_bvh2_nod
 
 size_t b2_lbvh_scratch_bytes(u32 n) {
   /* the larger of: fused path (meet words + hand-over list) and two-kernel path (2n-1 flags) */
-  const size_t fused = (((size_t)n * 4 + 15) & ~(size_t)15) + 16 + ((size_t)n / 8 + 1024) * sizeof(LbvhPending);
+  const size_t tiles = ((size_t)n + LBVH_TILE - 1) / LBVH_TILE;
+  const size_t fused = (((size_t)n * 4 + 15) & ~(size_t)15) + 16 + ((size_t)n / 8 + 1024) * sizeof(LbvhPending) + ((tiles * sizeof(uint2) + 15) & ~(size_t)15) +
+                       tiles * LBVH_TILE_CAP * sizeof(LbvhPending);
   const size_t two = (2 * (size_t)n - 1) * 4;
   return fused > two ? fused : two;
 }
@@ -396,24 +579,39 @@ int b2_launch_lbvh_fused(b2bvh_ctx* ctx, const u32* d_sortedKeys, const u32* d_s
     else
       lbvh_fused_kernel<false><<<grid, LBVH_THREADS, 0, ctx->stream>>>(d_sortedKeys, d_sortedVals, d_triAabb, n, d_nodes, d_parents, d_scratch, d_root);
   } else {
-    /* scratch: meet[n-1] | (16-byte aligned) pendingCount | pending[cap] */
+    /* scratch: meet[n-1] | (16-byte aligned) pendingCount | pending[cap] | tileInfo[tiles] | tileBuf[tiles][LBVH_TILE_CAP] */
     const size_t off = (((size_t)n * 4 + 15) & ~(size_t)15);
     u32* pendingCount = reinterpret_cast<u32*>(reinterpret_cast<unsigned char*>(d_scratch) + off);
     LbvhPending* pending = reinterpret_cast<LbvhPending*>(reinterpret_cast<unsigned char*>(d_scratch) + off + 16);
     const u32 cap = n / 8 + 1024;
     B2_CUDA(cudaMemsetAsync(pendingCount, 0, 4, ctx->stream));
     const u32 grid = (n + LBVH_TILE - 1) / LBVH_TILE;
+    /* second level only where it pays: below ~1 M primitives the extra launch costs more than the shorter climb saves */
+    const bool useGroups = ctx->lbvh_second_level == 1 ? true : (ctx->lbvh_second_level == 2 ? false : n >= (1u << 20));
+    uint2* tileInfo = reinterpret_cast<uint2*>(pending + cap);
+    LbvhPending* tileBuf = useGroups ? reinterpret_cast<LbvhPending*>(reinterpret_cast<unsigned char*>(tileInfo) + (((size_t)grid * sizeof(uint2) + 15) & ~(size_t)15)) : nullptr;
     static bool attrSet = false;
     if (!attrSet) {
+      B2_CUDA(cudaFuncSetAttribute(lbvh_group_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LbvhGroupSmem)));
+      B2_CUDA(cudaFuncSetAttribute(lbvh_group_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LbvhGroupSmem)));
       B2_CUDA(cudaFuncSetAttribute(lbvh_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LbvhTileSmem<true>)));
       B2_CUDA(cudaFuncSetAttribute(lbvh_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LbvhTileSmem<false>)));
       attrSet = true;
     }
     if (karrasNumbering)
-      lbvh_tile_kernel<true><<<grid, LBVH_TILE_THREADS, sizeof(LbvhTileSmem<true>), ctx->stream>>>(d_sortedKeys, d_sortedVals, d_triAabb, n, d_nodes, d_parents, d_scratch, d_root, pendingCount, pending, cap);
+      lbvh_tile_kernel<true><<<grid, LBVH_TILE_THREADS, sizeof(LbvhTileSmem<true>), ctx->stream>>>(d_sortedKeys, d_sortedVals, d_triAabb, n, d_nodes, d_parents, d_scratch, d_root, pendingCount, pending, cap, tileInfo, tileBuf);
     else
-      lbvh_tile_kernel<false><<<grid, LBVH_TILE_THREADS, sizeof(LbvhTileSmem<false>), ctx->stream>>>(d_sortedKeys, d_sortedVals, d_triAabb, n, d_nodes, d_parents, d_scratch, d_root, pendingCount, pending, cap);
+      lbvh_tile_kernel<false><<<grid, LBVH_TILE_THREADS, sizeof(LbvhTileSmem<false>), ctx->stream>>>(d_sortedKeys, d_sortedVals, d_triAabb, n, d_nodes, d_parents, d_scratch, d_root, pendingCount, pending, cap, tileInfo, tileBuf);
     B2_LAUNCH_CHECK(ctx);
+    if (useGroups) {
+      const u32 groups = (grid + LBVH_GROUP - 1) / LBVH_GROUP;
+      B2_KERNEL(ctx, "lbvh_group");
+      if (karrasNumbering)
+        lbvh_group_kernel<true><<<groups, 256, sizeof(LbvhGroupSmem), ctx->stream>>>(d_sortedKeys, n, d_nodes, d_parents, d_scratch, d_root, pendingCount, pending, cap, tileInfo, tileBuf, grid);
+      else
+        lbvh_group_kernel<false><<<groups, 256, sizeof(LbvhGroupSmem), ctx->stream>>>(d_sortedKeys, n, d_nodes, d_parents, d_scratch, d_root, pendingCount, pending, cap, tileInfo, tileBuf, grid);
+      B2_LAUNCH_CHECK(ctx);
+    }
     u32 grid2 = (cap + LBVH_THREADS - 1) / LBVH_THREADS;
     const u32 cap2 = (u32)ctx->sm_count * 8u;
     if (grid2 > cap2) grid2 = cap2;

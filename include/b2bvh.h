@@ -57,7 +57,8 @@ typedef struct b2bvh_build_opts {
   uint32_t boxes_ready;     /* 1: b2bvh_shard_extents ran on the same context and triangles: primitive boxes are in place, skip S1 */
   const float* d_scene_negmin_max; /* device, 6 floats {-min.xyz, max.xyz} (the all-reduced output of b2bvh_shard_extents): the
                                       global scene box without a host round trip; overrides scene_box when not NULL     */
-  uint32_t reserved[2];
+  uint32_t lbvh_second_level; /* LBVH builders: 0 = automatic (second merge level from 2^20 primitives), 1 = always, 2 = never; same output */
+  uint32_t reserved[1];
 } b2bvh_build_opts;
 
 /* Everything a build leaves on the device.  Pointers are DEVICE pointers owned by the context

@@ -59,6 +59,25 @@ def test_synthetic(ctx, oracle, algo, kind, n, seed):
     check_lbvh(ctx, oracle, random_tris(n, seed, kind), algo)
 
 
+SECOND_LEVEL = [("uniform", 300, 31), ("uniform", 8193, 32), ("uniform", 100_003, 33), ("clustered", 20_000, 34), ("duplicate", 9000, 35),
+                ("anisotropic", 30_000, 36)]
+
+
+@pytest.mark.parametrize("algo", [capi.TWO_PASS_LBVH, capi.SINGLE_PASS_LBVH], ids=["twopass", "singlepass"])
+@pytest.mark.parametrize("kind,n,seed", SECOND_LEVEL, ids=[f"{k}-{n}" for k, n, _ in SECOND_LEVEL])
+def test_second_merge_level_forced(ctx, oracle, algo, kind, n, seed):
+    """lbvh_group_kernel (automatic only from 2^20 primitives) forced on small inputs: same bytes as the oracle."""
+    check_lbvh(ctx, oracle, random_tris(n, seed, kind), algo, lbvh_second_level=1)
+
+
+@pytest.mark.parametrize("algo", [capi.TWO_PASS_LBVH, capi.SINGLE_PASS_LBVH], ids=["twopass", "singlepass"])
+def test_second_merge_level_on_sponza(ctx, oracle, algo):
+    tris = load_mesh("sponza")
+    if tris is None:
+        pytest.skip("sponza not staged")
+    check_lbvh(ctx, oracle, tris, algo, lbvh_second_level=1)
+
+
 @pytest.mark.parametrize("kind,n,seed", [("uniform", 5000, 21), ("clustered", 40_000, 22)])
 def test_twopass_two_kernel_variant(ctx, oracle, kind, n, seed):
     check_lbvh(ctx, oracle, random_tris(n, seed, kind), capi.TWO_PASS_LBVH, karras_two_kernel=True)
