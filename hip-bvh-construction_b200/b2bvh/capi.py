@@ -25,7 +25,7 @@ class Aabb(C.Structure):
 class BuildOpts(C.Structure):
     _fields_ = [("collapse", C.c_uint32), ("tris_on_device", C.c_uint32), ("use_scene_box", C.c_uint32), ("scene_box", Aabb),
                 ("stage_timing", C.c_uint32), ("karras_two_kernel", C.c_uint32), ("boxes_ready", C.c_uint32),
-                ("d_scene_negmin_max", C.c_void_p), ("lbvh_second_level", C.c_uint32), ("reserved", C.c_uint32 * 1)]
+                ("d_scene_negmin_max", C.c_void_p), ("lbvh_second_level", C.c_uint32), ("merge_max_ctas", C.c_uint32)]
 
 
 class Tree(C.Structure):
@@ -162,7 +162,7 @@ class Context:
 
     # ---- stages ----
     def build(self, algo, tris, n=None, collapse=True, tris_on_device=False, scene_box=None, karras_two_kernel=False, boxes_ready=False,
-              d_scene_negmin_max=None, lbvh_second_level=0):
+              d_scene_negmin_max=None, lbvh_second_level=0, merge_max_ctas=0):
         """tris: TRIANGLE[n] numpy array (host) or an int device/pinned-host pointer (then pass n)."""
         opts = BuildOpts()
         opts.collapse = 1 if collapse else 0
@@ -171,6 +171,7 @@ class Context:
         opts.karras_two_kernel = 1 if karras_two_kernel else 0
         opts.boxes_ready = 1 if boxes_ready else 0
         opts.lbvh_second_level = int(lbvh_second_level)
+        opts.merge_max_ctas = int(merge_max_ctas)
         if d_scene_negmin_max:
             opts.d_scene_negmin_max = int(d_scene_negmin_max)
         if scene_box is not None:

@@ -187,6 +187,7 @@ int b2bvh_build(b2bvh_ctx* ctx, int algo, const b2bvh_triangle* tris, uint32_t n
   B2_CUDA(cudaSetDevice(ctx->device));
   memset(out, 0, sizeof(*out));
   ctx->lbvh_second_level = opts.lbvh_second_level;
+  ctx->merge_max_ctas = opts.merge_max_ctas;
   const bool separate = (algo == B2BVH_PLOCPP || algo == B2BVH_HPLOC);
   const u32 launches0 = ctx->launches;
   cudaStream_t s = ctx->stream;

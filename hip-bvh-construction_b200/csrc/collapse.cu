@@ -52,16 +52,6 @@ struct ColSmem {
   u32 warpSum[3][NUM_THREADS / 32];
 };
 
-__device__ __forceinline__ void grid_barrier(u32* bar, u32 target) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(bar, 1u);
-    while (ld_acquire(bar) < target) {}
-  }
-  __syncthreads();
-}
-
 __device__ __forceinline__ void publish_level(CollapseCtrl* ctrl, u32 barrier, u32 level, u32 start, u32 end) {
   u32* nx = reinterpret_cast<u32*>(&ctrl->next[barrier & 1u]);
   st_relaxed(nx, level); st_relaxed(nx + 1, start); st_relaxed(nx + 2, end);

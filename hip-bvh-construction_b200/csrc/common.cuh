@@ -134,6 +134,23 @@ __device__ __forceinline__ u64 ld_relaxed64(const u64* p) {
 __device__ __forceinline__ void st_relaxed64(u64* p, u64 v) { asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
 __device__ __forceinline__ void st_relaxed(u32* p, u32 v) { asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
+/* Barrier among the first `threads` threads of the CTA (a multiple of 32; whole warps arrive). */
+__device__ __forceinline__ void named_barrier(u32 id, u32 threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+
+/* Grid-wide barrier of a cooperative launch (every CTA resident): `target` = arrivals expected so far (the counter is never
+ * reset: barrier number b of a launch of G CTAs waits for b * G). */
+__device__ __forceinline__ void grid_barrier(u32* bar, u32 target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1u);
+    u32 polls = 0;
+    while (ld_acquire(bar) < target)
+      if (++polls > (1u << 22)) __trap(); /* seconds: a CTA is missing (not a cooperative launch?) — fail, never hang the device */
+  }
+  __syncthreads();
+}
+
 /* order-preserving float <-> uint map: unsigned compare of the image == float compare (-0 < +0) */
 __device__ __forceinline__ u32 float_to_ordered(float f) {
   const u32 b = __float_as_uint(f);
@@ -174,6 +191,7 @@ struct b2bvh_ctx {
   } bufs[32];
   u32 launches;
   u32 lbvh_second_level; /* b2bvh_build_opts.lbvh_second_level of the running build */
+  u32 merge_max_ctas;    /* b2bvh_build_opts.merge_max_ctas of the running build */
   /* optional per-launch profiler (b2bvh_profile_*): one CUDA event pair per kernel launch */
   bool prof_on;
   int prof_n;

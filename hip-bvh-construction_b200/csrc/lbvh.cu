@@ -143,7 +143,6 @@ struct LbvhTileSmem {
 __device__ __forceinline__ int boundary_depth(u32 keyA, u32 keyB, u32 a /* b = a + 1 */) {
   return __clzll((long long)(((u64)(keyA ^ keyB) << 32) | (u64)(a ^ (a + 1u))));
 }
-__device__ __forceinline__ void named_barrier(u32 id, u32 threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
 template <bool KARRAS>
 __global__ void __launch_bounds__(LBVH_TILE_THREADS, 8) lbvh_tile_kernel(const u32* __restrict__ keys, const u32* __restrict__ vals,

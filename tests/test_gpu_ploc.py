@@ -14,9 +14,9 @@ pytestmark = pytest.mark.gpu
 KA = json.load(open(os.path.join(GOLDEN, "known_answers.json")))
 
 
-def check_ploc(ctx, oracle, tris, algo):
+def check_ploc(ctx, oracle, tris, algo, **opts):
     n = tris.size
-    tree = ctx.build(algo, tris)
+    tree = ctx.build(algo, tris, **opts)
     g = ctx.fetch(tree)
     o = oracle.build_ploc(tris, hierarchical=(algo == capi.HPLOC))
     assert np.array_equal(g["skeys"], o["skeys"]) and np.array_equal(g["svals"], o["svals"])
@@ -40,6 +40,16 @@ SYNTH = [("uniform", 2, 1), ("uniform", 3, 2), ("uniform", 17, 3), ("uniform", 3
 @pytest.mark.parametrize("kind,n,seed", SYNTH, ids=[f"{k}-{n}" for k, n, _ in SYNTH])
 def test_synthetic(ctx, oracle, algo, kind, n, seed):
     check_ploc(ctx, oracle, random_tris(n, seed, kind), algo)
+
+
+# PLOC++ merge kernel: windows decide 480 clusters, the tail kernel takes over at 1024; with few CTAs a chunk spans many windows
+PLOC_EDGES = [("uniform", 1026, 21, 0), ("uniform", 1504, 22, 0), ("uniform", 1505, 23, 0), ("uniform", 2400, 24, 2), ("uniform", 20_011, 25, 1),
+              ("uniform", 20_011, 25, 3), ("clustered", 50_000, 26, 7), ("uniform", 300_007, 27, 0), ("anisotropic", 100_000, 28, 16)]
+
+
+@pytest.mark.parametrize("kind,n,seed,ctas", PLOC_EDGES, ids=[f"{k}-{n}-ctas{c}" for k, n, _, c in PLOC_EDGES])
+def test_ploc_merge_chunks(ctx, oracle, kind, n, seed, ctas):
+    check_ploc(ctx, oracle, random_tris(n, seed, kind), capi.PLOCPP, merge_max_ctas=ctas)
 
 
 @pytest.mark.parametrize("algo,key", [(capi.PLOCPP, "ploc"), (capi.HPLOC, "hploc")], ids=["ploc", "hploc"])

@@ -22,9 +22,18 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--two-kernel", action="store_true")
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--mesh", default="", help="bunny | sponza | buddha (staged under oracle/_ref/meshes) instead of the synthetic soup")
     a = ap.parse_args()
     ctx = capi.Context(0)
-    d = ctx.synth_uniform(a.n, 0x00B20010)
+    if a.mesh:
+        import numpy as np
+        from b2bvh import types as T
+        tris = T.triangles_from_array(np.fromfile(os.path.join(ROOT, "oracle", "_ref", "meshes", a.mesh + ".tri"), dtype=np.float32).reshape(-1, 9))
+        a.n = tris.size
+        d = ctx.alloc(tris.nbytes)
+        ctx.h2d(d, tris)
+    else:
+        d = ctx.synth_uniform(a.n, 0x00B20010)
     for _ in range(a.warmup):
         tree = ctx.build(ALGOS[a.algo], d, n=a.n, tris_on_device=True, karras_two_kernel=a.two_kernel)
     agg = {}
