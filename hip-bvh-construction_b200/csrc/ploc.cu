@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(PLOC_THREADS, 4) ploc_merge_kernel(u32* ids0, 
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  u32 iter = 0, count = n, barriers = 0, phases = 0, arriveTarget = 0;
+  u32 iter = 0, count = n, barriers = 0, phases = 0, arriveTarget = 0, barTarget = 0;
   while (count > PLOC_TAIL) {
     const u32* idsIn = (iter & 1u) ? ids1 : ids0;
     u32* idsOut = (iter & 1u) ? ids0 : ids1;
@@ -201,6 +201,11 @@ __global__ void __launch_bounds__(PLOC_THREADS, 4) ploc_merge_kernel(u32* ids0, 
     const u32 chunk = ((count + G - 1) / G + PLOC_TILE - 1) / PLOC_TILE * PLOC_TILE;
     const u32 nActive = (count + chunk - 1) / chunk;
     arriveTarget += nActive;
+    /* once a chunk is a single window the number of chunks only falls: CTAs without one leave for good, and the barrier
+     * (like the arrival counter) is among the CTAs that still work */
+    const bool oneWindow = chunk == PLOC_TILE;
+    if (oneWindow && c >= nActive) break;
+    barTarget += oneWindow ? nActive : G;
     PL_TRACE(0);
     if (c < nActive) {
       const u32 cStart = c * chunk, cEnd = min(count, cStart + chunk);
@@ -353,7 +358,7 @@ __global__ void __launch_bounds__(PLOC_THREADS, 4) ploc_merge_kernel(u32* ids0, 
     if (tid == 0 && iter < 256 && (c == 0 || c == nActive - 1)) g_plocTrace[c == 0 ? 0 : 1][iter][6] = count;
 #endif
     barriers++;
-    grid_barrier(&ctrl->bar, barriers * G);
+    grid_barrier(&ctrl->bar, barTarget);
     if (tid == 0) asm volatile("fence.proxy.async.global;" ::: "memory"); /* the lists were written through the generic proxy, the bulk copies read them through the async proxy */
     PL_TRACE(5);
     {
