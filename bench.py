@@ -45,6 +45,10 @@ ALGO_BYTES = {
 }
 
 
+# nearest-neighbour merge stage, bytes per primitive over all iterations (uniform soup: sum of live clusters ~3.6 N)
+MERGE_BYTES = {"PLOC++": 160, "HPLOC": 130}
+
+
 def peak_hbm():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -295,6 +299,25 @@ def main():
             dt = time.perf_counter() - t0
             line["cpu_baseline"] = {"value": sample / dt / 1e6, "unit": "Mprims/s", "cores": 1, "kind": "port", "seconds": dt,
                                     "sample": f"first {sample} triangles of the workload, one build, binned-SAH CPU builder (BinnedSahBvh.cpp:13-204 restated in oracle/), 1 thread of {os.cpu_count()} host cores"}
+            # ---- the two nearest-neighbour builders on the same 10 M workload (north_star: PLOC++ merge vs roofline) ----
+            merge = {}
+            for nm, al, kerns, bpp in (("PLOC++", capi.PLOCPP, ("ploc_merge", "ploc_tail"), MERGE_BYTES["PLOC++"]),
+                                       ("HPLOC", capi.HPLOC, ("hploc",), MERGE_BYTES["HPLOC"])):
+                for _ in range(2):
+                    ctx.build(al, d_tris, n=n, tris_on_device=True)
+                ctx.profile(True)
+                t = ctx.build(al, d_tris, n=n, tris_on_device=True)
+                ctx.sync()
+                ent = ctx.profile_entries()
+                ctx.profile(False)
+                best = min((ctx.build(al, d_tris, n=n, tris_on_device=True) for _ in range(3)), key=lambda q: q.build_ms)
+                mms = sum(ms for name, ms in ent if name in kerns)
+                merge[nm] = {"build_ms": float(best.build_ms), "Mprims_s": n / best.build_ms / 1e3,
+                             "extents_morton_sort_build_collapse_ms": [float(best.stage_ms[k]) for k in (capi.T_EXTENTS, capi.T_MORTON, capi.T_SORT, capi.T_BUILD, capi.T_COLLAPSE)],
+                             "merge_kernels_ms": mms, "merge_algorithmic_bytes_per_prim": bpp, "merge_gbs": bpp * n / (mms * 1e-3) / 1e9,
+                             "merge_frac_of_peak": bpp * n / (mms * 1e-3) / 1e9 / peak, "iterations": int(t.n_iterations),
+                             "kernels_ms": {name: ms for name, ms in ent if "ploc" in name}}
+            line["merge_builders"] = merge
             # ---- the reference's own scenes (BASELINE configs[1]/[2]), when staged ----
             extras = {}
             mesh_dir = os.path.join(ROOT, "oracle", "_ref", "meshes")
