@@ -340,13 +340,14 @@ def main():
                                 best = (tot, [float(t.stage_ms[k]) for k in (capi.T_EXTENTS, capi.T_MORTON, capi.T_SORT, capi.T_BUILD, capi.T_COLLAPSE)])
                         res[nm] = {"total_ms": best[0], "Mprims_s": mt.size / best[0] / 1e3, "extents_morton_sort_build_collapse_ms": best[1],
                                    "bvh4_cost": ctx.tree_cost(t)}
-                        # primary rays on the built Bvh2 (TwoPassLbvh::traverseBvh, 512 x 512, while-while and speculative-while)
+                        # primary rays on the built tree (TwoPassLbvh::traverseBvh, 512 x 512): the reference's four Bvh2 kernels and the Bvh4 walk
                         pr = TRACE_PRESETS[mesh]
                         tr = T.make_transform(pr["t"], pr["s"], [0.0, 0.0, 0.0, 1.0] if pr["q"] is None else qt_rotation(pr["q"]))
                         cam = T.make_camera(pr["eye"], qt_rotation(pr["cq"]), np.float32(45.0) * np.float32(np.pi) / np.float32(180.0))
                         d_rays, ray_ms = ctx.generate_rays(cam, 512, 512)
                         trace = {"ray_gen_ms": ray_ms}
-                        for knm, kk in (("while_while", capi.TRAVERSE_WHILE), ("speculative_while", capi.TRAVERSE_SPECULATIVE_WHILE)):
+                        for knm, kk in (("while_while", capi.TRAVERSE_WHILE), ("speculative_while", capi.TRAVERSE_SPECULATIVE_WHILE),
+                                        ("if_if", capi.TRAVERSE_IFIF), ("restart_trail", capi.TRAVERSE_RESTART_TRAIL), ("bvh4", capi.TRAVERSE_WIDE4)):
                             tms = min(ctx.traverse(t, d_rays, 512 * 512, tr, kernel=kk)[2] for _ in range(5))
                             trace[knm] = {"ms": tms, "Mray_s": 512 * 512 / tms / 1e3}
                         ctx.free(d_rays)

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "libb2bvh.so")
 
 TWO_PASS_LBVH, SINGLE_PASS_LBVH, PLOCPP, HPLOC = 0, 1, 2, 3
-TRAVERSE_WHILE, TRAVERSE_SPECULATIVE_WHILE = 0, 1
+TRAVERSE_WHILE, TRAVERSE_SPECULATIVE_WHILE, TRAVERSE_IFIF, TRAVERSE_RESTART_TRAIL, TRAVERSE_WIDE4 = 0, 1, 2, 3, 4
 T_EXTENTS, T_MORTON, T_SORT, T_BUILD, T_TRAVERSAL, T_COLLAPSE, T_RAYGEN, T_COUNT = range(8)
 STAGE_NAMES = ["CalculateCentroidExtentsTime", "CalculateMortonCodesTime", "SortingTime", "BvhBuildTime", "TraversalTime",
                "CollapseTime", "RayGenTime"]
@@ -43,7 +43,7 @@ class Tree(C.Structure):
 SYMBOLS = ["b2bvh_ctx_create", "b2bvh_ctx_destroy", "b2bvh_device_name", "b2bvh_device_sm_count", "b2bvh_alloc", "b2bvh_free",
            "b2bvh_memset", "b2bvh_h2d", "b2bvh_d2h", "b2bvh_d2d", "b2bvh_sync", "b2bvh_host_alloc_pinned", "b2bvh_host_free_pinned",
            "b2bvh_last_error", "b2bvh_build", "b2bvh_scene_extents", "b2bvh_morton_codes", "b2bvh_sort_pairs", "b2bvh_generate_rays",
-           "b2bvh_traverse", "b2bvh_shard_extents", "b2bvh_top_level", "b2bvh_cost_bvh4", "b2bvh_cost_lbvh", "b2bvh_tree_cost",
+           "b2bvh_traverse", "b2bvh_traverse_ex", "b2bvh_heat_map", "b2bvh_shard_extents", "b2bvh_top_level", "b2bvh_cost_bvh4", "b2bvh_cost_lbvh", "b2bvh_tree_cost",
            "b2bvh_abi_version", "b2bvh_synth_uniform", "b2bvh_profile_enable", "b2bvh_profile_count", "b2bvh_profile_entry"]
 
 _lib = None
@@ -73,6 +73,7 @@ def load():
         "b2bvh_sort_pairs": [vp, vp, vp, vp, vp, u32, u32, u32],
         "b2bvh_generate_rays": [vp, vp, u32, u32, vp, fp],
         "b2bvh_traverse": [vp, C.POINTER(Tree), vp, u32, vp, C.c_int, vp, vp, fp],
+        "b2bvh_traverse_ex": [vp, C.POINTER(Tree), vp, u32, vp, C.c_int, vp, vp, vp, fp], "b2bvh_heat_map": [vp, u32, vp],
         "b2bvh_shard_extents": [vp, vp, u32, u32, vp], "b2bvh_top_level": [vp, vp, u32, vp],
         "b2bvh_cost_bvh4": [vp, vp, vp, u32, u32, u32], "b2bvh_cost_lbvh": [vp, u32, u32, u32],
         "b2bvh_tree_cost": [vp, C.POINTER(Tree), fp], "b2bvh_abi_version": [], "b2bvh_last_error": [],
@@ -259,21 +260,35 @@ class Context:
         check(self.lib.b2bvh_generate_rays(self.h, _hp(d_cam_host), width, height, C.c_void_p(d_rays), C.byref(ms)), "b2bvh_generate_rays")
         return d_rays, float(ms.value)
 
-    def traverse(self, tree, d_rays, n_rays, transform, kernel=TRAVERSE_WHILE, want_rgba=False):
+    def traverse(self, tree, d_rays, n_rays, transform, kernel=TRAVERSE_WHILE, want_rgba=False, want_counter=False):
+        """Returns hits, rgba (or None), ms — and the per-ray triangle-test counter as a fourth value when want_counter."""
         d_hits = self.alloc(n_rays * 32)
         d_rgba = self.alloc(n_rays * 4) if want_rgba else None
+        d_cnt = self.alloc(n_rays * 4) if want_counter else None
         ms = C.c_float()
         tr = np.ascontiguousarray(transform)
         try:
-            check(self.lib.b2bvh_traverse(self.h, C.byref(tree), C.c_void_p(d_rays), n_rays, _hp(tr), int(kernel), C.c_void_p(d_hits),
-                                          C.c_void_p(d_rgba) if d_rgba else None, C.byref(ms)), "b2bvh_traverse")
+            check(self.lib.b2bvh_traverse_ex(self.h, C.byref(tree), C.c_void_p(d_rays), n_rays, _hp(tr), int(kernel), C.c_void_p(d_hits),
+                                             C.c_void_p(d_rgba) if d_rgba else None, C.c_void_p(d_cnt) if d_cnt else None, C.byref(ms)), "b2bvh_traverse_ex")
             hits = self.download(d_hits, T.HIT, n_rays)
             rgba = self.download(d_rgba, np.uint8, n_rays * 4).reshape(-1, 4) if d_rgba else None
+            if want_counter:
+                return hits, rgba, float(ms.value), self.download(d_cnt, np.uint32, n_rays)
             return hits, rgba, float(ms.value)
         finally:
             self.free(d_hits)
             if d_rgba:
                 self.free(d_rgba)
+            if d_cnt:
+                self.free(d_cnt)
+
+
+def heat_map(counter):
+    """Utility::generateTraversalHeatMap colouring of a ray counter (host)."""
+    counter = np.ascontiguousarray(counter, dtype=np.uint32)
+    rgba = np.zeros((counter.size, 4), dtype=np.uint8)
+    check(load().b2bvh_heat_map(_hp(counter), counter.size, _hp(rgba)), "b2bvh_heat_map")
+    return rgba
 
 
 def cost_bvh4(wide, wide_leaves, prim_boxes, n):

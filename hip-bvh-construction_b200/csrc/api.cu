@@ -54,7 +54,7 @@ enum {
 
 extern "C" {
 
-uint32_t b2bvh_abi_version(void) { return 2; }
+uint32_t b2bvh_abi_version(void) { return 3; }
 const char* b2bvh_last_error(void) { return g_err; }
 
 int b2bvh_ctx_create(int device, void* cuda_stream, b2bvh_ctx** out) {

@@ -1,15 +1,18 @@
 /*
- * traverse.cu — primary-ray generation, while-while / speculative-while closest-hit traversal of the Bvh2, and the
- * top-level tree of a sharded build.
+ * traverse.cu — primary-ray generation, closest-hit traversal of the Bvh2 (while-while, speculative while-while, if-if,
+ * restart trail) and of the Bvh4, and the top-level tree of a sharded build.
  *
  * Replaces GenerateRays (CommonBlocksKernel.h:432-463), BvhTraversalWhile (TraversalKernel.h:238-335),
- * BvhTraversalSpeculativeWhile (:337-451) and their host side TwoPassLbvh::traverseBvh (TwoPassLbvh.cpp:199-311).
+ * BvhTraversalSpeculativeWhile (:337-451), BvhTraversalifif (:148-236), BvhTraversalRestartTrail (:49-146) and their host
+ * side TwoPassLbvh::traverseBvh (TwoPassLbvh.cpp:199-311).
  * Kept: pinhole camera with a 0.024 m sensor, ray index gIdx*height+gIdy at generation and gIdx*width+gIdy at traversal,
  * boxes tested in object space (inverse transform of the ray), triangles tested in world space, the slab test with
- * maxt = current hit distance, near child first / far child pushed, hit accepted when u,v,w,t > 0 and t < hit.t.
+ * maxt = current hit distance, near child first / far child pushed, hit accepted when u,v,w,t > 0 and t < hit.t, the
+ * per-ray count of triangle tests of the if-if and restart-trail kernels (rayCounter).
  * Changed: the stack has 64 entries (the reference's 32-entry stack overflows on sponza, depth 35); the tree may be in the
  * LBVH layout or in the separate-leaf layout of PLOC++/H-PLOC (the reference never traverses those); a HitInfo buffer can
- * be returned (parity is checked on hits, not pixels).  Arithmetic is evaluated without FMA, in the reference's order.
+ * be returned (parity is checked on hits, not pixels); the Bvh4 of the build can be traced (traverse_wide4_kernel; the
+ * reference builds it and only reports its cost).  Arithmetic is evaluated without FMA, in the reference's order.
  */
 #include <math.h>
 
@@ -66,6 +69,8 @@ struct TravArgs {
   b2bvh_transform tr;
   b2bvh_hit* hits;
   uint8_t* rgba;
+  u32* counter;                 /* leaf (triangle) tests per ray, or null */
+  const b2bvh_bvh4_node* wide;  /* 4-wide traversal only */
   u32 root, nInt, width, height;
 };
 
@@ -105,6 +110,20 @@ __device__ __forceinline__ void test_leaf(const TravArgs& A, u32 leaf, F3 ro, F3
   const float w = dot3(cross3(p2 + p1, e2), rd) / den;
   const float t = (dot3(p0, nrm) * 2.0f) / den;
   if (u > 0.0f && v > 0.0f && w > 0.0f && t > 0.0f && t < hit.t) { hit.prim = prim; hit.t = t; hit.u = u; hit.v = v; }
+}
+
+__device__ __forceinline__ void write_hit(const TravArgs& A, u32 index, const Hit& hit, u32 tests) {
+  if (A.hits) {
+    float4* h = reinterpret_cast<float4*>(A.hits + index);
+    h[0] = make_float4(__uint_as_float(hit.prim), hit.t, hit.u, hit.v);
+    h[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (A.counter) A.counter[index] = tests;
+  if (A.rgba && hit.prim != B2_INVALID) {
+    uchar4 c;
+    c.x = (unsigned char)(hit.u * 255); c.y = (unsigned char)(hit.v * 255); c.z = (unsigned char)((1 - hit.u - hit.v) * 255); c.w = 255;
+    reinterpret_cast<uchar4*>(A.rgba)[index] = c;
+  }
 }
 
 template <bool SEPARATE, bool SPECULATIVE>
@@ -167,16 +186,173 @@ __global__ void __launch_bounds__(64) traverse_kernel(TravArgs A) {
     }
   }
   if (!inside) return;
-  if (A.hits) {
-    float4* h = reinterpret_cast<float4*>(A.hits + index);
-    h[0] = make_float4(__uint_as_float(hit.prim), hit.t, hit.u, hit.v);
-    h[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+  write_hit(A, index, hit, 0u);
+}
+
+/* ---- the reference's two other Bvh2 kernels: BvhTraversalifif (TraversalKernel.h:148-236; one node per step, 64-entry
+ * stack — the kernel TwoPassLbvh::traverseBvh launches under IFIF, TwoPassLbvh.cpp:250-269) and BvhTraversalRestartTrail
+ * (:49-146 with pop() :32-47; stackless, a 64-bit trail, restarts from the root).  Both keep the per-ray count of triangle
+ * tests (rayCounter) that feeds the heat map (Utility.cpp:424-454).  Restart trail: the reference restarts from node 0
+ * (:44), which is the root only for the Karras numbering; the root index is used here.  On a tie of the entry distances the
+ * stack kernels visit the right child first (:219), the trail kernel the left one (:112-116). ---- */
+template <bool SEPARATE, bool RESTART>
+__global__ void __launch_bounds__(64) traverse_step_kernel(TravArgs A) {
+  const u32 gx = blockIdx.x * 8 + (threadIdx.x & 7u), gy = blockIdx.y * 8 + (threadIdx.x >> 3);
+  if (gx >= A.width || gy >= A.height) return;
+  const u32 index = gx * A.width + gy;
+  const float4* rp = reinterpret_cast<const float4*>(A.rays + index);
+  const float4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+  const F3 ro = f3(r0.x, r0.y, r0.z), rd = f3(r0.w, r1.x, r1.y);
+  const F3 ts = f3(A.tr.m_scale.x, A.tr.m_scale.y, A.tr.m_scale.z), tt = f3(A.tr.m_translation.x, A.tr.m_translation.y, A.tr.m_translation.z);
+  const F4 tq = F4{A.tr.m_quat.x, A.tr.m_quat.y, A.tr.m_quat.z, A.tr.m_quat.w};
+  const F3 oo = to_object(ro, ts, tq, tt), od = to_object(rd, ts, tq, f3(0.0f, 0.0f, 0.0f));
+  const F3 inv = f3(1.0f / od.x, 1.0f / od.y, 1.0f / od.z);
+  Hit hit = Hit{B2_INVALID, B2_FLT_MAX, 0.0f, 0.0f};
+  u32 tests = 0;
+  u32 node = A.root;
+  if (!RESTART) {
+    u32 stack[64];
+    u32 top = 0;
+    stack[top++] = B2_INVALID;
+    while (node != B2_INVALID) {
+      if (node >= A.nInt) {
+        test_leaf<SEPARATE>(A, node, ro, rd, ts, tq, tt, hit);
+        tests++;
+      } else {
+        const uint2 ch = __ldg(reinterpret_cast<const uint2*>(A.nodes + node));
+        const Box lb = child_box<SEPARATE>(A, ch.x), rb = child_box<SEPARATE>(A, ch.y);
+        float n0, f0, n1, f1;
+        slab(lb, oo, inv, hit.t, n0, f0);
+        slab(rb, oo, inv, hit.t, n1, f1);
+        const bool hl = n0 <= f0, hr = n1 <= f1;
+        if (hl || hr) {
+          if (hl && hr) {
+            const bool leftFirst = n0 < n1;
+            node = leftFirst ? ch.x : ch.y;
+            if (top < 64) stack[top++] = leftFirst ? ch.y : ch.x;
+          } else {
+            node = hl ? ch.x : ch.y;
+          }
+          continue;
+        }
+      }
+      node = stack[--top];
+    }
+  } else {
+    const u64 TOP = 0x8000000000000000ull;
+    u64 trail = TOP, level = TOP, popLevel = 0;
+    bool done = false;
+    auto pop = [&]() -> bool {
+      trail &= (0ull - level);
+      trail += level;
+      const u64 temp = trail >> 1;
+      level = ((temp - 1) ^ temp) + 1;
+      if (!(trail & TOP)) return true;
+      popLevel = level;
+      node = A.root;
+      level = TOP;
+      return false;
+    };
+    while (!done) {
+      if (node >= A.nInt) {
+        test_leaf<SEPARATE>(A, node, ro, rd, ts, tq, tt, hit);
+        tests++;
+        done = pop();
+      } else {
+        const uint2 ch = __ldg(reinterpret_cast<const uint2*>(A.nodes + node));
+        const Box lb = child_box<SEPARATE>(A, ch.x), rb = child_box<SEPARATE>(A, ch.y);
+        float n0, f0, n1, f1;
+        slab(lb, oo, inv, hit.t, n0, f0);
+        slab(rb, oo, inv, hit.t, n1, f1);
+        const bool hl = n0 <= f0, hr = n1 <= f1;
+        if (hl && hr) {
+          const bool swap = n0 > n1;
+          const u32 nearC = swap ? ch.y : ch.x, farC = swap ? ch.x : ch.y;
+          level >>= 1;
+          node = (trail & level) ? farC : nearC;
+        } else if (hl || hr) {
+          level >>= 1;
+          if (level != popLevel) { trail |= level; node = hr ? ch.y : ch.x; }
+          else done = pop();
+        } else {
+          done = pop();
+        }
+      }
+    }
   }
-  if (A.rgba && hit.prim != B2_INVALID) {
-    uchar4 c;
-    c.x = (unsigned char)(hit.u * 255); c.y = (unsigned char)(hit.v * 255); c.z = (unsigned char)((1 - hit.u - hit.v) * 255); c.w = 255;
-    reinterpret_cast<uchar4*>(A.rgba)[index] = c;
+  write_hit(A, index, hit, tests);
+}
+
+/* ---- closest hit through the 4-wide tree (new: the reference builds the Bvh4 but never walks it).  Visiting a wide node:
+ * leaf children first, in slot order — box and primitive from the Bvh2 leaf record (a wide node stores no box for them,
+ * TwoPassLbvhKernel.h:320-325), triangle tested when the slab test passes; then the internal children are slab-tested
+ * with the updated hit distance and visited nearest first (entry distance, slot order among equals), the others pushed
+ * far to near on a 128-entry stack.  Mirrors orc_traverse_wide4 of the oracle. ---- */
+template <bool SEPARATE>
+__global__ void __launch_bounds__(64) traverse_wide4_kernel(TravArgs A) {
+  const u32 gx = blockIdx.x * 8 + (threadIdx.x & 7u), gy = blockIdx.y * 8 + (threadIdx.x >> 3);
+  if (gx >= A.width || gy >= A.height) return;
+  const u32 index = gx * A.width + gy;
+  const float4* rp = reinterpret_cast<const float4*>(A.rays + index);
+  const float4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+  const F3 ro = f3(r0.x, r0.y, r0.z), rd = f3(r0.w, r1.x, r1.y);
+  const F3 ts = f3(A.tr.m_scale.x, A.tr.m_scale.y, A.tr.m_scale.z), tt = f3(A.tr.m_translation.x, A.tr.m_translation.y, A.tr.m_translation.z);
+  const F4 tq = F4{A.tr.m_quat.x, A.tr.m_quat.y, A.tr.m_quat.z, A.tr.m_quat.w};
+  const F3 oo = to_object(ro, ts, tq, tt), od = to_object(rd, ts, tq, f3(0.0f, 0.0f, 0.0f));
+  const F3 inv = f3(1.0f / od.x, 1.0f / od.y, 1.0f / od.z);
+  Hit hit = Hit{B2_INVALID, B2_FLT_MAX, 0.0f, 0.0f};
+  u32 tests = 0;
+  u32 stack[128];
+  u32 top = 0;
+  stack[top++] = B2_INVALID;
+  u32 node = 0;
+  while (node != B2_INVALID) {
+    const float2* wb = reinterpret_cast<const float2*>(A.wide + node); /* 4 boxes of 24 B, then m_child[4] at byte 96 */
+    const uint4 chv = __ldg(reinterpret_cast<const uint4*>(A.wide + node) + 6);
+    const u32 ch[4] = {chv.x, chv.y, chv.z, chv.w};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const u32 c = ch[k];
+      if (c == B2_INVALID || c < A.nInt) continue;
+      float n0, f0;
+      slab(child_box<SEPARATE>(A, c), oo, inv, hit.t, n0, f0);
+      if (!(n0 <= f0)) continue;
+      test_leaf<SEPARATE>(A, c, ro, rd, ts, tq, tt, hit);
+      tests++;
+    }
+    float tn[4];
+    bool hitK[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      hitK[k] = false; tn[k] = 0.0f;
+      const u32 c = ch[k];
+      if (c == B2_INVALID || c >= A.nInt) continue;
+      const float2 q0 = __ldg(wb + 3 * k), q1 = __ldg(wb + 3 * k + 1), q2 = __ldg(wb + 3 * k + 2);
+      float f0;
+      slab(Box{q0.x, q0.y, q1.x, q1.y, q2.x, q2.y}, oo, inv, hit.t, tn[k], f0);
+      hitK[k] = tn[k] <= f0;
+    }
+    /* rank among the children hit: by entry distance, slot order among equals */
+    u32 rank[4], m = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      rank[k] = 0;
+      if (hitK[k]) m++;
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+        if (j != k && hitK[j] && (tn[j] < tn[k] || (tn[j] == tn[k] && j < k))) rank[k]++;
+    }
+    if (m == 0) { node = stack[--top]; continue; }
+#pragma unroll
+    for (int r = 3; r >= 1; r--)
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        if (hitK[k] && rank[k] == (u32)r && top < 128) stack[top++] = ch[k];
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      if (hitK[k] && rank[k] == 0) node = ch[k];
   }
+  write_hit(A, index, hit, tests);
 }
 
 /* ---- top-level tree over the G sub-tree root boxes of a sharded build (G <= 256): Morton codes of the box centres in the
@@ -256,30 +432,67 @@ int b2bvh_generate_rays(b2bvh_ctx* ctx, const b2bvh_camera* cam, uint32_t width,
   return 0;
 }
 
-int b2bvh_traverse(b2bvh_ctx* ctx, const b2bvh_tree* tree, const b2bvh_ray* d_rays, uint32_t n_rays, const b2bvh_transform* xform, int kernel,
-                   b2bvh_hit* d_hits, uint8_t* d_rgba, float* ms) {
+int b2bvh_traverse_ex(b2bvh_ctx* ctx, const b2bvh_tree* tree, const b2bvh_ray* d_rays, uint32_t n_rays, const b2bvh_transform* xform, int kernel,
+                      b2bvh_hit* d_hits, uint8_t* d_rgba, uint32_t* d_rayCounter, float* ms) {
   if (!ctx || !tree || !d_rays || !xform || n_rays == 0) return b2_fail(B2BVH_ERR_INVALID, "traverse: bad argument");
-  if (kernel != B2BVH_TRAVERSE_WHILE && kernel != B2BVH_TRAVERSE_SPECULATIVE_WHILE) return b2_fail(B2BVH_ERR_INVALID, "traverse: unknown kernel %d", kernel);
+  if (kernel < B2BVH_TRAVERSE_WHILE || kernel > B2BVH_TRAVERSE_WIDE4) return b2_fail(B2BVH_ERR_INVALID, "traverse: unknown kernel %d", kernel);
+  if (kernel == B2BVH_TRAVERSE_WIDE4 && (tree->n_wide == 0 || !tree->d_wideBvhNodes))
+    return b2_fail(B2BVH_ERR_INVALID, "traverse: the tree has no 4-wide nodes (build with collapse = 1)");
+  if (d_rayCounter && (kernel == B2BVH_TRAVERSE_WHILE || kernel == B2BVH_TRAVERSE_SPECULATIVE_WHILE))
+    return b2_fail(B2BVH_ERR_INVALID, "traverse: the while-while kernels keep no ray counter (as in the reference); use IFIF, RESTART_TRAIL or WIDE4");
   /* the reference traces square images (width == height == 512, TwoPassLbvh.cpp:221-222); n_rays must be a square */
   const u32 side = (u32)(sqrt((double)n_rays) + 0.5);
   if ((uint64_t)side * side != n_rays) return b2_fail(B2BVH_ERR_INVALID, "traverse: n_rays=%u is not a square image", n_rays);
   TravArgs A;
   A.rays = d_rays; A.nodes = tree->d_bvhNodes; A.leaves = tree->leaves_separate ? tree->d_leafNodes : nullptr; A.tris = tree->d_triangleBuff;
-  A.tr = *xform; A.hits = d_hits; A.rgba = d_rgba; A.root = tree->root; A.nInt = tree->n_internal; A.width = side; A.height = side;
+  A.tr = *xform; A.hits = d_hits; A.rgba = d_rgba; A.counter = d_rayCounter; A.wide = tree->d_wideBvhNodes;
+  A.root = tree->root; A.nInt = tree->n_internal; A.width = side; A.height = side;
   if (d_rgba) B2_CUDA(cudaMemsetAsync(d_rgba, 0, (size_t)n_rays * 4, ctx->stream));
   const dim3 grid((side + 7) / 8, (side + 7) / 8);
+  static const char* const names[] = {"traverse_while", "traverse_speculative_while", "traverse_ifif", "traverse_restart_trail", "traverse_wide4"};
   B2_CUDA(cudaEventRecord(ctx->ev[10], ctx->stream));
-  B2_KERNEL(ctx, kernel == B2BVH_TRAVERSE_WHILE ? "traverse_while" : "traverse_speculative_while");
+  B2_KERNEL(ctx, names[kernel]);
   const bool sep = tree->leaves_separate != 0;
-  if (kernel == B2BVH_TRAVERSE_WHILE) {
-    if (sep) traverse_kernel<true, false><<<grid, 64, 0, ctx->stream>>>(A); else traverse_kernel<false, false><<<grid, 64, 0, ctx->stream>>>(A);
-  } else {
-    if (sep) traverse_kernel<true, true><<<grid, 64, 0, ctx->stream>>>(A); else traverse_kernel<false, true><<<grid, 64, 0, ctx->stream>>>(A);
+  switch (kernel) {
+    case B2BVH_TRAVERSE_WHILE:
+      if (sep) traverse_kernel<true, false><<<grid, 64, 0, ctx->stream>>>(A); else traverse_kernel<false, false><<<grid, 64, 0, ctx->stream>>>(A);
+      break;
+    case B2BVH_TRAVERSE_SPECULATIVE_WHILE:
+      if (sep) traverse_kernel<true, true><<<grid, 64, 0, ctx->stream>>>(A); else traverse_kernel<false, true><<<grid, 64, 0, ctx->stream>>>(A);
+      break;
+    case B2BVH_TRAVERSE_IFIF:
+      if (sep) traverse_step_kernel<true, false><<<grid, 64, 0, ctx->stream>>>(A); else traverse_step_kernel<false, false><<<grid, 64, 0, ctx->stream>>>(A);
+      break;
+    case B2BVH_TRAVERSE_RESTART_TRAIL:
+      if (sep) traverse_step_kernel<true, true><<<grid, 64, 0, ctx->stream>>>(A); else traverse_step_kernel<false, true><<<grid, 64, 0, ctx->stream>>>(A);
+      break;
+    default:
+      if (sep) traverse_wide4_kernel<true><<<grid, 64, 0, ctx->stream>>>(A); else traverse_wide4_kernel<false><<<grid, 64, 0, ctx->stream>>>(A);
+      break;
   }
   B2_LAUNCH_CHECK(ctx);
   B2_CUDA(cudaEventRecord(ctx->ev[11], ctx->stream));
   B2_CUDA(cudaEventSynchronize(ctx->ev[11]));
   if (ms) B2_CUDA(cudaEventElapsedTime(ms, ctx->ev[10], ctx->ev[11]));
+  return 0;
+}
+
+int b2bvh_traverse(b2bvh_ctx* ctx, const b2bvh_tree* tree, const b2bvh_ray* d_rays, uint32_t n_rays, const b2bvh_transform* xform, int kernel,
+                   b2bvh_hit* d_hits, uint8_t* d_rgba, float* ms) {
+  return b2bvh_traverse_ex(ctx, tree, d_rays, n_rays, xform, kernel, d_hits, d_rgba, nullptr, ms);
+}
+
+/* Utility::generateTraversalHeatMap (Utility.cpp:424-454) without the PNG write; host function on host buffers. */
+int b2bvh_heat_map(const uint32_t* rayCounter, uint32_t count, uint8_t* rgba) {
+  if (!rayCounter || !rgba || count == 0) return b2_fail(B2BVH_ERR_INVALID, "heat_map: bad argument");
+  uint32_t mx = 0;
+  for (uint32_t i = 0; i < count; i++) if (rayCounter[i] > mx) mx = rayCounter[i];
+  for (uint32_t i = 0; i < count; i++) {
+    rgba[i * 4 + 0] = (uint8_t)((rayCounter[i] / (float)mx) * 150);
+    rgba[i * 4 + 1] = (uint8_t)((rayCounter[i] / (float)mx) * 255);
+    rgba[i * 4 + 2] = 255;
+    rgba[i * 4 + 3] = 255;
+  }
   return 0;
 }
 

@@ -64,7 +64,7 @@ struct Api {
 #define B2_SYM(name) decltype(&::name) name = nullptr;
   B2_SYM(b2bvh_ctx_create) B2_SYM(b2bvh_ctx_destroy) B2_SYM(b2bvh_device_name) B2_SYM(b2bvh_device_sm_count) B2_SYM(b2bvh_alloc)
   B2_SYM(b2bvh_free) B2_SYM(b2bvh_memset) B2_SYM(b2bvh_h2d) B2_SYM(b2bvh_d2h) B2_SYM(b2bvh_sync) B2_SYM(b2bvh_last_error)
-  B2_SYM(b2bvh_build) B2_SYM(b2bvh_generate_rays) B2_SYM(b2bvh_traverse) B2_SYM(b2bvh_tree_cost) B2_SYM(b2bvh_cost_bvh4)
+  B2_SYM(b2bvh_build) B2_SYM(b2bvh_generate_rays) B2_SYM(b2bvh_traverse) B2_SYM(b2bvh_traverse_ex) B2_SYM(b2bvh_heat_map) B2_SYM(b2bvh_tree_cost) B2_SYM(b2bvh_cost_bvh4)
   B2_SYM(b2bvh_cost_lbvh) B2_SYM(b2bvh_synth_uniform) B2_SYM(b2bvh_abi_version)
 #undef B2_SYM
   void* handle = nullptr;
@@ -80,7 +80,7 @@ struct Api {
   if (!api.name) throw std::runtime_error(std::string("libb2bvh.so lacks symbol ") + #name);
     B2_SYM(b2bvh_ctx_create) B2_SYM(b2bvh_ctx_destroy) B2_SYM(b2bvh_device_name) B2_SYM(b2bvh_device_sm_count) B2_SYM(b2bvh_alloc)
     B2_SYM(b2bvh_free) B2_SYM(b2bvh_memset) B2_SYM(b2bvh_h2d) B2_SYM(b2bvh_d2h) B2_SYM(b2bvh_sync) B2_SYM(b2bvh_last_error)
-    B2_SYM(b2bvh_build) B2_SYM(b2bvh_generate_rays) B2_SYM(b2bvh_traverse) B2_SYM(b2bvh_tree_cost) B2_SYM(b2bvh_cost_bvh4)
+    B2_SYM(b2bvh_build) B2_SYM(b2bvh_generate_rays) B2_SYM(b2bvh_traverse) B2_SYM(b2bvh_traverse_ex) B2_SYM(b2bvh_heat_map) B2_SYM(b2bvh_tree_cost) B2_SYM(b2bvh_cost_bvh4)
     B2_SYM(b2bvh_cost_lbvh) B2_SYM(b2bvh_synth_uniform) B2_SYM(b2bvh_abi_version)
 #undef B2_SYM
     return api;
@@ -158,6 +158,7 @@ struct BuilderBase {
   float m_cost = 0.0f;
   b2bvh_tree m_tree{};
   std::vector<HitInfo> m_hits;
+  std::vector<u32> m_rayCounter; /* triangle tests per ray (if-if, restart trail, Bvh4); Utility::generateTraversalHeatMap input */
   Transformation m_transform{};
   Camera m_camera{};
   u32 m_width = 512, m_height = 512; /* TwoPassLbvh.cpp:221-222 */
@@ -233,11 +234,23 @@ struct BuilderBase {
       float ms = 0;
       checkStatus(api.b2bvh_generate_rays(context.m_ctx, &m_camera, m_width, m_height, (Ray*)dRays, &ms), "b2bvh_generate_rays");
       m_timer.timeRecord[RayGenTime] += ms;
-      checkStatus(api.b2bvh_traverse(context.m_ctx, &m_tree, (const Ray*)dRays, nRays, &m_transform, m_traversalKernel, (HitInfo*)dHits, nullptr, &ms),
-                  "b2bvh_traverse");
+      /* the if-if / restart-trail kernels of the reference (and the Bvh4 kernel) also count the triangle tests per ray:
+       * d_rayCounterBuffer, TwoPassLbvh.cpp:224,267,272 */
+      const bool counted = m_traversalKernel >= B2BVH_TRAVERSE_IFIF;
+      void* dCounter = nullptr;
+      if (counted) checkStatus(api.b2bvh_alloc(context.m_ctx, (size_t)nRays * sizeof(u32), &dCounter), "b2bvh_alloc");
+      checkStatus(api.b2bvh_traverse_ex(context.m_ctx, &m_tree, (const Ray*)dRays, nRays, &m_transform, m_traversalKernel, (HitInfo*)dHits, nullptr,
+                                        (u32*)dCounter, &ms),
+                  "b2bvh_traverse_ex");
       m_timer.timeRecord[TraversalTime] += ms;
       m_hits.resize(nRays);
       checkStatus(api.b2bvh_d2h(context.m_ctx, m_hits.data(), dHits, (size_t)nRays * sizeof(HitInfo)), "b2bvh_d2h");
+      m_rayCounter.clear();
+      if (counted) {
+        m_rayCounter.resize(nRays);
+        checkStatus(api.b2bvh_d2h(context.m_ctx, m_rayCounter.data(), dCounter, (size_t)nRays * sizeof(u32)), "b2bvh_d2h");
+        api.b2bvh_free(context.m_ctx, dCounter);
+      }
       api.b2bvh_free(context.m_ctx, dRays);
       api.b2bvh_free(context.m_ctx, dHits);
     }

@@ -41,7 +41,10 @@ typedef enum b2bvh_algo {
 
 typedef enum b2bvh_traversal {
   B2BVH_TRAVERSE_WHILE = 0,            /* BvhTraversalWhile            src/TraversalKernel.h:238 */
-  B2BVH_TRAVERSE_SPECULATIVE_WHILE = 1 /* BvhTraversalSpeculativeWhile src/TraversalKernel.h:337 */
+  B2BVH_TRAVERSE_SPECULATIVE_WHILE = 1, /* BvhTraversalSpeculativeWhile src/TraversalKernel.h:337 */
+  B2BVH_TRAVERSE_IFIF = 2,              /* BvhTraversalifif             src/TraversalKernel.h:148 (TwoPassLbvh.cpp:250-269 under IFIF) */
+  B2BVH_TRAVERSE_RESTART_TRAIL = 3,     /* BvhTraversalRestartTrail     src/TraversalKernel.h:49  (stackless)                         */
+  B2BVH_TRAVERSE_WIDE4 = 4              /* closest hit through the Bvh4 of the build (no reference kernel: the reference never walks it) */
 } b2bvh_traversal;
 
 typedef struct b2bvh_ctx b2bvh_ctx; /* opaque: device + stream + scratch arena; replaces Context (src/Context.cpp:7-15) */
@@ -124,6 +127,13 @@ int b2bvh_generate_rays(b2bvh_ctx* ctx, const b2bvh_camera* cam, uint32_t width,
                         float* ms);                       /* GenerateRays, CommonBlocksKernel.h:432-463 */
 int b2bvh_traverse(b2bvh_ctx* ctx, const b2bvh_tree* tree, const b2bvh_ray* d_rays, uint32_t n_rays, const b2bvh_transform* xform,
                    int kernel, b2bvh_hit* d_hits /* may be NULL */, uint8_t* d_rgba /* may be NULL */, float* ms);
+
+/* same, plus the per-ray count of triangle tests the reference's if-if / restart-trail kernels keep (rayCounter, u32 per ray,
+ * TwoPassLbvh.cpp:224,267; NULL: not wanted; not available for the two while-while kernels, as in the reference) */
+int b2bvh_traverse_ex(b2bvh_ctx* ctx, const b2bvh_tree* tree, const b2bvh_ray* d_rays, uint32_t n_rays, const b2bvh_transform* xform,
+                      int kernel, b2bvh_hit* d_hits, uint8_t* d_rgba, uint32_t* d_rayCounter, float* ms);
+/* Utility::generateTraversalHeatMap (Utility.cpp:424-454) on HOST buffers, without the PNG write: rgba = (c/max*150, c/max*255, 255, 255) */
+int b2bvh_heat_map(const uint32_t* rayCounter, uint32_t count, uint8_t* rgba);
 
 /* ---- sharded (multi-GPU) build helpers; new work specified by the north star, no reference counterpart.
  * rank-local steps only — the 6-float all-reduce and the root all-gather between them belong to the caller's

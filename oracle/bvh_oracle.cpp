@@ -820,6 +820,185 @@ u32 orc_traverse(const b2bvh_ray* rays, const b2bvh_bvh2_node* nodes, const b2bv
   return nHit;
 }
 
+/* The same closest-hit query with the reference's other two Bvh2 kernels, plus the per-ray leaf-test counter they keep
+ * (rayCounter, TraversalKernel.h:88,192) and the 4-wide traversal this project adds.
+ *   kind 0: BvhTraversalifif (TraversalKernel.h:148-236) — one node per step; same visiting order as orc_traverse.
+ *   kind 1: BvhTraversalRestartTrail (:49-146) with pop() (:32-47) — stackless, restarts from the root (the reference
+ *           restarts from node 0, :44, which is the root only for TwoPassLbvh; rootIdx is used here), near child on a tie
+ *           is the LEFT one (:112-116; the stack kernels take the right one, :219).  Trees deeper than 63 are not supported
+ *           by a 64-bit trail.
+ * counter may be NULL.  Returns the hit count. */
+u32 orc_traverse_kind(u32 kind, const b2bvh_ray* rays, const b2bvh_bvh2_node* nodes, const b2bvh_prim_ref* leaves, const b2bvh_triangle* tris,
+                      const b2bvh_transform* tr, u32 root, u32 nInt, u32 nRays, b2bvh_hit* hits, u32* counter) {
+  if (kind == 0) {
+    u32 nHit = orc_traverse(rays, nodes, leaves, tris, tr, root, nInt, nRays, hits);
+    if (counter) { /* leaf tests per ray: replay the walk, counting */
+      for (u32 idx = 0; idx < nRays; idx++) {
+        const b2bvh_ray& ray = rays[idx];
+        F3 o = inv_transform(ray.m_origin, tr->m_scale, tr->m_quat, tr->m_translation);
+        F3 d = inv_transform(ray.m_direction, tr->m_scale, tr->m_quat, f3(0, 0, 0));
+        F3 inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+        float ht = FLTMAX;
+        u32 stack[64]; u32 top = 0; stack[top++] = INVALID;
+        u32 node = root, cnt = 0;
+        while (node != INVALID) {
+          if (node >= nInt) {
+            u32 prim = leaves ? leaves[node - nInt].m_primIdx : nodes[node].m_leftChildIdx;
+            const b2bvh_triangle& t = tris[prim];
+            F3 a = fwd_transform(t.v1, tr->m_scale, tr->m_quat, tr->m_translation);
+            F3 b = fwd_transform(t.v2, tr->m_scale, tr->m_quat, tr->m_translation);
+            F3 c = fwd_transform(t.v3, tr->m_scale, tr->m_quat, tr->m_translation);
+            float r[4]; tri_hit(a, b, c, ray.m_origin, ray.m_direction, r);
+            cnt++;
+            if (r[0] > 0.0f && r[1] > 0.0f && r[2] > 0.0f && r[3] > 0.0f && r[3] < ht) ht = r[3];
+          } else {
+            u32 l = nodes[node].m_leftChildIdx, r = nodes[node].m_rightChildIdx;
+            const Box& lb = l >= nInt && leaves ? leaves[l - nInt].m_aabb : nodes[l].m_aabb;
+            const Box& rb = r >= nInt && leaves ? leaves[r - nInt].m_aabb : nodes[r].m_aabb;
+            float n0, f0, n1, f1; slab(lb, o, inv, ht, n0, f0); slab(rb, o, inv, ht, n1, f1);
+            bool hl = n0 <= f0, hr = n1 <= f1;
+            if (hl || hr) {
+              if (hl && hr) { node = n0 < n1 ? l : r; if (top < 64) stack[top++] = n0 < n1 ? r : l; }
+              else node = hl ? l : r;
+              continue;
+            }
+          }
+          node = stack[--top];
+        }
+        counter[idx] = cnt;
+      }
+    }
+    return nHit;
+  }
+  u32 nHit = 0;
+  const unsigned long long TOP = 0x8000000000000000ull;
+  for (u32 idx = 0; idx < nRays; idx++) {
+    const b2bvh_ray& ray = rays[idx];
+    F3 o = inv_transform(ray.m_origin, tr->m_scale, tr->m_quat, tr->m_translation);
+    F3 d = inv_transform(ray.m_direction, tr->m_scale, tr->m_quat, f3(0, 0, 0));
+    F3 inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    b2bvh_hit hit; hit.m_primIdx = INVALID; hit.m_t = FLTMAX; hit.m_u = 0; hit.m_v = 0;
+    unsigned long long trail = TOP, level = TOP, popLevel = 0;
+    u32 node = root, cnt = 0;
+    bool done = false;
+    auto pop = [&]() -> bool {   /* pop(), TraversalKernel.h:32-47 */
+      trail &= (0ull - level);
+      trail += level;
+      unsigned long long temp = trail >> 1;
+      level = (((temp - 1) ^ temp) + 1);
+      if (!(trail & TOP)) return true;
+      popLevel = level;
+      node = root;
+      level = TOP;
+      return false;
+    };
+    while (!done) {
+      if (node >= nInt) {
+        u32 prim = leaves ? leaves[node - nInt].m_primIdx : nodes[node].m_leftChildIdx;
+        const b2bvh_triangle& t = tris[prim];
+        F3 a = fwd_transform(t.v1, tr->m_scale, tr->m_quat, tr->m_translation);
+        F3 b = fwd_transform(t.v2, tr->m_scale, tr->m_quat, tr->m_translation);
+        F3 c = fwd_transform(t.v3, tr->m_scale, tr->m_quat, tr->m_translation);
+        float r[4]; tri_hit(a, b, c, ray.m_origin, ray.m_direction, r);
+        cnt++;
+        if (r[0] > 0.0f && r[1] > 0.0f && r[2] > 0.0f && r[3] > 0.0f && r[3] < hit.m_t) { hit.m_primIdx = prim; hit.m_t = r[3]; hit.m_u = r[0]; hit.m_v = r[1]; }
+        done = pop();
+      } else {
+        u32 l = nodes[node].m_leftChildIdx, r = nodes[node].m_rightChildIdx;
+        const Box& lb = l >= nInt && leaves ? leaves[l - nInt].m_aabb : nodes[l].m_aabb;
+        const Box& rb = r >= nInt && leaves ? leaves[r - nInt].m_aabb : nodes[r].m_aabb;
+        float n0, f0, n1, f1; slab(lb, o, inv, hit.m_t, n0, f0); slab(rb, o, inv, hit.m_t, n1, f1);
+        bool hl = n0 <= f0, hr = n1 <= f1;
+        if (hl || hr) {
+          if (hl && hr) {
+            u32 nearC = l, farC = r;
+            if (n0 > n1) { nearC = r; farC = l; }
+            level >>= 1;
+            node = (trail & level) ? farC : nearC;
+          } else {
+            level >>= 1;
+            if (level != popLevel) { trail |= level; node = hr ? r : l; }
+            else done = pop();
+          }
+        } else done = pop();
+      }
+    }
+    hits[idx] = hit;
+    if (counter) counter[idx] = cnt;
+    nHit += hit.m_primIdx != INVALID;
+  }
+  return nHit;
+}
+
+/* Closest hit through the 4-wide tree (the reference builds it, TwoPassLbvh.cpp:154-183, but has no kernel that walks it;
+ * defined here and mirrored by traverse_wide4_kernel).  Visiting a wide node: (1) its leaf children are handled in slot
+ * order — a wide node stores no box for them (TwoPassLbvhKernel.h:320-325), so box and primitive come from the Bvh2 leaf
+ * record (LBVH layout: nodes[c]; separate-leaf layout: leaves[c - nInt]); the triangle is intersected when the slab test
+ * with the current hit distance passes; (2) the boxes of its internal children are slab-tested with the hit distance
+ * after (1); (3) the children hit are visited nearest first (entry distance, slot order among equals): the nearest is
+ * next, the others are pushed far to near on a 128-entry stack (dropped when full).  Same triangle test, transform and
+ * acceptance rule as the Bvh2 kernels.  counter = triangle tests per ray. */
+u32 orc_traverse_wide4(const b2bvh_ray* rays, const b2bvh_bvh4_node* wide, const b2bvh_bvh2_node* nodes, const b2bvh_prim_ref* leaves,
+                       const b2bvh_triangle* tris, const b2bvh_transform* tr, u32 nInt, u32 nRays, b2bvh_hit* hits, u32* counter) {
+  u32 nHit = 0;
+  for (u32 idx = 0; idx < nRays; idx++) {
+    const b2bvh_ray& ray = rays[idx];
+    F3 o = inv_transform(ray.m_origin, tr->m_scale, tr->m_quat, tr->m_translation);
+    F3 d = inv_transform(ray.m_direction, tr->m_scale, tr->m_quat, f3(0, 0, 0));
+    F3 inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    b2bvh_hit hit; hit.m_primIdx = INVALID; hit.m_t = FLTMAX; hit.m_u = 0; hit.m_v = 0;
+    u32 stack[128]; u32 top = 0; stack[top++] = INVALID;
+    u32 node = 0, cnt = 0;
+    while (node != INVALID) {
+      const b2bvh_bvh4_node& w = wide[node];
+      for (int k = 0; k < 4; k++) {
+        const u32 c = w.m_child[k];
+        if (c == INVALID || c < nInt) continue;
+        const Box& lb = leaves ? leaves[c - nInt].m_aabb : nodes[c].m_aabb;
+        float n0, f0; slab(lb, o, inv, hit.m_t, n0, f0);
+        if (!(n0 <= f0)) continue;
+        const u32 prim = leaves ? leaves[c - nInt].m_primIdx : nodes[c].m_leftChildIdx;
+        const b2bvh_triangle& t = tris[prim];
+        F3 a = fwd_transform(t.v1, tr->m_scale, tr->m_quat, tr->m_translation);
+        F3 b = fwd_transform(t.v2, tr->m_scale, tr->m_quat, tr->m_translation);
+        F3 cc = fwd_transform(t.v3, tr->m_scale, tr->m_quat, tr->m_translation);
+        float r[4]; tri_hit(a, b, cc, ray.m_origin, ray.m_direction, r);
+        cnt++;
+        if (r[0] > 0.0f && r[1] > 0.0f && r[2] > 0.0f && r[3] > 0.0f && r[3] < hit.m_t) { hit.m_primIdx = prim; hit.m_t = r[3]; hit.m_u = r[0]; hit.m_v = r[1]; }
+      }
+      u32 ids[4]; float tn[4]; int m = 0;
+      for (int k = 0; k < 4; k++) {
+        const u32 c = w.m_child[k];
+        if (c == INVALID || c >= nInt) continue;
+        float n0, f0; slab(w.m_aabb[k], o, inv, hit.m_t, n0, f0);
+        if (!(n0 <= f0)) continue;
+        int pos = m++;   /* insertion by entry distance, stable in slot order */
+        while (pos > 0 && tn[pos - 1] > n0) { tn[pos] = tn[pos - 1]; ids[pos] = ids[pos - 1]; pos--; }
+        tn[pos] = n0; ids[pos] = c;
+      }
+      if (m == 0) { node = stack[--top]; continue; }
+      for (int k = m - 1; k >= 1; k--) if (top < 128) stack[top++] = ids[k];
+      node = ids[0];
+    }
+    hits[idx] = hit;
+    if (counter) counter[idx] = cnt;
+    nHit += hit.m_primIdx != INVALID;
+  }
+  return nHit;
+}
+
+/* Utility::generateTraversalHeatMap (Utility.cpp:424-454) without the PNG write: rgba[index] = (c/max*150, c/max*255, 255, 255). */
+void orc_heat_map(const u32* counter, u32 count, unsigned char* rgba) {
+  u32 mx = 0;
+  for (u32 i = 0; i < count; i++) if (counter[i] > mx) mx = counter[i];
+  for (u32 i = 0; i < count; i++) {
+    rgba[i * 4 + 0] = (unsigned char)((counter[i] / (float)mx) * 150);
+    rgba[i * 4 + 1] = (unsigned char)((counter[i] / (float)mx) * 255);
+    rgba[i * 4 + 2] = 255;
+    rgba[i * 4 + 3] = 255;
+  }
+}
+
 /* ------------------------------------------------- CPU baseline: binned SAH
  * SahBvh::build, BinnedSahBvh.cpp:13-204.  Faithful: BFS queue, 32 buckets,
  * O(32^2) sweep, min over buckets 0..30, std::partition / std::nth_element over

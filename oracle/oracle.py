@@ -39,7 +39,7 @@ def lib():
         _lib.orc_cost_binned_sah_proper.restype = C.c_float
         _lib.orc_ray_zdir.restype = C.c_float
         _lib.orc_ray_zdir.argtypes = [C.c_float]
-        for f in ("orc_fnv1a_words", "orc_lbvh_apetrei", "orc_collapse4", "orc_bvh2_depth", "orc_traverse", "orc_binned_sah_build",
+        for f in ("orc_fnv1a_words", "orc_lbvh_apetrei", "orc_collapse4", "orc_bvh2_depth", "orc_traverse", "orc_traverse_kind", "orc_traverse_wide4", "orc_binned_sah_build",
                   "orc_morton_code_cfg"):
             getattr(_lib, f).restype = C.c_uint32
     return _lib
@@ -195,6 +195,30 @@ def traverse(rays, nodes, leaves, tris, transform, root, n):
     hits = np.zeros(rays.size, dtype=T.HIT)
     cnt = lib().orc_traverse(_p(rays), _p(nodes), _p(leaves), _p(tris), _p(transform), _u32(root), _u32(n - 1), _u32(rays.size), _p(hits))
     return hits, int(cnt)
+
+
+def traverse_kind(kind, rays, nodes, leaves, tris, transform, root, n):
+    """kind 0: if-if (stack), 1: restart trail.  Returns hits, hit count, leaf tests per ray."""
+    hits = np.zeros(rays.size, dtype=T.HIT)
+    counter = np.zeros(rays.size, dtype=np.uint32)
+    cnt = lib().orc_traverse_kind(_u32(kind), _p(rays), _p(nodes), _p(leaves), _p(tris), _p(transform), _u32(root), _u32(n - 1), _u32(rays.size), _p(hits),
+                                  _p(counter))
+    return hits, int(cnt), counter
+
+
+def traverse_wide4(rays, wide, nodes, leaves, tris, transform, n):
+    """Bvh4 traversal; leaf boxes / primitive ids come from the Bvh2 leaf records (nodes, or leaves for the separate-leaf layout)."""
+    hits = np.zeros(rays.size, dtype=T.HIT)
+    counter = np.zeros(rays.size, dtype=np.uint32)
+    cnt = lib().orc_traverse_wide4(_p(rays), _p(wide), _p(nodes), _p(leaves), _p(tris), _p(transform), _u32(n - 1), _u32(rays.size), _p(hits), _p(counter))
+    return hits, int(cnt), counter
+
+
+def heat_map(counter):
+    counter = np.ascontiguousarray(counter, dtype=np.uint32)
+    rgba = np.zeros((counter.size, 4), dtype=np.uint8)
+    lib().orc_heat_map(_p(counter), _u32(counter.size), _p(rgba))
+    return rgba
 
 
 def binned_sah(tris):

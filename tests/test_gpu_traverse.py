@@ -71,6 +71,52 @@ def test_traversal_matches_oracle(ctx, oracle, mesh, size, algo):
     ctx.free(d_rays)
 
 
+@pytest.mark.parametrize("mesh,size", [("cornellbox", 256), ("bunny", 192), ("sponza", 128)])
+@pytest.mark.parametrize("algo", [capi.TWO_PASS_LBVH, capi.SINGLE_PASS_LBVH, capi.PLOCPP, capi.HPLOC], ids=["twopass", "singlepass", "ploc", "hploc"])
+def test_ifif_restart_trail_and_bvh4_traversal(ctx, oracle, mesh, size, algo):
+    """The reference's if-if and restart-trail kernels and the Bvh4 walk: HitInfo and the per-ray triangle-test counter
+    (rayCounter) bit-exact against the oracle's restatement of each; all of them find the hits of the while-while kernel."""
+    tris = load_mesh(mesh)
+    if tris is None:
+        pytest.skip(f"{mesh} not staged")
+    n = tris.size
+    tr, cam = scene(oracle, mesh)
+    tree = ctx.build(algo, tris, collapse=True)
+    g = ctx.fetch(tree)
+    d_rays, _ = ctx.generate_rays(cam, size, size)
+    rays = ctx.download(d_rays, T.RAY, size * size)
+    ref_hits, _, _ = ctx.traverse(tree, d_rays, size * size, tr, capi.TRAVERSE_WHILE)
+    for kind, kernel in ((0, capi.TRAVERSE_IFIF), (1, capi.TRAVERSE_RESTART_TRAIL)):
+        o_hits, o_cnt, o_counter = oracle.traverse_kind(kind, rays, g["nodes"], g["leaves"], tris, tr, tree.root, n)
+        hits, rgba, _, counter = ctx.traverse(tree, d_rays, size * size, tr, kernel, want_rgba=True, want_counter=True)
+        compare_hits(hits, o_hits)
+        assert np.array_equal(counter, o_counter), f"kernel {kernel}: ray counters differ on {int((counter != o_counter).sum())} rays"
+        assert np.array_equal(rgba[:, 3] == 255, hits["primIdx"] != 0xFFFFFFFF)
+        assert np.array_equal(hits["t"].view(np.uint32), ref_hits["t"].view(np.uint32))
+        assert capi.heat_map(counter).tobytes() == oracle.heat_map(o_counter).tobytes()
+    o_hits, o_cnt, o_counter = oracle.traverse_wide4(rays, g["wide"], g["nodes"], g["leaves"], tris, tr, n)
+    hits, _, _, counter = ctx.traverse(tree, d_rays, size * size, tr, capi.TRAVERSE_WIDE4, want_counter=True)
+    compare_hits(hits, o_hits)
+    assert np.array_equal(counter, o_counter)
+    assert o_cnt > 0 and (hits["t"].view(np.uint32) != ref_hits["t"].view(np.uint32)).mean() < 1e-4
+    ctx.free(d_rays)
+
+
+def test_traversal_argument_errors(ctx):
+    tris = random_tris(2000, 9)
+    tr = T.make_transform([0.0, 0.0, 0.0], [1.0, 1.0, 1.0], [0.0, 0.0, 0.0, 1.0])
+    cam = T.make_camera([0.0, 0.0, 400.0, 0.0], [0.0, 0.0, 0.0, 1.0], np.float32(0.6))
+    d_rays, _ = ctx.generate_rays(cam, 16, 16)
+    tree = ctx.build(capi.TWO_PASS_LBVH, tris, collapse=False)
+    with pytest.raises(capi.B2bvhError):
+        ctx.traverse(tree, d_rays, 256, tr, capi.TRAVERSE_WIDE4)  # no 4-wide nodes were built
+    with pytest.raises(capi.B2bvhError):
+        ctx.traverse(tree, d_rays, 256, tr, capi.TRAVERSE_WHILE, want_counter=True)  # the while-while kernels keep no counter
+    with pytest.raises(capi.B2bvhError):
+        ctx.traverse(tree, d_rays, 256, tr, 7)
+    ctx.free(d_rays)
+
+
 def test_traversal_synthetic_scene(ctx, oracle):
     tris = random_tris(20_000, 5)
     tr = T.make_transform([0.0, 0.0, 0.0], [1.0, 1.0, 1.0], [0.0, 0.0, 0.0, 1.0])
