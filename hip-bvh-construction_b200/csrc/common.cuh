@@ -109,6 +109,11 @@ __device__ __forceinline__ u32 atom_exch_acq_rel(u32* p, u32 v) {
   asm volatile("atom.exch.acq_rel.gpu.global.b32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
   return old;
 }
+__device__ __forceinline__ u32 atom_exch_relaxed(u32* p, u32 v) {
+  u32 old;
+  asm volatile("atom.exch.relaxed.gpu.global.b32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+  return old;
+}
 __device__ __forceinline__ u32 ld_acquire(const u32* p) {
   u32 v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");

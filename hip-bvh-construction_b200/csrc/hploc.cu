@@ -158,9 +158,15 @@ __global__ void __launch_bounds__(HP_THREADS) hploc_kernel(const u32* __restrict
         isLeft = (kR ^ kR1) < (kL1 ^ kL);
       }
       const u32 parent = isLeft ? R : L - 1;
-      const u32 other = atom_exch_acq_rel(meet + parent, isLeft ? L : R);
+      /* Relaxed exchange + fences where they are needed: what a lane hands over was either written by an earlier launch
+       * (leaves, initial lists) or is covered by the fence every lane executes after a merge call (below), so the first
+       * arriver needs no fence of its own; the second arriver fences once — acquire for what it is about to read and, by
+       * cumulativity, release for what it passes on at its next exchange.  (acq_rel on the atomic itself puts a fence on
+       * both sides of every one of the 2n exchanges: 28 % of the kernel's stall samples, profiles/r01m.) */
+      const u32 other = atom_exch_relaxed(meet + parent, isLeft ? L : R);
       if (other == B2_INVALID) active = false; /* first arriver stops; the sibling's lane continues */
       else {
+        __threadfence();
         if (isLeft) { split = R + 1; R = other; } else { split = L; L = other; }
         fin = (L == 0 && R == n - 1);
         wantMerge = (R - L + 1 > 16u) || fin;
