@@ -16,8 +16,9 @@
  *                                  The tasks of a level are a contiguous index range; CTA c owns chunk c of it.  Pass A
  *                                  copies the expansion of every task's node into the task's record (the gathers of the
  *                                  whole chunk are independent and overlap) and counts the internal children; the CTA posts
- *                                  the count in counts[c] (tagged with the level, never reset) and sums the counts of the
- *                                  chunks before it — all due at the same moment: no chain of dependent look-backs.  Pass C
+ *                                  the count in counts[c], counts itself in on an arrival counter (one polling thread per
+ *                                  CTA) and sums the counts of the chunks before it — all due at the same moment: no
+ *                                  chain of dependent look-backs.  Pass C
  *                                  numbers the children consecutively in (task, slot) order, appends their tasks and notes
  *                                  each task's first child index.  Runs of levels that fit one tile (the top of the tree,
  *                                  the tail of a deep one) are processed by CTA 0 alone between two barriers.
@@ -38,7 +39,8 @@
 struct CollapseCtrl {
   u32 bar;        /* grid barrier: arrivals so far */
   u32 nWide;      /* result: number of wide nodes */
-  u32 pad[2];
+  u32 arrive;     /* chunks that have posted their count, all levels so far */
+  u32 pad;
   uint4 next[2];  /* {level, start, end, -}: the level to process after barrier b is published in next[b & 1] (a CTA that
                      leaves barrier b early may publish the level after it before a late CTA has read this one) */
 };
@@ -173,7 +175,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 6) collapse_number_kernel(const u
                                                                         CollapseCtrl* ctrl, u64* counts) {
   __shared__ ColSmem S;
   const u32 G = gridDim.x, c = blockIdx.x, tid = threadIdx.x, w = tid >> 5, l = tid & 31u;
-  u32 level = 0, start = 0, end = 1, barriers = 0;
+  u32 level = 0, start = 0, end = 1, barriers = 0, arriveTarget = 0;
   if (c == 0 && tid == 0) { taskNode[0] = *rootIdx; taskParent[0] = B2_INVALID; }
   __syncthreads();
 
@@ -194,6 +196,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 6) collapse_number_kernel(const u
       /* ---- a level of many tiles: CTA c owns the contiguous chunk c of the level ---- */
       const u32 chunk = ((size + G - 1) / G + NUM_THREADS - 1) / NUM_THREADS * NUM_THREADS;
       const u32 nActive = (size + chunk - 1) / chunk;
+      arriveTarget += nActive;
       if (c < nActive) {
         const u32 cStart = start + c * chunk, cEnd = min(end, cStart + chunk);
         /* A. records + internal children of the whole chunk */
@@ -205,15 +208,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 6) collapse_number_kernel(const u
         u32 chunkTotal = 0;
 #pragma unroll
         for (int q = 0; q < NUM_THREADS / 32; q++) chunkTotal += S.warpSum[1][q];
-        const u64 tag = (u64)(level + 1u) << 32;
-        if (tid == 0) st_relaxed64(counts + c, tag | chunkTotal);
-        /* B. children of the chunks before this one: every CTA posts after the same pass, so the spin is short */
-        u32 before = 0;
-        for (u32 i = tid; i < c; i += NUM_THREADS) {
-          u64 v;
-          do { v = ld_relaxed64(counts + i); } while ((v >> 32) != (tag >> 32));
-          before += (u32)v;
+        /* B. children of the chunks before this one: every CTA posts after the same pass and counts itself in on an arrival
+         * counter that ONE thread per CTA watches (every thread spinning on the posted words — 227 K pollers — starves the
+         * CTAs still at work, as measured for the PLOC++ merge kernel, profiles/r01m) */
+        if (tid == 0) {
+          st_relaxed64(counts + c, (u64)chunkTotal);
+          __threadfence();
+          atomicAdd(&ctrl->arrive, 1u);
+          u32 polls = 0;
+          while (ld_acquire(&ctrl->arrive) < arriveTarget) {
+            __nanosleep(32);
+            if (++polls > (1u << 22)) __trap(); /* a chunk never posted: fail, never hang the device */
+          }
         }
+        __syncthreads();
+        u32 before = 0;
+        for (u32 i = tid; i < c; i += NUM_THREADS) before += (u32)ld_relaxed64(counts + i);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(B2_FULL, before, o);
         if (l == 0) S.warpSum[2][w] = before;
