@@ -33,6 +33,9 @@
 #include "common.cuh"
 
 #define COL_THREADS 256
+#ifndef NUM_SOLO
+#define NUM_SOLO 1024    /* levels of at most this many tasks are numbered by CTA 0 alone (a grid-wide level costs ~7 us of synchronisation) */
+#endif
 #define NUM_THREADS 256  /* numbering kernel (1024-thread CTAs make the grid barrier cheaper but the tile loop slower: measured a wash) */
 
 /* scratch layout: CollapseCtrl (256 B) | uint4 expansion[n] | uint4 taskCh[n] | u32 taskParent[n] | u32 firstChild[n] | u32 taskNode[n] | u64 counts[G] */
@@ -182,14 +185,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 6) collapse_number_kernel(const u
   while (true) {
     const u32 size = end - start;
     if (size == 0) break;
-    if (size <= NUM_THREADS) {
-      /* ---- a run of one-tile levels: CTA 0 alone, no grid barrier in between ---- */
+    if (size <= NUM_SOLO) {
+      /* ---- a run of small levels (the top of the tree, the tail of a deep one): CTA 0 alone, no grid-wide step in between ---- */
       if (c == 0) {
         do {
           number_fetch(expansion, nInt, taskNode, taskCh, start, end);
-          const u32 total = number_tile(nInt, taskNode, taskCh, taskParent, firstChild, S, start, end, end);
-          start = end; end += total; level++;
-        } while (end - start <= NUM_THREADS && end != start);
+          u32 running = end;
+          for (u32 tileStart = start; tileStart < end; tileStart += NUM_THREADS)
+            running += number_tile(nInt, taskNode, taskCh, taskParent, firstChild, S, tileStart, end, running);
+          start = end; end = running; level++;
+        } while (end - start <= NUM_SOLO && end != start);
         if (tid == 0) publish_level(ctrl, barriers + 1u, level, start, end);
       }
     } else {

@@ -32,11 +32,15 @@
 #define RS_WARPS (RS_THREADS / 32)
 #define RS_MAX_PASSES 4
 #define RS_SCAN_WARPS 32
+#ifndef RS_ITEMS
+#define RS_ITEMS 15   /* pairs per thread and tile of the scatter kernel (large inputs) */
+#define RS_MINB 2     /* resident scatter CTAs per SM: 3 x 30 KB tile buffers + counters, twice */
+#endif
 
 /* scratch (u32 words): counts[256][Gpad] (digit-major; after the scan: exclusive chunk offsets) | totals[256] */
 static inline u32 rs_grid(const b2bvh_ctx* ctx, u32 n, u32 tile) {
   const u32 tiles = (n + tile - 1) / tile;
-  const u32 cap = (u32)ctx->sm_count * 2u;
+  const u32 cap = (u32)ctx->sm_count * (tile == RS_THREADS * RS_ITEMS ? (u32)RS_MINB : 2u);
   return tiles < cap ? tiles : cap;
 }
 static inline u32 rs_gpad(u32 g) { return (g + 31u) & ~31u; }
@@ -154,7 +158,7 @@ struct ScatterSmem {
  * (a couple of distinct values, a few cycles) and order themselves by lane: stable, whatever order the hardware served
  * the atomics in. */
 template <int ITEMS, bool IOTA_VALUES>
-__global__ void __launch_bounds__(RS_THREADS, 2) radix_scatter_kernel(const u32* __restrict__ keysIn, const u32* __restrict__ valsIn,
+__global__ void __launch_bounds__(RS_THREADS, ITEMS == RS_ITEMS ? RS_MINB : 2) radix_scatter_kernel(const u32* __restrict__ keysIn, const u32* __restrict__ valsIn,
                                                                       u32* __restrict__ keysOut, u32* __restrict__ valsOut,
                                                                       const u32* __restrict__ counts, const u32* __restrict__ totals, u32 n,
                                                                       u32 chunk, u32 shift, u32 mask, u32 gpad) {
@@ -320,7 +324,7 @@ int b2_launch_sort(b2bvh_ctx* ctx, const u32* d_keysIn, const u32* d_valsIn, u32
   const u32 nPasses = (endBit - startBit + RS_RADIX_BITS - 1) / RS_RADIX_BITS;
   /* small inputs use 2048-pair tiles so that more SMs take part */
   const bool small = n < (1u << 20);
-  const u32 tile = RS_THREADS * (small ? 4u : 15u); /* 15: two CTAs of 3 x 30 KB tile buffers + counters fit one SM */
+  const u32 tile = RS_THREADS * (small ? 4u : (u32)RS_ITEMS);
   const u32 grid = rs_grid(ctx, n, tile);
   const u32 gpad = rs_gpad(grid);
   u32 chunk = (n + grid - 1) / grid;
@@ -344,7 +348,7 @@ int b2_launch_sort(b2bvh_ctx* ctx, const u32* d_keysIn, const u32* d_valsIn, u32
     radix_scan_kernel<<<RS_RADIX / RS_SCAN_WARPS, RS_SCAN_WARPS * 32, 0, ctx->stream>>>(counts, totals, grid, gpad);
     B2_LAUNCH_CHECK(ctx);
     if (small) B2_TRY(launch_scatter<4>(ctx, grid, kin, vin, kout, vout, counts, totals, n, chunk, shift, mask, gpad));
-    else B2_TRY(launch_scatter<15>(ctx, grid, kin, vin, kout, vout, counts, totals, n, chunk, shift, mask, gpad));
+    else B2_TRY(launch_scatter<RS_ITEMS>(ctx, grid, kin, vin, kout, vout, counts, totals, n, chunk, shift, mask, gpad));
     kin = kout;
     vin = vout;
   }

@@ -89,6 +89,22 @@ def ploc_setup(boxes, svals):
     return nodes, leaves, idx
 
 
+_emul_mt = None
+
+
+def ploc_build_mt(nodes, leaves, idx):
+    """Runs the reference Ploc / SinglePassPloc kernels (block-level emulation with one cooperative fiber per GPU thread, ref_shim/cuda_emul_mt.h) on
+    the SetupClusters output; returns the internal nodes (numbering inside an iteration is timing dependent, as on a GPU)."""
+    global _emul_mt
+    if _emul_mt is None:
+        _emul_mt = C.CDLL(os.path.join(_HERE, "_ref", "libref_emul_mt.so"))
+        _emul_mt.ref_ploc_build_mt.restype = C.c_uint32
+    n = leaves.size
+    nd = nodes.copy(); lv = leaves.copy(); i0 = idx.astype(np.int32).copy(); i1 = np.full(n, -1, dtype=np.int32)
+    launches = _emul_mt.ref_ploc_build_mt(_p(nd), _p(lv), _p(i0), _p(i1), _u32(n))
+    return nd, int(launches)
+
+
 def collapse(nodes, leaves, root, n):
     """Runs the reference CollapseToWide4Bvh (LBVH variant when leaves is None, PLOC variant otherwise)."""
     wide = np.zeros(2 * n, dtype=T.BVH4_NODE); wl = np.zeros(n, dtype=T.PRIM_NODE)

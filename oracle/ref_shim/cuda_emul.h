@@ -21,7 +21,11 @@
 #define __host__
 #define __device__
 #define __global__
+#ifdef B2_EMUL_MT
+#define __shared__ static /* one block runs at a time: a static is the block's shared memory (cuda_emul_mt.h) */
+#else
 #define __shared__
+#endif
 #define __forceinline__ inline
 
 struct float2 { float x, y; };
@@ -76,6 +80,9 @@ inline uint32_t __float_as_uint(float f) { uint32_t i; memcpy(&i, &f, 4); return
 inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
 inline float __uint_as_float(uint32_t i) { float f; memcpy(&f, &i, 4); return f; }
 
+#ifdef B2_EMUL_MT
+#include "cuda_emul_mt.h" /* atomics, __syncthreads and warp collectives for one block run by real threads */
+#else
 template <typename T> inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return o; }
 inline int atomicAdd(int* p, int v) { int o = *p; *p = o + v; return o; }
 inline uint32_t atomicAdd(uint32_t* p, int v) { uint32_t o = *p; *p = o + (uint32_t)v; return o; }
@@ -89,4 +96,4 @@ inline void __syncthreads() {}
 template <typename T> inline T __shfl(T v, int) { return v; }
 inline uint64_t __ballot(bool p) { return p ? 1ull : 0ull; }
 inline bool __any(bool p) { return p; }
-
+#endif /* B2_EMUL_MT */

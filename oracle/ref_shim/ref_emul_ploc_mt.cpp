@@ -1,0 +1,107 @@
+/* TEST INFRASTRUCTURE ONLY — the reference's Ploc and SinglePassPloc kernels (Ploc++Kernel.h:98-362), UNMODIFIED, run block
+ * by block with one cooperative fiber per GPU thread (cuda_emul_mt.h), driven by the host loop of PLOCNew::build
+ * (PLOC++Bvh.cpp:131-152).  Node numbering inside an iteration follows the order in which warps reach an atomicAdd
+ * (binaryWarpPrefixSum, :57-68) — timing dependent on a GPU, highest warp first here: callers compare trees up to numbering. */
+#include <functional>
+#include <vector>
+
+#include <src/Common.h>
+namespace {
+#include <src/Ploc++Kernel.h>
+}
+
+thread_local dim3e threadIdx, blockIdx, blockDim = {1, 1, 1}, gridDim = {1, 1, 1};
+namespace b2emul {
+Block g_blk;
+void yield_to_scheduler() { swapcontext(&g_blk.fibers[g_blk.current].ctx, &g_blk.main); }
+}
+static std::function<void()>* g_kernel;
+static void fiber_entry() {
+  (*g_kernel)();
+  b2emul::g_blk.fibers[b2emul::g_blk.current].state = b2emul::EXITED;
+  b2emul::yield_to_scheduler();
+}
+
+static void run_block(uint32_t block, uint32_t nThreads, uint32_t nBlocks, std::function<void()> kernel) {
+  using namespace b2emul;
+  const size_t stackBytes = 128 * 1024;
+  std::vector<Fiber> fibers(nThreads);
+  std::vector<char> stacks((size_t)nThreads * stackBytes);
+  g_blk.nThreads = (int)nThreads; g_blk.fibers = fibers.data();
+  g_kernel = &kernel;
+  for (uint32_t t = 0; t < nThreads; t++) {
+    Fiber& f = fibers[t];
+    getcontext(&f.ctx);
+    f.ctx.uc_stack.ss_sp = stacks.data() + (size_t)t * stackBytes;
+    f.ctx.uc_stack.ss_size = stackBytes;
+    f.ctx.uc_link = &g_blk.main;
+    makecontext(&f.ctx, fiber_entry, 0);
+    f.state = READY;
+  }
+  blockIdx = {block, 0, 0}; blockDim = {nThreads, 1, 1}; gridDim = {nBlocks, 1, 1};
+  const int nW = ((int)nThreads + kWarp - 1) / kWarp;
+  while (true) {
+    /* run every READY fiber once, highest index first */
+    bool ran = false;
+    for (int t = (int)nThreads - 1; t >= 0; t--) {
+      if (fibers[t].state != READY) continue;
+      g_blk.current = t;
+      threadIdx = {(uint32_t)t, 0, 0};
+      swapcontext(&g_blk.main, &fibers[t].ctx);
+      ran = true;
+    }
+    /* warp collectives: complete where every lane that is neither at the barrier nor gone has arrived */
+    bool progressed = false;
+    for (int w = 0; w < nW; w++) {
+      const int lo = w * kWarp, hi = std::min((int)nThreads, lo + kWarp);
+      int arrived = 0, ready = 0;
+      for (int t = lo; t < hi; t++) { arrived += fibers[t].state == AT_COLLECTIVE; ready += fibers[t].state == READY; }
+      if (arrived == 0 || ready != 0) continue;
+      uint64_t ballot = 0;
+      for (int t = lo; t < hi; t++) if (fibers[t].state == AT_COLLECTIVE && fibers[t].pred) ballot |= 1ull << (t - lo);
+      for (int t = lo; t < hi; t++)
+        if (fibers[t].state == AT_COLLECTIVE) {
+          fibers[t].resBallot = ballot;
+          fibers[t].resVal = fibers[lo + fibers[t].src < hi ? lo + fibers[t].src : lo].val;
+        }
+      for (int t = lo; t < hi; t++) if (fibers[t].state == AT_COLLECTIVE) fibers[t].state = READY;
+      progressed = true;
+    }
+    if (progressed) continue;
+    /* block barrier: everybody who has not returned waits */
+    int atBarrier = 0, exited = 0;
+    for (uint32_t t = 0; t < nThreads; t++) { atBarrier += fibers[t].state == AT_BARRIER; exited += fibers[t].state == EXITED; }
+    if (exited == (int)nThreads) break;
+    if (atBarrier + exited == (int)nThreads) {
+      for (uint32_t t = 0; t < nThreads; t++) if (fibers[t].state == AT_BARRIER) fibers[t].state = READY;
+      continue;
+    }
+    if (!ran) { fprintf(stderr, "ref_emul_ploc_mt: block %u cannot make progress (divergent barrier?)\n", block); abort(); }
+  }
+}
+
+extern "C" {
+/* nodeIdx0 = SetupClusters output (n entries), nodeIdx1 = scratch (n entries).  Returns the number of kernel launches.
+ * bvhNodes[n-1] internal nodes are written. */
+uint32_t ref_ploc_build_mt(Bvh2Node* bvhNodes, PrimRef* primRefs, int* nodeIdx0, int* nodeIdx1, uint32_t n) {
+  uint32_t nClusters = n, launches = 0;
+  const uint32_t nInternalNodes = n - 1;
+  bool swapBuffer = false;
+  while (nClusters > 1) {
+    int nMerged = 0, blockOffsetSum = 0, atomicBlockCounter = 0;
+    int* in = !swapBuffer ? nodeIdx0 : nodeIdx1;
+    int* out = !swapBuffer ? nodeIdx1 : nodeIdx0;
+    launches++;
+    if (nClusters < (uint32_t)PlocBlockSize) { /* PLOC++Bvh.cpp:138-143 */
+      run_block(0, PlocBlockSize, 1, [&] { SinglePassPloc(in, bvhNodes, primRefs, nClusters, nInternalNodes); });
+      break;
+    }
+    const uint32_t nBlocks = (nClusters + PlocBlockSize - 1) / PlocBlockSize;
+    for (uint32_t b = 0; b < nBlocks; b++)
+      run_block(b, PlocBlockSize, nBlocks, [&] { Ploc(in, out, bvhNodes, primRefs, &nMerged, &blockOffsetSum, &atomicBlockCounter, nClusters, nInternalNodes); });
+    nClusters -= (uint32_t)nMerged;
+    swapBuffer = !swapBuffer;
+  }
+  return launches;
+}
+}
