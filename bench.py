@@ -166,32 +166,40 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n = args.prims
     n_total = n * world
-    stream = torch.cuda.Stream()  # one explicit stream shared by torch (events, NCCL) and the library
+    class Lane:
+        """One context = one stream shared by torch (events, NCCL) and the library, plus the exchange buffers of a sharded step."""
+
+        def __init__(self):
+            self.stream = torch.cuda.Stream()
+            self.ctx = capi.Context(local, stream=self.stream.cuda_stream)
+            self.box6 = torch.zeros(6, dtype=torch.float32, device="cuda")
+            self.roots = torch.zeros(world * 6, dtype=torch.float32, device="cuda")
+            self.root_local = torch.zeros(6, dtype=torch.float32, device="cuda")
+            self.top_nodes = torch.zeros((2 * world - 1) * 8, dtype=torch.float32, device="cuda")
+
+    lane0 = Lane()
+    stream, ctx = lane0.stream, lane0.ctx
     torch.cuda.set_stream(stream)
-    ctx = capi.Context(local, stream=stream.cuda_stream)
     d_tris = ctx.synth_uniform(n_total, SEED, first=rank * n, count=n)
     ctx.sync()
     algo = capi.SINGLE_PASS_LBVH
-
-    box6 = torch.zeros(6, dtype=torch.float32, device="cuda")
-    roots = torch.zeros(world * 6, dtype=torch.float32, device="cuda")
-    root_local = torch.zeros(6, dtype=torch.float32, device="cuda")
-    top_nodes = torch.zeros((2 * world - 1) * 8, dtype=torch.float32, device="cuda")
     launches = [0]
 
-    def step(tris_ptr, on_device):
+    def step(tris_ptr, on_device, L=lane0):
+        c = L.ctx
         if world == 1:
-            tree = ctx.build(algo, tris_ptr, n=n, tris_on_device=on_device)
+            tree = c.build(algo, tris_ptr, n=n, tris_on_device=on_device)
             launches[0] += tree.n_launches
             return tree
         # sharded build: local boxes -> ONE all-reduce(MAX) of {-min,max} -> local build in the global frame (the reduced vector never
         # leaves the device, the boxes of the first pass are reused) -> ONE all-gather of roots -> top-level tree on every rank
-        capi.check(ctx.lib.b2bvh_shard_extents(ctx.h, tris_ptr, n, 1 if on_device else 0, box6.data_ptr()), "b2bvh_shard_extents")
-        dist.all_reduce(box6, op=dist.ReduceOp.MAX)
-        tree = ctx.build(algo, tris_ptr, n=n, tris_on_device=on_device, boxes_ready=True, d_scene_negmin_max=box6.data_ptr())
-        capi.check(ctx.lib.b2bvh_d2d(ctx.h, root_local.data_ptr(), tree.d_bvhNodes + 32 * tree.root + 8, 24), "b2bvh_d2d")
-        dist.all_gather_into_tensor(roots, root_local)
-        capi.check(ctx.lib.b2bvh_top_level(ctx.h, roots.data_ptr(), world, top_nodes.data_ptr()), "b2bvh_top_level")
+        with torch.cuda.stream(L.stream):
+            capi.check(c.lib.b2bvh_shard_extents(c.h, tris_ptr, n, 1 if on_device else 0, L.box6.data_ptr()), "b2bvh_shard_extents")
+            dist.all_reduce(L.box6, op=dist.ReduceOp.MAX)
+            tree = c.build(algo, tris_ptr, n=n, tris_on_device=on_device, boxes_ready=True, d_scene_negmin_max=L.box6.data_ptr())
+            capi.check(c.lib.b2bvh_d2d(c.h, L.root_local.data_ptr(), tree.d_bvhNodes + 32 * tree.root + 8, 24), "b2bvh_d2d")
+            dist.all_gather_into_tensor(L.roots, L.root_local)
+            capi.check(c.lib.b2bvh_top_level(c.h, L.roots.data_ptr(), world, L.top_nodes.data_ptr()), "b2bvh_top_level")
         launches[0] += tree.n_launches + 2
         return tree
 
@@ -263,29 +271,73 @@ def main():
             "kernels": kernels, "n_wide": int(tree.n_wide)}
 
     if not args.no_extras:
-        # ---- end to end through the public API with HOST triangles ----
+        # ---- end to end through the public API with HOST triangles: every step uploads its triangles from pinned host memory and
+        # reads its Bvh2 nodes, Bvh4 nodes and Bvh4 leaves back.  Two contexts (two streams) take the steps in turn, so the read-back
+        # of step i (PCIe up) overlaps the upload and build of step i+1 (PCIe down); the serial figure (one context, blocking copies)
+        # is reported next to it ----
         nbytes = n * 64
         h_tris = ctx.pinned(nbytes)
         capi.check(ctx.lib.b2bvh_d2h(ctx.h, h_tris, d_tris, nbytes), "d2h")
         out_bytes = (2 * n - 1) * 32 + n * 128 + n * 8
-        h_out = ctx.pinned(out_bytes)
+        lanes = [lane0, Lane()]
+        h_out = [ctx.pinned(out_bytes), ctx.pinned(out_bytes)]
         d2h = [0]
+        turn = [0]
 
-        def e2e_step():
+        def e2e_serial_step():
             t = step(h_tris, False)
             b0, b1, b2 = (2 * n - 1) * 32, t.n_wide * 128, n * 8
-            capi.check(ctx.lib.b2bvh_d2h(ctx.h, h_out, t.d_bvhNodes, b0), "d2h nodes")
-            capi.check(ctx.lib.b2bvh_d2h(ctx.h, h_out + b0, t.d_wideBvhNodes, b1), "d2h wide")
-            capi.check(ctx.lib.b2bvh_d2h(ctx.h, h_out + b0 + b1, t.d_wideLeafNodes, b2), "d2h wide leaves")
+            capi.check(ctx.lib.b2bvh_d2h(ctx.h, h_out[0], t.d_bvhNodes, b0), "d2h nodes")
+            capi.check(ctx.lib.b2bvh_d2h(ctx.h, h_out[0] + b0, t.d_wideBvhNodes, b1), "d2h wide")
+            capi.check(ctx.lib.b2bvh_d2h(ctx.h, h_out[0] + b0 + b1, t.d_wideLeafNodes, b2), "d2h wide leaves")
             d2h[0] = b0 + b1 + b2
 
+        def e2e_step():
+            k = turn[0] & 1
+            turn[0] += 1
+            L = lanes[k]
+            L.ctx.sync()  # this lane's previous read-back has landed: its device buffers and its host buffer are free again
+            t = step(h_tris, False, L)
+            b0, b1, b2 = (2 * n - 1) * 32, t.n_wide * 128, n * 8
+            capi.check(L.ctx.lib.b2bvh_d2h_async(L.ctx.h, h_out[k], t.d_bvhNodes, b0), "d2h nodes")
+            capi.check(L.ctx.lib.b2bvh_d2h_async(L.ctx.h, h_out[k] + b0, t.d_wideBvhNodes, b1), "d2h wide")
+            capi.check(L.ctx.lib.b2bvh_d2h_async(L.ctx.h, h_out[k] + b0 + b1, t.d_wideLeafNodes, b2), "d2h wide leaves")
+            d2h[0] = b0 + b1 + b2
+
+        def timed_lanes(fn, steps):
+            """CUDA-event time from before the first step to after the last read-back of BOTH streams, max over ranks."""
+            barrier()
+            e0, e1, join = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event()
+            e0.record(lanes[0].stream)
+            lanes[1].stream.wait_event(e0)
+            for _ in range(steps):
+                fn()
+            for L in lanes:  # the read-backs run on the contexts' own download streams: wait for them on the host, then close the interval
+                L.ctx.sync()
+            join.record(lanes[1].stream)
+            lanes[0].stream.wait_event(join)
+            e1.record(lanes[0].stream)
+            barrier()
+            ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+            if dist:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            return float(ms.item()) / steps
+
         for _ in range(2):
+            e2e_serial_step()
+        e2e_steps = max(8, args.steps)  # pipeline fill and drain are inside the timed region
+        ms_serial = timed(e2e_serial_step, max(3, args.steps // 4))
+        for _ in range(4):
             e2e_step()
-        e2e_steps = max(3, args.steps // 2)
-        ms_e2e = timed(e2e_step, e2e_steps)
+        ms_e2e = timed_lanes(e2e_step, e2e_steps)
+        for L in lanes:
+            L.ctx.sync()
         line["e2e"] = {"value": n_total / (ms_e2e * 1e-3) / 1e6, "unit": "Mprims/s", "ms_per_step": ms_e2e, "steps": e2e_steps,
                        "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": d2h[0],
-                       "api": "b2bvh_build(host triangles, pinned) + b2bvh_d2h of Bvh2 nodes, Bvh4 nodes, Bvh4 leaves"}
+                       "api": "b2bvh_build(host triangles, pinned) + b2bvh_d2h_async of Bvh2 nodes, Bvh4 nodes, Bvh4 leaves; steps alternate between "
+                              "two contexts so the read-back of one step overlaps the upload + build of the next (fill and drain timed)",
+                       "serial": {"value": n_total / (ms_serial * 1e-3) / 1e6, "ms_per_step": ms_serial,
+                                  "api": "one context, blocking b2bvh_d2h: upload, build and read-back strictly one after the other"}}
 
         if rank == 0 and world == 1:
             # ---- CPU baseline beside it: the reference's CPU builder on a bounded sample (oracle = checker/baseline only) ----

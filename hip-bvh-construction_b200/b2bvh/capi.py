@@ -41,7 +41,7 @@ class Tree(C.Structure):
 
 # every symbol include/b2bvh.h declares (tests check the library exports each of them)
 SYMBOLS = ["b2bvh_ctx_create", "b2bvh_ctx_destroy", "b2bvh_device_name", "b2bvh_device_sm_count", "b2bvh_alloc", "b2bvh_free",
-           "b2bvh_memset", "b2bvh_h2d", "b2bvh_d2h", "b2bvh_d2d", "b2bvh_sync", "b2bvh_host_alloc_pinned", "b2bvh_host_free_pinned",
+           "b2bvh_memset", "b2bvh_h2d", "b2bvh_d2h", "b2bvh_h2d_async", "b2bvh_d2h_async", "b2bvh_d2d", "b2bvh_sync", "b2bvh_host_alloc_pinned", "b2bvh_host_free_pinned",
            "b2bvh_last_error", "b2bvh_build", "b2bvh_scene_extents", "b2bvh_morton_codes", "b2bvh_sort_pairs", "b2bvh_generate_rays",
            "b2bvh_traverse", "b2bvh_traverse_ex", "b2bvh_heat_map", "b2bvh_shard_extents", "b2bvh_top_level", "b2bvh_cost_bvh4", "b2bvh_cost_lbvh", "b2bvh_tree_cost",
            "b2bvh_abi_version", "b2bvh_synth_uniform", "b2bvh_profile_enable", "b2bvh_profile_count", "b2bvh_profile_entry"]
@@ -66,7 +66,7 @@ def load():
     sig = {
         "b2bvh_ctx_create": [C.c_int, vp, C.POINTER(vp)], "b2bvh_ctx_destroy": [vp], "b2bvh_device_name": [vp, C.c_char_p, sz],
         "b2bvh_device_sm_count": [vp, C.POINTER(C.c_int)], "b2bvh_alloc": [vp, sz, C.POINTER(vp)], "b2bvh_free": [vp, vp],
-        "b2bvh_memset": [vp, vp, C.c_int, sz], "b2bvh_h2d": [vp, vp, vp, sz], "b2bvh_d2h": [vp, vp, vp, sz], "b2bvh_d2d": [vp, vp, vp, sz], "b2bvh_sync": [vp],
+        "b2bvh_memset": [vp, vp, C.c_int, sz], "b2bvh_h2d": [vp, vp, vp, sz], "b2bvh_d2h": [vp, vp, vp, sz], "b2bvh_d2d": [vp, vp, vp, sz], "b2bvh_h2d_async": [vp, vp, vp, sz], "b2bvh_d2h_async": [vp, vp, vp, sz], "b2bvh_sync": [vp],
         "b2bvh_host_alloc_pinned": [sz, C.POINTER(vp)], "b2bvh_host_free_pinned": [vp],
         "b2bvh_build": [vp, C.c_int, vp, u32, C.POINTER(BuildOpts), C.POINTER(Tree)],
         "b2bvh_scene_extents": [vp, vp, u32, vp, vp], "b2bvh_morton_codes": [vp, vp, vp, u32, vp, vp],

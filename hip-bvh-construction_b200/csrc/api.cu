@@ -76,6 +76,10 @@ int b2bvh_ctx_create(int device, void* cuda_stream, b2bvh_ctx** out) {
   if (cuda_stream) { c->stream = (cudaStream_t)cuda_stream; c->own_stream = false; }
   else { B2_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
   for (int i = 0; i < 16; i++) B2_CUDA(cudaEventCreate(&c->ev[i]));
+  B2_CUDA(cudaStreamCreateWithFlags(&c->dl_stream, cudaStreamNonBlocking));
+  B2_CUDA(cudaEventCreateWithFlags(&c->dl_event, cudaEventDisableTiming));
+  B2_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&c->mailbox), B2_MAILBOX_SLOTS * 16 * sizeof(u32), cudaHostAllocMapped));
+  B2_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&c->mailbox_dev), c->mailbox, 0));
   void* ctl;
   B2_TRY(b2_reserve(c, SLOT_CTL, 256, &ctl));
   B2_CUDA(cudaMemsetAsync(ctl, 0, 256, c->stream));
@@ -90,6 +94,10 @@ int b2bvh_ctx_destroy(b2bvh_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   for (int i = 0; i < 32; i++) if (ctx->bufs[i].p) cudaFree(ctx->bufs[i].p);
   for (int i = 0; i < 16; i++) cudaEventDestroy(ctx->ev[i]);
+  if (ctx->mailbox) cudaFreeHost(ctx->mailbox);
+  cudaStreamSynchronize(ctx->dl_stream);
+  cudaStreamDestroy(ctx->dl_stream);
+  cudaEventDestroy(ctx->dl_event);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return 0;
@@ -128,11 +136,27 @@ int b2bvh_h2d(b2bvh_ctx* ctx, void* dptr, const void* hptr, size_t bytes) {
   B2_CUDA(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
+/* device -> host copies of a context run on its download stream, after everything enqueued on the main stream so far */
+static int b2_download(b2bvh_ctx* ctx, void* hptr, const void* dptr, size_t bytes) {
+  B2_CUDA(cudaEventRecord(ctx->dl_event, ctx->stream));
+  B2_CUDA(cudaStreamWaitEvent(ctx->dl_stream, ctx->dl_event, 0));
+  B2_CUDA(cudaMemcpyAsync(hptr, dptr, bytes, cudaMemcpyDeviceToHost, ctx->dl_stream));
+  return 0;
+}
 int b2bvh_d2h(b2bvh_ctx* ctx, void* hptr, const void* dptr, size_t bytes) {
   if (!ctx || (bytes && (!dptr || !hptr))) return b2_fail(B2BVH_ERR_INVALID, "d2h: bad argument");
-  B2_CUDA(cudaMemcpyAsync(hptr, dptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-  B2_CUDA(cudaStreamSynchronize(ctx->stream));
+  B2_TRY(b2_download(ctx, hptr, dptr, bytes));
+  B2_CUDA(cudaStreamSynchronize(ctx->dl_stream));
   return 0;
+}
+int b2bvh_h2d_async(b2bvh_ctx* ctx, void* dptr, const void* hptr, size_t bytes) {
+  if (!ctx || (bytes && (!dptr || !hptr))) return b2_fail(B2BVH_ERR_INVALID, "h2d_async: bad argument");
+  B2_CUDA(cudaMemcpyAsync(dptr, hptr, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return 0;
+}
+int b2bvh_d2h_async(b2bvh_ctx* ctx, void* hptr, const void* dptr, size_t bytes) {
+  if (!ctx || (bytes && (!dptr || !hptr))) return b2_fail(B2BVH_ERR_INVALID, "d2h_async: bad argument");
+  return b2_download(ctx, hptr, dptr, bytes);
 }
 int b2bvh_d2d(b2bvh_ctx* ctx, void* dst, const void* src, size_t bytes) {
   if (!ctx || (bytes && (!dst || !src))) return b2_fail(B2BVH_ERR_INVALID, "d2d: bad argument");
@@ -142,6 +166,7 @@ int b2bvh_d2d(b2bvh_ctx* ctx, void* dst, const void* src, size_t bytes) {
 int b2bvh_sync(b2bvh_ctx* ctx) {
   if (!ctx) return b2_fail(B2BVH_ERR_INVALID, "sync: bad argument");
   B2_CUDA(cudaStreamSynchronize(ctx->stream));
+  B2_CUDA(cudaStreamSynchronize(ctx->dl_stream));
   return 0;
 }
 int b2bvh_host_alloc_pinned(size_t bytes, void** hptr) {
@@ -276,9 +301,9 @@ int b2bvh_build(b2bvh_ctx* ctx, int algo, const b2bvh_triangle* tris, uint32_t n
     B2_TRY(b2_launch_collapse(ctx, (const b2bvh_bvh2_node*)dNodes, (const b2bvh_prim_ref*)dLeaves, (const u32*)dSVals, dRoot, n, (b2bvh_bvh4_node*)dWide,
                               (b2bvh_prim_node*)dWLeaves, dCollapse, &nWide));
   B2_CUDA(cudaEventRecord(ctx->ev[5], s));
-  u32 root = 0;
-  B2_CUDA(cudaMemcpyAsync(&root, dRoot, 4, cudaMemcpyDeviceToHost, s));
+  B2_TRY(b2_fetch_words(ctx, dRoot, 1, B2_MB_ROOT));
   B2_CUDA(cudaStreamSynchronize(s));
+  const u32 root = b2_mailbox(ctx, B2_MB_ROOT)[0];
 
   out->algo = (u32)algo;
   out->n_prims = n;
@@ -307,7 +332,7 @@ int b2bvh_build(b2bvh_ctx* ctx, int algo, const b2bvh_triangle* tris, uint32_t n
   B2_CUDA(cudaEventElapsedTime(&out->stage_ms[B2BVH_T_BUILD], ctx->ev[3], ctx->ev[4]));
   B2_CUDA(cudaEventElapsedTime(&out->stage_ms[B2BVH_T_COLLAPSE], ctx->ev[4], ctx->ev[5]));
   if (!opts.tris_on_device) B2_CUDA(cudaEventElapsedTime(&out->h2d_ms, ctx->ev[8], ctx->ev[9]));
-  out->n_iterations = iterations;
+  out->n_iterations = algo == B2BVH_HPLOC ? b2_mailbox(ctx, B2_MB_HPLOC)[0] : iterations;
   out->n_launches = ctx->launches - launches0;
   return 0;
 }

@@ -368,9 +368,8 @@ int b2_launch_collapse(b2bvh_ctx* ctx, const b2bvh_bvh2_node* d_nodes, const b2b
   B2_KERNEL(ctx, "collapse_emit");
   collapse_emit_kernel<<<egrid, COL_THREADS, emitSmem, ctx->stream>>>(d_nodes, d_sortedVals, nInt, taskCh, taskParent, firstChild, ctrl, d_wide, d_wideLeaves);
   B2_LAUNCH_CHECK(ctx);
-  CollapseCtrl h;
-  B2_CUDA(cudaMemcpyAsync(&h, ctrl, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  B2_TRY(b2_fetch_words(ctx, ctrl, 4, B2_MB_COLLAPSE));
   B2_CUDA(cudaStreamSynchronize(ctx->stream));
-  *h_nWide = h.nWide;
+  *h_nWide = b2_mailbox(ctx, B2_MB_COLLAPSE)[1]; /* CollapseCtrl::nWide */
   return 0;
 }

@@ -187,6 +187,9 @@ struct b2bvh_ctx {
   int sm_count;
   cudaStream_t stream;
   bool own_stream;
+  cudaStream_t dl_stream; /* device -> host copies run here, ordered after `stream` by dl_event: a stream that has carried a D2H copy
+                             no longer overlaps its H2D copies with another context's D2H (measured, tools/micro/e2e_pipeline_probe.py) */
+  cudaEvent_t dl_event;
   cudaEvent_t ev[16];
   char name[256];
   /* build-owned device buffers, grown on demand and reused across builds */
@@ -194,6 +197,9 @@ struct b2bvh_ctx {
     void* p;
     size_t cap;
   } bufs[32];
+  u32* mailbox;          /* pinned + mapped host memory, B2_MAILBOX_SLOTS x 16 words: small results come back through a one-warp
+                            kernel instead of the copy engine, where a 4-byte read would queue behind another context's bulk copy */
+  u32* mailbox_dev;      /* the same memory as the device sees it */
   u32 launches;
   u32 lbvh_second_level; /* b2bvh_build_opts.lbvh_second_level of the running build */
   u32 merge_max_ctas;    /* b2bvh_build_opts.merge_max_ctas of the running build */
@@ -234,6 +240,11 @@ int b2_prof_end(b2bvh_ctx* ctx);
   } while (0)
 
 int b2_reserve(b2bvh_ctx* ctx, int slot, size_t bytes, void** out);
+/* words <= 16 from device memory into mailbox slot `slot`; readable at b2_mailbox(ctx, slot) after the next stream synchronisation */
+#define B2_MAILBOX_SLOTS 4
+enum { B2_MB_COLLAPSE = 0, B2_MB_PLOC = 1, B2_MB_HPLOC = 2, B2_MB_ROOT = 3 };
+int b2_fetch_words(b2bvh_ctx* ctx, const void* d_src, u32 words, int slot);
+static inline const u32* b2_mailbox(const b2bvh_ctx* ctx, int slot) { return ctx->mailbox + slot * 16; }
 
 /* stage launchers (one per .cu file) */
 int b2_launch_extents(b2bvh_ctx* ctx, const b2bvh_triangle* d_tris, u32 n, b2bvh_aabb* d_triAabb, b2bvh_aabb* d_scene, u32* d_scratch8,

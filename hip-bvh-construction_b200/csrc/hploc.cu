@@ -199,6 +199,7 @@ int b2_launch_hploc(b2bvh_ctx* ctx, const b2bvh_aabb* d_triAabb, const u32* d_so
   B2_KERNEL(ctx, "hploc");
   hploc_kernel<<<(n + HP_THREADS - 1) / HP_THREADS, HP_THREADS, 0, ctx->stream>>>(d_sortedKeys, n, d_nodes, d_leaves, nodeIdx, freeIdx, meet, ctrl);
   B2_LAUNCH_CHECK(ctx);
-  B2_CUDA(cudaMemcpyAsync(h_mergeCalls, ctrl, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  (void)h_mergeCalls; /* ctrl[0] travels through the mailbox: b2_mailbox(ctx, B2_MB_HPLOC)[0] after the build's final synchronisation */
+  B2_TRY(b2_fetch_words(ctx, ctrl, 1, B2_MB_HPLOC));
   return 0;
 }

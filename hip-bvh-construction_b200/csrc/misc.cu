@@ -91,3 +91,15 @@ int b2bvh_profile_entry(b2bvh_ctx* ctx, int index, char* name, size_t cap, float
   return 0;
 }
 }
+
+/* ---- small device -> host results through mapped pinned memory (b2_fetch_words, common.cuh) ---- */
+__global__ void fetch_words_kernel(const u32* __restrict__ src, u32 words, u32* dst) {
+  if (threadIdx.x < words) dst[threadIdx.x] = src[threadIdx.x];
+}
+int b2_fetch_words(b2bvh_ctx* ctx, const void* d_src, u32 words, int slot) {
+  if (words > 16 || slot < 0 || slot >= B2_MAILBOX_SLOTS) return b2_fail(B2BVH_ERR_INTERNAL, "fetch_words: bad request");
+  B2_KERNEL(ctx, "fetch_words");
+  fetch_words_kernel<<<1, 32, 0, ctx->stream>>>(reinterpret_cast<const u32*>(d_src), words, ctx->mailbox_dev + slot * 16);
+  B2_LAUNCH_CHECK(ctx);
+  return 0;
+}

@@ -484,9 +484,11 @@ int b2_launch_ploc(b2bvh_ctx* ctx, const b2bvh_aabb* d_triAabb, const u32* d_sor
   B2_KERNEL(ctx, "ploc_tail");
   ploc_tail_kernel<<<1, PLOC_TAIL_THREADS, sizeof(PlocTailSmem), ctx->stream>>>(ids[0], boxes[0], ids[1], boxes[1], d_nodes, ctrl);
   B2_LAUNCH_CHECK(ctx);
-  PlocCtrl h;
-  B2_CUDA(cudaMemcpyAsync(&h, ctrl, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  B2_TRY(b2_fetch_words(ctx, ctrl, 4, B2_MB_PLOC));
   B2_CUDA(cudaStreamSynchronize(ctx->stream));
+  PlocCtrl h;
+  h.count = b2_mailbox(ctx, B2_MB_PLOC)[1];
+  h.itersRun = b2_mailbox(ctx, B2_MB_PLOC)[2];
   if (h.count != 1) return b2_fail(B2BVH_ERR_INTERNAL, "ploc: %u clusters left after %u iterations", h.count, h.itersRun);
 #ifdef PLOC_TRACE
   {

@@ -106,6 +106,10 @@ int b2bvh_memset(b2bvh_ctx* ctx, void* dptr, int value, size_t bytes); /* GpuMem
 int b2bvh_h2d(b2bvh_ctx* ctx, void* dptr, const void* hptr, size_t bytes); /* OrochiUtils::copyHtoD                  */
 int b2bvh_d2h(b2bvh_ctx* ctx, void* hptr, const void* dptr, size_t bytes); /* GpuMemory::getData                     */
 int b2bvh_d2d(b2bvh_ctx* ctx, void* dst, const void* src, size_t bytes); /* OrochiUtils::copyDtoDAsync (stream-ordered)  */
+/* stream-ordered copies that do not wait (pinned host memory; b2bvh_sync ends them): with two contexts the read-back of one
+ * build overlaps the upload and build of the next */
+int b2bvh_h2d_async(b2bvh_ctx* ctx, void* dptr, const void* hptr, size_t bytes); /* OrochiUtils::copyHtoDAsync, OrochiUtils.h:137 */
+int b2bvh_d2h_async(b2bvh_ctx* ctx, void* hptr, const void* dptr, size_t bytes); /* OrochiUtils::copyDtoHAsync, OrochiUtils.h:144 */
 int b2bvh_sync(b2bvh_ctx* ctx);                                        /* OrochiUtils::waitForCompletion             */
 int b2bvh_host_alloc_pinned(size_t bytes, void** hptr);
 int b2bvh_host_free_pinned(void* hptr);
