@@ -302,8 +302,14 @@ int b2bvh_build(b2bvh_ctx* ctx, int algo, const b2bvh_triangle* tris, uint32_t n
                               (b2bvh_prim_node*)dWLeaves, dCollapse, &nWide));
   B2_CUDA(cudaEventRecord(ctx->ev[5], s));
   B2_TRY(b2_fetch_words(ctx, dRoot, 1, B2_MB_ROOT));
-  B2_CUDA(cudaStreamSynchronize(s));
+  B2_CUDA(cudaStreamSynchronize(s)); /* the only host synchronisation of a build */
   const u32 root = b2_mailbox(ctx, B2_MB_ROOT)[0];
+  if (opts.collapse) nWide = b2_mailbox(ctx, B2_MB_COLLAPSE)[1];
+  if (algo == B2BVH_PLOCPP) {
+    iterations = b2_mailbox(ctx, B2_MB_PLOC)[2];
+    if (b2_mailbox(ctx, B2_MB_PLOC)[1] != 1u)
+      return b2_fail(B2BVH_ERR_INTERNAL, "ploc: %u clusters left after %u iterations", b2_mailbox(ctx, B2_MB_PLOC)[1], iterations);
+  }
 
   out->algo = (u32)algo;
   out->n_prims = n;

@@ -368,8 +368,9 @@ int b2_launch_collapse(b2bvh_ctx* ctx, const b2bvh_bvh2_node* d_nodes, const b2b
   B2_KERNEL(ctx, "collapse_emit");
   collapse_emit_kernel<<<egrid, COL_THREADS, emitSmem, ctx->stream>>>(d_nodes, d_sortedVals, nInt, taskCh, taskParent, firstChild, ctrl, d_wide, d_wideLeaves);
   B2_LAUNCH_CHECK(ctx);
+  /* CollapseCtrl::nWide comes back through the mailbox: b2_mailbox(ctx, B2_MB_COLLAPSE)[1] after the build's final synchronisation
+   * (no host round trip in the middle of a build) */
+  (void)h_nWide;
   B2_TRY(b2_fetch_words(ctx, ctrl, 4, B2_MB_COLLAPSE));
-  B2_CUDA(cudaStreamSynchronize(ctx->stream));
-  *h_nWide = b2_mailbox(ctx, B2_MB_COLLAPSE)[1]; /* CollapseCtrl::nWide */
   return 0;
 }

@@ -484,17 +484,16 @@ int b2_launch_ploc(b2bvh_ctx* ctx, const b2bvh_aabb* d_triAabb, const u32* d_sor
   B2_KERNEL(ctx, "ploc_tail");
   ploc_tail_kernel<<<1, PLOC_TAIL_THREADS, sizeof(PlocTailSmem), ctx->stream>>>(ids[0], boxes[0], ids[1], boxes[1], d_nodes, ctrl);
   B2_LAUNCH_CHECK(ctx);
+  /* PlocCtrl::count (1 when the tree is complete) and ::itersRun come back through the mailbox, read by b2bvh_build after its
+   * final synchronisation: b2_mailbox(ctx, B2_MB_PLOC)[1], [2] */
+  (void)h_iterations;
   B2_TRY(b2_fetch_words(ctx, ctrl, 4, B2_MB_PLOC));
-  B2_CUDA(cudaStreamSynchronize(ctx->stream));
-  PlocCtrl h;
-  h.count = b2_mailbox(ctx, B2_MB_PLOC)[1];
-  h.itersRun = b2_mailbox(ctx, B2_MB_PLOC)[2];
-  if (h.count != 1) return b2_fail(B2BVH_ERR_INTERNAL, "ploc: %u clusters left after %u iterations", h.count, h.itersRun);
 #ifdef PLOC_TRACE
   {
+    cudaStreamSynchronize(ctx->stream);
     static unsigned long long tr[2][256][8];
     cudaMemcpyFromSymbol(tr, g_plocTrace, sizeof(tr));
-    for (u32 i = 0; i < 256 && i < h.itersRun && tr[0][i][0]; i++) {
+    for (u32 i = 0; i < 256 && tr[0][i][0]; i++) {
       fprintf(stderr, "ploc it %3u count %9llu |", i, tr[0][i][6]);
       for (int k = 0; k < 2; k++) {
         fprintf(stderr, " cta%s:", k ? "L" : "0");
@@ -502,9 +501,7 @@ int b2_launch_ploc(b2bvh_ctx* ctx, const b2bvh_aabb* d_triAabb, const u32* d_sor
       }
       fprintf(stderr, "\n");
     }
-    cudaMemset(0, 0, 0);
   }
 #endif
-  *h_iterations = h.itersRun;
   return 0;
 }
