@@ -25,7 +25,7 @@ class Aabb(C.Structure):
 class BuildOpts(C.Structure):
     _fields_ = [("collapse", C.c_uint32), ("tris_on_device", C.c_uint32), ("use_scene_box", C.c_uint32), ("scene_box", Aabb),
                 ("stage_timing", C.c_uint32), ("karras_two_kernel", C.c_uint32), ("boxes_ready", C.c_uint32),
-                ("d_scene_negmin_max", C.c_void_p), ("lbvh_second_level", C.c_uint32), ("merge_max_ctas", C.c_uint32)]
+                ("d_scene_negmin_max", C.c_void_p), ("lbvh_second_level", C.c_uint32), ("merge_max_ctas", C.c_uint32), ("use_graph", C.c_uint32), ("reserved2", C.c_uint32)]
 
 
 class Tree(C.Structure):
@@ -163,7 +163,7 @@ class Context:
 
     # ---- stages ----
     def build(self, algo, tris, n=None, collapse=True, tris_on_device=False, scene_box=None, karras_two_kernel=False, boxes_ready=False,
-              d_scene_negmin_max=None, lbvh_second_level=0, merge_max_ctas=0):
+              d_scene_negmin_max=None, lbvh_second_level=0, merge_max_ctas=0, use_graph=False):
         """tris: TRIANGLE[n] numpy array (host) or an int device/pinned-host pointer (then pass n)."""
         opts = BuildOpts()
         opts.collapse = 1 if collapse else 0
@@ -173,6 +173,7 @@ class Context:
         opts.boxes_ready = 1 if boxes_ready else 0
         opts.lbvh_second_level = int(lbvh_second_level)
         opts.merge_max_ctas = int(merge_max_ctas)
+        opts.use_graph = 1 if use_graph else 0
         if d_scene_negmin_max:
             opts.d_scene_negmin_max = int(d_scene_negmin_max)
         if scene_box is not None:

@@ -41,6 +41,7 @@ int b2_reserve(b2bvh_ctx* ctx, int slot, size_t bytes, void** out) {
     const size_t want = (bytes + 255) & ~(size_t)255;
     B2_CUDA(cudaMalloc(&b.p, want));
     b.cap = want;
+    ctx->alloc_epoch++;
   }
   *out = b.p;
   return 0;
@@ -54,7 +55,7 @@ enum {
 
 extern "C" {
 
-uint32_t b2bvh_abi_version(void) { return 3; }
+uint32_t b2bvh_abi_version(void) { return 4; }
 const char* b2bvh_last_error(void) { return g_err; }
 
 int b2bvh_ctx_create(int device, void* cuda_stream, b2bvh_ctx** out) {
@@ -94,6 +95,7 @@ int b2bvh_ctx_destroy(b2bvh_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   for (int i = 0; i < 32; i++) if (ctx->bufs[i].p) cudaFree(ctx->bufs[i].p);
   for (int i = 0; i < 16; i++) cudaEventDestroy(ctx->ev[i]);
+  if (ctx->graph.exec) cudaGraphExecDestroy(ctx->graph.exec);
   if (ctx->mailbox) cudaFreeHost(ctx->mailbox);
   cudaStreamSynchronize(ctx->dl_stream);
   cudaStreamDestroy(ctx->dl_stream);
@@ -245,30 +247,35 @@ int b2bvh_build(b2bvh_ctx* ctx, int algo, const b2bvh_triangle* tris, uint32_t n
     B2_TRY(b2_reserve(ctx, SLOT_COLLAPSE, b2_collapse_scratch_bytes(n), &dCollapse));
   }
 
-  /* ---- upload (TwoPassLbvh.cpp:19-20) ---- */
+  /* ---- the launch sequence: enqueued directly, or captured once into a CUDA graph and replayed (opts.use_graph) ---- */
   const b2bvh_triangle* dT = tris;
+  if (!opts.tris_on_device) dT = (const b2bvh_triangle*)dTris;
+  u32 iterations = 0, nWide = 0;
+  bool capturing = false;
+  /* stage events: inside a capture they must become event-record NODES (cudaEventRecordExternal), or they cannot be timed */
+  auto record = [&](int i) { return capturing ? cudaEventRecordWithFlags(ctx->ev[i], s, cudaEventRecordExternal) : cudaEventRecord(ctx->ev[i], s); };
+  auto enqueue = [&]() -> int {
+  /* ---- upload (TwoPassLbvh.cpp:19-20) ---- */
   if (!opts.tris_on_device) {
-    B2_CUDA(cudaEventRecord(ctx->ev[8], s));
+    B2_CUDA(record(8));
     /* boxes_ready: b2bvh_shard_extents already uploaded these triangles into the same buffer */
     if (!opts.boxes_ready) B2_CUDA(cudaMemcpyAsync(dTris, tris, (size_t)n * sizeof(b2bvh_triangle), cudaMemcpyHostToDevice, s));
-    B2_CUDA(cudaEventRecord(ctx->ev[9], s));
-    dT = (const b2bvh_triangle*)dTris;
+    B2_CUDA(record(9));
   }
 
   /* ---- S1 extents ---- */
-  B2_CUDA(cudaEventRecord(ctx->ev[0], s));
+  B2_CUDA(record(0));
   if (!opts.boxes_ready) B2_TRY(b2_launch_extents(ctx, dT, n, (b2bvh_aabb*)dAabb, dScene, dScratch8, nullptr));
   if (opts.d_scene_negmin_max) B2_TRY(b2_launch_scene_from_negmin_max(ctx, opts.d_scene_negmin_max, dScene));
   else if (opts.use_scene_box) B2_CUDA(cudaMemcpyAsync(dScene, &opts.scene_box, sizeof(b2bvh_aabb), cudaMemcpyHostToDevice, s));
-  B2_CUDA(cudaEventRecord(ctx->ev[1], s));
+  B2_CUDA(record(1));
   /* ---- S2 Morton (+ SetupClusters for PLOC/HPLOC is inside their launchers but is accounted under BUILD here) ---- */
   B2_TRY(b2_launch_morton(ctx, (const b2bvh_aabb*)dAabb, dScene, n, (u32*)dKeys, (u32*)dVals));
-  B2_CUDA(cudaEventRecord(ctx->ev[2], s));
+  B2_CUDA(record(2));
   /* ---- S3 sort (values of pass 0 are the iota written by S2: not re-read) ---- */
   B2_TRY(b2_launch_sort(ctx, (const u32*)dKeys, nullptr, (u32*)dSKeys, (u32*)dSVals, (u32*)dTKeys, (u32*)dTVals, dSort, n, 0, 32));
-  B2_CUDA(cudaEventRecord(ctx->ev[3], s));
+  B2_CUDA(record(3));
   /* ---- S4 / S6 / S7 hierarchy ---- */
-  u32 iterations = 0;
   switch (algo) {
     case B2BVH_TWO_PASS_LBVH:
       if (opts.karras_two_kernel)
@@ -294,14 +301,40 @@ int b2bvh_build(b2bvh_ctx* ctx, int algo, const b2bvh_triangle* tris, uint32_t n
       B2_CUDA(cudaMemsetAsync(dRoot, 0, 4, s));
       break;
   }
-  B2_CUDA(cudaEventRecord(ctx->ev[4], s));
+  B2_CUDA(record(4));
   /* ---- S5 collapse ---- */
-  u32 nWide = 0;
   if (opts.collapse)
     B2_TRY(b2_launch_collapse(ctx, (const b2bvh_bvh2_node*)dNodes, (const b2bvh_prim_ref*)dLeaves, (const u32*)dSVals, dRoot, n, (b2bvh_bvh4_node*)dWide,
                               (b2bvh_prim_node*)dWLeaves, dCollapse, &nWide));
-  B2_CUDA(cudaEventRecord(ctx->ev[5], s));
+  B2_CUDA(record(5));
   B2_TRY(b2_fetch_words(ctx, dRoot, 1, B2_MB_ROOT));
+  return 0;
+  };
+  const bool wantGraph = opts.use_graph && !ctx->prof_on && !(opts.use_scene_box && !opts.d_scene_negmin_max);
+  b2bvh_ctx::GraphCache& G = ctx->graph;
+  if (wantGraph && G.exec && G.algo == algo && G.n == n && G.tris == (const void*)tris && G.epoch == ctx->alloc_epoch &&
+      memcmp(&G.opts, &opts, sizeof(opts)) == 0) {
+    B2_CUDA(cudaGraphLaunch(G.exec, s));
+    ctx->launches += G.launches;
+  } else if (wantGraph) {
+    if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
+    const u32 before = ctx->launches;
+    B2_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    capturing = true;
+    const int st = enqueue();
+    capturing = false;
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(s, &graph);
+    if (st) { if (graph) cudaGraphDestroy(graph); return st; }
+    B2_CUDA(ce);
+    const cudaError_t ie = cudaGraphInstantiate(&G.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) { G.exec = nullptr; return b2_check(ie, "cudaGraphInstantiate"); }
+    G.algo = algo; G.n = n; G.tris = tris; G.epoch = ctx->alloc_epoch; G.opts = opts; G.launches = ctx->launches - before;
+    B2_CUDA(cudaGraphLaunch(G.exec, s));
+  } else {
+    B2_TRY(enqueue());
+  }
   B2_CUDA(cudaStreamSynchronize(s)); /* the only host synchronisation of a build */
   const u32 root = b2_mailbox(ctx, B2_MB_ROOT)[0];
   if (opts.collapse) nWide = b2_mailbox(ctx, B2_MB_COLLAPSE)[1];

@@ -200,6 +200,15 @@ struct b2bvh_ctx {
   u32* mailbox;          /* pinned + mapped host memory, B2_MAILBOX_SLOTS x 16 words: small results come back through a one-warp
                             kernel instead of the copy engine, where a 4-byte read would queue behind another context's bulk copy */
   u32* mailbox_dev;      /* the same memory as the device sees it */
+  /* one cached CUDA graph of a whole build (b2bvh_build_opts.use_graph) */
+  struct GraphCache {
+    cudaGraphExec_t exec;
+    int algo;
+    u32 n, launches, epoch;
+    const void* tris;
+    b2bvh_build_opts opts;
+  } graph;
+  u32 alloc_epoch;       /* bumped whenever a build-owned buffer is (re)allocated: a cached graph holds the old pointers */
   u32 launches;
   u32 lbvh_second_level; /* b2bvh_build_opts.lbvh_second_level of the running build */
   u32 merge_max_ctas;    /* b2bvh_build_opts.merge_max_ctas of the running build */

@@ -63,6 +63,11 @@ typedef struct b2bvh_build_opts {
   uint32_t lbvh_second_level; /* LBVH builders: 0 = automatic (second merge level from 2^20 primitives), 1 = always, 2 = never; same output */
   uint32_t merge_max_ctas;  /* PLOC++: cap on the CTAs of the cooperative merge launch, 0 = every resident CTA; same output (tests use it to
                                reach many-tile chunks with small inputs) */
+  uint32_t use_graph;       /* 1: capture the launch sequence of this build in a CUDA graph and REPLAY it when the next build on the context
+                               has the same algorithm, size, options and triangle pointer (rebuilds of an animated mesh, benchmark loops):
+                               one graph launch instead of ~20 kernel launches, which is what bounds builds of a few 100 K primitives.
+                               Same output; ignored while the per-launch profiler is on or when scene_box comes from the host */
+  uint32_t reserved2;
 } b2bvh_build_opts;
 
 /* Everything a build leaves on the device.  Pointers are DEVICE pointers owned by the context

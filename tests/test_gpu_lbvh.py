@@ -172,3 +172,28 @@ def test_profiler_reports_every_launch(ctx):
     names = [e[0] for e in entries]
     assert names[:3] == ["primref_extents", "morton30", "radix_count"] and names.count("radix_scatter") == 4
     assert all(ms >= 0 for _, ms in entries)
+
+
+@pytest.mark.parametrize("algo", [capi.TWO_PASS_LBVH, capi.SINGLE_PASS_LBVH, capi.PLOCPP, capi.HPLOC], ids=["twopass", "singlepass", "ploc", "hploc"])
+def test_graph_replay_builds_the_same_tree(ctx, oracle, algo):
+    """opts.use_graph: the launch sequence is captured once and replayed for the same (algorithm, size, options, triangle
+    pointer); every buffer equals the plain build, a different size or pointer re-captures, stage times are still reported."""
+    from b2bvh import types as T
+    tris = random_tris(30_011, 41)
+    d = ctx.upload(tris)
+    plain = ctx.fetch(ctx.build(algo, d, n=tris.size, tris_on_device=True))
+    for rep in range(3):  # capture + two replays
+        tree = ctx.build(algo, d, n=tris.size, tris_on_device=True, use_graph=True)
+        g = ctx.fetch(tree)
+        for k in ("skeys", "svals", "nodes", "wide", "wide_leaves"):
+            assert g[k].tobytes() == plain[k].tobytes(), (rep, k)
+        assert g["root"] == plain["root"] and g["n_wide"] == plain["n_wide"]
+        assert tree.build_ms > 0 and tree.stage_ms[capi.T_SORT] > 0 and tree.n_launches > 5
+    tris2 = random_tris(12_345, 42)  # another size and pointer on the same context: the cached graph must not be replayed
+    d2 = ctx.upload(tris2)
+    a = ctx.fetch(ctx.build(algo, d2, n=tris2.size, tris_on_device=True, use_graph=True))
+    b = ctx.fetch(ctx.build(algo, d2, n=tris2.size, tris_on_device=True))
+    assert a["nodes"].tobytes() == b["nodes"].tobytes() and a["wide"].tobytes() == b["wide"].tobytes()
+    h = ctx.fetch(ctx.build(algo, tris, use_graph=True))  # host triangles: the upload is part of the graph
+    assert h["nodes"].tobytes() == plain["nodes"].tobytes()
+    ctx.free(d); ctx.free(d2)

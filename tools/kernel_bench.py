@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--two-kernel", action="store_true")
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--graph", action="store_true", help="replay the build from a CUDA graph (use_graph)")
     ap.add_argument("--mesh", default="", help="bunny | sponza | buddha (staged under oracle/_ref/meshes) instead of the synthetic soup")
     a = ap.parse_args()
     ctx = capi.Context(0)
@@ -45,7 +46,8 @@ def main():
         for name, ms in ctx.profile_entries():
             agg.setdefault(name, []).append(ms)
         ctx.profile(False)
-        tree = ctx.build(ALGOS[a.algo], d, n=a.n, tris_on_device=True, karras_two_kernel=a.two_kernel)
+        tree = ctx.build(ALGOS[a.algo], d, n=a.n, tris_on_device=True, karras_two_kernel=a.two_kernel, use_graph=a.graph)
+        tree = ctx.build(ALGOS[a.algo], d, n=a.n, tris_on_device=True, karras_two_kernel=a.two_kernel, use_graph=a.graph)
         tot.append((tree.build_ms, [tree.stage_ms[k] for k in (0, 1, 2, 3, 5)]))
     print(f"lib={os.path.basename(capi.LIB_PATH)} algo={a.algo} n={a.n} launches={tree.n_launches} iterations={tree.n_iterations} n_wide={tree.n_wide}")
     best = min(tot)
