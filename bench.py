@@ -136,7 +136,8 @@ def workload_config(gpus):
     return {"workload": f"synth_uniform_v1 {PRIMS_PER_GPU // 1_000_000}M triangles per GPU (BASELINE configs[3]/[4]), single-pass LBVH + Bvh4 collapse",
             "prims_per_gpu": PRIMS_PER_GPU, "total_prims": PRIMS_PER_GPU * gpus, "seed": hex(SEED), "builder": "SinglePassLbvh",
             "parallelism": f"primitive-range shards x{gpus}" if gpus > 1 else "single GPU",
-            "l2": "inputs and intermediates (>=640 MB per GPU) exceed the 126 MB L2; no flush between steps"}
+            "l2": "inputs and intermediates (>=640 MB per GPU) exceed the 126 MB L2; no flush between steps",
+            "launch": "every step replays the build's launch sequence from a CUDA graph (b2bvh_build_opts.use_graph): same kernels, one graph launch"}
 
 
 def main():
@@ -188,7 +189,7 @@ def main():
     def step(tris_ptr, on_device, L=lane0):
         c = L.ctx
         if world == 1:
-            tree = c.build(algo, tris_ptr, n=n, tris_on_device=on_device)
+            tree = c.build(algo, tris_ptr, n=n, tris_on_device=on_device, use_graph=True)
             launches[0] += tree.n_launches
             return tree
         # sharded build: local boxes -> ONE all-reduce(MAX) of {-min,max} -> local build in the global frame (the reduced vector never
@@ -196,7 +197,7 @@ def main():
         with torch.cuda.stream(L.stream):
             capi.check(c.lib.b2bvh_shard_extents(c.h, tris_ptr, n, 1 if on_device else 0, L.box6.data_ptr()), "b2bvh_shard_extents")
             dist.all_reduce(L.box6, op=dist.ReduceOp.MAX)
-            tree = c.build(algo, tris_ptr, n=n, tris_on_device=on_device, boxes_ready=True, d_scene_negmin_max=L.box6.data_ptr())
+            tree = c.build(algo, tris_ptr, n=n, tris_on_device=on_device, boxes_ready=True, d_scene_negmin_max=L.box6.data_ptr(), use_graph=True)
             capi.check(c.lib.b2bvh_d2d(c.h, L.root_local.data_ptr(), tree.d_bvhNodes + 32 * tree.root + 8, 24), "b2bvh_d2d")
             dist.all_gather_into_tensor(L.roots, L.root_local)
             capi.check(c.lib.b2bvh_top_level(c.h, L.roots.data_ptr(), world, L.top_nodes.data_ptr()), "b2bvh_top_level")
@@ -382,16 +383,21 @@ def main():
                 res = {"n": int(mt.size)}
                 for nm, al in (("TwoPassLbvh", capi.TWO_PASS_LBVH), ("SinglePassLbvh", capi.SINGLE_PASS_LBVH), ("PLOC++", capi.PLOCPP), ("HPLOC", capi.HPLOC)):
                     try:
-                        for _ in range(3):
-                            ctx.build(al, dm, n=mt.size, tris_on_device=True)
-                        best = None
-                        for _ in range(10):
-                            t = ctx.build(al, dm, n=mt.size, tris_on_device=True)
-                            tot = sum(t.stage_ms[k] for k in (capi.T_EXTENTS, capi.T_MORTON, capi.T_SORT, capi.T_BUILD))
-                            if best is None or tot < best[0]:
-                                best = (tot, [float(t.stage_ms[k]) for k in (capi.T_EXTENTS, capi.T_MORTON, capi.T_SORT, capi.T_BUILD, capi.T_COLLAPSE)])
+                        def best_of(graph):
+                            for _ in range(3):
+                                ctx.build(al, dm, n=mt.size, tris_on_device=True, use_graph=graph)
+                            bst = None
+                            for _ in range(10):
+                                tt = ctx.build(al, dm, n=mt.size, tris_on_device=True, use_graph=graph)
+                                tot = sum(tt.stage_ms[k] for k in (capi.T_EXTENTS, capi.T_MORTON, capi.T_SORT, capi.T_BUILD))
+                                if bst is None or tot < bst[0]:
+                                    bst = (tot, [float(tt.stage_ms[k]) for k in (capi.T_EXTENTS, capi.T_MORTON, capi.T_SORT, capi.T_BUILD, capi.T_COLLAPSE)])
+                            return bst, tt
+                        plain, _ = best_of(False)
+                        best, t = best_of(True)
                         res[nm] = {"total_ms": best[0], "Mprims_s": mt.size / best[0] / 1e3, "extents_morton_sort_build_collapse_ms": best[1],
-                                   "bvh4_cost": ctx.tree_cost(t)}
+                                   "launch": "CUDA graph replay", "total_ms_plain_launches": plain[0],
+                                   "extents_morton_sort_build_collapse_ms_plain_launches": plain[1], "bvh4_cost": ctx.tree_cost(t)}
                         # primary rays on the built tree (TwoPassLbvh::traverseBvh, 512 x 512): the reference's four Bvh2 kernels and the Bvh4 walk
                         pr = TRACE_PRESETS[mesh]
                         tr = T.make_transform(pr["t"], pr["s"], [0.0, 0.0, 0.0, 1.0] if pr["q"] is None else qt_rotation(pr["q"]))

@@ -310,7 +310,11 @@ int b2bvh_build(b2bvh_ctx* ctx, int algo, const b2bvh_triangle* tris, uint32_t n
   B2_TRY(b2_fetch_words(ctx, dRoot, 1, B2_MB_ROOT));
   return 0;
   };
-  const bool wantGraph = opts.use_graph && !ctx->prof_on && !(opts.use_scene_box && !opts.d_scene_negmin_max);
+  bool wantGraph = opts.use_graph && !ctx->prof_on && !(opts.use_scene_box && !opts.d_scene_negmin_max);
+  if (wantGraph && !opts.tris_on_device) { /* an upload can only be part of a graph when it reads pinned memory */
+    cudaPointerAttributes pa;
+    if (cudaPointerGetAttributes(&pa, tris) != cudaSuccess || pa.type != cudaMemoryTypeHost) { cudaGetLastError(); wantGraph = false; }
+  }
   b2bvh_ctx::GraphCache& G = ctx->graph;
   if (wantGraph && G.exec && G.algo == algo && G.n == n && G.tris == (const void*)tris && G.epoch == ctx->alloc_epoch &&
       memcmp(&G.opts, &opts, sizeof(opts)) == 0) {

@@ -162,6 +162,7 @@ struct BuilderBase {
   Transformation m_transform{};
   Camera m_camera{};
   u32 m_width = 512, m_height = 512; /* TwoPassLbvh.cpp:221-222 */
+  bool m_useGraph = false;            /* replay repeated builds of the same size from a CUDA graph (b2bvh_build_opts.use_graph) */
   int m_traversalKernel = B2BVH_TRAVERSE_SPECULATIVE_WHILE; /* WHILEWHILE is defined at TwoPassLbvh.cpp:12 */
 
   BuilderBase() {
@@ -181,6 +182,7 @@ struct BuilderBase {
     b2bvh_build_opts opts{};
     opts.collapse = 1;
     opts.stage_timing = 1;
+    opts.use_graph = m_useGraph ? 1u : 0u; /* takes effect for device or pinned triangles; a std::vector upload is enqueued plainly */
     checkStatus(api.b2bvh_build(context.m_ctx, algo, primitives.data(), (u32)primitives.size(), &opts, &m_tree), "b2bvh_build");
     const b2bvh_tree& t = m_tree;
     b2bvh_ctx* c = context.m_ctx;
