@@ -8,7 +8,7 @@ NCU="ncu --set full --clock-control none --import-source on"
 for K in "$@"; do
   case $K in
     ploc_iter|ploc_setup|ploc_tail|ploc_merge) ALGO=ploc;;
-    hploc|hploc_setup) ALGO=hploc;;
+    hploc|hploc_setup|hploc_kernel) ALGO=hploc;;
     lbvh_karras_emit|lbvh_refit) ALGO="twopass --two-kernel";;
     lbvh_fused_karras) ALGO=twopass;;
     *) ALGO=singlepass;;
