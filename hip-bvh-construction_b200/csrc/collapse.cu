@@ -36,7 +36,11 @@
 #ifndef NUM_SOLO
 #define NUM_SOLO 1024    /* levels of at most this many tasks are numbered by CTA 0 alone (a grid-wide level costs ~7 us of synchronisation) */
 #endif
-#define NUM_THREADS 256  /* numbering kernel (1024-thread CTAs make the grid barrier cheaper but the tile loop slower: measured a wash) */
+/* numbering kernel: CTA size by input size (measured, 10 M / bunny / sponza in us: 128 threads x 12 CTAs per SM 325 / 52 / 78,
+ * 256 x 6 247 / 50 / 89, 512 x 2 210 / 60 / 121, 1024 x 1 234 / 85 / 129): large levels want few arrivals per grid-wide step,
+ * the deep thin trees of small scenes want a short tile loop */
+#define NUM_THREADS_LARGE 512
+#define NUM_THREADS_SMALL 128
 
 /* scratch layout: CollapseCtrl (256 B) | uint4 expansion[n] | uint4 taskCh[n] | u32 taskParent[n] | u32 firstChild[n] | u32 taskNode[n] | u64 counts[G] */
 struct CollapseCtrl {
@@ -53,6 +57,7 @@ size_t b2_collapse_scratch_bytes(u32 n) {
   return 256 + (size_t)n * (2 * sizeof(uint4) + 3 * sizeof(u32)) + 16 + 16384 * sizeof(u64);
 }
 
+template <int NUM_THREADS>
 struct ColSmem {
   u32 warpSum[3][NUM_THREADS / 32];
 };
@@ -116,6 +121,7 @@ __device__ __forceinline__ u32 count_internal(const uint4& t, u32 nInt) {
 
 /* A. tasks [a, b): fetch the expansion of each task's Bvh2 node into its record and count the internal children.  The
  * iterations are independent, so the gathers of several tiles are in flight together (four per thread). */
+template <int NUM_THREADS>
 __device__ __forceinline__ u32 number_fetch(const uint4* __restrict__ expansion, u32 nInt, const u32* taskNode, uint4* taskCh, u32 a, u32 b) {
   u32 cnt = 0;
   u32 g = a + threadIdx.x;
@@ -140,7 +146,8 @@ __device__ __forceinline__ u32 number_fetch(const uint4* __restrict__ expansion,
 /* C. one tile of NUM_THREADS tasks [tileStart, min(tileStart + NUM_THREADS, end)): number the internal children from
  * childBase + (exclusive count inside the tile) in (task, slot) order and append their tasks.  The records were written by
  * the same threads in number_fetch.  Returns the tile's number of internal children (same value in every thread). */
-__device__ __forceinline__ u32 number_tile(u32 nInt, u32* taskNode, const uint4* taskCh, u32* taskParent, u32* firstChild, ColSmem& S, u32 tileStart,
+template <int NUM_THREADS>
+__device__ __forceinline__ u32 number_tile(u32 nInt, u32* taskNode, const uint4* taskCh, u32* taskParent, u32* firstChild, ColSmem<NUM_THREADS>& S, u32 tileStart,
                                            u32 end, u32 childBase) {
   const u32 tid = threadIdx.x, w = tid >> 5, l = tid & 31u;
   const u32 g = tileStart + tid;
@@ -173,10 +180,11 @@ __device__ __forceinline__ u32 number_tile(u32 nInt, u32* taskNode, const uint4*
   return tileTotal;
 }
 
-__global__ void __launch_bounds__(NUM_THREADS, 6) collapse_number_kernel(const uint4* __restrict__ expansion, u32 nInt, const u32* __restrict__ rootIdx,
+template <int NUM_THREADS>
+__global__ void __launch_bounds__(NUM_THREADS, NUM_THREADS == NUM_THREADS_LARGE ? 2 : 12) collapse_number_kernel(const uint4* __restrict__ expansion, u32 nInt, const u32* __restrict__ rootIdx,
                                                                         u32* taskNode, uint4* taskCh, u32* taskParent, u32* firstChild,
                                                                         CollapseCtrl* ctrl, u64* counts) {
-  __shared__ ColSmem S;
+  __shared__ ColSmem<NUM_THREADS> S;
   const u32 G = gridDim.x, c = blockIdx.x, tid = threadIdx.x, w = tid >> 5, l = tid & 31u;
   u32 level = 0, start = 0, end = 1, barriers = 0, arriveTarget = 0;
   if (c == 0 && tid == 0) { taskNode[0] = *rootIdx; taskParent[0] = B2_INVALID; }
@@ -189,10 +197,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 6) collapse_number_kernel(const u
       /* ---- a run of small levels (the top of the tree, the tail of a deep one): CTA 0 alone, no grid-wide step in between ---- */
       if (c == 0) {
         do {
-          number_fetch(expansion, nInt, taskNode, taskCh, start, end);
+          number_fetch<NUM_THREADS>(expansion, nInt, taskNode, taskCh, start, end);
           u32 running = end;
           for (u32 tileStart = start; tileStart < end; tileStart += NUM_THREADS)
-            running += number_tile(nInt, taskNode, taskCh, taskParent, firstChild, S, tileStart, end, running);
+            running += number_tile<NUM_THREADS>(nInt, taskNode, taskCh, taskParent, firstChild, S, tileStart, end, running);
           start = end; end = running; level++;
         } while (end - start <= NUM_SOLO && end != start);
         if (tid == 0) publish_level(ctrl, barriers + 1u, level, start, end);
@@ -205,7 +213,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 6) collapse_number_kernel(const u
       if (c < nActive) {
         const u32 cStart = start + c * chunk, cEnd = min(end, cStart + chunk);
         /* A. records + internal children of the whole chunk */
-        u32 cnt = number_fetch(expansion, nInt, taskNode, taskCh, cStart, cEnd);
+        u32 cnt = number_fetch<NUM_THREADS>(expansion, nInt, taskNode, taskCh, cStart, cEnd);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(B2_FULL, cnt, o);
         if (l == 0) S.warpSum[1][w] = cnt;
@@ -239,7 +247,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 6) collapse_number_kernel(const u
         if (c == nActive - 1 && tid == 0) publish_level(ctrl, barriers + 1u, level + 1u, end, running + chunkTotal); /* last chunk of the level */
         /* C. the chunk tile by tile: no CTA waits for another one here */
         for (u32 tileStart = cStart; tileStart < cEnd; tileStart += NUM_THREADS)
-          running += number_tile(nInt, taskNode, taskCh, taskParent, firstChild, S, tileStart, cEnd, running);
+          running += number_tile<NUM_THREADS>(nInt, taskNode, taskCh, taskParent, firstChild, S, tileStart, cEnd, running);
       }
     }
     barriers++;
@@ -331,15 +339,18 @@ int b2_launch_collapse(b2bvh_ctx* ctx, const b2bvh_bvh2_node* d_nodes, const b2b
                        b2bvh_bvh4_node* d_wide, b2bvh_prim_node* d_wideLeaves, void* d_scratch, u32* h_nWide) {
   (void)d_leaves; /* both layouts name leaves by slot; the primitive index comes from the sorted value array */
   if (n < 2) return b2_fail(B2BVH_ERR_INVALID, "collapse needs at least 2 primitives");
-  static int occ = 0;
+  static int occLarge = 0, occSmall = 0;
   const size_t emitSmem = sizeof(EmitSmem);
-  if (!occ) {
+  if (!occLarge) {
     B2_CUDA(cudaFuncSetAttribute(collapse_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emitSmem));
-    B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, collapse_number_kernel, NUM_THREADS, 0));
-    if (occ < 1) return b2_fail(B2BVH_ERR_INTERNAL, "collapse: kernel does not fit on an SM");
+    B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occLarge, collapse_number_kernel<NUM_THREADS_LARGE>, NUM_THREADS_LARGE, 0));
+    B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occSmall, collapse_number_kernel<NUM_THREADS_SMALL>, NUM_THREADS_SMALL, 0));
+    if (occLarge < 1 || occSmall < 1) return b2_fail(B2BVH_ERR_INTERNAL, "collapse: kernel does not fit on an SM");
+    if (occLarge > 2) occLarge = 2; /* fewer arrivals per grid-wide step beat more warps (see NUM_THREADS_LARGE) */
   }
+  const bool large = n >= (1u << 20);
   /* every CTA must be resident (grid barrier): at most SMs x occupancy; small inputs use fewer CTAs (cheaper barriers) */
-  u32 grid = (u32)ctx->sm_count * (u32)occ;
+  u32 grid = (u32)ctx->sm_count * (u32)(large ? occLarge : occSmall);
   const u32 want = (n + 1023u) / 1024u;
   if (grid > want) grid = want;
   if (grid < 1) grid = 1;
@@ -359,7 +370,8 @@ int b2_launch_collapse(b2bvh_ctx* ctx, const b2bvh_bvh2_node* d_nodes, const b2b
   B2_LAUNCH_CHECK(ctx);
   B2_KERNEL(ctx, "collapse_number");
   void* args[] = {(void*)&expansion, (void*)&nInt, (void*)&d_rootIdx, (void*)&taskNode, (void*)&taskCh, (void*)&taskParent, (void*)&firstChild, (void*)&ctrl, (void*)&counts};
-  B2_CUDA(cudaLaunchCooperativeKernel((const void*)collapse_number_kernel, dim3(grid), dim3(NUM_THREADS), args, 0, ctx->stream));
+  if (large) B2_CUDA(cudaLaunchCooperativeKernel((const void*)collapse_number_kernel<NUM_THREADS_LARGE>, dim3(grid), dim3(NUM_THREADS_LARGE), args, 0, ctx->stream));
+  else B2_CUDA(cudaLaunchCooperativeKernel((const void*)collapse_number_kernel<NUM_THREADS_SMALL>, dim3(grid), dim3(NUM_THREADS_SMALL), args, 0, ctx->stream));
   B2_LAUNCH_CHECK(ctx);
   /* the number of wide nodes stays on the device: the emit grid is sized for the worst case and strides over ctrl->nWide */
   u32 egrid = (nInt + COL_THREADS - 1) / COL_THREADS;
