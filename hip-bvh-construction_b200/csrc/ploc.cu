@@ -470,7 +470,12 @@ int b2_launch_ploc(b2bvh_ctx* ctx, const b2bvh_aabb* d_triAabb, const u32* d_sor
   B2_LAUNCH_CHECK(ctx);
   if (n > PLOC_TAIL) {
     /* every CTA must be resident (grid barrier, posted counts): at most SMs x occupancy; small inputs use fewer CTAs */
-    u32 grid = (u32)ctx->sm_count * (u32)occ;
+    /* CTAs per SM by input size: every iteration ends in two grid-wide steps whose cost grows with the number of CTAs, the
+     * window work per CTA shrinks with it (measured build stage in us with 1 / 2 / 3 / 4 CTAs per SM: 262 K 274 / 297 / 328 / 348,
+     * 1 M 374 / 393 / 424 / 442, 2 M 548 / 544 / 573 / 598, 4 M 890 / 839 / 858 / 878, 10 M 1904 / 1668 / 1658 / 1684) */
+    u32 perSm = n <= (2u << 20) ? 1u : (n <= (6u << 20) ? 2u : 3u);
+    if (perSm > (u32)occ) perSm = (u32)occ;
+    u32 grid = (u32)ctx->sm_count * perSm;
     const u32 want = (n + PLOC_TILE - 1) / PLOC_TILE;
     if (grid > want) grid = want;
     if (grid > PLOC_MAX_GRID) grid = PLOC_MAX_GRID;
