@@ -585,8 +585,9 @@ int b2_launch_lbvh_fused(b2bvh_ctx* ctx, const u32* d_sortedKeys, const u32* d_s
     const u32 cap = n / 8 + 1024;
     B2_CUDA(cudaMemsetAsync(pendingCount, 0, 4, ctx->stream));
     const u32 grid = (n + LBVH_TILE - 1) / LBVH_TILE;
-    /* second level only where it pays: below ~1 M primitives the extra launch costs more than the shorter climb saves */
-    const bool useGroups = ctx->lbvh_second_level == 1 ? true : (ctx->lbvh_second_level == 2 ? false : n >= (1u << 20));
+    /* second level only where it pays (build stage in us without / with it: 1 M 104 / 119, 3 M 203 / 217, 7 M 379 / 399, 10 M 551 / 533,
+     * tools/micro/lbvh_level_sweep.py): below ~8 M primitives the extra launch costs more than the shorter climb saves */
+    const bool useGroups = ctx->lbvh_second_level == 1 ? true : (ctx->lbvh_second_level == 2 ? false : n >= (1u << 23));
     uint2* tileInfo = reinterpret_cast<uint2*>(pending + cap);
     LbvhPending* tileBuf = useGroups ? reinterpret_cast<LbvhPending*>(reinterpret_cast<unsigned char*>(tileInfo) + (((size_t)grid * sizeof(uint2) + 15) & ~(size_t)15)) : nullptr;
     static bool attrSet = false;
