@@ -25,7 +25,7 @@ class Aabb(C.Structure):
 class BuildOpts(C.Structure):
     _fields_ = [("collapse", C.c_uint32), ("tris_on_device", C.c_uint32), ("use_scene_box", C.c_uint32), ("scene_box", Aabb),
                 ("stage_timing", C.c_uint32), ("karras_two_kernel", C.c_uint32), ("boxes_ready", C.c_uint32),
-                ("d_scene_negmin_max", C.c_void_p), ("lbvh_second_level", C.c_uint32), ("merge_max_ctas", C.c_uint32), ("use_graph", C.c_uint32), ("reserved2", C.c_uint32)]
+                ("d_scene_negmin_max", C.c_void_p), ("lbvh_second_level", C.c_uint32), ("merge_max_ctas", C.c_uint32), ("use_graph", C.c_uint32), ("split_sa_max", C.c_float)]
 
 
 class Tree(C.Structure):
@@ -36,7 +36,8 @@ class Tree(C.Structure):
                 ("d_sortedMortonCodeValues", C.c_void_p), ("d_bvhNodes", C.c_void_p), ("d_parentIdxs", C.c_void_p),
                 ("d_leafNodes", C.c_void_p), ("d_wideBvhNodes", C.c_void_p), ("d_wideLeafNodes", C.c_void_p),
                 ("stage_ms", C.c_float * T_COUNT), ("build_ms", C.c_float), ("h2d_ms", C.c_float), ("n_iterations", C.c_uint32),
-                ("n_launches", C.c_uint32)]
+                ("n_launches", C.c_uint32), ("n_triangles", C.c_uint32), ("n_split_levels", C.c_uint32), ("split_ms", C.c_float),
+                ("reserved", C.c_uint32), ("d_primRefIdx", C.c_void_p)]
 
 
 # every symbol include/b2bvh.h declares (tests check the library exports each of them)
@@ -163,7 +164,7 @@ class Context:
 
     # ---- stages ----
     def build(self, algo, tris, n=None, collapse=True, tris_on_device=False, scene_box=None, karras_two_kernel=False, boxes_ready=False,
-              d_scene_negmin_max=None, lbvh_second_level=0, merge_max_ctas=0, use_graph=False):
+              d_scene_negmin_max=None, lbvh_second_level=0, merge_max_ctas=0, use_graph=False, split_sa_max=0.0):
         """tris: TRIANGLE[n] numpy array (host) or an int device/pinned-host pointer (then pass n)."""
         opts = BuildOpts()
         opts.collapse = 1 if collapse else 0
@@ -174,6 +175,7 @@ class Context:
         opts.lbvh_second_level = int(lbvh_second_level)
         opts.merge_max_ctas = int(merge_max_ctas)
         opts.use_graph = 1 if use_graph else 0
+        opts.split_sa_max = float(split_sa_max)
         if d_scene_negmin_max:
             opts.d_scene_negmin_max = int(d_scene_negmin_max)
         if scene_box is not None:
@@ -212,6 +214,7 @@ class Context:
         r["nodes"] = self.download(tree.d_bvhNodes, T.BVH2_NODE, n - 1 if separate else 2 * n - 1)
         r["parents"] = self.download(tree.d_parentIdxs, np.uint32, 2 * n - 1) if tree.d_parentIdxs else None
         r["leaves"] = self.download(tree.d_leafNodes, T.PRIM_REF, n) if separate else None
+        r["prim_idx"] = self.download(tree.d_primRefIdx, np.uint32, n) if tree.d_primRefIdx else None
         if tree.n_wide:
             r["wide"] = self.download(tree.d_wideBvhNodes, T.BVH4_NODE, tree.n_wide)
             r["wide_leaves"] = self.download(tree.d_wideLeafNodes, T.PRIM_NODE, n)

@@ -49,13 +49,14 @@ int b2_reserve(b2bvh_ctx* ctx, int slot, size_t bytes, void** out) {
 
 enum {
   SLOT_TRIS = 0, SLOT_AABB, SLOT_CTL, SLOT_KEYS, SLOT_VALS, SLOT_SKEYS, SLOT_SVALS, SLOT_TKEYS, SLOT_TVALS, SLOT_SORT, SLOT_NODES,
-  SLOT_PARENTS, SLOT_LBVH, SLOT_WIDE, SLOT_WLEAVES, SLOT_COLLAPSE, SLOT_LEAVES, SLOT_PLOC, SLOT_HPLOC, SLOT_MISC, SLOT_COUNT
+  SLOT_PARENTS, SLOT_LBVH, SLOT_WIDE, SLOT_WLEAVES, SLOT_COLLAPSE, SLOT_LEAVES, SLOT_PLOC, SLOT_HPLOC, SLOT_MISC,
+  SLOT_SPLIT_BOX, SLOT_SPLIT_PRIM, SLOT_SPLIT_LIST_A, SLOT_SPLIT_LIST_B, SLOT_SPLIT_STATUS, SLOT_SPLIT_LEAFPRIM, SLOT_COUNT
 };
 /* SLOT_CTL (256 B): [0..23] scene box, [32..63] extents scratch8, [64..87] {-min,max}, [96] root index, [128..] misc */
 
 extern "C" {
 
-uint32_t b2bvh_abi_version(void) { return 4; }
+uint32_t b2bvh_abi_version(void) { return 5; }
 const char* b2bvh_last_error(void) { return g_err; }
 
 int b2bvh_ctx_create(int device, void* cuda_stream, b2bvh_ctx** out) {
@@ -218,6 +219,13 @@ int b2bvh_build(b2bvh_ctx* ctx, int algo, const b2bvh_triangle* tris, uint32_t n
   const bool separate = (algo == B2BVH_PLOCPP || algo == B2BVH_HPLOC);
   const u32 launches0 = ctx->launches;
   cudaStream_t s = ctx->stream;
+  /* early split clipping (USE_PRIM_SPLITTING): only TwoPassLbvh builds over PrimRefs end to end — SinglePassLbvh with the macro
+   * indexes the triangle array with reference indices (InitBvhNodes, SinglePassLbvh.cpp:112), PLOC++/H-PLOC never split */
+  const bool split = opts.split_sa_max > 0.0f;
+  if (split && algo != B2BVH_TWO_PASS_LBVH) return b2_fail(B2BVH_ERR_INVALID, "build: split_sa_max needs B2BVH_TWO_PASS_LBVH (algo %d)", algo);
+  if (split && (opts.boxes_ready || opts.use_scene_box || opts.d_scene_negmin_max))
+    return b2_fail(B2BVH_ERR_INVALID, "build: split_sa_max cannot be combined with the sharded-build options");
+  const u32 nTris = n;
 
   /* ---- buffers (grown on demand, reused) ---- */
   void *dTris = nullptr, *dAabb, *dKeys, *dVals, *dSKeys, *dSVals, *dTKeys, *dTVals, *dSort, *dNodes, *dParents = nullptr, *dLbvh = nullptr,
@@ -228,6 +236,31 @@ int b2bvh_build(b2bvh_ctx* ctx, int algo, const b2bvh_triangle* tris, uint32_t n
   u32* dRoot = (u32*)(ctl + 96);
   if (!opts.tris_on_device) B2_TRY(b2_reserve(ctx, SLOT_TRIS, (size_t)n * sizeof(b2bvh_triangle), &dTris));
   B2_TRY(b2_reserve(ctx, SLOT_AABB, (size_t)n * sizeof(b2bvh_aabb), &dAabb));
+  const b2bvh_triangle* dT = tris;
+  if (!opts.tris_on_device) dT = (const b2bvh_triangle*)dTris;
+  u32* dRefPrim = nullptr;
+  void* dLeafPrim = nullptr;
+  u32 splitLevels = 0;
+  if (split) {
+    /* upload + S1 + the split run ahead of everything whose size depends on the reference count (one sync per generation) */
+    if (!opts.tris_on_device) {
+      B2_CUDA(cudaEventRecord(ctx->ev[8], s));
+      B2_CUDA(cudaMemcpyAsync(dTris, tris, (size_t)n * sizeof(b2bvh_triangle), cudaMemcpyHostToDevice, s));
+      B2_CUDA(cudaEventRecord(ctx->ev[9], s));
+    }
+    B2_CUDA(cudaEventRecord(ctx->ev[0], s));
+    B2_TRY(b2_launch_extents(ctx, dT, n, (b2bvh_aabb*)dAabb, dScene, dScratch8, nullptr));
+    B2_CUDA(cudaEventRecord(ctx->ev[10], s));
+    b2bvh_aabb* refBox = nullptr;
+    u32 m = 0;
+    B2_TRY(b2_launch_split(ctx, (const b2bvh_aabb*)dAabb, n, opts.split_sa_max, SLOT_SPLIT_BOX, SLOT_SPLIT_PRIM, SLOT_SPLIT_LIST_A, SLOT_SPLIT_LIST_B,
+                           SLOT_SPLIT_STATUS, &refBox, &dRefPrim, &m, &splitLevels));
+    B2_CUDA(cudaEventRecord(ctx->ev[11], s));
+    if (m < 2) return b2_fail(B2BVH_ERR_INTERNAL, "early split produced %u references", m);
+    n = m;               /* from here on the primitives of the build are the references */
+    dAabb = refBox;
+    B2_TRY(b2_reserve(ctx, SLOT_SPLIT_LEAFPRIM, (size_t)n * 4, &dLeafPrim));
+  }
   B2_TRY(b2_reserve(ctx, SLOT_KEYS, (size_t)n * 4, &dKeys));
   B2_TRY(b2_reserve(ctx, SLOT_VALS, (size_t)n * 4, &dVals));
   B2_TRY(b2_reserve(ctx, SLOT_SKEYS, (size_t)n * 4, &dSKeys));
@@ -248,15 +281,13 @@ int b2bvh_build(b2bvh_ctx* ctx, int algo, const b2bvh_triangle* tris, uint32_t n
   }
 
   /* ---- the launch sequence: enqueued directly, or captured once into a CUDA graph and replayed (opts.use_graph) ---- */
-  const b2bvh_triangle* dT = tris;
-  if (!opts.tris_on_device) dT = (const b2bvh_triangle*)dTris;
   u32 iterations = 0, nWide = 0;
   bool capturing = false;
   /* stage events: inside a capture they must become event-record NODES (cudaEventRecordExternal), or they cannot be timed */
   auto record = [&](int i) { return capturing ? cudaEventRecordWithFlags(ctx->ev[i], s, cudaEventRecordExternal) : cudaEventRecord(ctx->ev[i], s); };
   auto enqueue = [&]() -> int {
   /* ---- upload (TwoPassLbvh.cpp:19-20) ---- */
-  if (!opts.tris_on_device) {
+  if (!opts.tris_on_device && !split) {
     B2_CUDA(record(8));
     /* boxes_ready: b2bvh_shard_extents already uploaded these triangles into the same buffer */
     if (!opts.boxes_ready) B2_CUDA(cudaMemcpyAsync(dTris, tris, (size_t)n * sizeof(b2bvh_triangle), cudaMemcpyHostToDevice, s));
@@ -264,8 +295,8 @@ int b2bvh_build(b2bvh_ctx* ctx, int algo, const b2bvh_triangle* tris, uint32_t n
   }
 
   /* ---- S1 extents ---- */
-  B2_CUDA(record(0));
-  if (!opts.boxes_ready) B2_TRY(b2_launch_extents(ctx, dT, n, (b2bvh_aabb*)dAabb, dScene, dScratch8, nullptr));
+  if (!split) B2_CUDA(record(0));
+  if (!opts.boxes_ready && !split) B2_TRY(b2_launch_extents(ctx, dT, n, (b2bvh_aabb*)dAabb, dScene, dScratch8, nullptr));
   if (opts.d_scene_negmin_max) B2_TRY(b2_launch_scene_from_negmin_max(ctx, opts.d_scene_negmin_max, dScene));
   else if (opts.use_scene_box) B2_CUDA(cudaMemcpyAsync(dScene, &opts.scene_box, sizeof(b2bvh_aabb), cudaMemcpyHostToDevice, s));
   B2_CUDA(record(1));
@@ -284,6 +315,7 @@ int b2bvh_build(b2bvh_ctx* ctx, int algo, const b2bvh_triangle* tris, uint32_t n
       else
         B2_TRY(b2_launch_lbvh_fused(ctx, (const u32*)dSKeys, (const u32*)dSVals, (const b2bvh_aabb*)dAabb, n, (b2bvh_bvh2_node*)dNodes,
                                     (u32*)dParents, (u32*)dLbvh, dRoot, 1));
+      if (split) B2_TRY(b2_launch_split_remap(ctx, (const u32*)dSVals, dRefPrim, n, (b2bvh_bvh2_node*)dNodes, (u32*)dLeafPrim));
       B2_CUDA(cudaMemsetAsync(dRoot, 0, 4, s));
       break;
     case B2BVH_SINGLE_PASS_LBVH:
@@ -304,13 +336,13 @@ int b2bvh_build(b2bvh_ctx* ctx, int algo, const b2bvh_triangle* tris, uint32_t n
   B2_CUDA(record(4));
   /* ---- S5 collapse ---- */
   if (opts.collapse)
-    B2_TRY(b2_launch_collapse(ctx, (const b2bvh_bvh2_node*)dNodes, (const b2bvh_prim_ref*)dLeaves, (const u32*)dSVals, dRoot, n, (b2bvh_bvh4_node*)dWide,
+    B2_TRY(b2_launch_collapse(ctx, (const b2bvh_bvh2_node*)dNodes, (const b2bvh_prim_ref*)dLeaves, split ? (const u32*)dLeafPrim : (const u32*)dSVals, dRoot, n, (b2bvh_bvh4_node*)dWide,
                               (b2bvh_prim_node*)dWLeaves, dCollapse, &nWide));
   B2_CUDA(record(5));
   B2_TRY(b2_fetch_words(ctx, dRoot, 1, B2_MB_ROOT));
   return 0;
   };
-  bool wantGraph = opts.use_graph && !ctx->prof_on && !(opts.use_scene_box && !opts.d_scene_negmin_max);
+  bool wantGraph = opts.use_graph && !split && !ctx->prof_on && !(opts.use_scene_box && !opts.d_scene_negmin_max);
   if (wantGraph && !opts.tris_on_device) { /* an upload can only be part of a graph when it reads pinned memory */
     cudaPointerAttributes pa;
     if (cudaPointerGetAttributes(&pa, tris) != cudaSuccess || pa.type != cudaMemoryTypeHost) { cudaGetLastError(); wantGraph = false; }
@@ -377,6 +409,10 @@ int b2bvh_build(b2bvh_ctx* ctx, int algo, const b2bvh_triangle* tris, uint32_t n
   if (!opts.tris_on_device) B2_CUDA(cudaEventElapsedTime(&out->h2d_ms, ctx->ev[8], ctx->ev[9]));
   out->n_iterations = algo == B2BVH_HPLOC ? b2_mailbox(ctx, B2_MB_HPLOC)[0] : iterations;
   out->n_launches = ctx->launches - launches0;
+  out->n_triangles = nTris;
+  out->d_primRefIdx = dRefPrim;
+  out->n_split_levels = splitLevels;
+  if (split) B2_CUDA(cudaEventElapsedTime(&out->split_ms, ctx->ev[10], ctx->ev[11]));
   return 0;
 }
 
@@ -452,6 +488,16 @@ int b2bvh_tree_cost(b2bvh_ctx* ctx, const b2bvh_tree* tree, float* cost) {
   B2_TRY(b2bvh_d2h(ctx, w.data(), tree->d_wideBvhNodes, w.size() * sizeof(b2bvh_bvh4_node)));
   B2_TRY(b2bvh_d2h(ctx, wl.data(), tree->d_wideLeafNodes, wl.size() * sizeof(b2bvh_prim_node)));
   B2_TRY(b2bvh_d2h(ctx, pb.data(), tree->d_triangleAabb, pb.size() * sizeof(b2bvh_aabb)));
+  if (tree->d_primRefIdx) {
+    /* split references: the reference fills triangleAabb[ref.m_primIdx] = ref.m_aabb in reference order, so the LAST fragment of a
+     * triangle is the one the cost counts, and the table has one (otherwise empty) entry per reference (TwoPassLbvh.cpp:188-193) */
+    std::vector<u32> rp(tree->n_prims);
+    B2_TRY(b2bvh_d2h(ctx, rp.data(), tree->d_primRefIdx, rp.size() * 4));
+    const b2bvh_aabb empty = {{B2BVH_FLT_MAX, B2BVH_FLT_MAX, B2BVH_FLT_MAX}, {-B2BVH_FLT_MAX, -B2BVH_FLT_MAX, -B2BVH_FLT_MAX}};
+    std::vector<b2bvh_aabb> table(tree->n_prims, empty);
+    for (size_t i = 0; i < rp.size(); i++) table[rp[i]] = pb[i];
+    pb.swap(table);
+  }
   *cost = b2bvh_cost_bvh4(w.data(), wl.data(), pb.data(), 0, tree->n_wide, tree->n_internal);
   return 0;
 }

@@ -250,8 +250,8 @@ int b2_prof_end(b2bvh_ctx* ctx);
 
 int b2_reserve(b2bvh_ctx* ctx, int slot, size_t bytes, void** out);
 /* words <= 16 from device memory into mailbox slot `slot`; readable at b2_mailbox(ctx, slot) after the next stream synchronisation */
-#define B2_MAILBOX_SLOTS 4
-enum { B2_MB_COLLAPSE = 0, B2_MB_PLOC = 1, B2_MB_HPLOC = 2, B2_MB_ROOT = 3 };
+#define B2_MAILBOX_SLOTS 6
+enum { B2_MB_COLLAPSE = 0, B2_MB_PLOC = 1, B2_MB_HPLOC = 2, B2_MB_ROOT = 3, B2_MB_SPLIT = 4, B2_MB_BATCH = 5 };
 int b2_fetch_words(b2bvh_ctx* ctx, const void* d_src, u32 words, int slot);
 static inline const u32* b2_mailbox(const b2bvh_ctx* ctx, int slot) { return ctx->mailbox + slot * 16; }
 
@@ -275,6 +275,10 @@ int b2_launch_collapse(b2bvh_ctx* ctx, const b2bvh_bvh2_node* d_nodes, const b2b
 size_t b2_ploc_scratch_bytes(u32 n);
 int b2_launch_ploc(b2bvh_ctx* ctx, const b2bvh_aabb* d_triAabb, const u32* d_sortedVals, u32 n, b2bvh_bvh2_node* d_nodes,
                    b2bvh_prim_ref* d_leaves, void* d_scratch, u32* h_iterations);
+/* early split clipping (split.cu): references of all generations in emission order; synchronises the stream once per generation */
+int b2_launch_split(b2bvh_ctx* ctx, const b2bvh_aabb* d_triAabb, u32 n, float saMax, int slotOutBox, int slotOutPrim, int slotListA, int slotListB,
+                    int slotStatus, b2bvh_aabb** d_refBox, u32** d_refPrim, u32* h_count, u32* h_levels);
+int b2_launch_split_remap(b2bvh_ctx* ctx, const u32* d_sortedVals, const u32* d_refPrim, u32 n, b2bvh_bvh2_node* d_nodes, u32* d_leafPrim);
 size_t b2_hploc_scratch_bytes(u32 n);
 int b2_launch_hploc(b2bvh_ctx* ctx, const b2bvh_aabb* d_triAabb, const u32* d_sortedKeys, const u32* d_sortedVals, u32 n,
                     b2bvh_bvh2_node* d_nodes, b2bvh_prim_ref* d_leaves, void* d_scratch, u32* h_mergeCalls);

@@ -67,7 +67,11 @@ typedef struct b2bvh_build_opts {
                                has the same algorithm, size, options and triangle pointer (rebuilds of an animated mesh, benchmark loops):
                                one graph launch instead of ~20 kernel launches, which is what bounds builds of a few 100 K primitives.
                                Same output; ignored while the per-launch profiler is on or when scene_box comes from the host */
-  uint32_t reserved2;
+  float split_sa_max;       /* TWO_PASS only. > 0: early split clipping on the device before the build — TwoPassLbvh compiled with
+                               USE_PRIM_SPLITTING (TwoPassLbvh.cpp:23-28; Utility::doEarlySplitClipping(prims, refs, saMax), Utility.cpp:456-538):
+                               every primitive box with area > saMax is halved along its largest extent until all pieces fit; the build
+                               then runs over the REFERENCES (b2bvh_tree.n_prims = their count, d_primRefIdx = their triangles).
+                               0: off (the reference's default, saMax = FltMax) */
 } b2bvh_build_opts;
 
 /* Everything a build leaves on the device.  Pointers are DEVICE pointers owned by the context
@@ -97,6 +101,14 @@ typedef struct b2bvh_tree {
   float h2d_ms;                               /* device time of the triangle upload when tris_on_device == 0      */
   uint32_t n_iterations;                      /* PLOC++: iterations run; HPLOC: merge calls; else 0               */
   uint32_t n_launches;                        /* kernels launched by this build                                   */
+  /* early split clipping (split_sa_max > 0): the build's primitives are PrimRefs; n_prims counts them, d_triangleAabb holds their
+   * boxes (PrimRef::m_aabb) and d_primRefIdx their triangles (PrimRef::m_primIdx), both in the emission order of
+   * doEarlySplitClipping; Bvh2 leaves and PrimNodes name TRIANGLES (InitBvhNodesPrimRef, TwoPassLbvhKernel.h:178-182) */
+  uint32_t n_triangles;                       /* triangles uploaded (== n_prims without splitting)                */
+  uint32_t n_split_levels;                    /* generations the split ran (0 without splitting)                  */
+  float split_ms;                             /* device time of the split (inside stage_ms[extents])              */
+  uint32_t reserved;
+  const uint32_t* d_primRefIdx;               /* n_prims, or NULL without splitting                               */
 } b2bvh_tree;
 
 /* ---- context / memory: replaces Context (src/Context.cpp:7-22) and OrochiUtils malloc/copy helpers

@@ -138,6 +138,51 @@ void orc_primrefs(const b2bvh_triangle* tris, u32 n, b2bvh_prim_ref* refs, Box* 
   *scene = s;
 }
 
+/* ------------------------------------------------- S0: early split clipping
+ * Utility::doEarlySplitClipping (Utility.cpp:456-538), the host step in front of the path when the builders are
+ * compiled with USE_PRIM_SPLITTING (TwoPassLbvh.cpp:23-28, saMax = 10): a FIFO of PrimRefs, seeded with one per
+ * triangle in input order; a reference whose box area is <= saMax is emitted, any other is cut at the MIDDLE of its
+ * box along the largest extent (no triangle clipping: the two halves are plain box halves carrying the same m_primIdx)
+ * and both halves go to the back of the queue.  The emission order is therefore level by level, and inside a level
+ * the order of the queue.  Returns the number of references; writes at most `cap` of them.  `maxLevels` bounds the
+ * generations (the reference loops forever when a box never gets small enough, e.g. an infinite or NaN area — those
+ * are reported at once): 0 is returned then. */
+u32 orc_early_split(const b2bvh_triangle* tris, u32 n, float saMax, b2bvh_prim_ref* out, u32 cap, u32 maxLevels) {
+  std::queue<std::pair<b2bvh_prim_ref, u32>> q; /* reference + generation */
+  for (u32 i = 0; i < n; i++) {
+    b2bvh_prim_ref r; r.m_primIdx = i; r.m_aabb = tri_box(tris[i]);
+    q.push(std::make_pair(r, 0u));
+  }
+  u64 count = 0;
+  while (!q.empty()) {
+    const b2bvh_prim_ref ref = q.front().first; const u32 gen = q.front().second; q.pop();
+    if (box_area(ref.m_aabb) <= saMax) {            /* :477-480 */
+      if (count < cap && out) out[count] = ref;
+      count++;
+      continue;
+    }
+    if (gen + 1 >= maxLevels) return 0;
+    if (!(box_area(ref.m_aabb) < INFINITY)) return 0; /* inf / NaN area: halving never gets below saMax */
+    const int dim = box_max_dim(ref.m_aabb);        /* :484 */
+    const F3 c = box_center(ref.m_aabb);            /* :485 */
+    b2bvh_prim_ref L = ref, R = ref;                /* :488-532: L = [min, max with centre on dim], R = [min with centre on dim, max] */
+    if (dim == 0) { L.m_aabb.m_max.x = c.x; R.m_aabb.m_min.x = c.x; }
+    if (dim == 1) { L.m_aabb.m_max.y = c.y; R.m_aabb.m_min.y = c.y; }
+    if (dim == 2) { L.m_aabb.m_max.z = c.z; R.m_aabb.m_min.z = c.z; }
+    q.push(std::make_pair(L, gen + 1)); q.push(std::make_pair(R, gen + 1));
+    if (count + q.size() > 0x3FFFFFFFull) return 0;
+  }
+  return (u32)count;
+}
+
+/* the per-triangle box table of the cost report when references were split (TwoPassLbvh.cpp:188-193):
+ * triangleAabb[ref.m_primIdx] = ref.m_aabb in reference order, so the LAST fragment of a triangle wins;
+ * the table has one entry per REFERENCE (entries past the triangle count stay empty). */
+void orc_split_cost_boxes(const b2bvh_prim_ref* refs, u32 m, Box* table) {
+  for (u32 i = 0; i < m; i++) table[i] = box_empty();
+  for (u32 i = 0; i < m; i++) table[refs[i].m_primIdx] = refs[i].m_aabb;
+}
+
 /* ------------------------------------------------- S2: extended Morton code
  * computeExtendedMortonCode, CommonBlocksKernel.h:159-359.  The bit allocation
  * depends only on the scene extent, so it is computed once (orc_morton_config)

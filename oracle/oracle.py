@@ -40,7 +40,7 @@ def lib():
         _lib.orc_ray_zdir.restype = C.c_float
         _lib.orc_ray_zdir.argtypes = [C.c_float]
         for f in ("orc_fnv1a_words", "orc_lbvh_apetrei", "orc_collapse4", "orc_bvh2_depth", "orc_traverse", "orc_traverse_kind", "orc_traverse_wide4", "orc_binned_sah_build",
-                  "orc_morton_code_cfg"):
+                  "orc_morton_code_cfg", "orc_early_split"):
             getattr(_lib, f).restype = C.c_uint32
     return _lib
 
@@ -71,6 +71,30 @@ def primrefs(tris):
     scene = np.zeros(1, dtype=T.AABB)
     lib().orc_primrefs(_p(tris), _u32(n), _p(refs), _p(boxes), _p(scene))
     return refs, boxes, scene
+
+
+def early_split(tris, sa_max, max_levels=64):
+    """Utility::doEarlySplitClipping with a finite saMax: PRIM_REF[m] in the reference's emission order."""
+    args = (_p(tris), _u32(tris.size), C.c_float(float(sa_max)))
+    cnt = int(lib().orc_early_split(*args, None, _u32(0), _u32(max_levels)))
+    if cnt == 0:
+        raise ValueError("early split does not terminate within max_levels (or exceeds 2^30 references)")
+    out = np.zeros(cnt, dtype=T.PRIM_REF)
+    lib().orc_early_split(*args, _p(out), _u32(cnt), _u32(max_levels))
+    return out
+
+
+def split_cost_boxes(refs):
+    table = np.zeros(refs.size, dtype=T.AABB)
+    lib().orc_split_cost_boxes(_p(refs), _u32(refs.size), _p(table))
+    return table
+
+
+def scene_of(boxes):
+    scene = np.zeros(1, dtype=T.AABB)
+    scene["mn"] = boxes["mn"].min(axis=0)
+    scene["mx"] = boxes["mx"].max(axis=0)
+    return scene
 
 
 def morton_config(extent):
@@ -259,9 +283,12 @@ def top_level(root_boxes):
 
 
 # ---- full pipelines (launch order of the reference builders) ----
-def build_lbvh(tris, single_pass=False, scene_override=None):
+def build_lbvh(tris, single_pass=False, scene_override=None, split_sa_max=None):
     """TwoPassLbvh::build (TwoPassLbvh.cpp:17-197) / SinglePassLbvh::build (SinglePassLbvh.cpp:17-188).
-    scene_override: AABB[1] global scene box of a sharded build (replaces the local union for Morton coding)."""
+    scene_override: AABB[1] global scene box of a sharded build (replaces the local union for Morton coding).
+    split_sa_max: TwoPassLbvh compiled with USE_PRIM_SPLITTING (TwoPassLbvh.cpp:23-28): the build runs over the split references."""
+    if split_sa_max is not None:
+        return _build_lbvh_split(tris, split_sa_max)
     n = tris.size
     refs, boxes, scene = primrefs(tris)
     if scene_override is not None:
@@ -277,6 +304,21 @@ def build_lbvh(tris, single_pass=False, scene_override=None):
     cost = cost_bvh4(wide, wl, boxes, 0, n)
     return dict(scene=scene, keys=keys, vals=vals, skeys=sk, svals=sv, nodes=nodes, root=root, wide=wide, wide_leaves=wl,
                 wide_count=cnt, cost=cost, boxes=boxes, refs=refs)
+
+
+def _build_lbvh_split(tris, sa_max):
+    refs = early_split(tris, sa_max)
+    m = refs.size
+    boxes = np.zeros(m, dtype=T.AABB)
+    boxes["mn"] = refs["mn"]; boxes["mx"] = refs["mx"]
+    scene = scene_of(boxes)                      # CalculatePrimRefExtents over the references
+    keys, vals = morton_codes(refs, scene)
+    sk, sv = sort_kv(keys, vals)
+    nodes, parents = lbvh_karras(refs, sk, sv)   # leaf.left = refs[sv[g]].m_primIdx (InitBvhNodesPrimRef)
+    wide, wl, cnt = collapse4(nodes, None, 0, m)
+    cost = cost_bvh4(wide, wl, split_cost_boxes(refs), 0, m)
+    return dict(scene=scene, keys=keys, vals=vals, skeys=sk, svals=sv, nodes=nodes, parents=parents, root=0, wide=wide, wide_leaves=wl,
+                wide_count=cnt, cost=cost, boxes=boxes, refs=refs, prim_idx=refs["primIdx"].copy())
 
 
 def build_ploc(tris, hierarchical=False, scene_override=None):

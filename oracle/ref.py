@@ -34,7 +34,7 @@ def util():
         _util = C.CDLL(os.path.join(_HERE, "_ref", "libref_utility.so"))
         for f in ("ref_cost_bvh4", "ref_cost_lbvh", "ref_cost_sah"):
             getattr(_util, f).restype = C.c_float
-        for f in ("ref_early_split", "ref_load_obj"):
+        for f in ("ref_early_split", "ref_early_split_sa", "ref_load_obj"):
             getattr(_util, f).restype = C.c_uint32
     return _util
 
@@ -144,6 +144,14 @@ def early_split(tris):
     out = np.zeros(tris.size, dtype=T.PRIM_REF)
     cnt = util().ref_early_split(_p(tris), _u32(tris.size), _p(out))
     assert cnt == tris.size
+    return out
+
+
+def early_split_sa(tris, sa_max):
+    """Utility::doEarlySplitClipping(prims, refs, saMax), the reference's own code."""
+    cnt = util().ref_early_split_sa(_p(tris), _u32(tris.size), C.c_float(float(sa_max)), None, _u32(0))
+    out = np.zeros(cnt, dtype=T.PRIM_REF)
+    util().ref_early_split_sa(_p(tris), _u32(tris.size), C.c_float(float(sa_max)), _p(out), _u32(cnt))
     return out
 
 

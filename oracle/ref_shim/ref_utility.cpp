@@ -19,6 +19,14 @@ uint32_t ref_early_split(const Triangle* tris, uint32_t n, PrimRef* out) {
   memcpy(out, refs.data(), refs.size() * sizeof(PrimRef));
   return (uint32_t)refs.size();
 }
+/* doEarlySplitClipping with a finite saMax (USE_PRIM_SPLITTING, TwoPassLbvh.cpp:23-28); returns the count, writes <= cap */
+uint32_t ref_early_split_sa(const Triangle* tris, uint32_t n, float saMax, PrimRef* out, uint32_t cap) {
+  std::vector<Triangle> in(tris, tris + n);
+  std::vector<PrimRef> refs;
+  Utility::doEarlySplitClipping(in, refs, saMax);
+  if (out) memcpy(out, refs.data(), std::min<size_t>(cap, refs.size()) * sizeof(PrimRef));
+  return (uint32_t)refs.size();
+}
 /* OBJ -> triangles with the reference's loader; returns the count (call with out == nullptr to size) */
 uint32_t ref_load_obj(const char* file, const char* mtlDir, Triangle* out, uint32_t cap) {
   static std::vector<Triangle> cache; static std::string cached;
