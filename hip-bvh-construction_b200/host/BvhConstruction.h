@@ -163,6 +163,9 @@ struct BuilderBase {
   Camera m_camera{};
   u32 m_width = 512, m_height = 512; /* TwoPassLbvh.cpp:221-222 */
   bool m_useGraph = false;            /* replay repeated builds of the same size from a CUDA graph (b2bvh_build_opts.use_graph) */
+  float m_saMax = 0.0f;               /* TwoPassLbvh only: > 0 builds over early-split references, the reference compiled with USE_PRIM_SPLITTING
+                                         (`float saMax = 10.0f`, TwoPassLbvh.cpp:23-28); 0 = the reference's default (no splitting) */
+  GpuMemory<u32> d_primRefIdx;        /* PrimRef::m_primIdx of every reference when m_saMax > 0 (d_triangleAabb then holds PrimRef::m_aabb) */
   int m_traversalKernel = B2BVH_TRAVERSE_SPECULATIVE_WHILE; /* WHILEWHILE is defined at TwoPassLbvh.cpp:12 */
 
   BuilderBase() {
@@ -182,12 +185,14 @@ struct BuilderBase {
     b2bvh_build_opts opts{};
     opts.collapse = 1;
     opts.stage_timing = 1;
+    opts.split_sa_max = algo == B2BVH_TWO_PASS_LBVH ? m_saMax : 0.0f;
     opts.use_graph = m_useGraph ? 1u : 0u; /* takes effect for device or pinned triangles; a std::vector upload is enqueued plainly */
     checkStatus(api.b2bvh_build(context.m_ctx, algo, primitives.data(), (u32)primitives.size(), &opts, &m_tree), "b2bvh_build");
     const b2bvh_tree& t = m_tree;
     b2bvh_ctx* c = context.m_ctx;
     const size_t n = t.n_prims;
-    d_triangleBuff.bind(c, t.d_triangleBuff, n);
+    d_triangleBuff.bind(c, t.d_triangleBuff, t.n_triangles);
+    d_primRefIdx.bind(c, t.d_primRefIdx, n);
     d_triangleAabb.bind(c, t.d_triangleAabb, n);
     d_sceneExtents.bind(c, t.d_sceneExtents, 1);
     d_mortonCodeKeys.bind(c, t.d_mortonCodeKeys, n);

@@ -24,17 +24,19 @@ def test_library_exports_every_declared_symbol():
     assert sorted(capi.SYMBOLS) == declared
     for s in declared:
         assert hasattr(lib, s), s
-    assert lib.b2bvh_abi_version() == 4
+    assert lib.b2bvh_abi_version() == 5
 
 
 def test_struct_layouts_match_header(tmp_path):
     src = tmp_path / "layout.c"
-    src.write_text('#include <stdio.h>\n#include "b2bvh.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n", sizeof(b2bvh_tree), sizeof(b2bvh_build_opts),'
-                   ' offsetof(b2bvh_tree, d_bvhNodes), offsetof(b2bvh_tree, stage_ms), offsetof(b2bvh_tree, n_launches));return 0;}\n')
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "b2bvh.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(b2bvh_tree), sizeof(b2bvh_build_opts),'
+                   ' offsetof(b2bvh_tree, d_bvhNodes), offsetof(b2bvh_tree, stage_ms), offsetof(b2bvh_tree, n_launches), offsetof(b2bvh_tree, d_primRefIdx),'
+                   ' offsetof(b2bvh_build_opts, split_sa_max));return 0;}\n')
     exe = tmp_path / "layout"
     subprocess.check_call(["gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])  # the header is plain C
     got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
-    assert got == [C.sizeof(capi.Tree), C.sizeof(capi.BuildOpts), capi.Tree.d_bvhNodes.offset, capi.Tree.stage_ms.offset, capi.Tree.n_launches.offset]
+    assert got == [C.sizeof(capi.Tree), C.sizeof(capi.BuildOpts), capi.Tree.d_bvhNodes.offset, capi.Tree.stage_ms.offset, capi.Tree.n_launches.offset,
+                   capi.Tree.d_primRefIdx.offset, capi.BuildOpts.split_sa_max.offset]
     assert T.TRIANGLE.itemsize == 64 and T.BVH2_NODE.itemsize == 32 and T.BVH4_NODE.itemsize == 128 and T.PRIM_REF.itemsize == 28
 
 
