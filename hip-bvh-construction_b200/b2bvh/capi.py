@@ -40,10 +40,17 @@ class Tree(C.Structure):
                 ("reserved", C.c_uint32), ("d_primRefIdx", C.c_void_p)]
 
 
+class Batch(C.Structure):
+    _fields_ = [("n_items", C.c_uint32), ("n_prims_total", C.c_uint32), ("n_nodes_total", C.c_uint32), ("reserved", C.c_uint32),
+                ("d_triangles", C.c_void_p), ("d_bvhNodes", C.c_void_p), ("d_primRefs", C.c_void_p), ("d_rootNodes", C.c_void_p),
+                ("d_sceneExtents", C.c_void_p), ("d_leafOffsets", C.c_void_p), ("d_nodeOffsets", C.c_void_p), ("build_ms", C.c_float),
+                ("h2d_ms", C.c_float)]
+
+
 # every symbol include/b2bvh.h declares (tests check the library exports each of them)
 SYMBOLS = ["b2bvh_ctx_create", "b2bvh_ctx_destroy", "b2bvh_device_name", "b2bvh_device_sm_count", "b2bvh_alloc", "b2bvh_free",
            "b2bvh_memset", "b2bvh_h2d", "b2bvh_d2h", "b2bvh_h2d_async", "b2bvh_d2h_async", "b2bvh_d2d", "b2bvh_sync", "b2bvh_host_alloc_pinned", "b2bvh_host_free_pinned",
-           "b2bvh_last_error", "b2bvh_build", "b2bvh_scene_extents", "b2bvh_morton_codes", "b2bvh_sort_pairs", "b2bvh_generate_rays",
+           "b2bvh_last_error", "b2bvh_build", "b2bvh_build_batched", "b2bvh_scene_extents", "b2bvh_morton_codes", "b2bvh_sort_pairs", "b2bvh_generate_rays",
            "b2bvh_traverse", "b2bvh_traverse_ex", "b2bvh_heat_map", "b2bvh_shard_extents", "b2bvh_top_level", "b2bvh_cost_bvh4", "b2bvh_cost_lbvh", "b2bvh_tree_cost",
            "b2bvh_abi_version", "b2bvh_synth_uniform", "b2bvh_profile_enable", "b2bvh_profile_count", "b2bvh_profile_entry"]
 
@@ -70,6 +77,7 @@ def load():
         "b2bvh_memset": [vp, vp, C.c_int, sz], "b2bvh_h2d": [vp, vp, vp, sz], "b2bvh_d2h": [vp, vp, vp, sz], "b2bvh_d2d": [vp, vp, vp, sz], "b2bvh_h2d_async": [vp, vp, vp, sz], "b2bvh_d2h_async": [vp, vp, vp, sz], "b2bvh_sync": [vp],
         "b2bvh_host_alloc_pinned": [sz, C.POINTER(vp)], "b2bvh_host_free_pinned": [vp],
         "b2bvh_build": [vp, C.c_int, vp, u32, C.POINTER(BuildOpts), C.POINTER(Tree)],
+        "b2bvh_build_batched": [vp, vp, u32, vp, u32, C.POINTER(Batch)],
         "b2bvh_scene_extents": [vp, vp, u32, vp, vp], "b2bvh_morton_codes": [vp, vp, vp, u32, vp, vp],
         "b2bvh_sort_pairs": [vp, vp, vp, vp, vp, u32, u32, u32],
         "b2bvh_generate_rays": [vp, vp, u32, u32, vp, fp],
@@ -194,6 +202,23 @@ class Context:
         tree = Tree()
         check(self.lib.b2bvh_build(self.h, int(algo), ptr, int(n), C.byref(opts), C.byref(tree)), "b2bvh_build")
         return tree
+
+    def build_batched(self, tris, counts, n_total=None, tris_on_device=False):
+        """BatchedBvhBuilder::build: tris = TRIANGLE array of all items back to back (or a device pointer), counts = triangles per item."""
+        counts = np.ascontiguousarray(counts, dtype=np.uint32)
+        if isinstance(tris, np.ndarray):
+            assert tris.dtype == T.TRIANGLE and tris.flags["C_CONTIGUOUS"] and tris.size == int(counts.sum())
+            ptr = _hp(tris)
+        else:
+            ptr = C.c_void_p(int(tris))
+        b = Batch()
+        check(self.lib.b2bvh_build_batched(self.h, ptr, 1 if tris_on_device else 0, _hp(counts), counts.size, C.byref(b)), "b2bvh_build_batched")
+        return b
+
+    def fetch_batch(self, b):
+        return dict(nodes=self.download(b.d_bvhNodes, T.BVH2_NODE, b.n_nodes_total), leaves=self.download(b.d_primRefs, T.PRIM_REF, b.n_prims_total),
+                    roots=self.download(b.d_rootNodes, np.uint32, b.n_items), scenes=self.download(b.d_sceneExtents, T.AABB, b.n_items),
+                    leaf_off=self.download(b.d_leafOffsets, np.uint32, b.n_items + 1), node_off=self.download(b.d_nodeOffsets, np.uint32, b.n_items + 1))
 
     def tree_cost(self, tree):
         c = C.c_float()

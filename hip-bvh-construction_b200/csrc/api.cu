@@ -50,7 +50,8 @@ int b2_reserve(b2bvh_ctx* ctx, int slot, size_t bytes, void** out) {
 enum {
   SLOT_TRIS = 0, SLOT_AABB, SLOT_CTL, SLOT_KEYS, SLOT_VALS, SLOT_SKEYS, SLOT_SVALS, SLOT_TKEYS, SLOT_TVALS, SLOT_SORT, SLOT_NODES,
   SLOT_PARENTS, SLOT_LBVH, SLOT_WIDE, SLOT_WLEAVES, SLOT_COLLAPSE, SLOT_LEAVES, SLOT_PLOC, SLOT_HPLOC, SLOT_MISC,
-  SLOT_SPLIT_BOX, SLOT_SPLIT_PRIM, SLOT_SPLIT_LIST_A, SLOT_SPLIT_LIST_B, SLOT_SPLIT_STATUS, SLOT_SPLIT_LEAFPRIM, SLOT_COUNT
+  SLOT_SPLIT_BOX, SLOT_SPLIT_PRIM, SLOT_SPLIT_LIST_A, SLOT_SPLIT_LIST_B, SLOT_SPLIT_STATUS, SLOT_SPLIT_LEAFPRIM,
+  SLOT_BATCH_NODES, SLOT_BATCH_LEAVES, SLOT_BATCH_ROOTS, SLOT_BATCH_SCENES, SLOT_BATCH_OFFSETS, SLOT_COUNT
 };
 /* SLOT_CTL (256 B): [0..23] scene box, [32..63] extents scratch8, [64..87] {-min,max}, [96] root index, [128..] misc */
 
@@ -413,6 +414,62 @@ int b2bvh_build(b2bvh_ctx* ctx, int algo, const b2bvh_triangle* tris, uint32_t n
   out->d_primRefIdx = dRefPrim;
   out->n_split_levels = splitLevels;
   if (split) B2_CUDA(cudaEventElapsedTime(&out->split_ms, ctx->ev[10], ctx->ev[11]));
+  return 0;
+}
+
+/* ------------------------------------------------------------------ batched builder (BatchedBvhBuilder::build, BatchedBuilder.cpp:16-77) */
+int b2bvh_build_batched(b2bvh_ctx* ctx, const b2bvh_triangle* tris, uint32_t tris_on_device, const uint32_t* counts, uint32_t n_items, b2bvh_batch* out) {
+  static_assert(SLOT_COUNT <= 32, "b2bvh_ctx::bufs has 32 slots");
+  if (!ctx || !tris || !counts || !out) return b2_fail(B2BVH_ERR_INVALID, "build_batched: null argument");
+  if (n_items == 0) return b2_fail(B2BVH_ERR_INVALID, "build_batched: no items");
+  B2_CUDA(cudaSetDevice(ctx->device));
+  memset(out, 0, sizeof(*out));
+  std::vector<u32> off(2 * ((size_t)n_items + 1));
+  u32* leafOff = off.data();
+  u32* nodeOff = off.data() + n_items + 1;
+  u64 total = 0;
+  for (u32 i = 0; i < n_items; i++) {
+    if (counts[i] == 0 || counts[i] > 32u)
+      return b2_fail(B2BVH_ERR_INVALID, "build_batched: item %u has %u primitives; the batched builder takes 1..32 (MaxBatchedBlockSize, Common.h:597)", i, counts[i]);
+    leafOff[i] = (u32)total; nodeOff[i] = (u32)(total - i);
+    total += counts[i];
+    if (total > 0x7FFFFFFFull) return b2_fail(B2BVH_ERR_INVALID, "build_batched: more than 2^31-1 primitives in one batch");
+  }
+  leafOff[n_items] = (u32)total; nodeOff[n_items] = (u32)(total - n_items);
+  const u32 nPrims = (u32)total, nNodes = nPrims - n_items;
+  cudaStream_t s = ctx->stream;
+  void *dTris = nullptr, *dNodes, *dLeaves, *dRoots, *dScenes, *dOff;
+  if (!tris_on_device) B2_TRY(b2_reserve(ctx, SLOT_TRIS, (size_t)nPrims * sizeof(b2bvh_triangle), &dTris));
+  B2_TRY(b2_reserve(ctx, SLOT_BATCH_NODES, (size_t)nNodes * sizeof(b2bvh_bvh2_node), &dNodes));
+  B2_TRY(b2_reserve(ctx, SLOT_BATCH_LEAVES, (size_t)nPrims * sizeof(b2bvh_prim_ref), &dLeaves));
+  B2_TRY(b2_reserve(ctx, SLOT_BATCH_ROOTS, (size_t)n_items * 4, &dRoots));
+  B2_TRY(b2_reserve(ctx, SLOT_BATCH_SCENES, (size_t)n_items * sizeof(b2bvh_aabb), &dScenes));
+  B2_TRY(b2_reserve(ctx, SLOT_BATCH_OFFSETS, off.size() * 4, &dOff));
+  const b2bvh_triangle* dT = tris;
+  B2_CUDA(cudaEventRecord(ctx->ev[14], s));
+  if (!tris_on_device) {
+    B2_CUDA(cudaMemcpyAsync(dTris, tris, (size_t)nPrims * sizeof(b2bvh_triangle), cudaMemcpyHostToDevice, s));
+    dT = (const b2bvh_triangle*)dTris;
+  }
+  B2_CUDA(cudaMemcpyAsync(dOff, off.data(), off.size() * 4, cudaMemcpyHostToDevice, s));
+  B2_CUDA(cudaEventRecord(ctx->ev[15], s));
+  B2_CUDA(cudaEventRecord(ctx->ev[12], s));
+  B2_TRY(b2_launch_batched(ctx, dT, (const u32*)dOff, (const u32*)dOff + n_items + 1, n_items, (b2bvh_bvh2_node*)dNodes, (b2bvh_prim_ref*)dLeaves, (u32*)dRoots,
+                           (b2bvh_aabb*)dScenes));
+  B2_CUDA(cudaEventRecord(ctx->ev[13], s));
+  B2_CUDA(cudaStreamSynchronize(s)); /* `off` is pageable host memory: the copy must have left it before it goes out of scope */
+  out->n_items = n_items;
+  out->n_prims_total = nPrims;
+  out->n_nodes_total = nNodes;
+  out->d_triangles = dT;
+  out->d_bvhNodes = (const b2bvh_bvh2_node*)dNodes;
+  out->d_primRefs = (const b2bvh_prim_ref*)dLeaves;
+  out->d_rootNodes = (const u32*)dRoots;
+  out->d_sceneExtents = (const b2bvh_aabb*)dScenes;
+  out->d_leafOffsets = (const u32*)dOff;
+  out->d_nodeOffsets = (const u32*)dOff + n_items + 1;
+  B2_CUDA(cudaEventElapsedTime(&out->build_ms, ctx->ev[12], ctx->ev[13]));
+  B2_CUDA(cudaEventElapsedTime(&out->h2d_ms, ctx->ev[14], ctx->ev[15]));
   return 0;
 }
 

@@ -64,7 +64,7 @@ struct Api {
 #define B2_SYM(name) decltype(&::name) name = nullptr;
   B2_SYM(b2bvh_ctx_create) B2_SYM(b2bvh_ctx_destroy) B2_SYM(b2bvh_device_name) B2_SYM(b2bvh_device_sm_count) B2_SYM(b2bvh_alloc)
   B2_SYM(b2bvh_free) B2_SYM(b2bvh_memset) B2_SYM(b2bvh_h2d) B2_SYM(b2bvh_d2h) B2_SYM(b2bvh_sync) B2_SYM(b2bvh_last_error)
-  B2_SYM(b2bvh_build) B2_SYM(b2bvh_generate_rays) B2_SYM(b2bvh_traverse) B2_SYM(b2bvh_traverse_ex) B2_SYM(b2bvh_heat_map) B2_SYM(b2bvh_tree_cost) B2_SYM(b2bvh_cost_bvh4)
+  B2_SYM(b2bvh_build) B2_SYM(b2bvh_build_batched) B2_SYM(b2bvh_generate_rays) B2_SYM(b2bvh_traverse) B2_SYM(b2bvh_traverse_ex) B2_SYM(b2bvh_heat_map) B2_SYM(b2bvh_tree_cost) B2_SYM(b2bvh_cost_bvh4)
   B2_SYM(b2bvh_cost_lbvh) B2_SYM(b2bvh_synth_uniform) B2_SYM(b2bvh_abi_version)
 #undef B2_SYM
   void* handle = nullptr;
@@ -80,7 +80,7 @@ struct Api {
   if (!api.name) throw std::runtime_error(std::string("libb2bvh.so lacks symbol ") + #name);
     B2_SYM(b2bvh_ctx_create) B2_SYM(b2bvh_ctx_destroy) B2_SYM(b2bvh_device_name) B2_SYM(b2bvh_device_sm_count) B2_SYM(b2bvh_alloc)
     B2_SYM(b2bvh_free) B2_SYM(b2bvh_memset) B2_SYM(b2bvh_h2d) B2_SYM(b2bvh_d2h) B2_SYM(b2bvh_sync) B2_SYM(b2bvh_last_error)
-    B2_SYM(b2bvh_build) B2_SYM(b2bvh_generate_rays) B2_SYM(b2bvh_traverse) B2_SYM(b2bvh_traverse_ex) B2_SYM(b2bvh_heat_map) B2_SYM(b2bvh_tree_cost) B2_SYM(b2bvh_cost_bvh4)
+    B2_SYM(b2bvh_build) B2_SYM(b2bvh_build_batched) B2_SYM(b2bvh_generate_rays) B2_SYM(b2bvh_traverse) B2_SYM(b2bvh_traverse_ex) B2_SYM(b2bvh_heat_map) B2_SYM(b2bvh_tree_cost) B2_SYM(b2bvh_cost_bvh4)
     B2_SYM(b2bvh_cost_lbvh) B2_SYM(b2bvh_synth_uniform) B2_SYM(b2bvh_abi_version)
 #undef B2_SYM
     return api;
@@ -296,6 +296,52 @@ class HPLOC : public detail::BuilderBase {
   void traverseBvh(Context& context) { traceAndReport(context, false); }
   void traceBvh(Context& context) { traceAndReport(context, true); }
   GpuMemory<PrimRef> d_leafNodes;
+};
+
+/* BatchedBvhBuilder (src/BatchedBuilder.h:12-30): many small BVHs (<= MaxBatchedBlockSize = 32 triangles each) in one launch.
+ * Same members as the reference; item i's internal nodes start at d_bvhNodes[m_nodeOffsets[i]], its leaves (PrimRefs in sorted order)
+ * at d_primRefs[m_leafOffsets[i]], child indices are local to the item (leaf g = (n-1) + g), d_rootNodes[i] is its local root. */
+struct BatchedBuildInput {
+  std::vector<Triangle> m_primitives;
+};
+
+class BatchedBvhBuilder {
+ public:
+  void build(Context& context, std::vector<BatchedBuildInput>& batch) {
+    std::vector<u32> counts(batch.size());
+    size_t total = 0;
+    for (size_t i = 0; i < batch.size(); i++) { counts[i] = (u32)batch[i].m_primitives.size(); total += counts[i]; }
+    std::vector<Triangle> flat;
+    flat.reserve(total);
+    for (const BatchedBuildInput& b : batch) flat.insert(flat.end(), b.m_primitives.begin(), b.m_primitives.end());
+    checkStatus(Api::get().b2bvh_build_batched(context.m_ctx, flat.data(), 0, counts.data(), (u32)counts.size(), &m_batch), "b2bvh_build_batched");
+    b2bvh_ctx* c = context.m_ctx;
+    d_bvhNodes.bind(c, m_batch.d_bvhNodes, m_batch.n_nodes_total);
+    d_primRefs.bind(c, m_batch.d_primRefs, m_batch.n_prims_total);
+    d_rootNodes.bind(c, m_batch.d_rootNodes, m_batch.n_items);
+    d_sceneExtents.bind(c, m_batch.d_sceneExtents, m_batch.n_items);
+    m_leafOffsets.assign(counts.size() + 1, 0);
+    m_nodeOffsets.assign(counts.size() + 1, 0);
+    for (size_t i = 0; i < counts.size(); i++) { m_leafOffsets[i + 1] = m_leafOffsets[i] + counts[i]; m_nodeOffsets[i + 1] = m_nodeOffsets[i] + counts[i] - 1; }
+    m_timer.timeRecord[BvhBuildTime] += m_batch.build_ms;
+    /* wording of BatchedBuilder.cpp:72-76 */
+    std::cout << "==========================Perf Times==========================" << std::endl;
+    std::cout << "BatchSize : " << batch.size() << std::endl;
+    std::cout << "BvhBuildTime : " << m_timer.getTimeRecord(BvhBuildTime) << "ms" << std::endl;
+    std::cout << "==============================================================" << std::endl;
+  }
+  void traverseBvh(Context&) {} /* empty in the reference as well (BatchedBuilder.cpp:79-82) */
+
+  GpuMemory<Bvh2Node> d_bvhNodes;
+  GpuMemory<PrimRef> d_primRefs;
+  GpuMemory<u32> d_rootNodes;
+  GpuMemory<Aabb> d_sceneExtents;
+  std::vector<u32> m_leafOffsets, m_nodeOffsets;
+  u32 m_rootNodeIdx = 0;
+  Timer m_timer;
+  u32 m_nInternalNodes = 0;
+  float m_cost = 0.0f;
+  b2bvh_batch m_batch{};
 };
 
 }  // namespace BvhConstruction

@@ -5,6 +5,9 @@
  * the mesh staging script of the test infrastructure with the reference's own OBJ loader) or a synthetic stream.
  *
  *   b2bvh_demo <twopass|singlepass|ploc|hploc> <mesh.tri | synth:N> [expected_cost]
+ *   b2bvh_demo batched <mesh.tri | synth:N>      the USE_BATCHED_BUILDER branch (main.cpp:38-52): 4096 items; a mesh of <= 32
+ *                                                 triangles is one item repeated (the reference's cornell box), a larger one is cut
+ *                                                 into items of 32 consecutive triangles
  * exits 0 when the build succeeded (and the cost matches expected_cost to 1e-5 relative, when given).
  */
 #include <cstdio>
@@ -65,6 +68,31 @@ int main(int argc, char* argv[]) {
     std::cout << "triangles : " << triangles.size() << std::endl;
     const std::string which = argv[1];
     float cost;
+    if (which == "batched") {
+      constexpr u32 batchSize = 2048 * 2; /* main.cpp:42 */
+      std::vector<BatchedBuildInput> batches(batchSize);
+      for (u32 i = 0; i < batchSize; i++) {
+        if (triangles.size() <= 32) batches[i].m_primitives = triangles;
+        else {
+          const size_t first = ((size_t)i * 32) % (triangles.size() - 31);
+          batches[i].m_primitives.assign(triangles.begin() + first, triangles.begin() + first + 32);
+        }
+      }
+      BatchedBvhBuilder bvh;
+      bvh.build(context, batches);
+      bvh.traverseBvh(context);
+      const std::vector<u32> roots = bvh.d_rootNodes.getData();
+      const std::vector<Bvh2Node> nodes = bvh.d_bvhNodes.getData();
+      const std::vector<Aabb> scenes = bvh.d_sceneExtents.getData();
+      /* every item's root box is its scene box */
+      for (u32 i = 0; i < batchSize; i++) {
+        if (batches[i].m_primitives.size() < 2) continue;
+        const Bvh2Node& r = nodes[bvh.m_nodeOffsets[i] + roots[i]];
+        if (memcmp(&r.m_aabb, &scenes[i], sizeof(Aabb)) != 0) { fprintf(stderr, "item %u: root box differs from the item's scene box\n", i); return 1; }
+      }
+      std::cout << "items : " << batchSize << "  nodes : " << nodes.size() << "  root of item 0 : " << roots[0] << std::endl;
+      return 0;
+    }
     if (which == "twopass") cost = run<TwoPassLbvh>(context, triangles);
     else if (which == "singlepass") cost = run<SinglePassLbvh>(context, triangles);
     else if (which == "ploc") cost = run<PLOCNew>(context, triangles);

@@ -135,6 +135,30 @@ const char* b2bvh_last_error(void);
 /* ---- the build: replaces the body of <Builder>::build(Context&, std::vector<Triangle>&). ---- */
 int b2bvh_build(b2bvh_ctx* ctx, int algo, const b2bvh_triangle* tris, uint32_t n, const b2bvh_build_opts* opts, b2bvh_tree* out);
 
+/* ---- the batched builder: replaces BatchedBvhBuilder::build(Context&, std::vector<BatchedBuildInput>&) (src/BatchedBuilder.cpp:16-77,
+ * kernel BatchedBuildKernelLbvh, src/BatchedBuildKernel.h:218-312): one small BVH per item, 1..32 triangles each (MaxBatchedBlockSize,
+ * Common.h:597), all items in one launch.  `tris` = the items' triangles back to back (the reference's D_BatchedBuildInputs array of
+ * pointers, Common.h:587-591, flattened), host or device; `counts` = HOST array, triangles per item.  Per item: scene box, plain
+ * 10/10/10 Morton codes, stable sort, Apetrei hierarchy; leaves in sorted order; node / leaf indices LOCAL to the item (internal k in
+ * [0, n-1), leaf g = (n-1)+g), item i's nodes at d_bvhNodes + d_nodeOffsets[i], its leaves at d_primRefs + d_leafOffsets[i]. ---- */
+typedef struct b2bvh_batch {
+  uint32_t n_items;
+  uint32_t n_prims_total;                 /* sum of counts                                            */
+  uint32_t n_nodes_total;                 /* sum of (count - 1)                                       */
+  uint32_t reserved;
+  const b2bvh_triangle* d_triangles;      /* n_prims_total                                            */
+  const b2bvh_bvh2_node* d_bvhNodes;      /* BatchedBvhBuilder::d_bvhNodes, n_nodes_total             */
+  const b2bvh_prim_ref* d_primRefs;       /* BatchedBvhBuilder::d_primRefs, n_prims_total             */
+  const uint32_t* d_rootNodes;            /* BatchedBvhBuilder::d_rootNodes, n_items (local index)    */
+  const b2bvh_aabb* d_sceneExtents;       /* d_sceneExtent of the kernel, n_items                     */
+  const uint32_t* d_leafOffsets;          /* n_items + 1                                              */
+  const uint32_t* d_nodeOffsets;          /* n_items + 1                                              */
+  float build_ms;                         /* BvhBuildTime (BatchedBuilder.cpp:61)                     */
+  float h2d_ms;
+} b2bvh_batch;
+int b2bvh_build_batched(b2bvh_ctx* ctx, const b2bvh_triangle* tris, uint32_t tris_on_device, const uint32_t* counts, uint32_t n_items,
+                        b2bvh_batch* out);
+
 /* Stages, individually callable (all pointers are device pointers).  Each names the reference kernel(s) it replaces. */
 int b2bvh_scene_extents(b2bvh_ctx* ctx, const b2bvh_triangle* d_tris, uint32_t n, b2bvh_aabb* d_triAabb,
                         b2bvh_aabb* d_scene);             /* CalculateSceneExtents / CalculatePrimRefExtents, CommonBlocksKernel.h:92,116 */

@@ -428,6 +428,64 @@ u32 orc_lbvh_apetrei(const b2bvh_triangle* tris, const u32* keys, const u32* val
   return root;
 }
 
+/* ------------------------------------------------- batched builder
+ * BatchedBuildKernelLbvh (BatchedBuildKernel.h:218-312), one small BVH per batch item (<= MaxBatchedBlockSize = 32
+ * triangles, Common.h:597), built by one block: per-item scene box (:237-259), PLAIN 10/10/10 Morton code of the
+ * normalised centroid (computeMortonCode, :98-110 = CommonBlocksKernel.h:361-372), stable sort of (code, index)
+ * (32 one-bit split passes, :285-297, == stable sort), Apetrei build + fit on the sorted codes (:136-216, the code of
+ * SinglePassLbvhKernel.h:64-126), root in rootNodes[item] (:311).  Node / leaf indices are LOCAL to the item
+ * (ptrBvhNodes / ptrLeafNodes, :300-303): internal k in [0, n-1), leaf g = (n-1) + g.
+ * The reference kernel is work in progress (it does not compile: ExtentCacheSize is undefined; main.cpp:38-52 keeps
+ * it behind USE_BATCHED_BUILDER).  Three repairs, each stated in DESIGN.md: (1) leaf slot g holds the primitive with the
+ * g-th smallest code — the reference fills the leaf records before sorting and never permutes them (:241-242), so its
+ * tree joins sorted codes to unsorted boxes; (2) item offsets are prefix sums of the item sizes (the reference uses
+ * item * itemSize, :234-235, correct only for equal sizes); (3) a one-triangle item has no internal node and root 0.
+ * normalisation: 0/0 -> NaN -> 0 through fmaxf (GPU min/max semantics), as in orc_morton_codes. */
+static inline u32 morton3d_10(u32 x) {                   /* BatchedBuildKernel.h:89-96 */
+  x = (x * 0x00010001u) & 0xFF0000FFu;
+  x = (x * 0x00000101u) & 0x0F00F00Fu;
+  x = (x * 0x00000011u) & 0xC30C30C3u;
+  x = (x * 0x00000005u) & 0x49249249u;
+  return x;
+}
+u32 orc_morton_plain(const float p[3]) {                 /* :98-110 */
+  float x = fminr(fmaxr(p[0] * 1024.0f, 0.0f), 1023.0f);
+  float y = fminr(fmaxr(p[1] * 1024.0f, 0.0f), 1023.0f);
+  float z = fminr(fmaxr(p[2] * 1024.0f, 0.0f), 1023.0f);
+  return morton3d_10((u32)x) * 4 + morton3d_10((u32)y) * 2 + morton3d_10((u32)z);
+}
+u32 orc_lbvh_apetrei(const b2bvh_triangle* tris, const u32* keys, const u32* vals, u32 n, b2bvh_bvh2_node* nodes);
+/* tris: all items back to back; counts[item]; nodes: sum(n-1); leaves: sum(n); roots, scenes: one per item. */
+void orc_batched_build(const b2bvh_triangle* tris, const u32* counts, u32 nItems, b2bvh_bvh2_node* nodes, b2bvh_prim_ref* leaves, u32* roots, Box* scenes) {
+  u64 triOff = 0, nodeOff = 0;
+  for (u32 it = 0; it < nItems; it++) {
+    const u32 n = counts[it];
+    const b2bvh_triangle* T = tris + triOff;
+    std::vector<Box> box(n);
+    Box scene = box_empty();
+    for (u32 i = 0; i < n; i++) { box[i] = tri_box(T[i]); box_grow(scene, box[i]); }
+    scenes[it] = scene;
+    const F3 ext = box_extent(scene);
+    std::vector<std::pair<u32, u32>> kv(n);
+    for (u32 i = 0; i < n; i++) {
+      const F3 q = vdiv(vsub(box_center(box[i]), scene.m_min), ext);   /* :276-278 */
+      const float qq[3] = {q.x, q.y, q.z};
+      kv[i] = std::make_pair(orc_morton_plain(qq), i);
+    }
+    std::stable_sort(kv.begin(), kv.end(), [](const std::pair<u32, u32>& a, const std::pair<u32, u32>& b) { return a.first < b.first; });
+    std::vector<u32> sk(n), sv(n);
+    for (u32 i = 0; i < n; i++) { sk[i] = kv[i].first; sv[i] = kv[i].second; }
+    for (u32 g = 0; g < n; g++) { leaves[triOff + g].m_primIdx = sv[g]; leaves[triOff + g].m_aabb = box[sv[g]]; }
+    if (n == 1) roots[it] = 0;
+    else {
+      std::vector<b2bvh_bvh2_node> tmp(2 * (size_t)n - 1);
+      roots[it] = orc_lbvh_apetrei(T, sk.data(), sv.data(), n, tmp.data());
+      for (u32 k = 0; k + 1 < n; k++) nodes[nodeOff + k] = tmp[k];
+    }
+    triOff += n; nodeOff += n - 1;
+  }
+}
+
 /* ------------------------------------------------- SetupClusters
  * Ploc++Kernel.h:39-55 / HplocKernel.h:39-56.                               */
 static void setup_clusters(const Box* triAabb, const u32* vals, u32 n, b2bvh_bvh2_node* nodes, b2bvh_prim_ref* leaves) {

@@ -40,7 +40,7 @@ def lib():
         _lib.orc_ray_zdir.restype = C.c_float
         _lib.orc_ray_zdir.argtypes = [C.c_float]
         for f in ("orc_fnv1a_words", "orc_lbvh_apetrei", "orc_collapse4", "orc_bvh2_depth", "orc_traverse", "orc_traverse_kind", "orc_traverse_wide4", "orc_binned_sah_build",
-                  "orc_morton_code_cfg", "orc_early_split"):
+                  "orc_morton_code_cfg", "orc_early_split", "orc_morton_plain"):
             getattr(_lib, f).restype = C.c_uint32
     return _lib
 
@@ -319,6 +319,26 @@ def _build_lbvh_split(tris, sa_max):
     cost = cost_bvh4(wide, wl, split_cost_boxes(refs), 0, m)
     return dict(scene=scene, keys=keys, vals=vals, skeys=sk, svals=sv, nodes=nodes, parents=parents, root=0, wide=wide, wide_leaves=wl,
                 wide_count=cnt, cost=cost, boxes=boxes, refs=refs, prim_idx=refs["primIdx"].copy())
+
+
+def morton_plain(p):
+    q = (C.c_float * 3)(*[float(x) for x in p])
+    return int(lib().orc_morton_plain(q))
+
+
+def build_batched(tris, counts):
+    """BatchedBvhBuilder::build (BatchedBuilder.cpp:16-77) restated: tris = all items back to back, counts[item] <= 32.
+    Returns nodes (sum(n-1)), leaves (sum(n), sorted order per item), roots, scenes, node/leaf offsets."""
+    counts = np.ascontiguousarray(counts, dtype=np.uint32)
+    assert int(counts.sum()) == tris.size and counts.min() >= 1 and counts.max() <= 32
+    nodes = np.zeros(max(int(counts.sum()) - counts.size, 1), dtype=T.BVH2_NODE)
+    leaves = np.zeros(tris.size, dtype=T.PRIM_REF)
+    roots = np.zeros(counts.size, dtype=np.uint32)
+    scenes = np.zeros(counts.size, dtype=T.AABB)
+    lib().orc_batched_build(_p(tris), _p(counts), _u32(counts.size), _p(nodes), _p(leaves), _p(roots), _p(scenes))
+    leaf_off = np.concatenate([[0], np.cumsum(counts)]).astype(np.uint32)
+    node_off = np.concatenate([[0], np.cumsum(counts - 1)]).astype(np.uint32)
+    return dict(nodes=nodes[:int(node_off[-1])], leaves=leaves, roots=roots, scenes=scenes, node_off=node_off, leaf_off=leaf_off)
 
 
 def build_ploc(tris, hierarchical=False, scene_override=None):

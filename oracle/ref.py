@@ -22,7 +22,7 @@ def emul():
     global _emul
     if _emul is None:
         _emul = C.CDLL(os.path.join(_HERE, "_ref", "libref_emul.so"))
-        for f in ("ref_morton_code", "ref_tea16", "ref_collapse_lbvh", "ref_collapse_ploc", "ref_singlepass_build"):
+        for f in ("ref_morton_code", "ref_morton_plain", "ref_tea16", "ref_collapse_lbvh", "ref_collapse_ploc", "ref_singlepass_build"):
             getattr(_emul, f).restype = C.c_uint32
         _emul.ref_randf.restype = C.c_float
     return _emul
@@ -145,6 +145,12 @@ def early_split(tris):
     cnt = util().ref_early_split(_p(tris), _u32(tris.size), _p(out))
     assert cnt == tris.size
     return out
+
+
+def morton_plain(p):
+    """computeMortonCode (plain 10/10/10, CommonBlocksKernel.h:361-372 == BatchedBuildKernel.h:98-110), the reference's own code."""
+    q = (C.c_float * 3)(*[float(x) for x in p])
+    return int(emul().ref_morton_plain(q))
 
 
 def early_split_sa(tris, sa_max):

@@ -21,6 +21,7 @@ void ref_morton_primref(const PrimRef* refs, const Aabb* scene, uint32_t* keys, 
 void ref_morton_aabb(const Aabb* boxes, const Aabb* scene, uint32_t* keys, uint32_t* vals, uint32_t n) {
   run1d(n, [&] { CalculateMortonCodes(boxes, scene, keys, vals, n); });
 }
+uint32_t ref_morton_plain(const float p[3]) { return computeMortonCode(float3{p[0], p[1], p[2]}, float3{1.0f, 1.0f, 1.0f}); } /* CommonBlocksKernel.h:361-372 */
 uint32_t ref_tea16(uint32_t a, uint32_t b) { return tea<16>(a, b).x; }
 float ref_randf(uint32_t* seed) { return randf(*seed); }
 }

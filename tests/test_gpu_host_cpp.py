@@ -26,3 +26,12 @@ def test_demo_matches_oracle_cost(oracle, which, hier):
     for token in ("Executing on", "CalculateCentroidExtentsTime", "SortingTime", "BvhBuildTime", "CollapseTime", "Bvh Cost", "Total Time"):
         assert token in r.stdout
     assert f"wide nodes : {o['wide_count']}" in r.stdout
+
+
+def test_demo_batched_builder():
+    """The USE_BATCHED_BUILDER branch of main.cpp:38-52: 4096 copies of the cornell box through BatchedBvhBuilder."""
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "hip-bvh-construction_b200", "host"), "all"], stdout=subprocess.DEVNULL)
+    env = dict(os.environ, B2BVH_LIB=capi.LIB_PATH)
+    r = subprocess.run([EXE, "batched", os.path.join(GOLDEN, "cornellbox.tri")], env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "BatchSize : 4096" in r.stdout and "BvhBuildTime" in r.stdout and f"nodes : {4096 * 31}" in r.stdout
