@@ -371,6 +371,44 @@ def main():
                              "merge_frac_of_peak": bpp * n / (mms * 1e-3) / 1e9 / peak, "iterations": int(t.n_iterations),
                              "kernels_ms": {name: ms for name, ms in ent if "ploc" in name}}
             line["merge_builders"] = merge
+            # ---- the two paths either side of the hot path: early split clipping in front of TwoPassLbvh, and the
+            # batched builder; same workload triangles, per-kernel CUDA-event times against the same roofline ----
+            widened = {}
+            try:
+                half = float(np.float32(1000.0 * n ** (-1.0 / 3.0)))
+                sa = 6.0 * half * half  # about the median primitive-box area: roughly every second box is cut at least once
+                for _ in range(2):
+                    ctx.build(capi.TWO_PASS_LBVH, d_tris, n=n, tris_on_device=True, split_sa_max=sa)
+                ctx.profile(True)
+                t = ctx.build(capi.TWO_PASS_LBVH, d_tris, n=n, tris_on_device=True, split_sa_max=sa)
+                ctx.sync()
+                ent = ctx.profile_entries()
+                ctx.profile(False)
+                lv = [ms for name, ms in ent if name == "split_level"]
+                m = int(t.n_prims)
+                # generation 0 reads n boxes (24 B); every reference is written once where it is accepted (28 B) and every rejected one is
+                # written as two halves (56 B) and read again in the next generation (28 B)
+                split_bytes = 24 * n + 28 * m + (56 + 28) * (m - n)
+                best = min((ctx.build(capi.TWO_PASS_LBVH, d_tris, n=n, tris_on_device=True, split_sa_max=sa) for _ in range(3)), key=lambda q: q.split_ms)
+                widened["early_split"] = {"triangles": n, "references": m, "sa_max": sa, "generations": int(t.n_split_levels), "split_ms": float(best.split_ms),
+                                          "split_kernels_ms": lv, "algorithmic_bytes": split_bytes, "gbs_kernels": split_bytes / (sum(lv) * 1e-3) / 1e9,
+                                          "frac_of_peak_kernels": split_bytes / (sum(lv) * 1e-3) / 1e9 / peak, "build_ms_over_references": float(best.build_ms),
+                                          "Mrefs_s_build": m / best.build_ms / 1e3}
+            except capi.B2bvhError as e:
+                widened["early_split"] = {"error": str(e)[:120]}
+            try:
+                items = n // 32
+                counts = np.full(items, 32, dtype=np.uint32)
+                for _ in range(3):
+                    ctx.build_batched(d_tris, counts, tris_on_device=True)
+                bb = min((ctx.build_batched(d_tris, counts, tris_on_device=True) for _ in range(5)), key=lambda q: q.build_ms)
+                bbytes = (64 + 28 + 32) * items * 32
+                widened["batched_builder"] = {"items": items, "prims_per_item": 32, "build_ms": float(bb.build_ms), "Mprims_s": items * 32 / bb.build_ms / 1e3,
+                                              "Mitems_s": items / bb.build_ms / 1e3, "algorithmic_bytes": bbytes, "gbs": bbytes / (bb.build_ms * 1e-3) / 1e9,
+                                              "frac_of_peak": bbytes / (bb.build_ms * 1e-3) / 1e9 / peak}
+            except capi.B2bvhError as e:
+                widened["batched_builder"] = {"error": str(e)[:120]}
+            line["widened_paths"] = widened
             # ---- the reference's own scenes (BASELINE configs[1]/[2]), when staged ----
             extras = {}
             mesh_dir = os.path.join(ROOT, "oracle", "_ref", "meshes")

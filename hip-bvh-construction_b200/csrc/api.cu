@@ -217,6 +217,8 @@ int b2bvh_build(b2bvh_ctx* ctx, int algo, const b2bvh_triangle* tris, uint32_t n
   memset(out, 0, sizeof(*out));
   ctx->lbvh_second_level = opts.lbvh_second_level;
   ctx->merge_max_ctas = opts.merge_max_ctas;
+  ctx->ref_prim = nullptr;
+  ctx->ref_leaf_prim = nullptr;
   const bool separate = (algo == B2BVH_PLOCPP || algo == B2BVH_HPLOC);
   const u32 launches0 = ctx->launches;
   cudaStream_t s = ctx->stream;
@@ -240,7 +242,6 @@ int b2bvh_build(b2bvh_ctx* ctx, int algo, const b2bvh_triangle* tris, uint32_t n
   const b2bvh_triangle* dT = tris;
   if (!opts.tris_on_device) dT = (const b2bvh_triangle*)dTris;
   u32* dRefPrim = nullptr;
-  void* dLeafPrim = nullptr;
   u32 splitLevels = 0;
   if (split) {
     /* upload + S1 + the split run ahead of everything whose size depends on the reference count (one sync per generation) */
@@ -259,8 +260,11 @@ int b2bvh_build(b2bvh_ctx* ctx, int algo, const b2bvh_triangle* tris, uint32_t n
     B2_CUDA(cudaEventRecord(ctx->ev[11], s));
     if (m < 2) return b2_fail(B2BVH_ERR_INTERNAL, "early split produced %u references", m);
     n = m;               /* from here on the primitives of the build are the references */
-    dAabb = refBox;
+    void* dLeafPrim = nullptr;
     B2_TRY(b2_reserve(ctx, SLOT_SPLIT_LEAFPRIM, (size_t)n * 4, &dLeafPrim));
+    ctx->ref_leaf_prim = (u32*)dLeafPrim;
+    ctx->ref_prim = dRefPrim; /* leaves and PrimNodes name the reference's TRIANGLE (InitBvhNodesPrimRef, TwoPassLbvhKernel.h:178-182, :324) */
+    dAabb = refBox;
   }
   B2_TRY(b2_reserve(ctx, SLOT_KEYS, (size_t)n * 4, &dKeys));
   B2_TRY(b2_reserve(ctx, SLOT_VALS, (size_t)n * 4, &dVals));
@@ -316,7 +320,6 @@ int b2bvh_build(b2bvh_ctx* ctx, int algo, const b2bvh_triangle* tris, uint32_t n
       else
         B2_TRY(b2_launch_lbvh_fused(ctx, (const u32*)dSKeys, (const u32*)dSVals, (const b2bvh_aabb*)dAabb, n, (b2bvh_bvh2_node*)dNodes,
                                     (u32*)dParents, (u32*)dLbvh, dRoot, 1));
-      if (split) B2_TRY(b2_launch_split_remap(ctx, (const u32*)dSVals, dRefPrim, n, (b2bvh_bvh2_node*)dNodes, (u32*)dLeafPrim));
       B2_CUDA(cudaMemsetAsync(dRoot, 0, 4, s));
       break;
     case B2BVH_SINGLE_PASS_LBVH:
@@ -337,7 +340,7 @@ int b2bvh_build(b2bvh_ctx* ctx, int algo, const b2bvh_triangle* tris, uint32_t n
   B2_CUDA(record(4));
   /* ---- S5 collapse ---- */
   if (opts.collapse)
-    B2_TRY(b2_launch_collapse(ctx, (const b2bvh_bvh2_node*)dNodes, (const b2bvh_prim_ref*)dLeaves, split ? (const u32*)dLeafPrim : (const u32*)dSVals, dRoot, n, (b2bvh_bvh4_node*)dWide,
+    B2_TRY(b2_launch_collapse(ctx, (const b2bvh_bvh2_node*)dNodes, (const b2bvh_prim_ref*)dLeaves, split ? (const u32*)ctx->ref_leaf_prim : (const u32*)dSVals, dRoot, n, (b2bvh_bvh4_node*)dWide,
                               (b2bvh_prim_node*)dWLeaves, dCollapse, &nWide));
   B2_CUDA(record(5));
   B2_TRY(b2_fetch_words(ctx, dRoot, 1, B2_MB_ROOT));

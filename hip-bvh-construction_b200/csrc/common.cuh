@@ -212,6 +212,8 @@ struct b2bvh_ctx {
   u32 launches;
   u32 lbvh_second_level; /* b2bvh_build_opts.lbvh_second_level of the running build */
   u32 merge_max_ctas;    /* b2bvh_build_opts.merge_max_ctas of the running build */
+  u32* ref_leaf_prim;    /* early split: triangle of Bvh2 leaf g, written by the LBVH kernels for the collapse */
+  const u32* ref_prim;   /* early split (b2bvh_build_opts.split_sa_max): triangle of every reference of the running build, else NULL */
   /* optional per-launch profiler (b2bvh_profile_*): one CUDA event pair per kernel launch */
   bool prof_on;
   int prof_n;
@@ -278,7 +280,6 @@ int b2_launch_ploc(b2bvh_ctx* ctx, const b2bvh_aabb* d_triAabb, const u32* d_sor
 /* early split clipping (split.cu): references of all generations in emission order; synchronises the stream once per generation */
 int b2_launch_split(b2bvh_ctx* ctx, const b2bvh_aabb* d_triAabb, u32 n, float saMax, int slotOutBox, int slotOutPrim, int slotListA, int slotListB,
                     int slotStatus, b2bvh_aabb** d_refBox, u32** d_refPrim, u32* h_count, u32* h_levels);
-int b2_launch_split_remap(b2bvh_ctx* ctx, const u32* d_sortedVals, const u32* d_refPrim, u32 n, b2bvh_bvh2_node* d_nodes, u32* d_leafPrim);
 int b2_launch_batched(b2bvh_ctx* ctx, const b2bvh_triangle* d_tris, const u32* d_leafOff, const u32* d_nodeOff, u32 nItems, b2bvh_bvh2_node* d_nodes,
                       b2bvh_prim_ref* d_leaves, u32* d_roots, b2bvh_aabb* d_scenes);
 size_t b2_hploc_scratch_bytes(u32 n);

@@ -80,13 +80,17 @@ __device__ __forceinline__ void climb_global(const u32* __restrict__ keys, u32 n
 template <bool KARRAS>
 __global__ void __launch_bounds__(LBVH_THREADS) lbvh_fused_kernel(const u32* __restrict__ keys, const u32* __restrict__ vals,
                                                                   const b2bvh_aabb* __restrict__ triAabb, u32 n, b2bvh_bvh2_node* nodes,
-                                                                  u32* parents, u32* meet /* n-1 words, 0xFFFFFFFF */, u32* rootOut) {
+                                                                  u32* parents, u32* meet /* n-1 words, 0xFFFFFFFF */, u32* rootOut,
+                                                                  const u32* __restrict__ refPrim /* early split: triangle of each reference, else NULL */,
+                                                                  u32* __restrict__ leafPrim /* early split: triangle of leaf g, dense (for the collapse) */) {
   const u32 g = blockIdx.x * LBVH_THREADS + threadIdx.x;
   if (g >= n) return;
   const u32 nInt = n - 1;
   const u32 prim = __ldg(vals + g);
   const Box box = load_aabb(triAabb + prim);
-  store_node2(nodes + nInt + g, prim, B2_INVALID, box);
+  u32 leafId = prim;
+  if (refPrim) { leafId = ldg_gather_u32(refPrim + prim); leafPrim[g] = leafId; }
+  store_node2(nodes + nInt + g, leafId, B2_INVALID, box);
   if (n == 1) { if (rootOut) *rootOut = 0; return; }
   bool isLeft;
   const u32 p = choose_parent(keys, n, g, g + 1, isLeft);
@@ -148,7 +152,7 @@ template <bool KARRAS>
 __global__ void __launch_bounds__(LBVH_TILE_THREADS, 8) lbvh_tile_kernel(const u32* __restrict__ keys, const u32* __restrict__ vals,
                                                                       const b2bvh_aabb* __restrict__ triAabb, u32 n, b2bvh_bvh2_node* nodes, u32* parents,
                                                                       u32* meet, u32* rootOut, u32* pendingCount, LbvhPending* pending, u32 pendingCap,
-                                                                      uint2* tileInfo, LbvhPending* tileBuf) {
+                                                                      uint2* tileInfo, LbvhPending* tileBuf, const u32* __restrict__ refPrim, u32* __restrict__ leafPrim) {
   constexpr bool PARENTS = KARRAS; /* only TwoPassLbvh publishes d_parentIdxs */
   constexpr u32 T = LBVH_TILE;
   static_assert(LBVH_TILE == LBVH_TILE_THREADS, "one leaf per thread");
@@ -171,7 +175,10 @@ __global__ void __launch_bounds__(LBVH_TILE_THREADS, 8) lbvh_tile_kernel(const u
     const float2 q0 = ldg_gather_f2(bp), q1 = ldg_gather_f2(bp + 1), q2 = ldg_gather_f2(bp + 2);
     int d = -1;
     if (g + 1 < n) d = boundary_depth(k0, __ldg(keys + g + 1), g);
-    S.stage[2 * (T + tid)] = make_uint4(prim, B2_INVALID, __float_as_uint(q0.x), __float_as_uint(q0.y));
+    /* the leaf names the primitive; over early-split references that is the reference's triangle (InitBvhNodesPrimRef, TwoPassLbvhKernel.h:182) */
+    u32 leafId = prim;
+    if (refPrim) { leafId = ldg_gather_u32(refPrim + prim); leafPrim[g] = leafId; }
+    S.stage[2 * (T + tid)] = make_uint4(leafId, B2_INVALID, __float_as_uint(q0.x), __float_as_uint(q0.y));
     S.stage[2 * (T + tid) + 1] = make_uint4(__float_as_uint(q1.x), __float_as_uint(q1.y), __float_as_uint(q2.x), __float_as_uint(q2.y));
     S.w[0][tid + 2] = ((u32)(d + 1) << LW_D_SHIFT) | ((T + tid) << LW_ID_SHIFT) | tid;
   }
@@ -499,13 +506,15 @@ __device__ __forceinline__ int delta_aug(const u32* __restrict__ keys, u32 n, u3
 
 __global__ void __launch_bounds__(LBVH_THREADS) lbvh_karras_emit_kernel(const u32* __restrict__ keys, const u32* __restrict__ vals,
                                                                         const b2bvh_aabb* __restrict__ triAabb, u32 n, b2bvh_bvh2_node* nodes,
-                                                                        u32* parents) {
+                                                                        u32* parents, const u32* __restrict__ refPrim, u32* __restrict__ leafPrim) {
   const u32 g = blockIdx.x * LBVH_THREADS + threadIdx.x;
   if (g >= n) return;
   const u32 nInt = n - 1;
   {
     const u32 prim = __ldg(vals + g);
-    store_node2(nodes + nInt + g, prim, B2_INVALID, load_aabb(triAabb + prim));
+    u32 leafId = prim;
+    if (refPrim) { leafId = ldg_gather_u32(refPrim + prim); leafPrim[g] = leafId; }
+    store_node2(nodes + nInt + g, leafId, B2_INVALID, load_aabb(triAabb + prim));
   }
   if (g == 0) parents[0] = B2_INVALID;
   if (g >= nInt) return;
@@ -574,9 +583,9 @@ int b2_launch_lbvh_fused(b2bvh_ctx* ctx, const u32* d_sortedKeys, const u32* d_s
   if (globalOnly) {
     const u32 grid = (n + LBVH_THREADS - 1) / LBVH_THREADS;
     if (karrasNumbering)
-      lbvh_fused_kernel<true><<<grid, LBVH_THREADS, 0, ctx->stream>>>(d_sortedKeys, d_sortedVals, d_triAabb, n, d_nodes, d_parents, d_scratch, d_root);
+      lbvh_fused_kernel<true><<<grid, LBVH_THREADS, 0, ctx->stream>>>(d_sortedKeys, d_sortedVals, d_triAabb, n, d_nodes, d_parents, d_scratch, d_root, ctx->ref_prim, ctx->ref_leaf_prim);
     else
-      lbvh_fused_kernel<false><<<grid, LBVH_THREADS, 0, ctx->stream>>>(d_sortedKeys, d_sortedVals, d_triAabb, n, d_nodes, d_parents, d_scratch, d_root);
+      lbvh_fused_kernel<false><<<grid, LBVH_THREADS, 0, ctx->stream>>>(d_sortedKeys, d_sortedVals, d_triAabb, n, d_nodes, d_parents, d_scratch, d_root, ctx->ref_prim, ctx->ref_leaf_prim);
   } else {
     /* scratch: meet[n-1] | (16-byte aligned) pendingCount | pending[cap] | tileInfo[tiles] | tileBuf[tiles][LBVH_TILE_CAP] */
     const size_t off = (((size_t)n * 4 + 15) & ~(size_t)15);
@@ -599,9 +608,9 @@ int b2_launch_lbvh_fused(b2bvh_ctx* ctx, const u32* d_sortedKeys, const u32* d_s
       attrSet = true;
     }
     if (karrasNumbering)
-      lbvh_tile_kernel<true><<<grid, LBVH_TILE_THREADS, sizeof(LbvhTileSmem<true>), ctx->stream>>>(d_sortedKeys, d_sortedVals, d_triAabb, n, d_nodes, d_parents, d_scratch, d_root, pendingCount, pending, cap, tileInfo, tileBuf);
+      lbvh_tile_kernel<true><<<grid, LBVH_TILE_THREADS, sizeof(LbvhTileSmem<true>), ctx->stream>>>(d_sortedKeys, d_sortedVals, d_triAabb, n, d_nodes, d_parents, d_scratch, d_root, pendingCount, pending, cap, tileInfo, tileBuf, ctx->ref_prim, ctx->ref_leaf_prim);
     else
-      lbvh_tile_kernel<false><<<grid, LBVH_TILE_THREADS, sizeof(LbvhTileSmem<false>), ctx->stream>>>(d_sortedKeys, d_sortedVals, d_triAabb, n, d_nodes, d_parents, d_scratch, d_root, pendingCount, pending, cap, tileInfo, tileBuf);
+      lbvh_tile_kernel<false><<<grid, LBVH_TILE_THREADS, sizeof(LbvhTileSmem<false>), ctx->stream>>>(d_sortedKeys, d_sortedVals, d_triAabb, n, d_nodes, d_parents, d_scratch, d_root, pendingCount, pending, cap, tileInfo, tileBuf, ctx->ref_prim, ctx->ref_leaf_prim);
     B2_LAUNCH_CHECK(ctx);
     if (useGroups) {
       const u32 groups = (grid + LBVH_GROUP - 1) / LBVH_GROUP;
@@ -630,7 +639,7 @@ int b2_launch_lbvh_karras_two_kernel(b2bvh_ctx* ctx, const u32* d_sortedKeys, co
   const u32 grid = (n + LBVH_THREADS - 1) / LBVH_THREADS;
   B2_CUDA(cudaMemsetAsync(d_flags, 0, (size_t)(2 * (size_t)n - 1) * sizeof(u32), ctx->stream));
   B2_KERNEL(ctx, "lbvh_karras_emit");
-  lbvh_karras_emit_kernel<<<grid, LBVH_THREADS, 0, ctx->stream>>>(d_sortedKeys, d_sortedVals, d_triAabb, n, d_nodes, d_parents);
+  lbvh_karras_emit_kernel<<<grid, LBVH_THREADS, 0, ctx->stream>>>(d_sortedKeys, d_sortedVals, d_triAabb, n, d_nodes, d_parents, ctx->ref_prim, ctx->ref_leaf_prim);
   B2_LAUNCH_CHECK(ctx);
   B2_KERNEL(ctx, "lbvh_refit");
   lbvh_refit_kernel<<<grid, LBVH_THREADS, 0, ctx->stream>>>(d_nodes, d_parents, d_flags, n);

@@ -19,6 +19,24 @@
 #include "lookback.cuh"
 
 #define SPLIT_THREADS 512
+#ifndef SPLIT_GROUP
+#define SPLIT_GROUP 1                                   /* references per thread re-read together in pass 2 (measured 1/2/4/8: 145/148/164/176 us per generation) */
+#endif
+#define SPLIT_ITEMS 16                                  /* references per thread */
+#define SPLIT_TILE (SPLIT_THREADS * SPLIT_ITEMS)        /* 8192 references per tile: the look-back costs a few L2 round trips PER TILE, and with
+                                                           512-reference tiles those round trips were the whole run time (458 us for 10 M boxes,
+                                                           86 % of the warp stalls at the barrier behind the look-back, profiles/r01q) */
+
+/* 24-byte boxes are 8-byte aligned: three 8-byte accesses instead of six 4-byte ones halve the L2 requests */
+__device__ __forceinline__ Box split_load_box(const b2bvh_aabb* p) {
+  const float2* q = reinterpret_cast<const float2*>(p);
+  const float2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+  return Box{a.x, a.y, b.x, b.y, c.x, c.y};
+}
+__device__ __forceinline__ void split_store_box(b2bvh_aabb* p, const Box& b) {
+  float2* q = reinterpret_cast<float2*>(p);
+  q[0] = make_float2(b.lx, b.ly); q[1] = make_float2(b.lz, b.hx); q[2] = make_float2(b.hy, b.hz);
+}
 
 struct SplitCtl {
   u32 ticket;   /* next tile */
@@ -27,7 +45,10 @@ struct SplitCtl {
   u32 nonFinite; /* a rejected box has an infinite or NaN area: halving it never ends (the reference's loop would not terminate) */
 };
 
-__global__ void __launch_bounds__(SPLIT_THREADS) split_level_kernel(const b2bvh_aabb* __restrict__ inBox, const u32* __restrict__ inPrim /* NULL: identity */,
+/* warp w of a tile owns 32 x SPLIT_ITEMS consecutive references; reference (k, lane) = warpBase + 32 k + lane, so every load is
+ * coalesced and the order inside the warp is k-major.  Pass 1 keeps only the two ballots per k; pass 2 reads the boxes again
+ * (L2 hits: the tile was just streamed) and scatters them. */
+__global__ void __launch_bounds__(SPLIT_THREADS, 2) split_level_kernel(const b2bvh_aabb* __restrict__ inBox, const u32* __restrict__ inPrim /* NULL: identity */,
                                                                     u32 count, float saMax, b2bvh_aabb* outBox, u32* outPrim, u32 outBase,
                                                                     b2bvh_aabb* nextBox, u32* nextPrim, u64* status, SplitCtl* ctl) {
   __shared__ u32 sTile;
@@ -37,21 +58,27 @@ __global__ void __launch_bounds__(SPLIT_THREADS) split_level_kernel(const b2bvh_
   if (tid == 0) sTile = atomicAdd(&ctl->ticket, 1u); /* ticket order == tile order: a tile only waits for tiles that already run */
   __syncthreads();
   const u32 tile = sTile;
-  const u32 i = tile * SPLIT_THREADS + tid;
-  const bool valid = i < count;
-  Box b = box_empty();
-  u32 prim = i;
-  bool accept = false;
-  if (valid) {
-    b = load_aabb(inBox + i);
-    if (inPrim) prim = __ldg(inPrim + i);
-    const float area = box_area(b);
-    accept = area <= saMax; /* Utility.cpp:477 (a NaN area is never accepted, as in the reference) */
-    if (!accept && !(area < __int_as_float(0x7f800000))) ctl->nonFinite = 1u;
+  const u32 warpBase = tile * SPLIT_TILE + warp * (32u * SPLIT_ITEMS);
+  u32 balA[SPLIT_ITEMS], balR[SPLIT_ITEMS];
+  u32 wA = 0, wR = 0;
+  bool bad = false;
+#pragma unroll
+  for (int k = 0; k < SPLIT_ITEMS; k++) {
+    const u32 i = warpBase + 32u * k + lane;
+    bool accept = false, reject = false;
+    if (i < count) {
+      const float area = box_area(split_load_box(inBox + i));
+      accept = area <= saMax; /* Utility.cpp:477 (a NaN area is never accepted, as in the reference) */
+      reject = !accept;
+      bad |= reject && !(area < __int_as_float(0x7f800000));
+    }
+    balA[k] = __ballot_sync(B2_FULL, accept);
+    balR[k] = __ballot_sync(B2_FULL, reject);
+    wA += __popc(balA[k]);
+    wR += __popc(balR[k]);
   }
-  const bool reject = valid && !accept;
-  const u32 balA = __ballot_sync(B2_FULL, accept), balR = __ballot_sync(B2_FULL, reject);
-  if (lane == 0) { sWarp[0][warp] = __popc(balA); sWarp[1][warp] = __popc(balR); }
+  if (bad) ctl->nonFinite = 1u;
+  if (lane == 0) { sWarp[0][warp] = wA; sWarp[1][warp] = wR; }
   __syncthreads();
   if (warp == 0) {
     /* exclusive scan of the 16 per-warp counts, both flags at once (lanes 0-15: accepted, 16-31: rejected) */
@@ -76,35 +103,44 @@ __global__ void __launch_bounds__(SPLIT_THREADS) split_level_kernel(const b2bvh_
     }
   }
   __syncthreads();
-  if (accept) {
-    const u32 o = outBase + sBase[0] + sWarp[0][warp] + __popc(balA & lanemask_lt());
-    store_aabb(outBox + o, b);
-    outPrim[o] = prim;
-  } else if (reject) {
-    const u32 o = 2u * (sBase[1] + sWarp[1][warp] + __popc(balR & lanemask_lt()));
-    /* Aabb::maximumExtentDim / center (Common.h:347-359), Utility.cpp:483-527 */
-    const float ex = __fsub_rn(b.hx, b.lx), ey = __fsub_rn(b.hy, b.ly), ez = __fsub_rn(b.hz, b.lz);
-    const int dim = (ex > ey && ex > ez) ? 0 : (ey > ez ? 1 : 2);
-    Box L = b, R = b;
-    if (dim == 0) { const float c = __fmul_rn(__fadd_rn(b.hx, b.lx), 0.5f); L.hx = c; R.lx = c; }
-    if (dim == 1) { const float c = __fmul_rn(__fadd_rn(b.hy, b.ly), 0.5f); L.hy = c; R.ly = c; }
-    if (dim == 2) { const float c = __fmul_rn(__fadd_rn(b.hz, b.lz), 0.5f); L.hz = c; R.lz = c; }
-    store_aabb(nextBox + o, L);
-    store_aabb(nextBox + o + 1, R);
-    *reinterpret_cast<uint2*>(nextPrim + o) = make_uint2(prim, prim);
+  u32 runA = outBase + sBase[0] + sWarp[0][warp], runR = sBase[1] + sWarp[1][warp];
+  const u32 lt = lanemask_lt();
+  /* four references per thread in flight: the re-read is latency-bound when every load waits for the store before it */
+#pragma unroll
+  for (int k0 = 0; k0 < SPLIT_ITEMS; k0 += SPLIT_GROUP) {
+    Box bx[SPLIT_GROUP];
+    u32 pr[SPLIT_GROUP];
+#pragma unroll
+    for (int j = 0; j < SPLIT_GROUP; j++) {
+      const u32 i = warpBase + 32u * (k0 + j) + lane;
+      if (i < count) { bx[j] = split_load_box(inBox + i); pr[j] = inPrim ? __ldg(inPrim + i) : i; }
+    }
+#pragma unroll
+    for (int j = 0; j < SPLIT_GROUP; j++) {
+      const int k = k0 + j;
+      const bool accept = (balA[k] >> lane) & 1u, reject = (balR[k] >> lane) & 1u;
+      const Box b = bx[j];
+      if (accept) {
+        const u32 o = runA + __popc(balA[k] & lt);
+        split_store_box(outBox + o, b);
+        outPrim[o] = pr[j];
+      } else if (reject) {
+        const u32 o = 2u * (runR + __popc(balR[k] & lt));
+        /* Aabb::maximumExtentDim / center (Common.h:347-359), Utility.cpp:483-527 */
+        const float ex = __fsub_rn(b.hx, b.lx), ey = __fsub_rn(b.hy, b.ly), ez = __fsub_rn(b.hz, b.lz);
+        const int dim = (ex > ey && ex > ez) ? 0 : (ey > ez ? 1 : 2);
+        Box L = b, R = b;
+        if (dim == 0) { const float c = __fmul_rn(__fadd_rn(b.hx, b.lx), 0.5f); L.hx = c; R.lx = c; }
+        if (dim == 1) { const float c = __fmul_rn(__fadd_rn(b.hy, b.ly), 0.5f); L.hy = c; R.ly = c; }
+        if (dim == 2) { const float c = __fmul_rn(__fadd_rn(b.hz, b.lz), 0.5f); L.hz = c; R.lz = c; }
+        split_store_box(nextBox + o, L);
+        split_store_box(nextBox + o + 1, R);
+        *reinterpret_cast<uint2*>(nextPrim + o) = make_uint2(pr[j], pr[j]);
+      }
+      runA += __popc(balA[k]);
+      runR += __popc(balR[k]);
+    }
   }
-}
-
-/* after the build over split references: Bvh2 leaf g names reference sortedVals[g]; the reference's leaf carries the
- * TRIANGLE (InitBvhNodesPrimRef: node.m_leftChildIdx = primitives[idx].m_primIdx, TwoPassLbvhKernel.h:178-182).
- * leafPrim[g] is the same id as a dense array for the collapse (PrimNode.m_primIdx = leaf.m_leftChildIdx, :324). */
-__global__ void __launch_bounds__(256) split_remap_kernel(const u32* __restrict__ sortedVals, const u32* __restrict__ refPrim, u32 n,
-                                                          b2bvh_bvh2_node* nodes, u32* leafPrim) {
-  const u32 g = blockIdx.x * 256u + threadIdx.x;
-  if (g >= n) return;
-  const u32 p = ldg_gather_u32(refPrim + __ldg(sortedVals + g));
-  leafPrim[g] = p;
-  nodes[(n - 1) + g].m_leftChildIdx = p;
 }
 
 /* grow a build-owned buffer and KEEP its first `keep` bytes (b2_reserve discards the contents) */
@@ -148,7 +184,7 @@ int b2_launch_split(b2bvh_ctx* ctx, const b2bvh_aabb* d_triAabb, u32 n, float sa
     B2_TRY(b2_reserve(ctx, listSlot[cur], primOff + 2 * (size_t)count * 4, &list));
     b2bvh_aabb* nextBox = (b2bvh_aabb*)list;
     u32* nextPrim = (u32*)((unsigned char*)list + primOff);
-    const u32 tiles = (count + SPLIT_THREADS - 1) / SPLIT_THREADS;
+    const u32 tiles = (count + SPLIT_TILE - 1) / SPLIT_TILE;
     B2_TRY(b2_reserve(ctx, slotStatus, (size_t)tiles * 8 + 64, &status));
     B2_CUDA(cudaMemsetAsync(status, 0, (size_t)tiles * 8 + 64, s));
     SplitCtl* ctl = (SplitCtl*)status;
@@ -173,12 +209,5 @@ int b2_launch_split(b2bvh_ctx* ctx, const b2bvh_aabb* d_triAabb, u32 n, float sa
   *d_refPrim = (u32*)outPrim;
   *h_count = outCount;
   *h_levels = level;
-  return 0;
-}
-
-int b2_launch_split_remap(b2bvh_ctx* ctx, const u32* d_sortedVals, const u32* d_refPrim, u32 n, b2bvh_bvh2_node* d_nodes, u32* d_leafPrim) {
-  B2_KERNEL(ctx, "split_remap");
-  split_remap_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_sortedVals, d_refPrim, n, d_nodes, d_leafPrim);
-  B2_LAUNCH_CHECK(ctx);
   return 0;
 }

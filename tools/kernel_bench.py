@@ -1,5 +1,6 @@
 """Per-kernel CUDA-event times of one build (development tool; not part of the bench contract).
-usage: python tools/kernel_bench.py [--n 10000000] [--algo singlepass|twopass|ploc|hploc] [--reps 5]
+usage: python tools/kernel_bench.py [--n 10000000] [--algo singlepass|twopass|ploc|hploc|split|batched] [--reps 5]
+(split = TwoPassLbvh over early-split references with saMax = 6 h^2; batched = n/32 items of 32 triangles)
 B2BVH_LIB=/path/to/variant.so selects another build of the library."""
 import argparse
 import os
@@ -35,6 +36,20 @@ def main():
         ctx.h2d(d, tris)
     else:
         d = ctx.synth_uniform(a.n, 0x00B20010)
+    if a.algo == "batched":
+        import numpy as np
+        counts = np.full(a.n // 32, 32, dtype=np.uint32)
+        for _ in range(a.warmup):
+            ctx.build_batched(d, counts, tris_on_device=True)
+        best = min(ctx.build_batched(d, counts, tris_on_device=True).build_ms for _ in range(a.reps))
+        print(f"batched: items={counts.size} x 32  build_ms(best)={best:.4f} -> {counts.size * 32 / best / 1e3:.1f} Mprims/s, {124 * counts.size * 32 / best / 1e6:.0f} GB/s algorithmic")
+        return
+    kw = {}
+    if a.algo == "split":
+        a.algo = "twopass"
+        kw["split_sa_max"] = 6.0 * (1000.0 * a.n ** (-1.0 / 3.0)) ** 2
+        global_build = ctx.build
+        ctx.build = lambda *x, **y: global_build(*x, **{k: v for k, v in y.items() if k != "use_graph"}, **kw)
     for _ in range(a.warmup):
         tree = ctx.build(ALGOS[a.algo], d, n=a.n, tris_on_device=True, karras_two_kernel=a.two_kernel)
     agg = {}
@@ -49,6 +64,8 @@ def main():
         tree = ctx.build(ALGOS[a.algo], d, n=a.n, tris_on_device=True, karras_two_kernel=a.two_kernel, use_graph=a.graph)
         tree = ctx.build(ALGOS[a.algo], d, n=a.n, tris_on_device=True, karras_two_kernel=a.two_kernel, use_graph=a.graph)
         tot.append((tree.build_ms, [tree.stage_ms[k] for k in (0, 1, 2, 3, 5)]))
+    if kw:
+        print(f"split: references={tree.n_prims} generations={tree.n_split_levels} split_ms={tree.split_ms:.4f}")
     print(f"lib={os.path.basename(capi.LIB_PATH)} algo={a.algo} n={a.n} launches={tree.n_launches} iterations={tree.n_iterations} n_wide={tree.n_wide}")
     best = min(tot)
     print(f"  build_ms(best)={best[0]:.4f}  stages ext/morton/sort/build/collapse = " + " / ".join(f"{x:.4f}" for x in best[1]) +

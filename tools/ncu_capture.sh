@@ -11,6 +11,8 @@ for K in "$@"; do
     hploc|hploc_setup|hploc_kernel) ALGO=hploc;;
     lbvh_karras_emit|lbvh_refit) ALGO="twopass --two-kernel";;
     lbvh_fused_karras) ALGO=twopass;;
+    split_level|split_remap) ALGO=split;;
+    batched_lbvh) ALGO=batched;;
     *) ALGO=singlepass;;
   esac
   case $K in
