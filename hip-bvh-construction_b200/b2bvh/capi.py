@@ -25,7 +25,7 @@ class Aabb(C.Structure):
 class BuildOpts(C.Structure):
     _fields_ = [("collapse", C.c_uint32), ("tris_on_device", C.c_uint32), ("use_scene_box", C.c_uint32), ("scene_box", Aabb),
                 ("stage_timing", C.c_uint32), ("karras_two_kernel", C.c_uint32), ("boxes_ready", C.c_uint32),
-                ("d_scene_negmin_max", C.c_void_p), ("lbvh_second_level", C.c_uint32), ("merge_max_ctas", C.c_uint32), ("use_graph", C.c_uint32), ("split_sa_max", C.c_float)]
+                ("d_scene_negmin_max", C.c_void_p), ("lbvh_second_level", C.c_uint32), ("merge_max_ctas", C.c_uint32), ("use_graph", C.c_uint32), ("split_sa_max", C.c_float), ("morton_bits", C.c_uint32), ("reserved3", C.c_uint32)]
 
 
 class Tree(C.Structure):
@@ -37,7 +37,8 @@ class Tree(C.Structure):
                 ("d_leafNodes", C.c_void_p), ("d_wideBvhNodes", C.c_void_p), ("d_wideLeafNodes", C.c_void_p),
                 ("stage_ms", C.c_float * T_COUNT), ("build_ms", C.c_float), ("h2d_ms", C.c_float), ("n_iterations", C.c_uint32),
                 ("n_launches", C.c_uint32), ("n_triangles", C.c_uint32), ("n_split_levels", C.c_uint32), ("split_ms", C.c_float),
-                ("reserved", C.c_uint32), ("d_primRefIdx", C.c_void_p)]
+                ("reserved", C.c_uint32), ("d_primRefIdx", C.c_void_p), ("d_mortonCodeKeys64", C.c_void_p), ("d_sortedMortonCodeKeys64", C.c_void_p),
+                ("morton_bits", C.c_uint32), ("reserved4", C.c_uint32)]
 
 
 class Batch(C.Structure):
@@ -172,7 +173,7 @@ class Context:
 
     # ---- stages ----
     def build(self, algo, tris, n=None, collapse=True, tris_on_device=False, scene_box=None, karras_two_kernel=False, boxes_ready=False,
-              d_scene_negmin_max=None, lbvh_second_level=0, merge_max_ctas=0, use_graph=False, split_sa_max=0.0):
+              d_scene_negmin_max=None, lbvh_second_level=0, merge_max_ctas=0, use_graph=False, split_sa_max=0.0, morton_bits=0):
         """tris: TRIANGLE[n] numpy array (host) or an int device/pinned-host pointer (then pass n)."""
         opts = BuildOpts()
         opts.collapse = 1 if collapse else 0
@@ -184,6 +185,7 @@ class Context:
         opts.merge_max_ctas = int(merge_max_ctas)
         opts.use_graph = 1 if use_graph else 0
         opts.split_sa_max = float(split_sa_max)
+        opts.morton_bits = int(morton_bits)
         if d_scene_negmin_max:
             opts.d_scene_negmin_max = int(d_scene_negmin_max)
         if scene_box is not None:
@@ -234,6 +236,8 @@ class Context:
         r["scene"] = self.download(tree.d_sceneExtents, T.AABB, 1)
         r["keys"] = self.download(tree.d_mortonCodeKeys, np.uint32, n)
         r["vals"] = self.download(tree.d_mortonCodeValues, np.uint32, n)
+        r["keys64"] = self.download(tree.d_mortonCodeKeys64, np.uint64, n) if tree.d_mortonCodeKeys64 else None
+        r["skeys64"] = self.download(tree.d_sortedMortonCodeKeys64, np.uint64, n) if tree.d_sortedMortonCodeKeys64 else None
         r["skeys"] = self.download(tree.d_sortedMortonCodeKeys, np.uint32, n)
         r["svals"] = self.download(tree.d_sortedMortonCodeValues, np.uint32, n)
         r["nodes"] = self.download(tree.d_bvhNodes, T.BVH2_NODE, n - 1 if separate else 2 * n - 1)

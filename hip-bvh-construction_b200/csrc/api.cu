@@ -51,7 +51,8 @@ enum {
   SLOT_TRIS = 0, SLOT_AABB, SLOT_CTL, SLOT_KEYS, SLOT_VALS, SLOT_SKEYS, SLOT_SVALS, SLOT_TKEYS, SLOT_TVALS, SLOT_SORT, SLOT_NODES,
   SLOT_PARENTS, SLOT_LBVH, SLOT_WIDE, SLOT_WLEAVES, SLOT_COLLAPSE, SLOT_LEAVES, SLOT_PLOC, SLOT_HPLOC, SLOT_MISC,
   SLOT_SPLIT_BOX, SLOT_SPLIT_PRIM, SLOT_SPLIT_LIST_A, SLOT_SPLIT_LIST_B, SLOT_SPLIT_STATUS, SLOT_SPLIT_LEAFPRIM,
-  SLOT_BATCH_NODES, SLOT_BATCH_LEAVES, SLOT_BATCH_ROOTS, SLOT_BATCH_SCENES, SLOT_BATCH_OFFSETS, SLOT_COUNT
+  SLOT_BATCH_NODES, SLOT_BATCH_LEAVES, SLOT_BATCH_ROOTS, SLOT_BATCH_SCENES, SLOT_BATCH_OFFSETS,
+  SLOT_KEYS_LO, SLOT_KEYS64, SLOT_SKEYS64, SLOT_M60_KEYS, SLOT_M60_VALS, SLOT_COUNT
 };
 /* SLOT_CTL (256 B): [0..23] scene box, [32..63] extents scratch8, [64..87] {-min,max}, [96] root index, [128..] misc */
 
@@ -95,7 +96,7 @@ int b2bvh_ctx_destroy(b2bvh_ctx* ctx) {
   if (!ctx) return 0;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  for (int i = 0; i < 32; i++) if (ctx->bufs[i].p) cudaFree(ctx->bufs[i].p);
+  for (int i = 0; i < 48; i++) if (ctx->bufs[i].p) cudaFree(ctx->bufs[i].p);
   for (int i = 0; i < 16; i++) cudaEventDestroy(ctx->ev[i]);
   if (ctx->graph.exec) cudaGraphExecDestroy(ctx->graph.exec);
   if (ctx->mailbox) cudaFreeHost(ctx->mailbox);
@@ -229,6 +230,11 @@ int b2bvh_build(b2bvh_ctx* ctx, int algo, const b2bvh_triangle* tris, uint32_t n
   if (split && (opts.boxes_ready || opts.use_scene_box || opts.d_scene_negmin_max))
     return b2_fail(B2BVH_ERR_INVALID, "build: split_sa_max cannot be combined with the sharded-build options");
   const u32 nTris = n;
+  const bool m60 = opts.morton_bits == 60;
+  if (opts.morton_bits != 0 && opts.morton_bits != 30 && opts.morton_bits != 60)
+    return b2_fail(B2BVH_ERR_INVALID, "build: morton_bits must be 0/30 (the reference's extended 30-bit code) or 60, got %u", opts.morton_bits);
+  if (m60 && algo == B2BVH_HPLOC) return b2_fail(B2BVH_ERR_INVALID, "build: morton_bits=60 is not available for B2BVH_HPLOC (its hierarchy walks the 32-bit codes)");
+  if (m60 && opts.karras_two_kernel) return b2_fail(B2BVH_ERR_INVALID, "build: morton_bits=60 cannot be combined with karras_two_kernel");
 
   /* ---- buffers (grown on demand, reused) ---- */
   void *dTris = nullptr, *dAabb, *dKeys, *dVals, *dSKeys, *dSVals, *dTKeys, *dTVals, *dSort, *dNodes, *dParents = nullptr, *dLbvh = nullptr,
@@ -273,6 +279,14 @@ int b2bvh_build(b2bvh_ctx* ctx, int algo, const b2bvh_triangle* tris, uint32_t n
   B2_TRY(b2_reserve(ctx, SLOT_TKEYS, (size_t)n * 4, &dTKeys));
   B2_TRY(b2_reserve(ctx, SLOT_TVALS, (size_t)n * 4, &dTVals));
   B2_TRY(b2_reserve(ctx, SLOT_SORT, b2_sort_scratch_bytes(n), &dSort));
+  void *dKeysLo = nullptr, *dKeys64 = nullptr, *dSKeys64 = nullptr, *dM60K = nullptr, *dM60V = nullptr;
+  if (m60) {
+    B2_TRY(b2_reserve(ctx, SLOT_KEYS_LO, (size_t)n * 4, &dKeysLo));
+    B2_TRY(b2_reserve(ctx, SLOT_KEYS64, (size_t)n * 8, &dKeys64));
+    B2_TRY(b2_reserve(ctx, SLOT_SKEYS64, (size_t)n * 8, &dSKeys64));
+    B2_TRY(b2_reserve(ctx, SLOT_M60_KEYS, (size_t)n * 4, &dM60K));
+    B2_TRY(b2_reserve(ctx, SLOT_M60_VALS, (size_t)n * 4, &dM60V));
+  }
   B2_TRY(b2_reserve(ctx, SLOT_NODES, (size_t)(separate ? n - 1 : 2 * (size_t)n - 1) * sizeof(b2bvh_bvh2_node), &dNodes));
   if (algo == B2BVH_TWO_PASS_LBVH) B2_TRY(b2_reserve(ctx, SLOT_PARENTS, (2 * (size_t)n - 1) * 4, &dParents));
   if (!separate) B2_TRY(b2_reserve(ctx, SLOT_LBVH, b2_lbvh_scratch_bytes(n), &dLbvh));
@@ -306,15 +320,23 @@ int b2bvh_build(b2bvh_ctx* ctx, int algo, const b2bvh_triangle* tris, uint32_t n
   else if (opts.use_scene_box) B2_CUDA(cudaMemcpyAsync(dScene, &opts.scene_box, sizeof(b2bvh_aabb), cudaMemcpyHostToDevice, s));
   B2_CUDA(record(1));
   /* ---- S2 Morton (+ SetupClusters for PLOC/HPLOC is inside their launchers but is accounted under BUILD here) ---- */
-  B2_TRY(b2_launch_morton(ctx, (const b2bvh_aabb*)dAabb, dScene, n, (u32*)dKeys, (u32*)dVals));
+  if (m60) B2_TRY(b2_launch_morton60(ctx, (const b2bvh_aabb*)dAabb, dScene, n, (u32*)dKeys /* upper 30 bits */, (u32*)dKeysLo, (u64*)dKeys64));
+  else B2_TRY(b2_launch_morton(ctx, (const b2bvh_aabb*)dAabb, dScene, n, (u32*)dKeys, (u32*)dVals));
   B2_CUDA(record(2));
   /* ---- S3 sort (values of pass 0 are the iota written by S2: not re-read) ---- */
-  B2_TRY(b2_launch_sort(ctx, (const u32*)dKeys, nullptr, (u32*)dSKeys, (u32*)dSVals, (u32*)dTKeys, (u32*)dTVals, dSort, n, 0, 32));
+  if (m60)
+    B2_TRY(b2_launch_sort60(ctx, (const u32*)dKeys, (const u32*)dKeysLo, n, (u32*)dM60K, (u32*)dM60V, (u32*)dSKeys, (u32*)dSVals, (u64*)dSKeys64, (u32*)dTKeys,
+                            (u32*)dTVals, dSort));
+  else
+    B2_TRY(b2_launch_sort(ctx, (const u32*)dKeys, nullptr, (u32*)dSKeys, (u32*)dSVals, (u32*)dTKeys, (u32*)dTVals, dSort, n, 0, 32));
   B2_CUDA(record(3));
   /* ---- S4 / S6 / S7 hierarchy ---- */
   switch (algo) {
     case B2BVH_TWO_PASS_LBVH:
-      if (opts.karras_two_kernel)
+      if (m60)
+        B2_TRY(b2_launch_lbvh_fused64(ctx, (const u64*)dSKeys64, (const u32*)dSVals, (const b2bvh_aabb*)dAabb, n, (b2bvh_bvh2_node*)dNodes, (u32*)dParents,
+                                      (u32*)dLbvh, dRoot, 1));
+      else if (opts.karras_two_kernel)
         B2_TRY(b2_launch_lbvh_karras_two_kernel(ctx, (const u32*)dSKeys, (const u32*)dSVals, (const b2bvh_aabb*)dAabb, n, (b2bvh_bvh2_node*)dNodes,
                                                 (u32*)dParents, (u32*)dLbvh));
       else
@@ -323,6 +345,10 @@ int b2bvh_build(b2bvh_ctx* ctx, int algo, const b2bvh_triangle* tris, uint32_t n
       B2_CUDA(cudaMemsetAsync(dRoot, 0, 4, s));
       break;
     case B2BVH_SINGLE_PASS_LBVH:
+      if (m60)
+        B2_TRY(b2_launch_lbvh_fused64(ctx, (const u64*)dSKeys64, (const u32*)dSVals, (const b2bvh_aabb*)dAabb, n, (b2bvh_bvh2_node*)dNodes, nullptr, (u32*)dLbvh,
+                                      dRoot, 0));
+      else
       B2_TRY(b2_launch_lbvh_fused(ctx, (const u32*)dSKeys, (const u32*)dSVals, (const b2bvh_aabb*)dAabb, n, (b2bvh_bvh2_node*)dNodes, nullptr,
                                   (u32*)dLbvh, dRoot, 0));
       break;
@@ -415,6 +441,9 @@ int b2bvh_build(b2bvh_ctx* ctx, int algo, const b2bvh_triangle* tris, uint32_t n
   out->n_launches = ctx->launches - launches0;
   out->n_triangles = nTris;
   out->d_primRefIdx = dRefPrim;
+  out->morton_bits = m60 ? 60u : 30u;
+  out->d_mortonCodeKeys64 = (const uint64_t*)dKeys64;
+  out->d_sortedMortonCodeKeys64 = (const uint64_t*)dSKeys64;
   out->n_split_levels = splitLevels;
   if (split) B2_CUDA(cudaEventElapsedTime(&out->split_ms, ctx->ev[10], ctx->ev[11]));
   return 0;
@@ -422,7 +451,7 @@ int b2bvh_build(b2bvh_ctx* ctx, int algo, const b2bvh_triangle* tris, uint32_t n
 
 /* ------------------------------------------------------------------ batched builder (BatchedBvhBuilder::build, BatchedBuilder.cpp:16-77) */
 int b2bvh_build_batched(b2bvh_ctx* ctx, const b2bvh_triangle* tris, uint32_t tris_on_device, const uint32_t* counts, uint32_t n_items, b2bvh_batch* out) {
-  static_assert(SLOT_COUNT <= 32, "b2bvh_ctx::bufs has 32 slots");
+  static_assert(SLOT_COUNT <= 48, "b2bvh_ctx::bufs has 48 slots");
   if (!ctx || !tris || !counts || !out) return b2_fail(B2BVH_ERR_INVALID, "build_batched: null argument");
   if (n_items == 0) return b2_fail(B2BVH_ERR_INVALID, "build_batched: no items");
   B2_CUDA(cudaSetDevice(ctx->device));

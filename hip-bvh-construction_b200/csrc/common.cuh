@@ -196,7 +196,7 @@ struct b2bvh_ctx {
   struct Buf {
     void* p;
     size_t cap;
-  } bufs[32];
+  } bufs[48];
   u32* mailbox;          /* pinned + mapped host memory, B2_MAILBOX_SLOTS x 16 words: small results come back through a one-warp
                             kernel instead of the copy engine, where a 4-byte read would queue behind another context's bulk copy */
   u32* mailbox_dev;      /* the same memory as the device sees it */
@@ -270,6 +270,12 @@ int b2_launch_lbvh_fused(b2bvh_ctx* ctx, const u32* d_sortedKeys, const u32* d_s
                          b2bvh_bvh2_node* d_nodes, u32* d_parents, u32* d_scratch /* b2_lbvh_scratch_bytes(n) */, u32* d_root, int karrasNumbering);
 int b2_launch_lbvh_karras_two_kernel(b2bvh_ctx* ctx, const u32* d_sortedKeys, const u32* d_sortedVals, const b2bvh_aabb* d_triAabb, u32 n,
                                      b2bvh_bvh2_node* d_nodes, u32* d_parents, u32* d_flags);
+int b2_launch_lbvh_fused64(b2bvh_ctx* ctx, const u64* d_sortedKeys64, const u32* d_sortedVals, const b2bvh_aabb* d_triAabb, u32 n,
+                           b2bvh_bvh2_node* d_nodes, u32* d_parents, u32* d_scratch, u32* d_root, int karrasNumbering);
+/* 60-bit Morton variant (morton60.cu) */
+int b2_launch_morton60(b2bvh_ctx* ctx, const b2bvh_aabb* d_triAabb, const b2bvh_aabb* d_scene, u32 n, u32* d_hi, u32* d_lo, u64* d_keys64);
+int b2_launch_sort60(b2bvh_ctx* ctx, const u32* d_hi, const u32* d_lo, u32 n, u32* d_a, u32* d_aVals, u32* d_hiSorted, u32* d_valsSorted, u64* d_keys64Sorted,
+                     u32* d_keysTmp, u32* d_valsTmp, void* d_sortScratch);
 size_t b2_collapse_scratch_bytes(u32 n);
 int b2_launch_collapse(b2bvh_ctx* ctx, const b2bvh_bvh2_node* d_nodes, const b2bvh_prim_ref* d_leaves, const u32* d_sortedVals, const u32* d_rootIdx,
                        u32 n,

@@ -31,20 +31,30 @@ __device__ __forceinline__ u64 aug_key(const u32* __restrict__ keys, u32 i) { re
 /* Parent choice for the node covering leaves [lo, hi) (findParent, SinglePassLbvhKernel.h:64-86):
  * returns the split position p of the parent and whether this node is its LEFT child.  The parent splits
  * between leaves p and p+1.  Must not be called for the root. */
-__device__ __forceinline__ u32 choose_parent(const u32* __restrict__ keys, u32 n, u32 lo, u32 hi, bool& isLeft) {
-  if (lo == 0) { isLeft = true; return hi - 1; }
-  if (hi == n) { isLeft = false; return lo - 1; }
+__device__ __forceinline__ bool right_boundary_deeper(const u32* __restrict__ keys, u32 lo, u32 hi) {
   const u64 xr = aug_key(keys, hi - 1) ^ aug_key(keys, hi);
   const u64 xl = aug_key(keys, lo - 1) ^ aug_key(keys, lo);
-  isLeft = xr < xl;
+  return xr < xl;
+}
+/* 64-bit keys (60-bit Morton variant): the augmented key is 96 bits wide — compare the key XORs, then the index XORs */
+__device__ __forceinline__ bool right_boundary_deeper(const u64* __restrict__ keys, u32 lo, u32 hi) {
+  const u64 xr = __ldg(keys + hi - 1) ^ __ldg(keys + hi), xl = __ldg(keys + lo - 1) ^ __ldg(keys + lo);
+  if (xr != xl) return xr < xl;
+  return ((hi - 1) ^ hi) < ((lo - 1) ^ lo);
+}
+template <typename K>
+__device__ __forceinline__ u32 choose_parent(const K* __restrict__ keys, u32 n, u32 lo, u32 hi, bool& isLeft) {
+  if (lo == 0) { isLeft = true; return hi - 1; }
+  if (hi == n) { isLeft = false; return lo - 1; }
+  isLeft = right_boundary_deeper(keys, lo, hi);
   return isLeft ? hi - 1 : lo - 1;
 }
 
 /* The climb through GLOBAL memory, starting from a finished node `self` covering [lo, hi) with box `box` whose parent has
  * split `p` (this node being its left child iff isLeft).  Returns when the node is the first to arrive at some parent
  * (the sibling's thread takes over) or when the root has been written. */
-template <bool KARRAS>
-__device__ __forceinline__ void climb_global(const u32* __restrict__ keys, u32 n, b2bvh_bvh2_node* nodes, u32* parents, u32* meet, u32* rootOut,
+template <bool KARRAS, typename K>
+__device__ __forceinline__ void climb_global(const K* __restrict__ keys, u32 n, b2bvh_bvh2_node* nodes, u32* parents, u32* meet, u32* rootOut,
                                              u32 self, u32 lo, u32 hi, Box box, u32 p, bool isLeft) {
   const u32 nInt = n - 1;
   while (true) {
@@ -77,8 +87,8 @@ __device__ __forceinline__ void climb_global(const u32* __restrict__ keys, u32 n
   }
 }
 
-template <bool KARRAS>
-__global__ void __launch_bounds__(LBVH_THREADS) lbvh_fused_kernel(const u32* __restrict__ keys, const u32* __restrict__ vals,
+template <bool KARRAS, typename K>
+__global__ void __launch_bounds__(LBVH_THREADS) lbvh_fused_kernel(const K* __restrict__ keys, const u32* __restrict__ vals,
                                                                   const b2bvh_aabb* __restrict__ triAabb, u32 n, b2bvh_bvh2_node* nodes,
                                                                   u32* parents, u32* meet /* n-1 words, 0xFFFFFFFF */, u32* rootOut,
                                                                   const u32* __restrict__ refPrim /* early split: triangle of each reference, else NULL */,
@@ -583,9 +593,9 @@ int b2_launch_lbvh_fused(b2bvh_ctx* ctx, const u32* d_sortedKeys, const u32* d_s
   if (globalOnly) {
     const u32 grid = (n + LBVH_THREADS - 1) / LBVH_THREADS;
     if (karrasNumbering)
-      lbvh_fused_kernel<true><<<grid, LBVH_THREADS, 0, ctx->stream>>>(d_sortedKeys, d_sortedVals, d_triAabb, n, d_nodes, d_parents, d_scratch, d_root, ctx->ref_prim, ctx->ref_leaf_prim);
+      lbvh_fused_kernel<true, u32><<<grid, LBVH_THREADS, 0, ctx->stream>>>(d_sortedKeys, d_sortedVals, d_triAabb, n, d_nodes, d_parents, d_scratch, d_root, ctx->ref_prim, ctx->ref_leaf_prim);
     else
-      lbvh_fused_kernel<false><<<grid, LBVH_THREADS, 0, ctx->stream>>>(d_sortedKeys, d_sortedVals, d_triAabb, n, d_nodes, d_parents, d_scratch, d_root, ctx->ref_prim, ctx->ref_leaf_prim);
+      lbvh_fused_kernel<false, u32><<<grid, LBVH_THREADS, 0, ctx->stream>>>(d_sortedKeys, d_sortedVals, d_triAabb, n, d_nodes, d_parents, d_scratch, d_root, ctx->ref_prim, ctx->ref_leaf_prim);
   } else {
     /* scratch: meet[n-1] | (16-byte aligned) pendingCount | pending[cap] | tileInfo[tiles] | tileBuf[tiles][LBVH_TILE_CAP] */
     const size_t off = (((size_t)n * 4 + 15) & ~(size_t)15);
@@ -630,6 +640,21 @@ int b2_launch_lbvh_fused(b2bvh_ctx* ctx, const u32* d_sortedKeys, const u32* d_s
     else
       lbvh_climb_kernel<false><<<grid2, LBVH_THREADS, 0, ctx->stream>>>(d_sortedKeys, n, d_nodes, d_parents, d_scratch, d_root, pendingCount, pending, cap);
   }
+  B2_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+/* 64-bit sorted keys (60-bit Morton variant): the all-global-memory climb — one thread per leaf, the two children of a node meet
+ * through one atomic exchange; the tile / group kernels above pack 32-bit keys into their cluster words and are not used here */
+int b2_launch_lbvh_fused64(b2bvh_ctx* ctx, const u64* d_sortedKeys64, const u32* d_sortedVals, const b2bvh_aabb* d_triAabb, u32 n,
+                           b2bvh_bvh2_node* d_nodes, u32* d_parents, u32* d_scratch, u32* d_root, int karrasNumbering) {
+  if (n > 1) B2_CUDA(cudaMemsetAsync(d_scratch, 0xFF, (size_t)(n - 1) * sizeof(u32), ctx->stream));
+  const u32 grid = (n + LBVH_THREADS - 1) / LBVH_THREADS;
+  B2_KERNEL(ctx, karrasNumbering ? "lbvh_fused64_karras" : "lbvh_fused64_apetrei");
+  if (karrasNumbering)
+    lbvh_fused_kernel<true, u64><<<grid, LBVH_THREADS, 0, ctx->stream>>>(d_sortedKeys64, d_sortedVals, d_triAabb, n, d_nodes, d_parents, d_scratch, d_root, ctx->ref_prim, ctx->ref_leaf_prim);
+  else
+    lbvh_fused_kernel<false, u64><<<grid, LBVH_THREADS, 0, ctx->stream>>>(d_sortedKeys64, d_sortedVals, d_triAabb, n, d_nodes, d_parents, d_scratch, d_root, ctx->ref_prim, ctx->ref_leaf_prim);
   B2_LAUNCH_CHECK(ctx);
   return 0;
 }

@@ -72,6 +72,12 @@ typedef struct b2bvh_build_opts {
                                every primitive box with area > saMax is halved along its largest extent until all pieces fit; the build
                                then runs over the REFERENCES (b2bvh_tree.n_prims = their count, d_primRefIdx = their triangles).
                                0: off (the reference's default, saMax = FltMax) */
+  uint32_t morton_bits;     /* 0 or 30: the reference's extended 30-bit code (computeExtendedMortonCode, CommonBlocksKernel.h:159-359).
+                               60: plain 60-bit code, 20 bits per axis — computeMortonCode (:361-372) with 2^20 instead of 2^10 cells; no reference
+                               counterpart (its codes stop at 30 bits), defined by the oracle.  LBVH builders and PLOC++ (which only needs the
+                               order); not H-PLOC.  b2bvh_tree.d_mortonCodeKeys64 / d_sortedMortonCodeKeys64 hold the codes, the 32-bit key
+                               arrays their upper 30 bits, d_mortonCodeValues is not written (the values are the iota) */
+  uint32_t reserved3;
 } b2bvh_build_opts;
 
 /* Everything a build leaves on the device.  Pointers are DEVICE pointers owned by the context
@@ -109,6 +115,11 @@ typedef struct b2bvh_tree {
   float split_ms;                             /* device time of the split (inside stage_ms[extents])              */
   uint32_t reserved;
   const uint32_t* d_primRefIdx;               /* n_prims, or NULL without splitting                               */
+  /* 60-bit Morton variant (morton_bits = 60) */
+  const uint64_t* d_mortonCodeKeys64;         /* n_prims, or NULL                                                 */
+  const uint64_t* d_sortedMortonCodeKeys64;   /* n_prims, or NULL                                                 */
+  uint32_t morton_bits;                       /* 30 or 60                                                         */
+  uint32_t reserved4;
 } b2bvh_tree;
 
 /* ---- context / memory: replaces Context (src/Context.cpp:7-22) and OrochiUtils malloc/copy helpers

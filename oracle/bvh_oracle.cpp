@@ -330,15 +330,24 @@ void orc_sort_kv(const u32* keys, const u32* vals, u32 n, u32* keysOut, u32* val
 /* ------------------------------------------------- S4a: Karras two-pass LBVH
  * InitBvhNodesPrimRef (TwoPassLbvhKernel.h:164-194), determineRange (:42-100),
  * findSplit (:102-130), BvhBuild (:196-216), FitBvhNodes (:217-235).          */
+}  /* extern "C" */
 static inline int clz32(u32 v) { return v ? __builtin_clz(v) : 32; }
 static inline int karras_delta(const u32* k, u32 n, int i, int j) {
   if (j < 0 || j >= (int)n) return -1;
   if (k[i] != k[j]) return clz32(k[i] ^ k[j]);     /* :27-30 */
   return 32 + clz32((u32)i ^ (u32)j);             /* :32-40 (clzll of (0<<32 | i^j)) */
 }
+/* 64-bit keys (the 60-bit Morton variant, no reference counterpart): the same rule one word wider —
+ * common prefix of the keys, ties broken by the common prefix of the indices. */
+static inline int karras_delta(const u64* k, u32 n, int i, int j) {
+  if (j < 0 || j >= (int)n) return -1;
+  if (k[i] != k[j]) return __builtin_clzll(k[i] ^ k[j]);
+  return 64 + clz32((u32)i ^ (u32)j);
+}
 
-void orc_lbvh_karras(const b2bvh_prim_ref* refs, const u32* keys, const u32* vals, u32 n,
-                     b2bvh_bvh2_node* nodes, u32* parents) {
+template <typename K>
+static void lbvh_karras_t(const b2bvh_prim_ref* refs, const K* keys, const u32* vals, u32 n,
+                          b2bvh_bvh2_node* nodes, u32* parents) {
   const u32 nInt = n - 1;
   std::vector<u32> par(2 * (size_t)n - 1, INVALID);
   for (u32 g = 0; g < n; g++) {                       /* leaves */
@@ -386,17 +395,32 @@ void orc_lbvh_karras(const b2bvh_prim_ref* refs, const u32* keys, const u32* val
   }
   if (parents) memcpy(parents, par.data(), par.size() * sizeof(u32));
 }
+extern "C" {
+void orc_lbvh_karras(const b2bvh_prim_ref* refs, const u32* keys, const u32* vals, u32 n, b2bvh_bvh2_node* nodes, u32* parents) {
+  lbvh_karras_t<u32>(refs, keys, vals, n, nodes, parents);
+}
+void orc_lbvh_karras64(const b2bvh_prim_ref* refs, const u64* keys, const u32* vals, u32 n, b2bvh_bvh2_node* nodes, u32* parents) {
+  lbvh_karras_t<u64>(refs, keys, vals, n, nodes, parents);
+}
 
 /* ------------------------------------------------- S4b: Apetrei single-pass LBVH
  * InitBvhNodes (SinglePassLbvhKernel.h:27-54), findHighestDiffBit (:56-62),
  * findParent (:64-86), BvhBuildAndFit (:88-126).  Returns the root index that
  * the kernel leaves in bvhNodeCounter[nLeafNodes-1] (:118).                   */
+}  /* extern "C" */
 static inline u64 aug_xor(const u32* k, int n, int i, int j) {
   if (j < 0 || j >= n) return ~0ull;
   return (((u64)k[i] << 32) | (u32)i) ^ (((u64)k[j] << 32) | (u32)j);
 }
+/* 64-bit keys: the augmented XOR is 96 bits wide (key XOR, then index XOR); out of range = all ones */
+typedef unsigned __int128 u128;
+static inline u128 aug_xor(const u64* k, int n, int i, int j) {
+  if (j < 0 || j >= n) return ~(u128)0;
+  return ((u128)(k[i] ^ k[j]) << 32) | (u32)((u32)i ^ (u32)j);
+}
 
-u32 orc_lbvh_apetrei(const b2bvh_triangle* tris, const u32* keys, const u32* vals, u32 n, b2bvh_bvh2_node* nodes) {
+template <typename K>
+static u32 lbvh_apetrei_t(const b2bvh_triangle* tris, const K* keys, const u32* vals, u32 n, b2bvh_bvh2_node* nodes) {
   const u32 nInt = n - 1;
   const int N = (int)n;
   for (u32 g = 0; g < n; g++) {
@@ -427,6 +451,45 @@ u32 orc_lbvh_apetrei(const b2bvh_triangle* tris, const u32* keys, const u32* val
   }
   return root;
 }
+extern "C" {
+u32 orc_lbvh_apetrei(const b2bvh_triangle* tris, const u32* keys, const u32* vals, u32 n, b2bvh_bvh2_node* nodes) {
+  return lbvh_apetrei_t<u32>(tris, keys, vals, n, nodes);
+}
+u32 orc_lbvh_apetrei64(const b2bvh_triangle* tris, const u64* keys, const u32* vals, u32 n, b2bvh_bvh2_node* nodes) {
+  return lbvh_apetrei_t<u64>(tris, keys, vals, n, nodes);
+}
+
+/* ------------------------------------------------- 60-bit Morton codes (north star "30/60-bit Morton coding")
+ * The reference has 30-bit codes only; at 100 M primitives neighbouring primitives share codes and the order below the
+ * code resolution falls back to the input index.  Defined here: the PLAIN interleave of computeMortonCode
+ * (CommonBlocksKernel.h:361-372) with 20 bits per axis instead of 10 — x = min(max(p.x * 2^20, 0), 2^20 - 1) per axis
+ * (float, then truncation), bits interleaved x,y,z from the top.  Equivalently: (30-bit interleave of the upper 10 bits
+ * of each axis) << 30 | (30-bit interleave of the lower 10 bits).  Parity unpinned by the reference (there is nothing
+ * to pin it to); the 10-bit interleave it is made of is pinned (orc_morton_plain). */
+static inline u32 morton3d_10(u32 x);
+u64 orc_morton60_point(const float p[3]) {
+  u32 q[3];
+  for (int a = 0; a < 3; a++) q[a] = (u32)fminr(fmaxr(p[a] * 1048576.0f, 0.0f), 1048575.0f);
+  const u32 hi = morton3d_10(q[0] >> 10) * 4 + morton3d_10(q[1] >> 10) * 2 + morton3d_10(q[2] >> 10);
+  const u32 lo = morton3d_10(q[0] & 1023u) * 4 + morton3d_10(q[1] & 1023u) * 2 + morton3d_10(q[2] & 1023u);
+  return ((u64)hi << 30) | lo;
+}
+void orc_morton60_codes(const void* boxes, u32 strideBytes, const Box* scene, u32 n, u64* keys, u32* vals) {
+  F3 ext = box_extent(*scene);
+  for (u32 i = 0; i < n; i++) {
+    const Box* b = (const Box*)((const char*)boxes + (size_t)i * strideBytes);
+    F3 q = vdiv(vsub(box_center(*b), scene->m_min), ext);
+    float p[3] = {q.x, q.y, q.z};
+    keys[i] = orc_morton60_point(p);
+    vals[i] = i;
+  }
+}
+void orc_sort_kv64(const u64* keys, const u32* vals, u32 n, u64* keysOut, u32* valsOut) {
+  std::vector<u32> perm(n);
+  for (u32 i = 0; i < n; i++) perm[i] = i;
+  std::stable_sort(perm.begin(), perm.end(), [&](u32 a, u32 b) { return keys[a] < keys[b]; });
+  for (u32 i = 0; i < n; i++) { keysOut[i] = keys[perm[i]]; valsOut[i] = vals[perm[i]]; }
+}
 
 /* ------------------------------------------------- batched builder
  * BatchedBuildKernelLbvh (BatchedBuildKernel.h:218-312), one small BVH per batch item (<= MaxBatchedBlockSize = 32
@@ -454,7 +517,6 @@ u32 orc_morton_plain(const float p[3]) {                 /* :98-110 */
   float z = fminr(fmaxr(p[2] * 1024.0f, 0.0f), 1023.0f);
   return morton3d_10((u32)x) * 4 + morton3d_10((u32)y) * 2 + morton3d_10((u32)z);
 }
-u32 orc_lbvh_apetrei(const b2bvh_triangle* tris, const u32* keys, const u32* vals, u32 n, b2bvh_bvh2_node* nodes);
 /* tris: all items back to back; counts[item]; nodes: sum(n-1); leaves: sum(n); roots, scenes: one per item. */
 void orc_batched_build(const b2bvh_triangle* tris, const u32* counts, u32 nItems, b2bvh_bvh2_node* nodes, b2bvh_prim_ref* leaves, u32* roots, Box* scenes) {
   u64 triOff = 0, nodeOff = 0;

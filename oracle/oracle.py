@@ -40,8 +40,9 @@ def lib():
         _lib.orc_ray_zdir.restype = C.c_float
         _lib.orc_ray_zdir.argtypes = [C.c_float]
         for f in ("orc_fnv1a_words", "orc_lbvh_apetrei", "orc_collapse4", "orc_bvh2_depth", "orc_traverse", "orc_traverse_kind", "orc_traverse_wide4", "orc_binned_sah_build",
-                  "orc_morton_code_cfg", "orc_early_split", "orc_morton_plain"):
+                  "orc_morton_code_cfg", "orc_early_split", "orc_morton_plain", "orc_lbvh_apetrei64"):
             getattr(_lib, f).restype = C.c_uint32
+        _lib.orc_morton60_point.restype = C.c_uint64
     return _lib
 
 
@@ -122,6 +123,29 @@ def morton_codes(boxes, scene):
     return keys, vals
 
 
+def morton60_point(p):
+    q = (C.c_float * 3)(*[float(x) for x in p])
+    return int(lib().orc_morton60_point(q))
+
+
+def morton60_codes(boxes, scene):
+    """60-bit plain Morton codes (20 bits per axis) of AABB[n] or PRIM_REF[n] centroids: uint64 keys, iota values."""
+    n = boxes.size
+    keys = np.zeros(n, dtype=np.uint64)
+    vals = np.zeros(n, dtype=np.uint32)
+    base, stride = (C.c_void_p(boxes.ctypes.data + 4), 28) if boxes.dtype == T.PRIM_REF else (C.c_void_p(boxes.ctypes.data), 24)
+    lib().orc_morton60_codes(base, _u32(stride), _p(scene), _u32(n), _p(keys), _p(vals))
+    return keys, vals
+
+
+def sort_kv64(keys, vals):
+    n = keys.size
+    ko = np.zeros(n, dtype=np.uint64)
+    vo = np.zeros(n, dtype=np.uint32)
+    lib().orc_sort_kv64(_p(keys), _p(vals), _u32(n), _p(ko), _p(vo))
+    return ko, vo
+
+
 def sort_kv(keys, vals):
     n = keys.size
     ko = np.zeros(n, dtype=np.uint32)
@@ -131,17 +155,20 @@ def sort_kv(keys, vals):
 
 
 def lbvh_karras(refs, skeys, svals):
+    """skeys: uint32 (reference, 30-bit codes) or uint64 (60-bit variant)."""
     n = skeys.size
     nodes = np.zeros(2 * n - 1, dtype=T.BVH2_NODE)
     parents = np.zeros(2 * n - 1, dtype=np.uint32)
-    lib().orc_lbvh_karras(_p(refs), _p(skeys), _p(svals), _u32(n), _p(nodes), _p(parents))
+    f = lib().orc_lbvh_karras64 if skeys.dtype == np.uint64 else lib().orc_lbvh_karras
+    f(_p(refs), _p(skeys), _p(svals), _u32(n), _p(nodes), _p(parents))
     return nodes, parents
 
 
 def lbvh_apetrei(tris, skeys, svals):
     n = skeys.size
     nodes = np.zeros(2 * n - 1, dtype=T.BVH2_NODE)
-    root = lib().orc_lbvh_apetrei(_p(tris), _p(skeys), _p(svals), _u32(n), _p(nodes))
+    f = lib().orc_lbvh_apetrei64 if skeys.dtype == np.uint64 else lib().orc_lbvh_apetrei
+    root = f(_p(tris), _p(skeys), _p(svals), _u32(n), _p(nodes))
     return nodes, int(root)
 
 
@@ -283,7 +310,7 @@ def top_level(root_boxes):
 
 
 # ---- full pipelines (launch order of the reference builders) ----
-def build_lbvh(tris, single_pass=False, scene_override=None, split_sa_max=None):
+def build_lbvh(tris, single_pass=False, scene_override=None, split_sa_max=None, morton_bits=30):
     """TwoPassLbvh::build (TwoPassLbvh.cpp:17-197) / SinglePassLbvh::build (SinglePassLbvh.cpp:17-188).
     scene_override: AABB[1] global scene box of a sharded build (replaces the local union for Morton coding).
     split_sa_max: TwoPassLbvh compiled with USE_PRIM_SPLITTING (TwoPassLbvh.cpp:23-28): the build runs over the split references."""
@@ -293,8 +320,12 @@ def build_lbvh(tris, single_pass=False, scene_override=None, split_sa_max=None):
     refs, boxes, scene = primrefs(tris)
     if scene_override is not None:
         scene = scene_override
-    keys, vals = morton_codes(refs, scene)
-    sk, sv = sort_kv(keys, vals)
+    if morton_bits == 60:
+        keys, vals = morton60_codes(refs, scene)
+        sk, sv = sort_kv64(keys, vals)
+    else:
+        keys, vals = morton_codes(refs, scene)
+        sk, sv = sort_kv(keys, vals)
     if single_pass:
         nodes, root = lbvh_apetrei(tris, sk, sv)
     else:
@@ -341,14 +372,19 @@ def build_batched(tris, counts):
     return dict(nodes=nodes[:int(node_off[-1])], leaves=leaves, roots=roots, scenes=scenes, node_off=node_off, leaf_off=leaf_off)
 
 
-def build_ploc(tris, hierarchical=False, scene_override=None):
-    """PLOCNew::build (PLOC++Bvh.cpp:16-196) / HPLOC::build (Hploc.cpp:16-165)."""
+def build_ploc(tris, hierarchical=False, scene_override=None, morton_bits=30):
+    """PLOCNew::build (PLOC++Bvh.cpp:16-196) / HPLOC::build (Hploc.cpp:16-165).  morton_bits=60: PLOC++ only (it uses the sorted order alone)."""
     n = tris.size
     refs, boxes, scene = primrefs(tris)
     if scene_override is not None:
         scene = scene_override
-    keys, vals = morton_codes(boxes, scene)
-    sk, sv = sort_kv(keys, vals)
+    if morton_bits == 60:
+        assert not hierarchical
+        keys, vals = morton60_codes(boxes, scene)
+        sk, sv = sort_kv64(keys, vals)
+    else:
+        keys, vals = morton_codes(boxes, scene)
+        sk, sv = sort_kv(keys, vals)
     if hierarchical:
         nodes, leaves, stats = hploc(boxes, sk, sv)
     else:

@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--two-kernel", action="store_true")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--graph", action="store_true", help="replay the build from a CUDA graph (use_graph)")
+    ap.add_argument("--morton60", action="store_true", help="60-bit Morton variant (morton_bits=60)")
     ap.add_argument("--mesh", default="", help="bunny | sponza | buddha (staged under oracle/_ref/meshes) instead of the synthetic soup")
     a = ap.parse_args()
     ctx = capi.Context(0)
@@ -45,6 +46,12 @@ def main():
         print(f"batched: items={counts.size} x 32  build_ms(best)={best:.4f} -> {counts.size * 32 / best / 1e3:.1f} Mprims/s, {124 * counts.size * 32 / best / 1e6:.0f} GB/s algorithmic")
         return
     kw = {}
+    if a.morton60:
+        kw["morton_bits"] = 60
+        global_build0 = ctx.build
+        ctx.build = lambda *x, **y: global_build0(*x, **y, **kw)
+        kw_saved = dict(kw)
+        kw = {}
     if a.algo == "split":
         a.algo = "twopass"
         kw["split_sa_max"] = 6.0 * (1000.0 * a.n ** (-1.0 / 3.0)) ** 2
