@@ -408,6 +408,15 @@ def main():
                                               "frac_of_peak": bbytes / (bb.build_ms * 1e-3) / 1e9 / peak}
             except capi.B2bvhError as e:
                 widened["batched_builder"] = {"error": str(e)[:120]}
+            try:
+                for _ in range(3):
+                    ctx.build(capi.SINGLE_PASS_LBVH, d_tris, n=n, tris_on_device=True, morton_bits=60, use_graph=True)
+                b60 = min((ctx.build(capi.SINGLE_PASS_LBVH, d_tris, n=n, tris_on_device=True, morton_bits=60, use_graph=True) for _ in range(5)), key=lambda q: q.build_ms)
+                widened["morton60"] = {"builder": "SinglePassLbvh, morton_bits=60 (plain 20 bits per axis; two-digit LSD sort over the 32-bit radix sort)",
+                                       "build_ms": float(b60.build_ms), "Mprims_s": n / b60.build_ms / 1e3,
+                                       "extents_morton_sort_build_collapse_ms": [float(b60.stage_ms[k]) for k in (capi.T_EXTENTS, capi.T_MORTON, capi.T_SORT, capi.T_BUILD, capi.T_COLLAPSE)]}
+            except capi.B2bvhError as e:
+                widened["morton60"] = {"error": str(e)[:120]}
             line["widened_paths"] = widened
             # ---- the reference's own scenes (BASELINE configs[1]/[2]), when staged ----
             extras = {}

@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(LBVH_THREADS) lbvh_fused_kernel(const K* __res
 #define LBVH_GROUP_CAP (LBVH_GROUP * LBVH_TILE_CAP)
 #define LBVH_OVERFLOW 0xFFFFFFFFu
 #define LBVH_PAR_UNSET 0xFFFFFFFEu
-/* one cluster = one 32-bit word: [27:21] d + 1 (0 = outside the key array), [20:10] local index of the root node in the
+/* one cluster = one 32-bit word: [31:21] d + 1 (0 = outside the key array; at most 64 with 32-bit keys, 96 with 64-bit keys), [20:10] local index of the root node in the
  * staging buffer, [9:0] range start - b0 */
 #define LW_D_SHIFT 21
 #define LW_ID_SHIFT 10
@@ -157,9 +157,14 @@ struct LbvhTileSmem {
 __device__ __forceinline__ int boundary_depth(u32 keyA, u32 keyB, u32 a /* b = a + 1 */) {
   return __clzll((long long)(((u64)(keyA ^ keyB) << 32) | (u64)(a ^ (a + 1u))));
 }
+/* 64-bit keys (60-bit Morton variant): common prefix of the 96-bit augmented keys, 0..95 — still fits the depth field of a cluster word */
+__device__ __forceinline__ int boundary_depth(u64 keyA, u64 keyB, u32 a) {
+  const u64 kx = keyA ^ keyB;
+  return kx ? __clzll((long long)kx) : 64 + __clz((int)(a ^ (a + 1u)));
+}
 
-template <bool KARRAS>
-__global__ void __launch_bounds__(LBVH_TILE_THREADS, 8) lbvh_tile_kernel(const u32* __restrict__ keys, const u32* __restrict__ vals,
+template <bool KARRAS, typename K>
+__global__ void __launch_bounds__(LBVH_TILE_THREADS, 8) lbvh_tile_kernel(const K* __restrict__ keys, const u32* __restrict__ vals,
                                                                       const b2bvh_aabb* __restrict__ triAabb, u32 n, b2bvh_bvh2_node* nodes, u32* parents,
                                                                       u32* meet, u32* rootOut, u32* pendingCount, LbvhPending* pending, u32 pendingCap,
                                                                       uint2* tileInfo, LbvhPending* tileBuf, const u32* __restrict__ refPrim, u32* __restrict__ leafPrim) {
@@ -180,7 +185,7 @@ __global__ void __launch_bounds__(LBVH_TILE_THREADS, 8) lbvh_tile_kernel(const u
   if (tid < cnt0) {
     const u32 g = b0 + tid;
     const u32 prim = __ldg(vals + g);
-    const u32 k0 = __ldg(keys + g);
+    const K k0 = __ldg(keys + g);
     const float2* bp = reinterpret_cast<const float2*>(triAabb + prim); /* 24-byte boxes: 8-byte aligned */
     const float2 q0 = ldg_gather_f2(bp), q1 = ldg_gather_f2(bp + 1), q2 = ldg_gather_f2(bp + 2);
     int d = -1;
@@ -340,8 +345,8 @@ struct LbvhGroupSmem {
   u32 total, pendBase, forward;
 };
 
-template <bool KARRAS>
-__global__ void __launch_bounds__(256) lbvh_group_kernel(const u32* __restrict__ keys, u32 n, b2bvh_bvh2_node* nodes, u32* parents, u32* meet, u32* rootOut,
+template <bool KARRAS, typename K>
+__global__ void __launch_bounds__(256) lbvh_group_kernel(const K* __restrict__ keys, u32 n, b2bvh_bvh2_node* nodes, u32* parents, u32* meet, u32* rootOut,
                                                          u32* pendingCount, LbvhPending* pending, u32 pendingCap, const uint2* __restrict__ tileInfo,
                                                          const LbvhPending* __restrict__ tileBuf, u32 nTiles) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
@@ -495,8 +500,8 @@ __global__ void __launch_bounds__(256) lbvh_group_kernel(const u32* __restrict__
   }
 }
 
-template <bool KARRAS>
-__global__ void __launch_bounds__(LBVH_THREADS) lbvh_climb_kernel(const u32* __restrict__ keys, u32 n, b2bvh_bvh2_node* nodes, u32* parents, u32* meet,
+template <bool KARRAS, typename K>
+__global__ void __launch_bounds__(LBVH_THREADS) lbvh_climb_kernel(const K* __restrict__ keys, u32 n, b2bvh_bvh2_node* nodes, u32* parents, u32* meet,
                                                                   u32* rootOut, const u32* __restrict__ pendingCount,
                                                                   const LbvhPending* __restrict__ pending, u32 pendingCap) {
   const u32 count = min(*pendingCount, pendingCap);
@@ -585,17 +590,18 @@ size_t b2_lbvh_scratch_bytes(u32 n) {
   return fused > two ? fused : two;
 }
 
-int b2_launch_lbvh_fused(b2bvh_ctx* ctx, const u32* d_sortedKeys, const u32* d_sortedVals, const b2bvh_aabb* d_triAabb, u32 n,
+template <typename K>
+static int launch_lbvh_fused_t(b2bvh_ctx* ctx, const K* d_sortedKeys, const u32* d_sortedVals, const b2bvh_aabb* d_triAabb, u32 n,
                          b2bvh_bvh2_node* d_nodes, u32* d_parents, u32* d_scratch, u32* d_root, int karrasNumbering) {
   if (n > 1) B2_CUDA(cudaMemsetAsync(d_scratch, 0xFF, (size_t)(n - 1) * sizeof(u32), ctx->stream));
-  B2_KERNEL(ctx, karrasNumbering ? "lbvh_fused_karras" : "lbvh_fused_apetrei");
+  B2_KERNEL(ctx, sizeof(K) == 8 ? (karrasNumbering ? "lbvh_fused64_karras" : "lbvh_fused64_apetrei") : (karrasNumbering ? "lbvh_fused_karras" : "lbvh_fused_apetrei"));
   static const bool globalOnly = getenv("B2BVH_LBVH_GLOBAL_ONLY") != nullptr; /* development switch: the all-global-memory variant */
   if (globalOnly) {
     const u32 grid = (n + LBVH_THREADS - 1) / LBVH_THREADS;
     if (karrasNumbering)
-      lbvh_fused_kernel<true, u32><<<grid, LBVH_THREADS, 0, ctx->stream>>>(d_sortedKeys, d_sortedVals, d_triAabb, n, d_nodes, d_parents, d_scratch, d_root, ctx->ref_prim, ctx->ref_leaf_prim);
+      lbvh_fused_kernel<true, K><<<grid, LBVH_THREADS, 0, ctx->stream>>>(d_sortedKeys, d_sortedVals, d_triAabb, n, d_nodes, d_parents, d_scratch, d_root, ctx->ref_prim, ctx->ref_leaf_prim);
     else
-      lbvh_fused_kernel<false, u32><<<grid, LBVH_THREADS, 0, ctx->stream>>>(d_sortedKeys, d_sortedVals, d_triAabb, n, d_nodes, d_parents, d_scratch, d_root, ctx->ref_prim, ctx->ref_leaf_prim);
+      lbvh_fused_kernel<false, K><<<grid, LBVH_THREADS, 0, ctx->stream>>>(d_sortedKeys, d_sortedVals, d_triAabb, n, d_nodes, d_parents, d_scratch, d_root, ctx->ref_prim, ctx->ref_leaf_prim);
   } else {
     /* scratch: meet[n-1] | (16-byte aligned) pendingCount | pending[cap] | tileInfo[tiles] | tileBuf[tiles][LBVH_TILE_CAP] */
     const size_t off = (((size_t)n * 4 + 15) & ~(size_t)15);
@@ -611,24 +617,24 @@ int b2_launch_lbvh_fused(b2bvh_ctx* ctx, const u32* d_sortedKeys, const u32* d_s
     LbvhPending* tileBuf = useGroups ? reinterpret_cast<LbvhPending*>(reinterpret_cast<unsigned char*>(tileInfo) + (((size_t)grid * sizeof(uint2) + 15) & ~(size_t)15)) : nullptr;
     static bool attrSet = false;
     if (!attrSet) {
-      B2_CUDA(cudaFuncSetAttribute(lbvh_group_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LbvhGroupSmem)));
-      B2_CUDA(cudaFuncSetAttribute(lbvh_group_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LbvhGroupSmem)));
-      B2_CUDA(cudaFuncSetAttribute(lbvh_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LbvhTileSmem<true>)));
-      B2_CUDA(cudaFuncSetAttribute(lbvh_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LbvhTileSmem<false>)));
+      B2_CUDA(cudaFuncSetAttribute(lbvh_group_kernel<true, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LbvhGroupSmem)));
+      B2_CUDA(cudaFuncSetAttribute(lbvh_group_kernel<false, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LbvhGroupSmem)));
+      B2_CUDA(cudaFuncSetAttribute(lbvh_tile_kernel<true, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LbvhTileSmem<true>)));
+      B2_CUDA(cudaFuncSetAttribute(lbvh_tile_kernel<false, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LbvhTileSmem<false>)));
       attrSet = true;
     }
     if (karrasNumbering)
-      lbvh_tile_kernel<true><<<grid, LBVH_TILE_THREADS, sizeof(LbvhTileSmem<true>), ctx->stream>>>(d_sortedKeys, d_sortedVals, d_triAabb, n, d_nodes, d_parents, d_scratch, d_root, pendingCount, pending, cap, tileInfo, tileBuf, ctx->ref_prim, ctx->ref_leaf_prim);
+      lbvh_tile_kernel<true, K><<<grid, LBVH_TILE_THREADS, sizeof(LbvhTileSmem<true>), ctx->stream>>>(d_sortedKeys, d_sortedVals, d_triAabb, n, d_nodes, d_parents, d_scratch, d_root, pendingCount, pending, cap, tileInfo, tileBuf, ctx->ref_prim, ctx->ref_leaf_prim);
     else
-      lbvh_tile_kernel<false><<<grid, LBVH_TILE_THREADS, sizeof(LbvhTileSmem<false>), ctx->stream>>>(d_sortedKeys, d_sortedVals, d_triAabb, n, d_nodes, d_parents, d_scratch, d_root, pendingCount, pending, cap, tileInfo, tileBuf, ctx->ref_prim, ctx->ref_leaf_prim);
+      lbvh_tile_kernel<false, K><<<grid, LBVH_TILE_THREADS, sizeof(LbvhTileSmem<false>), ctx->stream>>>(d_sortedKeys, d_sortedVals, d_triAabb, n, d_nodes, d_parents, d_scratch, d_root, pendingCount, pending, cap, tileInfo, tileBuf, ctx->ref_prim, ctx->ref_leaf_prim);
     B2_LAUNCH_CHECK(ctx);
     if (useGroups) {
       const u32 groups = (grid + LBVH_GROUP - 1) / LBVH_GROUP;
       B2_KERNEL(ctx, "lbvh_group");
       if (karrasNumbering)
-        lbvh_group_kernel<true><<<groups, 256, sizeof(LbvhGroupSmem), ctx->stream>>>(d_sortedKeys, n, d_nodes, d_parents, d_scratch, d_root, pendingCount, pending, cap, tileInfo, tileBuf, grid);
+        lbvh_group_kernel<true, K><<<groups, 256, sizeof(LbvhGroupSmem), ctx->stream>>>(d_sortedKeys, n, d_nodes, d_parents, d_scratch, d_root, pendingCount, pending, cap, tileInfo, tileBuf, grid);
       else
-        lbvh_group_kernel<false><<<groups, 256, sizeof(LbvhGroupSmem), ctx->stream>>>(d_sortedKeys, n, d_nodes, d_parents, d_scratch, d_root, pendingCount, pending, cap, tileInfo, tileBuf, grid);
+        lbvh_group_kernel<false, K><<<groups, 256, sizeof(LbvhGroupSmem), ctx->stream>>>(d_sortedKeys, n, d_nodes, d_parents, d_scratch, d_root, pendingCount, pending, cap, tileInfo, tileBuf, grid);
       B2_LAUNCH_CHECK(ctx);
     }
     u32 grid2 = (cap + LBVH_THREADS - 1) / LBVH_THREADS;
@@ -636,27 +642,23 @@ int b2_launch_lbvh_fused(b2bvh_ctx* ctx, const u32* d_sortedKeys, const u32* d_s
     if (grid2 > cap2) grid2 = cap2;
     B2_KERNEL(ctx, "lbvh_climb");
     if (karrasNumbering)
-      lbvh_climb_kernel<true><<<grid2, LBVH_THREADS, 0, ctx->stream>>>(d_sortedKeys, n, d_nodes, d_parents, d_scratch, d_root, pendingCount, pending, cap);
+      lbvh_climb_kernel<true, K><<<grid2, LBVH_THREADS, 0, ctx->stream>>>(d_sortedKeys, n, d_nodes, d_parents, d_scratch, d_root, pendingCount, pending, cap);
     else
-      lbvh_climb_kernel<false><<<grid2, LBVH_THREADS, 0, ctx->stream>>>(d_sortedKeys, n, d_nodes, d_parents, d_scratch, d_root, pendingCount, pending, cap);
+      lbvh_climb_kernel<false, K><<<grid2, LBVH_THREADS, 0, ctx->stream>>>(d_sortedKeys, n, d_nodes, d_parents, d_scratch, d_root, pendingCount, pending, cap);
   }
   B2_LAUNCH_CHECK(ctx);
   return 0;
 }
 
-/* 64-bit sorted keys (60-bit Morton variant): the all-global-memory climb — one thread per leaf, the two children of a node meet
- * through one atomic exchange; the tile / group kernels above pack 32-bit keys into their cluster words and are not used here */
+int b2_launch_lbvh_fused(b2bvh_ctx* ctx, const u32* d_sortedKeys, const u32* d_sortedVals, const b2bvh_aabb* d_triAabb, u32 n,
+                         b2bvh_bvh2_node* d_nodes, u32* d_parents, u32* d_scratch, u32* d_root, int karrasNumbering) {
+  return launch_lbvh_fused_t<u32>(ctx, d_sortedKeys, d_sortedVals, d_triAabb, n, d_nodes, d_parents, d_scratch, d_root, karrasNumbering);
+}
+/* 64-bit sorted keys (60-bit Morton variant): the same tile / group / climb kernels instantiated for the wider key — only the boundary
+ * depth (common prefix of the 96-bit augmented keys) and the parent choice of the global climb look at key bits */
 int b2_launch_lbvh_fused64(b2bvh_ctx* ctx, const u64* d_sortedKeys64, const u32* d_sortedVals, const b2bvh_aabb* d_triAabb, u32 n,
                            b2bvh_bvh2_node* d_nodes, u32* d_parents, u32* d_scratch, u32* d_root, int karrasNumbering) {
-  if (n > 1) B2_CUDA(cudaMemsetAsync(d_scratch, 0xFF, (size_t)(n - 1) * sizeof(u32), ctx->stream));
-  const u32 grid = (n + LBVH_THREADS - 1) / LBVH_THREADS;
-  B2_KERNEL(ctx, karrasNumbering ? "lbvh_fused64_karras" : "lbvh_fused64_apetrei");
-  if (karrasNumbering)
-    lbvh_fused_kernel<true, u64><<<grid, LBVH_THREADS, 0, ctx->stream>>>(d_sortedKeys64, d_sortedVals, d_triAabb, n, d_nodes, d_parents, d_scratch, d_root, ctx->ref_prim, ctx->ref_leaf_prim);
-  else
-    lbvh_fused_kernel<false, u64><<<grid, LBVH_THREADS, 0, ctx->stream>>>(d_sortedKeys64, d_sortedVals, d_triAabb, n, d_nodes, d_parents, d_scratch, d_root, ctx->ref_prim, ctx->ref_leaf_prim);
-  B2_LAUNCH_CHECK(ctx);
-  return 0;
+  return launch_lbvh_fused_t<u64>(ctx, d_sortedKeys64, d_sortedVals, d_triAabb, n, d_nodes, d_parents, d_scratch, d_root, karrasNumbering);
 }
 
 int b2_launch_lbvh_karras_two_kernel(b2bvh_ctx* ctx, const u32* d_sortedKeys, const u32* d_sortedVals, const b2bvh_aabb* d_triAabb, u32 n,

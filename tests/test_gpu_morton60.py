@@ -48,6 +48,14 @@ def test_morton60_synthetic(ctx, oracle, algo, kind, n, seed):
     check60(ctx, oracle, random_tris(n, seed, kind), algo)
 
 
+@pytest.mark.parametrize("algo", ALGOS[:2], ids=["twopass", "singlepass"])
+@pytest.mark.parametrize("kind,n,seed", [("uniform", 70_001, 94), ("clustered", 50_000, 95), ("duplicate", 9000, 96)])
+def test_morton60_second_merge_level_forced(ctx, oracle, algo, kind, n, seed):
+    """The group kernel (second merge level, automatic only from 2^23 primitives) instantiated for 64-bit keys."""
+    check60(ctx, oracle, random_tris(n, seed, kind), algo, lbvh_second_level=1)
+    check60(ctx, oracle, random_tris(n, seed, kind), algo, lbvh_second_level=2)
+
+
 @pytest.mark.parametrize("mesh", ["cornellbox", "bunny"])
 def test_morton60_meshes(ctx, oracle, mesh):
     tris = load_mesh(mesh)
@@ -59,9 +67,13 @@ def test_morton60_meshes(ctx, oracle, mesh):
 
 def test_morton60_resolves_what_30_bits_cannot(ctx):
     """2 M uniform triangles: the sorted 60-bit codes are non-decreasing, (code, index) strictly increasing, the values a permutation, and
-    far fewer neighbours share a code than share its upper 30 bits (thousands of 30-bit collisions at this size)."""
+    far fewer neighbours share a code than share its upper 30 bits (thousands of 30-bit collisions at this size).  (numpy points: the
+    bench's synth_uniform_v1 stream repeats triangles — the reference's lcg/randf yields 24-bit sequences that depend on 24 seed bits.)"""
     n = 2_000_000
-    d = ctx.synth_uniform(n, 0xB20010)
+    rng = np.random.default_rng(93)
+    c = rng.uniform(-1000, 1000, size=(n, 1, 3))
+    tris = T.triangles_from_array((c + rng.uniform(-1, 1, size=(n, 3, 3))).astype(np.float32))
+    d = ctx.upload(tris)
     tree = ctx.build(capi.SINGLE_PASS_LBVH, d, n=n, tris_on_device=True, morton_bits=60)
     sk = ctx.download(tree.d_sortedMortonCodeKeys64, np.uint64, n)
     sv = ctx.download(tree.d_sortedMortonCodeValues, np.uint32, n)

@@ -49,8 +49,8 @@ def main():
     if a.morton60:
         kw["morton_bits"] = 60
         global_build0 = ctx.build
-        ctx.build = lambda *x, **y: global_build0(*x, **y, **kw)
-        kw_saved = dict(kw)
+        kw60 = dict(kw)
+        ctx.build = lambda *x, **y: global_build0(*x, **y, **kw60)
         kw = {}
     if a.algo == "split":
         a.algo = "twopass"
