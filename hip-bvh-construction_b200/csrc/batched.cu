@@ -12,7 +12,8 @@
  *                     deeper of its two boundaries (findParent, BatchedBuildKernel.h:136-159: smaller XOR of the augmented
  *                     keys = longer common prefix); two neighbours that pick the boundary between them become node hi-1 of
  *                     the left one — the index the reference's walk gives it.  All such pairs merge in the same round, the
- *                     list is compacted with one ballot + __fns, and the next round starts; no atomics, no fences.
+ *                     list is compacted with one ballot (survivor lanes through 32 words of shared memory), and the next round
+ *                     starts; no atomics, no fences.
  * Eight items per CTA; nodes leave as two 16-byte stores, leaf records (28 bytes) through a shared-memory transpose as
  * consecutive words.  Algorithmic traffic per triangle: 64 B read + 28 B leaf + 32 B node written.
  *
@@ -142,8 +143,13 @@ __global__ void __launch_bounds__(BATCH_WARPS * 32) batched_lbvh_kernel(const b2
       id = node;
       hi = nbHi;
     }
-    const u32 aliveMask = __ballot_sync(B2_FULL, active && !absorbed);
-    const u32 src = __fns(aliveMask, 0, lane + 1) & 31u; /* lane of the (lane+1)-th surviving cluster (garbage past the new count: unused) */
+    const bool alive = active && !absorbed;
+    const u32 aliveMask = __ballot_sync(B2_FULL, alive);
+    /* lane of the (lane+1)-th surviving cluster, through shared memory (__fns is a software loop: a fifth of the kernel's instructions) */
+    __syncwarp();
+    if (alive) S.val[__popc(aliveMask & lanemask_lt())] = lane;
+    __syncwarp();
+    const u32 src = S.val[lane] & 31u; /* stale past the new count: unused */
     lo = __shfl_sync(B2_FULL, lo, src); hi = __shfl_sync(B2_FULL, hi, src); id = __shfl_sync(B2_FULL, id, src);
     cb.lx = __shfl_sync(B2_FULL, cb.lx, src); cb.ly = __shfl_sync(B2_FULL, cb.ly, src); cb.lz = __shfl_sync(B2_FULL, cb.lz, src);
     cb.hx = __shfl_sync(B2_FULL, cb.hx, src); cb.hy = __shfl_sync(B2_FULL, cb.hy, src); cb.hz = __shfl_sync(B2_FULL, cb.hz, src);
