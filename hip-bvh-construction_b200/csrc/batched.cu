@@ -6,14 +6,16 @@
  * Morton codes, 32 one-bit split passes with a block prefix sum and two barriers each (a stable LSD sort), then the Apetrei
  * build with atomic counters in shared memory and __threadfence().  Here an item is ONE WARP and nothing leaves its registers
  * but the results:
- *   box + scene box   one triangle per lane (2 x 16-byte + 1 x 4-byte load), min/max butterflies
- *   sort              rank of (code, lane) by 32 broadcasts — the rank IS the stable sorted position
+ *   box + scene box   one triangle per lane (2 x 16-byte + 1 x 4-byte load), six redux.sync reductions on the integer image of the floats
+ *   sort              rank of (code, lane) against the 32 codes read back from shared memory — the rank IS the stable sorted position
  *   hierarchy         the sorted leaves are an ordered list of clusters, one per lane.  A cluster [lo, hi) joins the node at the
  *                     deeper of its two boundaries (findParent, BatchedBuildKernel.h:136-159: smaller XOR of the augmented
  *                     keys = longer common prefix); two neighbours that pick the boundary between them become node hi-1 of
- *                     the left one — the index the reference's walk gives it.  All such pairs merge in the same round, the
- *                     list is compacted with one ballot (survivor lanes through 32 words of shared memory), and the next round
- *                     starts; no atomics, no fences.
+ *                     the left one — the index the reference's walk gives it.  All such pairs merge in the same round; the list
+ *                     is a mask of live lanes and neighbour decisions are bit tests on ballots, so a round costs 7 shuffles
+ *                     (the absorbed neighbour's packed range/index word and box); no atomics, no fences.
+ * The shuffle pipe bounds this kernel: the first version (butterfly reductions, rank by 32 shuffles, register compaction after every
+ * round: ~260 shuffles per item) ran 0.46 ms for 312 500 items with mio_throttle as the top stall.
  * Eight items per CTA; nodes leave as two 16-byte stores, leaf records (28 bytes) through a shared-memory transpose as
  * consecutive words.  Algorithmic traffic per triangle: 64 B read + 28 B leaf + 32 B node written.
  *
@@ -37,6 +39,7 @@ __device__ __forceinline__ u32 morton3d_10(u32 x) { /* BatchedBuildKernel.h:89-9
 
 struct BatchWarpSmem {
   u64 xb[BATCH_MAX + 1];      /* xb[b] = augmented-key XOR across boundary b (between sorted leaves b-1 and b); ~0 outside */
+  __align__(16) u32 raw[BATCH_MAX]; /* codes in input order (rank computation) */
   u32 val[BATCH_MAX];         /* sorted position -> lane (= primitive) */
   u32 key[BATCH_MAX];
   u32 leaf[BATCH_MAX * 7];    /* PrimRef records of the item, staged for consecutive-word stores */
@@ -64,13 +67,13 @@ __global__ void __launch_bounds__(BATCH_WARPS * 32) batched_lbvh_kernel(const b2
     b.ly = fminf(fminf(fminf(b.ly, a.y), c.x), c.w); b.hy = fmaxf(fmaxf(fmaxf(b.hy, a.y), c.x), c.w);
     b.lz = fminf(fminf(fminf(b.lz, a.z), c.y), v3z); b.hz = fmaxf(fmaxf(fmaxf(b.hz, a.z), c.y), v3z);
   }
-  Box sc = b;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    sc.lx = fminf(sc.lx, __shfl_xor_sync(B2_FULL, sc.lx, o)); sc.ly = fminf(sc.ly, __shfl_xor_sync(B2_FULL, sc.ly, o));
-    sc.lz = fminf(sc.lz, __shfl_xor_sync(B2_FULL, sc.lz, o)); sc.hx = fmaxf(sc.hx, __shfl_xor_sync(B2_FULL, sc.hx, o));
-    sc.hy = fmaxf(sc.hy, __shfl_xor_sync(B2_FULL, sc.hy, o)); sc.hz = fmaxf(sc.hz, __shfl_xor_sync(B2_FULL, sc.hz, o));
-  }
+  /* six warp reductions in the integer image of the floats (redux.sync; unsigned order == float order, -0 < +0 as fminf/fmaxf
+   * order them; the boxes hold no NaN: fminf/fmaxf drop NaN vertices): 6 instructions instead of 30 shuffles — the kernel is bound
+   * by the shuffle pipe (profiles/r01s: mio_throttle on top with 260 shuffles per item) */
+  Box sc;
+  sc.lx = ordered_to_float(__reduce_min_sync(B2_FULL, float_to_ordered(b.lx))); sc.ly = ordered_to_float(__reduce_min_sync(B2_FULL, float_to_ordered(b.ly)));
+  sc.lz = ordered_to_float(__reduce_min_sync(B2_FULL, float_to_ordered(b.lz))); sc.hx = ordered_to_float(__reduce_max_sync(B2_FULL, float_to_ordered(b.hx)));
+  sc.hy = ordered_to_float(__reduce_max_sync(B2_FULL, float_to_ordered(b.hy))); sc.hz = ordered_to_float(__reduce_max_sync(B2_FULL, float_to_ordered(b.hz)));
   if (lane == 0) store_aabb(scenes + item, sc);
 
   /* ---- plain Morton code of the normalised centroid (:272-282, computeMortonCode :98-110); idle lanes sort last ---- */
@@ -87,11 +90,16 @@ __global__ void __launch_bounds__(BATCH_WARPS * 32) batched_lbvh_kernel(const b2
   }
 
   /* ---- stable sort (:285-297): position = number of (code, lane) pairs that order before mine ---- */
+  S.raw[lane] = key;
+  __syncwarp();
   u32 rank = 0;
 #pragma unroll
-  for (u32 j = 0; j < 32; j++) {
-    const u32 kj = __shfl_sync(B2_FULL, key, j);
-    rank += (kj < key || (kj == key && j < lane)) ? 1u : 0u;
+  for (u32 j = 0; j < 32; j += 4) { /* eight 16-byte broadcast reads instead of 32 shuffles */
+    const uint4 k4 = *reinterpret_cast<const uint4*>(S.raw + j);
+    rank += (k4.x < key || (k4.x == key && j + 0 < lane)) ? 1u : 0u;
+    rank += (k4.y < key || (k4.y == key && j + 1 < lane)) ? 1u : 0u;
+    rank += (k4.z < key || (k4.z == key && j + 2 < lane)) ? 1u : 0u;
+    rank += (k4.w < key || (k4.w == key && j + 3 < lane)) ? 1u : 0u;
   }
   S.key[rank] = key;
   S.val[rank] = lane;
@@ -122,39 +130,39 @@ __global__ void __launch_bounds__(BATCH_WARPS * 32) batched_lbvh_kernel(const b2
     for (u32 q = lane; q < n * 7; q += 32) dst[q] = S.leaf[q];
   }
 
-  /* ---- hierarchy: rounds of pairwise merges over the ordered cluster list (one cluster per lane) ---- */
-  u32 lo = lane, hi = lane + 1, id = (n - 1) + lane, count = n;
+  /* ---- hierarchy: rounds of pairwise merges over the ordered cluster list.  A cluster stays in the lane of its first leaf; the list
+   * is the set of live lanes (a mask), neighbours are the next live lanes, and every per-round decision that involves a neighbour is
+   * a bit test on a ballot — the only shuffles of a round fetch the absorbed neighbour's packed range/index word and its box ---- */
+  u32 meta = lane | ((lane + 1u) << 6) | (((n - 1u) + lane) << 12); /* [5:0] lo, [11:6] hi, [17:12] node id (leaf g = n-1+g <= 62) */
   Box cb = lb;
-  while (count > 1) {
-    const bool active = lane < count;
+  u32 aliveMask = n >= 32u ? B2_FULL : ((1u << n) - 1u);
+  const u32 gt = ~lanemask_lt() << 1; /* lanes above mine */
+  while (aliveMask & (aliveMask - 1u)) { /* more than one cluster */
+    const bool alive = (aliveMask >> lane) & 1u;
+    const u32 lo = meta & 63u, hi = (meta >> 6) & 63u;
     /* findParent (:136-159): right boundary when it is deeper than the left one (or there is no left one) */
-    const bool goRight = active && hi != n && (lo == 0 || S.xb[hi] < S.xb[lo]);
-    const bool nbGoRight = __shfl_down_sync(B2_FULL, goRight, 1);
-    const bool merge = active && (lane + 1 < count) && goRight && !nbGoRight; /* my right neighbour picked the same boundary */
-    const bool absorbed = __shfl_up_sync(B2_FULL, merge, 1) && lane > 0;
-    const u32 nbHi = __shfl_down_sync(B2_FULL, hi, 1), nbId = __shfl_down_sync(B2_FULL, id, 1);
+    const bool goRight = alive && hi != n && (lo == 0 || S.xb[hi] < S.xb[lo]);
+    const u32 grMask = __ballot_sync(B2_FULL, goRight);
+    const u32 above = aliveMask & gt;
+    const u32 r = above ? (u32)__ffs((int)above) - 1u : lane; /* my right neighbour */
+    const bool merge = goRight && above && !((grMask >> r) & 1u); /* it picked the boundary between us as well */
+    const u32 mergeMask = __ballot_sync(B2_FULL, merge);
+    const u32 nbMeta = __shfl_sync(B2_FULL, meta, r);
     Box nb;
-    nb.lx = __shfl_down_sync(B2_FULL, cb.lx, 1); nb.ly = __shfl_down_sync(B2_FULL, cb.ly, 1); nb.lz = __shfl_down_sync(B2_FULL, cb.lz, 1);
-    nb.hx = __shfl_down_sync(B2_FULL, cb.hx, 1); nb.hy = __shfl_down_sync(B2_FULL, cb.hy, 1); nb.hz = __shfl_down_sync(B2_FULL, cb.hz, 1);
+    nb.lx = __shfl_sync(B2_FULL, cb.lx, r); nb.ly = __shfl_sync(B2_FULL, cb.ly, r); nb.lz = __shfl_sync(B2_FULL, cb.lz, r);
+    nb.hx = __shfl_sync(B2_FULL, cb.hx, r); nb.hy = __shfl_sync(B2_FULL, cb.hy, r); nb.hz = __shfl_sync(B2_FULL, cb.hz, r);
     if (merge) {
-      const u32 node = hi - 1; /* Apetrei: the node's index is its split position */
+      const u32 node = hi - 1u; /* Apetrei: the node's index is its split position */
       cb = box_union(cb, nb);
-      store_node2(nodes + nOff + node, id, nbId, cb);
-      id = node;
-      hi = nbHi;
+      store_node2(nodes + nOff + node, meta >> 12, nbMeta >> 12, cb);
+      meta = lo | (nbMeta & (63u << 6)) | (node << 12);
     }
-    const bool alive = active && !absorbed;
-    const u32 aliveMask = __ballot_sync(B2_FULL, alive);
-    /* lane of the (lane+1)-th surviving cluster, through shared memory (__fns is a software loop: a fifth of the kernel's instructions) */
-    __syncwarp();
-    if (alive) S.val[__popc(aliveMask & lanemask_lt())] = lane;
-    __syncwarp();
-    const u32 src = S.val[lane] & 31u; /* stale past the new count: unused */
-    lo = __shfl_sync(B2_FULL, lo, src); hi = __shfl_sync(B2_FULL, hi, src); id = __shfl_sync(B2_FULL, id, src);
-    cb.lx = __shfl_sync(B2_FULL, cb.lx, src); cb.ly = __shfl_sync(B2_FULL, cb.ly, src); cb.lz = __shfl_sync(B2_FULL, cb.lz, src);
-    cb.hx = __shfl_sync(B2_FULL, cb.hx, src); cb.hy = __shfl_sync(B2_FULL, cb.hy, src); cb.hz = __shfl_sync(B2_FULL, cb.hz, src);
-    count = __popc(aliveMask);
+    /* the absorbed clusters are the right neighbours of the merging ones: the live lane just above each set bit of mergeMask */
+    const u32 below = aliveMask & lanemask_lt();
+    const bool absorbed = alive && below && ((mergeMask >> (31u - (u32)__clz((int)below))) & 1u);
+    aliveMask &= ~__ballot_sync(B2_FULL, absorbed);
   }
+  const u32 id = meta >> 12; /* lane 0 is never absorbed: it holds the root */
   if (lane == 0) roots[item] = (n == 1) ? 0u : id; /* rootNodes[item] (:311) */
 }
 
