@@ -9,7 +9,12 @@ Rank r owns triangles [r*N/G, (r+1)*N/G).  Per build:
   5. every rank builds the same top-level tree over the G roots     (b2bvh_top_level, on the GPU)
 The collectives carry bytes, not bandwidth; they ride on torch.distributed (NCCL over NVLink on the GPUs; gloo in the
 CPU tests, where the per-rank engine is a test double).  No other data-path exchange exists: the result is G sub-trees +
-a top tree (not node-identical to a single-GPU build of the whole input; parity is per shard and for the top tree)."""
+a top tree (not node-identical to a single-GPU build of the whole input; parity is per shard and for the top tree).
+
+Primary rays through the sharded tree: the rays are replicated, every rank traces its own sub-tree with the
+single-GPU traversal kernel, and the closest hit per ray is ONE all-reduce(MIN) over packed 64-bit words
+(bits of t << 32 | global primitive index; t >= 0, so the bit pattern orders like the value; a miss is all ones) followed by
+one all-reduce(SUM) in which only the winning rank contributes the barycentrics."""
 import numpy as np
 
 
@@ -52,6 +57,34 @@ class ShardedBuild:
         top = self.engine.top_level(roots)
         return dict(scene=scene, tree=tree, roots=roots, top=top)
 
+    MISS = (1 << 63) - 1
+
+    def trace(self, built, rays, n_rays, transform, prim_offset, kernel=0):
+        """Closest hits of `rays` (replicated on every rank) through the sharded tree.  built: the dict build() returned;
+        prim_offset: first global primitive index of this rank's shard.  Returns (t float32[n], prim int64[n] global index or -1,
+        uv float32[n,2]) as tensors on the collective's device, identical on every rank."""
+        import torch
+        key, uv = self.engine.trace(built["tree"], rays, n_rays, transform, prim_offset, kernel)
+        best = key.clone()
+        if self.world > 1:
+            self.dist.all_reduce(best, op=self.dist.ReduceOp.MIN)
+        hit = best != self.MISS
+        mine = (key == best) & hit
+        uv = torch.where(mine.unsqueeze(1), uv, torch.zeros_like(uv))
+        if self.world > 1:
+            self.dist.all_reduce(uv, op=self.dist.ReduceOp.SUM)
+        t = torch.where(hit, (best >> 32).to(torch.int32).view(torch.float32), torch.full_like(best, 0, dtype=torch.float32))
+        prim = torch.where(hit, best & 0xFFFFFFFF, torch.full_like(best, -1))
+        return t, prim, uv
+
+
+def pack_hits(torch, prim_u32_as_i32, t_f32, prim_offset):
+    """(t bits << 32) | (primIdx + prim_offset), all ones... MISS for primIdx == 0xFFFFFFFF.  t >= 0: bit order == value order."""
+    prim = prim_u32_as_i32.to(torch.int64) & 0xFFFFFFFF
+    tb = t_f32.view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+    key = (tb << 32) | (prim + int(prim_offset))
+    return torch.where(prim == 0xFFFFFFFF, torch.full_like(key, ShardedBuild.MISS), key)
+
 
 class GpuEngine:
     """The real engine: one b2bvh Context on this rank's GPU (stream shared with torch so NCCL and the kernels are ordered)."""
@@ -93,3 +126,15 @@ class GpuEngine:
             self.top_nodes = self.torch.zeros((2 * g - 1) * 8, dtype=self.torch.float32, device="cuda")
         self.capi.check(self.ctx.lib.b2bvh_top_level(self.ctx.h, roots.data_ptr(), g, self.top_nodes.data_ptr()), "b2bvh_top_level")
         return self.top_nodes
+
+    def trace(self, tree, rays, n_rays, transform, prim_offset, kernel=0):
+        """rays: device pointer of RAY[n_rays] (b2bvh_generate_rays).  HitInfo lands in a torch buffer on the shared stream."""
+        torch = self.torch
+        hits = torch.empty((n_rays, 8), dtype=torch.int32, device="cuda")  # HitInfo: primIdx, t, u, v, pad[4] (32 B)
+        tr = np.ascontiguousarray(transform)
+        ms = self.capi.C.c_float()
+        self.capi.check(self.ctx.lib.b2bvh_traverse(self.ctx.h, self.capi.C.byref(tree), self.capi.C.c_void_p(int(rays)), n_rays,
+                                                    tr.ctypes.data_as(self.capi.C.c_void_p), int(kernel), self.capi.C.c_void_p(hits.data_ptr()), None,
+                                                    self.capi.C.byref(ms)), "b2bvh_traverse")
+        key = pack_hits(torch, hits[:, 0], hits[:, 1].view(torch.float32), prim_offset)
+        return key, hits[:, 2:4].view(torch.float32).contiguous()

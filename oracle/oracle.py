@@ -408,3 +408,28 @@ def build_sharded(tris, world, single_pass=True):
     for r, s in enumerate(shards):
         roots[r]["mn"] = s["nodes"][s["root"]]["mn"]; roots[r]["mx"] = s["nodes"][s["root"]]["mx"]
     return scene, shards, top_level(roots)
+
+
+def trace_sharded(tris, world, rays, transform, single_pass=True):
+    """Primary rays through a sharded build, restated sequentially (b2bvh/sharded.py ShardedBuild.trace): every shard's sub-tree is
+    traced on its own, the closest hit per ray is the minimum over (bits of t << 32 | global primitive index).
+    Returns t float32[n], prim int64[n] (global index, -1 = miss), uv float32[n,2]."""
+    n = tris.size
+    _, shards, _ = build_sharded(tris, world, single_pass=single_pass)
+    miss = np.int64((1 << 63) - 1)
+    best = np.full(rays.size, miss, dtype=np.int64)
+    uv = np.zeros((rays.size, 2), dtype=np.float32)
+    for r, s in enumerate(shards):
+        a, b = (n * r) // world, (n * (r + 1)) // world
+        hits, _ = traverse(rays, s["nodes"], None, np.ascontiguousarray(tris[a:b]), transform, s["root"], b - a)
+        hit = hits["primIdx"] != 0xFFFFFFFF
+        key = (hits["t"].view(np.uint32).astype(np.int64) << 32) | (hits["primIdx"].astype(np.int64) + a)
+        key = np.where(hit, key, miss)
+        better = key < best
+        best = np.where(better, key, best)
+        uv[better] = hits["uv"][better]
+    hit = best != miss
+    t = np.where(hit, (best >> 32).astype(np.uint32).view(np.float32), np.float32(0))
+    prim = np.where(hit, best & 0xFFFFFFFF, -1)
+    return t.astype(np.float32), prim.astype(np.int64), uv
+

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from conftest import GOLDEN, load_mesh, random_tris
-from b2bvh import capi
+from b2bvh import capi, types as T
 
 pytestmark = pytest.mark.gpu
 KA = json.load(open(os.path.join(GOLDEN, "known_answers.json")))
@@ -197,3 +197,57 @@ def test_graph_replay_builds_the_same_tree(ctx, oracle, algo):
     h = ctx.fetch(ctx.build(algo, tris, use_graph=True))  # host triangles: the upload is part of the graph
     assert h["nodes"].tobytes() == plain["nodes"].tobytes()
     ctx.free(d); ctx.free(d2)
+
+
+def test_baseline_config_10m_properties(ctx):
+    """BASELINE configs[3] at full size — 10 M synth_uniform_v1 triangles, single-pass LBVH + Bvh4 collapse (the bench workload) —
+    through size-independent properties, vectorised: sorted + stable + a permutation; every Bvh2 box is the union of its children;
+    every node has exactly one parent and the root none; the root box is the scene box; Bvh4: child slots are packed, every wide node
+    but the root is the child of exactly one wide node, every leaf slot appears once, parents point back."""
+    n = 10_000_000
+    d = ctx.synth_uniform(n, 0x00B20010)
+    tree = ctx.build(capi.SINGLE_PASS_LBVH, d, n=n, tris_on_device=True)
+    nInt = n - 1
+    sk = ctx.download(tree.d_sortedMortonCodeKeys, np.uint32, n)
+    sv = ctx.download(tree.d_sortedMortonCodeValues, np.uint32, n)
+    keys = ctx.download(tree.d_mortonCodeKeys, np.uint32, n)
+    assert np.all(sk[1:] >= sk[:-1])
+    eq = sk[1:] == sk[:-1]
+    assert np.all(sv[1:][eq] > sv[:-1][eq])
+    seen = np.zeros(n, dtype=np.uint8); seen[sv] = 1
+    assert seen.all() and np.array_equal(keys[sv], sk)
+    del keys, seen, eq
+    nodes = ctx.download(tree.d_bvhNodes, T.BVH2_NODE, 2 * n - 1)
+    boxes = ctx.download(tree.d_triangleAabb, T.AABB, n)
+    assert np.array_equal(nodes["left"][nInt:], sv) and (nodes["right"][nInt:] == 0xFFFFFFFF).all()
+    assert np.array_equal(nodes["mn"][nInt:], boxes["mn"][sv]) and np.array_equal(nodes["mx"][nInt:], boxes["mx"][sv])
+    l, r = nodes["left"][:nInt].astype(np.int64), nodes["right"][:nInt].astype(np.int64)
+    assert l.max() < 2 * n - 1 and r.max() < 2 * n - 1
+    assert np.array_equal(nodes["mn"][:nInt], np.minimum(nodes["mn"][l], nodes["mn"][r]))
+    assert np.array_equal(nodes["mx"][:nInt], np.maximum(nodes["mx"][l], nodes["mx"][r]))
+    refs = np.bincount(np.concatenate([l, r]), minlength=2 * n - 1)
+    assert refs[tree.root] == 0 and (np.delete(refs, tree.root) == 1).all()
+    scene = ctx.download(tree.d_sceneExtents, T.AABB, 1)
+    assert np.array_equal(nodes["mn"][tree.root], scene["mn"][0]) and np.array_equal(nodes["mx"][tree.root], scene["mx"][0])
+    del refs, boxes
+    nw = tree.n_wide
+    wide = ctx.download(tree.d_wideBvhNodes, T.BVH4_NODE, nw)
+    wl = ctx.download(tree.d_wideLeafNodes, T.PRIM_NODE, n)
+    ch = wide["child"]
+    valid = ch != 0xFFFFFFFF
+    cnt = valid.sum(axis=1)
+    assert np.array_equal(cnt, wide["childCount"]) and cnt.min() >= 2
+    assert (valid[:, :-1] >= valid[:, 1:]).all()                      # packed: no hole before a used slot
+    internal = valid & (ch < nInt)
+    leaf = valid & (ch >= nInt)
+    ic = ch[internal]
+    assert ic.max() < nw and np.array_equal(np.sort(ic), np.arange(1, nw, dtype=np.uint32))   # BFS numbering: every non-root node once
+    owner = np.repeat(np.arange(nw, dtype=np.uint32), 4).reshape(nw, 4)
+    assert np.array_equal(wide["parent"][ic], owner[internal]) and wide["parent"][0] == 0xFFFFFFFF
+    lc = ch[leaf] - nInt
+    assert np.array_equal(np.sort(lc), np.arange(n, dtype=np.uint32))
+    assert np.array_equal(wl["primIdx"][lc], sv[lc]) and np.array_equal(wl["parent"][lc], owner[leaf])
+    # internal child boxes of a wide node are the Bvh2 boxes... of SOME Bvh2 node: check containment in the root box and non-emptiness
+    ib = wide["aabb"][internal]
+    assert (ib[:, :3] <= ib[:, 3:]).all() and (ib[:, :3] >= scene["mn"][0]).all() and (ib[:, 3:] <= scene["mx"][0]).all()
+    ctx.free(d)

@@ -41,3 +41,55 @@ def test_shard_with_device_scene_box(ctx, oracle, algo):
     finally:
         ctx.free(d_box6)
         ctx.free(d_local)
+
+
+def test_sharded_trace_on_one_gpu(oracle):
+    """Primary rays through a 2-shard build: each shard's GpuEngine traces its sub-tree on the device and packs (bits of t, global
+    primitive) words; their element-wise minimum — what the all-reduce(MIN) of ShardedBuild.trace computes across ranks (covered with gloo
+    in tests/test_sharded_gloo.py) — equals the oracle's sequential restatement, and world = 1 through ShardedBuild equals the plain kernel."""
+    import torch
+    from b2bvh import types as T
+    from b2bvh.sharded import GpuEngine, ShardedBuild, shard_range
+    n, world = 40_000, 2
+    tris = random_tris(n, 78)
+    tr = T.make_transform([0.0, 0.0, 0.0], [1.0, 1.0, 1.0], [0.0, 0.0, 0.0, 1.0])
+    cam = T.make_camera([0.0, 0.0, 400.0, 0.0], [0.0, 0.0, 0.0, 1.0], np.float32(0.6))
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        ctxs = [capi.Context(0, stream=stream.cuda_stream) for _ in range(world)]
+        d_rays, _ = ctxs[0].generate_rays(cam, 128, 128)
+        rays = ctxs[0].download(d_rays, T.RAY, 128 * 128)
+        v = tris["v"].reshape(-1, 3)
+        box6 = torch.from_numpy(np.concatenate([-v.min(axis=0), v.max(axis=0)]).astype(np.float32)).cuda()
+        keys, uvs = [], []
+        for r in range(world):
+            a, b = shard_range(n, r, world)
+            shard = np.ascontiguousarray(tris[a:b])
+            eng = GpuEngine(ctxs[r], capi.SINGLE_PASS_LBVH)
+            eng.shard_extents(shard)
+            _, tree = eng.build(shard, box6)
+            k, uv = eng.trace(tree, d_rays, 128 * 128, tr, a)
+            keys.append(k); uvs.append(uv)
+        best = torch.minimum(keys[0], keys[1])
+        uv = torch.where((keys[0] == best).unsqueeze(1), uvs[0], uvs[1])
+        stream.synchronize()
+        t, prim, ouv = oracle.trace_sharded(tris, world, rays, tr)
+        hit = prim >= 0
+        assert hit.sum() > 500
+        bk = best.cpu().numpy()
+        assert np.array_equal(bk != ShardedBuild.MISS, hit)
+        assert np.array_equal((bk[hit] >> 32).astype(np.uint32), t[hit].view(np.uint32)) and np.array_equal(bk[hit] & 0xFFFFFFFF, prim[hit])
+        assert np.array_equal(uv.cpu().numpy()[hit].view(np.uint32), ouv[hit].view(np.uint32))
+        # world = 1: ShardedBuild.trace is the plain kernel
+        eng = GpuEngine(ctxs[0], capi.SINGLE_PASS_LBVH)
+        sb = ShardedBuild(eng)
+        built = sb.build(tris)
+        t1, p1, uv1 = sb.trace(built, d_rays, 128 * 128, tr, 0)
+        hits, _, _ = ctxs[0].traverse(built["tree"], d_rays, 128 * 128, tr)
+        h = hits["primIdx"] != 0xFFFFFFFF
+        assert np.array_equal(p1.cpu().numpy() >= 0, h) and np.array_equal(p1.cpu().numpy()[h], hits["primIdx"][h].astype(np.int64))
+        assert np.array_equal(t1.cpu().numpy()[h].view(np.uint32), hits["t"][h].view(np.uint32))
+        assert np.array_equal(uv1.cpu().numpy()[h].view(np.uint32), hits["uv"][h].view(np.uint32))
+        ctxs[0].free(d_rays)
+        for c in ctxs:
+            c.close()

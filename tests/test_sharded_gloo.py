@@ -32,8 +32,15 @@ class OracleEngine:
         sc = np.zeros(1, dtype=T.AABB)
         sc["mn"] = scene6[:3]; sc["mx"] = scene6[3:]
         b = self.orc.build_lbvh(tris, single_pass=True, scene_override=sc)
+        b["tris"] = tris
         root = b["nodes"][b["root"]]
         return np.concatenate([root["mn"], root["mx"]]), b
+
+    def trace(self, tree, rays, n_rays, transform, prim_offset, kernel=0):
+        from b2bvh.sharded import pack_hits
+        hits, _ = self.orc.traverse(rays, tree["nodes"], None, tree["tris"], transform, tree["root"], tree["tris"].size)
+        key = pack_hits(torch, torch.from_numpy(hits["primIdx"].view(np.int32).copy()), torch.from_numpy(hits["t"].copy()), prim_offset)
+        return key, torch.from_numpy(hits["uv"].copy())
 
     def top_level(self, roots):
         from b2bvh import types as T
@@ -41,6 +48,13 @@ class OracleEngine:
         boxes = np.zeros(r.shape[0], dtype=T.AABB)
         boxes["mn"] = r[:, :3]; boxes["mx"] = r[:, 3:]
         return self.orc.top_level(boxes)
+
+
+def _scene(orc):
+    from b2bvh import types as T
+    tr = T.make_transform([0.0, 0.0, 0.0], [1.0, 1.0, 1.0], [0.0, 0.0, 0.0, 1.0])
+    cam = T.make_camera([0.0, 0.0, 400.0, 0.0], [0.0, 0.0, 0.0, 1.0], np.float32(0.6))
+    return tr, orc.generate_rays(cam, 48, 48)
 
 
 def _worker(rank, world, port, n, out_dir):
@@ -55,6 +69,12 @@ def _worker(rank, world, port, n, out_dir):
     np.save(os.path.join(out_dir, f"top{rank}.npy"), res["top"].view(np.uint8))
     np.save(os.path.join(out_dir, f"scene{rank}.npy"), res["scene"])
     np.save(os.path.join(out_dir, f"nodes{rank}.npy"), res["tree"]["nodes"].view(np.uint8))
+    # primary rays through the sharded tree: replicated rays, one all-reduce(MIN) of packed hits + one all-reduce(SUM) of the barycentrics
+    tr, rays = _scene(orc)
+    sb = ShardedBuild(OracleEngine(orc), dist, rank, world)
+    t, prim, uv = sb.trace(res, rays, rays.size, tr, a)
+    np.save(os.path.join(out_dir, f"trace_t{rank}.npy"), t.numpy()); np.save(os.path.join(out_dir, f"trace_p{rank}.npy"), prim.numpy())
+    np.save(os.path.join(out_dir, f"trace_uv{rank}.npy"), uv.numpy())
     dist.destroy_process_group()
 
 
@@ -70,6 +90,16 @@ def test_sharded_build_two_ranks(oracle, tmp_path, world):
         assert np.array_equal(np.load(tmp_path / f"scene{r}.npy"), np.concatenate([scene["mn"][0], scene["mx"][0]]))
         assert np.load(tmp_path / f"top{r}.npy").tobytes() == top.tobytes()          # every rank holds the same top-level tree
         assert np.load(tmp_path / f"nodes{r}.npy").tobytes() == shards[r]["nodes"].tobytes()  # shard tree in the GLOBAL frame
+    # sharded primary rays: every rank ends with the sequential restatement's hits, and those are the hits of ONE tree over all triangles
+    tr, rays = _scene(oracle)
+    t, prim, uv = oracle.trace_sharded(tris, world, rays, tr)
+    for r in range(world):
+        assert np.array_equal(np.load(tmp_path / f"trace_t{r}.npy").view(np.uint32), t.view(np.uint32))
+        assert np.array_equal(np.load(tmp_path / f"trace_p{r}.npy"), prim) and np.array_equal(np.load(tmp_path / f"trace_uv{r}.npy").view(np.uint32), uv.view(np.uint32))
+    whole = oracle.build_lbvh(tris, single_pass=True)
+    hits, cnt = oracle.traverse(rays, whole["nodes"], None, tris, tr, whole["root"], n)
+    assert cnt > 20 and np.array_equal(hits["primIdx"] != 0xFFFFFFFF, prim >= 0)
+    assert np.array_equal(hits["t"][prim >= 0].view(np.uint32), t[prim >= 0].view(np.uint32))
     # shards partition the input
     from b2bvh.sharded import shard_range
     cover = [shard_range(n, r, world) for r in range(world)]
