@@ -44,6 +44,21 @@ def main():
     stream.synchronize()
     ms = e0.elapsed_time(e1) / 5
     if rank == 0:
+        import time
+        eng = sb.engine
+        def timed(f, reps=5):
+            stream.synchronize(); t0 = time.perf_counter()
+            for _ in range(reps):
+                r = f()
+            stream.synchronize(); return (time.perf_counter() - t0) / reps * 1e3, r
+        ta, (key, uvv) = timed(lambda: eng.trace(built["tree"], d_rays, nr, tr, first))
+        hitsbuf = torch.empty((nr, 8), dtype=torch.int32, device="cuda")
+        from b2bvh.sharded import pack_hits
+        tb, _ = timed(lambda: pack_hits(torch, hitsbuf[:, 0], hitsbuf[:, 1].view(torch.float32), first))
+        tc, _ = timed(lambda: ctx.lib.b2bvh_traverse(ctx.h, capi.C.byref(built["tree"]), capi.C.c_void_p(int(d_rays)), nr, tr.ctypes.data_as(capi.C.c_void_p), 0,
+                                                     capi.C.c_void_p(hitsbuf.data_ptr()), None, capi.C.byref(capi.C.c_float())))
+        print(f"  pieces (host ms): engine.trace {ta:.3f} = b2bvh_traverse {tc:.3f} + pack {tb:.3f}; whole ShardedBuild.trace {ms:.3f}")
+    if rank == 0:
         d_all = ctx.synth_uniform(a.n, 0x00B20010, half=half)
         whole = ctx.build(capi.SINGLE_PASS_LBVH, d_all, n=a.n, tris_on_device=True, collapse=False)
         hits, _, ms1 = ctx.traverse(whole, d_rays, nr, tr)
