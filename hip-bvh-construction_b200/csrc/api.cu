@@ -233,7 +233,6 @@ int b2bvh_build(b2bvh_ctx* ctx, int algo, const b2bvh_triangle* tris, uint32_t n
   const bool m60 = opts.morton_bits == 60;
   if (opts.morton_bits != 0 && opts.morton_bits != 30 && opts.morton_bits != 60)
     return b2_fail(B2BVH_ERR_INVALID, "build: morton_bits must be 0/30 (the reference's extended 30-bit code) or 60, got %u", opts.morton_bits);
-  if (m60 && algo == B2BVH_HPLOC) return b2_fail(B2BVH_ERR_INVALID, "build: morton_bits=60 is not available for B2BVH_HPLOC (its hierarchy walks the 32-bit codes)");
   if (m60 && opts.karras_two_kernel) return b2_fail(B2BVH_ERR_INVALID, "build: morton_bits=60 cannot be combined with karras_two_kernel");
 
   /* ---- buffers (grown on demand, reused) ---- */
@@ -358,8 +357,8 @@ int b2bvh_build(b2bvh_ctx* ctx, int algo, const b2bvh_triangle* tris, uint32_t n
       B2_CUDA(cudaMemsetAsync(dRoot, 0, 4, s));
       break;
     case B2BVH_HPLOC:
-      B2_TRY(b2_launch_hploc(ctx, (const b2bvh_aabb*)dAabb, (const u32*)dSKeys, (const u32*)dSVals, n, (b2bvh_bvh2_node*)dNodes,
-                             (b2bvh_prim_ref*)dLeaves, dMerge, &iterations));
+      B2_TRY(b2_launch_hploc_keys(ctx, (const b2bvh_aabb*)dAabb, (const u32*)dSKeys, m60 ? (const u64*)dSKeys64 : nullptr, (const u32*)dSVals, n,
+                                  (b2bvh_bvh2_node*)dNodes, (b2bvh_prim_ref*)dLeaves, dMerge, &iterations));
       B2_CUDA(cudaMemsetAsync(dRoot, 0, 4, s));
       break;
   }

@@ -139,7 +139,21 @@ __device__ void hploc_merge_warp(u32 L, u32 R, u32 split, bool fin, u32 n, b2bvh
   }
 }
 
-__global__ void __launch_bounds__(HP_THREADS) hploc_kernel(const u32* __restrict__ keys, u32 n, b2bvh_bvh2_node* nodes,
+/* findParent's comparison (HplocKernel.h:58-81): is the boundary right of leaf R deeper than the boundary left of leaf L? */
+__device__ __forceinline__ bool hp_right_deeper(const u32* __restrict__ keys, u32 L, u32 R) {
+  const u64 kR = ((u64)__ldg(keys + R) << 32) | R, kR1 = ((u64)__ldg(keys + R + 1) << 32) | (R + 1);
+  const u64 kL = ((u64)__ldg(keys + L) << 32) | L, kL1 = ((u64)__ldg(keys + L - 1) << 32) | (L - 1);
+  return (kR ^ kR1) < (kL1 ^ kL);
+}
+/* 64-bit keys (60-bit Morton variant): 96-bit augmented keys — key XORs first, index XORs on a tie */
+__device__ __forceinline__ bool hp_right_deeper(const u64* __restrict__ keys, u32 L, u32 R) {
+  const u64 xr = __ldg(keys + R) ^ __ldg(keys + R + 1), xl = __ldg(keys + L - 1) ^ __ldg(keys + L);
+  if (xr != xl) return xr < xl;
+  return (R ^ (R + 1)) < ((L - 1) ^ L);
+}
+
+template <typename K>
+__global__ void __launch_bounds__(HP_THREADS) hploc_kernel(const K* __restrict__ keys, u32 n, b2bvh_bvh2_node* nodes,
                                                           const b2bvh_prim_ref* __restrict__ leaves, u32* nodeIdx, u32* freeIdx, u32* meet, u32* ctrl) {
   const u32 i = blockIdx.x * HP_THREADS + threadIdx.x;
   bool active = i < n;
@@ -152,11 +166,7 @@ __global__ void __launch_bounds__(HP_THREADS) hploc_kernel(const u32* __restrict
       bool isLeft;
       if (L == 0) isLeft = true;
       else if (R == n - 1) isLeft = false;
-      else {
-        const u64 kR = ((u64)__ldg(keys + R) << 32) | R, kR1 = ((u64)__ldg(keys + R + 1) << 32) | (R + 1);
-        const u64 kL = ((u64)__ldg(keys + L) << 32) | L, kL1 = ((u64)__ldg(keys + L - 1) << 32) | (L - 1);
-        isLeft = (kR ^ kR1) < (kL1 ^ kL);
-      }
+      else isLeft = hp_right_deeper(keys, L, R);
       const u32 parent = isLeft ? R : L - 1;
       /* Relaxed exchange + fences where they are needed: what a lane hands over was either written by an earlier launch
        * (leaves, initial lists) or is covered by the fence every lane executes after a merge call (below), so the first
@@ -189,6 +199,12 @@ __global__ void __launch_bounds__(HP_THREADS) hploc_kernel(const u32* __restrict
 
 int b2_launch_hploc(b2bvh_ctx* ctx, const b2bvh_aabb* d_triAabb, const u32* d_sortedKeys, const u32* d_sortedVals, u32 n,
                     b2bvh_bvh2_node* d_nodes, b2bvh_prim_ref* d_leaves, void* d_scratch, u32* h_mergeCalls) {
+  return b2_launch_hploc_keys(ctx, d_triAabb, d_sortedKeys, nullptr, d_sortedVals, n, d_nodes, d_leaves, d_scratch, h_mergeCalls);
+}
+
+/* d_sortedKeys64 != NULL: the walk compares 64-bit codes (60-bit Morton variant) */
+int b2_launch_hploc_keys(b2bvh_ctx* ctx, const b2bvh_aabb* d_triAabb, const u32* d_sortedKeys, const u64* d_sortedKeys64, const u32* d_sortedVals, u32 n,
+                         b2bvh_bvh2_node* d_nodes, b2bvh_prim_ref* d_leaves, void* d_scratch, u32* h_mergeCalls) {
   u32* ctrl = reinterpret_cast<u32*>(d_scratch);
   u32* nodeIdx = ctrl + 64;
   u32* freeIdx = nodeIdx + n;
@@ -197,7 +213,10 @@ int b2_launch_hploc(b2bvh_ctx* ctx, const b2bvh_aabb* d_triAabb, const u32* d_so
   hploc_setup_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_triAabb, d_sortedVals, n, d_leaves, nodeIdx, freeIdx, meet, ctrl);
   B2_LAUNCH_CHECK(ctx);
   B2_KERNEL(ctx, "hploc");
-  hploc_kernel<<<(n + HP_THREADS - 1) / HP_THREADS, HP_THREADS, 0, ctx->stream>>>(d_sortedKeys, n, d_nodes, d_leaves, nodeIdx, freeIdx, meet, ctrl);
+  if (d_sortedKeys64)
+    hploc_kernel<u64><<<(n + HP_THREADS - 1) / HP_THREADS, HP_THREADS, 0, ctx->stream>>>(d_sortedKeys64, n, d_nodes, d_leaves, nodeIdx, freeIdx, meet, ctrl);
+  else
+    hploc_kernel<u32><<<(n + HP_THREADS - 1) / HP_THREADS, HP_THREADS, 0, ctx->stream>>>(d_sortedKeys, n, d_nodes, d_leaves, nodeIdx, freeIdx, meet, ctrl);
   B2_LAUNCH_CHECK(ctx);
   (void)h_mergeCalls; /* ctrl[0] travels through the mailbox: b2_mailbox(ctx, B2_MB_HPLOC)[0] after the build's final synchronisation */
   B2_TRY(b2_fetch_words(ctx, ctrl, 1, B2_MB_HPLOC));

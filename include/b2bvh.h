@@ -74,8 +74,8 @@ typedef struct b2bvh_build_opts {
                                0: off (the reference's default, saMax = FltMax) */
   uint32_t morton_bits;     /* 0 or 30: the reference's extended 30-bit code (computeExtendedMortonCode, CommonBlocksKernel.h:159-359).
                                60: plain 60-bit code, 20 bits per axis — computeMortonCode (:361-372) with 2^20 instead of 2^10 cells; no reference
-                               counterpart (its codes stop at 30 bits), defined by the oracle.  LBVH builders and PLOC++ (which only needs the
-                               order); not H-PLOC.  b2bvh_tree.d_mortonCodeKeys64 / d_sortedMortonCodeKeys64 hold the codes, the 32-bit key
+                               counterpart (its codes stop at 30 bits), defined by the oracle.  All four builders (PLOC++ only needs the order,
+                               the LBVH kernels and the H-PLOC walk are instantiated for 64-bit keys).  b2bvh_tree.d_mortonCodeKeys64 / d_sortedMortonCodeKeys64 hold the codes, the 32-bit key
                                arrays their upper 30 bits, d_mortonCodeValues is not written (the values are the iota) */
   uint32_t reserved3;
 } b2bvh_build_opts;

@@ -625,7 +625,8 @@ void orc_ploc(const Box* triAabb, const u32* vals, u32 n, b2bvh_bvh2_node* nodes
  * (the last allocation of :167 is index 0).
  * stats[0] = number of plocMerge calls, stats[1] = nodes created.             */
 struct HplocState {
-  const u32* keys; u32 n; b2bvh_bvh2_node* nodes; b2bvh_prim_ref* leaves;
+  const u32* keys; const u64* keys64; /* one of the two: the reference's 32-bit codes, or the 60-bit variant */
+  u32 n; b2bvh_bvh2_node* nodes; b2bvh_prim_ref* leaves;
   std::vector<u32> nodeIdx, freeIdx; u32 allocated; u32 calls;
 };
 static void hploc_merge(HplocState& S, u32 L, u32 R, u32 split, bool fin) {
@@ -681,13 +682,15 @@ static void hploc_merge(HplocState& S, u32 L, u32 R, u32 split, bool fin) {
 static void hploc_visit(HplocState& S, u32 L, u32 R) {
   if (L == R) return;
   /* radix-tree split of [L,R] on the augmented key (key<<32 | index) */
-  u64 aL = ((u64)S.keys[L] << 32) | L, aR = ((u64)S.keys[R] << 32) | R;
-  int top = 63 - __builtin_clzll(aL ^ aR);
+  typedef unsigned __int128 u128;
+  auto aug = [&](u32 i) -> u128 { return ((u128)(S.keys64 ? S.keys64[i] : (u64)S.keys[i]) << 32) | i; };
+  const u128 x = aug(L) ^ aug(R);
+  const u64 xh = (u64)(x >> 64), xl = (u64)x;
+  int top = xh ? 127 - __builtin_clzll(xh) : 63 - __builtin_clzll(xl);
   u32 lo = L, hi = R;                 /* first index whose bit `top` is set */
   while (lo < hi) {
     u32 mid = lo + (hi - lo) / 2;
-    u64 a = ((u64)S.keys[mid] << 32) | mid;
-    if ((a >> top) & 1) hi = mid; else lo = mid + 1;
+    if ((aug(mid) >> top) & 1) hi = mid; else lo = mid + 1;
   }
   u32 split = lo;
   hploc_visit(S, L, split - 1);
@@ -696,9 +699,17 @@ static void hploc_visit(HplocState& S, u32 L, u32 R) {
   bool fin = size == S.n;
   if (size > 16 || fin) hploc_merge(S, L, R, split, fin);
 }
+static void hploc_run(const Box* triAabb, const u32* keys, const u64* keys64, const u32* vals, u32 n, b2bvh_bvh2_node* nodes, b2bvh_prim_ref* leaves, u32* stats);
 void orc_hploc(const Box* triAabb, const u32* keys, const u32* vals, u32 n, b2bvh_bvh2_node* nodes, b2bvh_prim_ref* leaves, u32* stats) {
+  hploc_run(triAabb, keys, nullptr, vals, n, nodes, leaves, stats);
+}
+/* the same walk over 64-bit sorted keys (60-bit Morton variant; no reference counterpart) */
+void orc_hploc64(const Box* triAabb, const u64* keys64, const u32* vals, u32 n, b2bvh_bvh2_node* nodes, b2bvh_prim_ref* leaves, u32* stats) {
+  hploc_run(triAabb, nullptr, keys64, vals, n, nodes, leaves, stats);
+}
+static void hploc_run(const Box* triAabb, const u32* keys, const u64* keys64, const u32* vals, u32 n, b2bvh_bvh2_node* nodes, b2bvh_prim_ref* leaves, u32* stats) {
   setup_clusters(triAabb, vals, n, nodes, leaves);
-  HplocState S; S.keys = keys; S.n = n; S.nodes = nodes; S.leaves = leaves; S.allocated = 0; S.calls = 0;
+  HplocState S; S.keys = keys; S.keys64 = keys64; S.n = n; S.nodes = nodes; S.leaves = leaves; S.allocated = 0; S.calls = 0;
   S.nodeIdx.resize(n); S.freeIdx.resize(n);
   for (u32 g = 0; g < n; g++) { S.nodeIdx[g] = g + (n - 1); S.freeIdx[g] = g ? g - 1 : INVALID; }
   hploc_visit(S, 0, n - 1);

@@ -186,7 +186,8 @@ def hploc(boxes, skeys, svals):
     nodes = np.zeros(n - 1, dtype=T.BVH2_NODE)
     leaves = np.zeros(n, dtype=T.PRIM_REF)
     stats = np.zeros(2, dtype=np.uint32)
-    lib().orc_hploc(_p(boxes), _p(skeys), _p(svals), _u32(n), _p(nodes), _p(leaves), _p(stats))
+    f = lib().orc_hploc64 if skeys.dtype == np.uint64 else lib().orc_hploc
+    f(_p(boxes), _p(skeys), _p(svals), _u32(n), _p(nodes), _p(leaves), _p(stats))
     return nodes, leaves, {"merge_calls": int(stats[0]), "allocated": int(stats[1])}
 
 
@@ -373,13 +374,12 @@ def build_batched(tris, counts):
 
 
 def build_ploc(tris, hierarchical=False, scene_override=None, morton_bits=30):
-    """PLOCNew::build (PLOC++Bvh.cpp:16-196) / HPLOC::build (Hploc.cpp:16-165).  morton_bits=60: PLOC++ only (it uses the sorted order alone)."""
+    """PLOCNew::build (PLOC++Bvh.cpp:16-196) / HPLOC::build (Hploc.cpp:16-165).  morton_bits=60: the 60-bit variant (PLOC++ uses the sorted order alone, H-PLOC walks the 64-bit codes)."""
     n = tris.size
     refs, boxes, scene = primrefs(tris)
     if scene_override is not None:
         scene = scene_override
     if morton_bits == 60:
-        assert not hierarchical
         keys, vals = morton60_codes(boxes, scene)
         sk, sv = sort_kv64(keys, vals)
     else:

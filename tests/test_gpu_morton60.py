@@ -16,8 +16,8 @@ def check60(ctx, oracle, tris, algo, **kw):
     tree = ctx.build(algo, tris, morton_bits=60, **kw)
     g = ctx.fetch(tree)
     assert tree.morton_bits == 60
-    if algo == capi.PLOCPP:
-        o = oracle.build_ploc(tris, morton_bits=60)
+    if algo in (capi.PLOCPP, capi.HPLOC):
+        o = oracle.build_ploc(tris, hierarchical=(algo == capi.HPLOC), morton_bits=60)
     else:
         o = oracle.build_lbvh(tris, single_pass=(algo == capi.SINGLE_PASS_LBVH), morton_bits=60)
     assert np.array_equal(g["keys64"], o["keys"]), "60-bit codes"
@@ -28,7 +28,7 @@ def check60(ctx, oracle, tris, algo, **kw):
     if algo == capi.TWO_PASS_LBVH:
         _, parents = oracle.lbvh_karras(o["refs"], o["skeys"], o["svals"])
         assert np.array_equal(g["parents"], parents)
-    if algo == capi.PLOCPP:
+    if algo in (capi.PLOCPP, capi.HPLOC):
         assert_same_struct(g["leaves"], o["leaves"], "ploc leaves")
     assert g["n_wide"] == o["wide_count"]
     assert_same_struct(g["wide"], o["wide"], "bvh4 nodes")
@@ -37,12 +37,12 @@ def check60(ctx, oracle, tris, algo, **kw):
     return tree, g, o
 
 
-ALGOS = [capi.TWO_PASS_LBVH, capi.SINGLE_PASS_LBVH, capi.PLOCPP]
+ALGOS = [capi.TWO_PASS_LBVH, capi.SINGLE_PASS_LBVH, capi.PLOCPP, capi.HPLOC]
 SYNTH = [("uniform", 2, 81), ("uniform", 3, 82), ("uniform", 1000, 83), ("uniform", 100_003, 84), ("clustered", 20_000, 85), ("flat", 5000, 86),
          ("duplicate", 700, 87), ("anisotropic", 30_000, 88)]
 
 
-@pytest.mark.parametrize("algo", ALGOS, ids=["twopass", "singlepass", "ploc"])
+@pytest.mark.parametrize("algo", ALGOS, ids=["twopass", "singlepass", "ploc", "hploc"])
 @pytest.mark.parametrize("kind,n,seed", SYNTH, ids=[f"{k}-{n}" for k, n, _ in SYNTH])
 def test_morton60_synthetic(ctx, oracle, algo, kind, n, seed):
     check60(ctx, oracle, random_tris(n, seed, kind), algo)
@@ -94,8 +94,6 @@ def test_morton60_resolves_what_30_bits_cannot(ctx):
 
 def test_morton60_argument_errors(ctx):
     tris = random_tris(1000, 89)
-    with pytest.raises(capi.B2bvhError, match="HPLOC"):
-        ctx.build(capi.HPLOC, tris, morton_bits=60)
     with pytest.raises(capi.B2bvhError, match="morton_bits"):
         ctx.build(capi.TWO_PASS_LBVH, tris, morton_bits=64)
     with pytest.raises(capi.B2bvhError, match="karras_two_kernel"):
