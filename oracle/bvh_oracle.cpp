@@ -503,7 +503,10 @@ void orc_sort_kv64(const u64* keys, const u32* vals, u32 n, u64* keysOut, u32* v
  * g-th smallest code — the reference fills the leaf records before sorting and never permutes them (:241-242), so its
  * tree joins sorted codes to unsorted boxes; (2) item offsets are prefix sums of the item sizes (the reference uses
  * item * itemSize, :234-235, correct only for equal sizes); (3) a one-triangle item has no internal node and root 0.
- * normalisation: 0/0 -> NaN -> 0 through fmaxf (GPU min/max semantics), as in orc_morton_codes. */
+ * normalisation: 0/0 -> NaN -> 0 through fmaxf (GPU min/max semantics), as in orc_morton_codes.
+ * PINNED: the reference kernel itself, run by the block emulator (ref_shim/ref_emul_ploc_mt.cpp, ref_batched_build_mt), gives the
+ * same topology / roots / scene boxes on any input and byte-identical nodes and leaves on items pre-sorted by code, where repair (1)
+ * changes nothing (tests/test_oracle_batched.py). */
 static inline u32 morton3d_10(u32 x) {                   /* BatchedBuildKernel.h:89-96 */
   x = (x * 0x00010001u) & 0xFF0000FFu;
   x = (x * 0x00000101u) & 0x0F00F00Fu;

@@ -105,6 +105,22 @@ def ploc_build_mt(nodes, leaves, idx):
     return nd, int(launches)
 
 
+def batched_build_mt(tris, n_items, prim_count):
+    """Runs the reference's BatchedBuildKernelLbvh (BatchedBuildKernel.h:218-312; one 32-thread block per item, block-level emulation)
+    on n_items items of prim_count triangles each.  Returns nodes, leaves, roots, scenes as the kernel writes them."""
+    global _emul_mt
+    if _emul_mt is None:
+        _emul_mt = C.CDLL(os.path.join(_HERE, "_ref", "libref_emul_mt.so"))
+        _emul_mt.ref_ploc_build_mt.restype = C.c_uint32
+    assert tris.size == n_items * prim_count and 2 <= prim_count <= 32
+    nodes = np.zeros(n_items * (prim_count - 1), dtype=T.BVH2_NODE)
+    leaves = np.zeros(n_items * prim_count, dtype=T.PRIM_REF)
+    roots = np.zeros(n_items, dtype=np.uint32)
+    scenes = np.zeros(n_items, dtype=T.AABB)
+    _emul_mt.ref_batched_build_mt(_p(tris), _u32(n_items), _u32(prim_count), _p(nodes), _p(leaves), _p(roots), _p(scenes))
+    return nodes, leaves, roots, scenes
+
+
 def collapse(nodes, leaves, root, n):
     """Runs the reference CollapseToWide4Bvh (LBVH variant when leaves is None, PLOC variant otherwise)."""
     wide = np.zeros(2 * n, dtype=T.BVH4_NODE); wl = np.zeros(n, dtype=T.PRIM_NODE)

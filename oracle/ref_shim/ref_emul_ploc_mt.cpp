@@ -105,3 +105,21 @@ uint32_t ref_ploc_build_mt(Bvh2Node* bvhNodes, PrimRef* primRefs, int* nodeIdx0,
   return launches;
 }
 }
+
+/* ---- the reference's batched build kernel (BatchedBuildKernel.h:218-312) under the same block emulator.  The header is compiled from
+ * a temporary copy in which ONE token is removed — `__shared__` in the parameter list of blockReduce (:76), where this prelude's
+ * `static` cannot stand (oracle/Makefile makes and deletes the copy) — and with ExtentCacheSize, which the reference never defines,
+ * set on the command line.  One 32-thread block per item; all items must have the same size (the kernel's offsets, :234-235). ---- */
+#ifdef B2_BATCHED_KERNEL
+namespace refbatched {
+#include B2_BATCHED_KERNEL
+}
+extern "C" void ref_batched_build_mt(const Triangle* tris, uint32_t nItems, uint32_t primCount, Bvh2Node* nodes, PrimRef* leaves, uint32_t* roots, Aabb* scenes) {
+  std::vector<D_BatchedBuildInputs> in(nItems);
+  for (uint32_t i = 0; i < nItems; i++) { in[i].m_prims = const_cast<Triangle*>(tris) + (size_t)i * primCount; in[i].m_nPrimtives = primCount; }
+  std::vector<uint2> spans((size_t)nItems * primCount);
+  for (uint32_t b = 0; b < nItems; b++)
+    run_block(b, MaxBatchedBlockSize, nItems, [&] { refbatched::BatchedBuildKernelLbvh(in.data(), nodes, leaves, spans.data(), roots, nItems, scenes); });
+}
+#endif
+

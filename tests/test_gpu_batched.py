@@ -25,6 +25,22 @@ def check_batch(ctx, oracle, tris, counts):
     return b, g, o
 
 
+def test_batched_golden_cases(ctx, oracle):
+    """The committed known answers (each checked against the emulated reference kernel when they were generated)."""
+    import json
+    import os
+    from conftest import GOLDEN
+    from test_gpu_lbvh import h32
+    ka = json.load(open(os.path.join(GOLDEN, "batched_known_answers.json")))
+    for key, want in ka.items():
+        if key.startswith("_"):
+            continue
+        kind, pc, items, seed = key.rsplit("_", 3)
+        pc, items = int(pc), int(items)
+        _, g, _ = check_batch(ctx, oracle, random_tris(items * pc, int(seed), kind), np.full(items, pc, dtype=np.uint32))
+        assert h32(oracle, g["nodes"]) == want["nodes_fnv"] and h32(oracle, g["leaves"]) == want["leaves_fnv"] and h32(oracle, g["roots"]) == want["roots_fnv"]
+
+
 def test_batched_cornell_box_copies(ctx, oracle):
     """main.cpp:38-52: the cornell box (32 triangles) as every item of the batch."""
     box = load_mesh("cornellbox")
