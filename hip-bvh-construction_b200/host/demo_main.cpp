@@ -5,6 +5,7 @@
  * the mesh staging script of the test infrastructure with the reference's own OBJ loader) or a synthetic stream.
  *
  *   b2bvh_demo <twopass|singlepass|ploc|hploc> <mesh.tri | synth:N> [expected_cost]
+ *   b2bvh_demo twopass-split:<saMax> <mesh.tri | synth:N> [expected_cost]   TwoPassLbvh compiled with USE_PRIM_SPLITTING (TwoPassLbvh.cpp:23-28)
  *   b2bvh_demo batched <mesh.tri | synth:N>      the USE_BATCHED_BUILDER branch (main.cpp:38-52): 4096 items; a mesh of <= 32
  *                                                 triangles is one item repeated (the reference's cornell box), a larger one is cut
  *                                                 into items of 32 consecutive triangles
@@ -49,9 +50,11 @@ static std::vector<Triangle> loadTriangles(Context& ctx, const std::string& arg)
 }
 
 template <class Builder>
-static float run(Context& ctx, std::vector<Triangle>& tris) {
+static float run(Context& ctx, std::vector<Triangle>& tris, float saMax = 0.0f) {
   Builder bvh;
+  bvh.m_saMax = saMax;
   bvh.build(ctx, tris);
+  if (saMax > 0.0f) std::cout << "references : " << bvh.d_primRefIdx.size() << " of " << bvh.d_triangleBuff.size() << " triangles" << std::endl;
   bvh.traverseBvh(ctx);
   std::cout << "wide nodes : " << bvh.m_wideNodeCount << "  root : " << bvh.m_rootNodeIdx << "  internal nodes : " << bvh.m_nInternalNodes << std::endl;
   size_t hits = 0;
@@ -94,6 +97,7 @@ int main(int argc, char* argv[]) {
       return 0;
     }
     if (which == "twopass") cost = run<TwoPassLbvh>(context, triangles);
+    else if (which.rfind("twopass-split:", 0) == 0) cost = run<TwoPassLbvh>(context, triangles, (float)atof(which.c_str() + 14));
     else if (which == "singlepass") cost = run<SinglePassLbvh>(context, triangles);
     else if (which == "ploc") cost = run<PLOCNew>(context, triangles);
     else if (which == "hploc") cost = run<HPLOC>(context, triangles);

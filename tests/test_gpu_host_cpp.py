@@ -35,3 +35,15 @@ def test_demo_batched_builder():
     r = subprocess.run([EXE, "batched", os.path.join(GOLDEN, "cornellbox.tri")], env=env, capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "BatchSize : 4096" in r.stdout and "BvhBuildTime" in r.stdout and f"nodes : {4096 * 31}" in r.stdout
+
+
+def test_demo_twopass_with_prim_splitting(oracle):
+    """TwoPassLbvh::m_saMax = the reference's USE_PRIM_SPLITTING build (saMax = 10 there): reference count and cost equal the oracle's."""
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "hip-bvh-construction_b200", "host"), "all"], stdout=subprocess.DEVNULL)
+    tris = load_mesh("cornellbox")
+    o = oracle.build_lbvh(tris, split_sa_max=10.0)
+    env = dict(os.environ, B2BVH_LIB=capi.LIB_PATH)
+    r = subprocess.run([EXE, "twopass-split:10", os.path.join(GOLDEN, "cornellbox.tri"), repr(float(np.float32(o["cost"])))], env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert f"references : {o['refs'].size} of {tris.size} triangles" in r.stdout and f"wide nodes : {o['wide_count']}" in r.stdout
+
