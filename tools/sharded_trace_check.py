@@ -1,5 +1,5 @@
 """Sharded build + sharded primary rays over NCCL, checked on rank 0 against ONE tree over all triangles on one GPU.
-usage: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tools/sharded_trace_check.py [--n 2000000]"""
+usage: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tools/sharded_trace_check.py [--prims 2000000]"""
 import argparse
 import os
 import sys
@@ -16,7 +16,7 @@ from b2bvh.sharded import GpuEngine, ShardedBuild, shard_range  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=2_000_000)
+    ap.add_argument("--prims", dest="n", type=int, default=2_000_000)
     ap.add_argument("--size", type=int, default=512)
     a = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
