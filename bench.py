@@ -418,6 +418,22 @@ def main():
             except capi.B2bvhError as e:
                 widened["morton60"] = {"error": str(e)[:120]}
             line["widened_paths"] = widened
+            # ---- the optional second distribution of SURVEY §8d: synth_clustered_v1, 4096 clusters (many primitives per Morton cell) ----
+            try:
+                dc = ctx.synth_uniform(n, SEED, clustered=True)
+                second = {"workload": "synth_clustered_v1 10M triangles, 4096 clusters of radius 10"}
+                for nm, al in (("SinglePassLbvh", capi.SINGLE_PASS_LBVH), ("PLOC++", capi.PLOCPP), ("HPLOC", capi.HPLOC)):
+                    for _ in range(2):
+                        ctx.build(al, dc, n=n, tris_on_device=True, use_graph=True)
+                    bb = min((ctx.build(al, dc, n=n, tris_on_device=True, use_graph=True) for _ in range(4)), key=lambda q: q.build_ms)
+                    second[nm] = {"build_ms": float(bb.build_ms), "Mprims_s": n / bb.build_ms / 1e3,
+                                  "extents_morton_sort_build_collapse_ms": [float(bb.stage_ms[k]) for k in (capi.T_EXTENTS, capi.T_MORTON, capi.T_SORT, capi.T_BUILD, capi.T_COLLAPSE)]}
+                sk = ctx.download(bb.d_sortedMortonCodeKeys, np.uint32, n)
+                second["equal_neighbour_keys"] = int((sk[1:] == sk[:-1]).sum())
+                ctx.free(dc)
+                line["second_distribution"] = second
+            except capi.B2bvhError as e:
+                line["second_distribution"] = {"error": str(e)[:120]}
             # ---- the reference's own scenes (BASELINE configs[1]/[2]), when staged ----
             extras = {}
             mesh_dir = os.path.join(ROOT, "oracle", "_ref", "meshes")

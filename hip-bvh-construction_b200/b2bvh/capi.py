@@ -53,7 +53,7 @@ SYMBOLS = ["b2bvh_ctx_create", "b2bvh_ctx_destroy", "b2bvh_device_name", "b2bvh_
            "b2bvh_memset", "b2bvh_h2d", "b2bvh_d2h", "b2bvh_h2d_async", "b2bvh_d2h_async", "b2bvh_d2d", "b2bvh_sync", "b2bvh_host_alloc_pinned", "b2bvh_host_free_pinned",
            "b2bvh_last_error", "b2bvh_build", "b2bvh_build_batched", "b2bvh_scene_extents", "b2bvh_morton_codes", "b2bvh_sort_pairs", "b2bvh_generate_rays",
            "b2bvh_traverse", "b2bvh_traverse_ex", "b2bvh_heat_map", "b2bvh_shard_extents", "b2bvh_top_level", "b2bvh_cost_bvh4", "b2bvh_cost_lbvh", "b2bvh_tree_cost",
-           "b2bvh_abi_version", "b2bvh_synth_uniform", "b2bvh_profile_enable", "b2bvh_profile_count", "b2bvh_profile_entry"]
+           "b2bvh_abi_version", "b2bvh_synth_uniform", "b2bvh_synth_clustered", "b2bvh_profile_enable", "b2bvh_profile_count", "b2bvh_profile_entry"]
 
 _lib = None
 
@@ -87,7 +87,7 @@ def load():
         "b2bvh_shard_extents": [vp, vp, u32, u32, vp], "b2bvh_top_level": [vp, vp, u32, vp],
         "b2bvh_cost_bvh4": [vp, vp, vp, u32, u32, u32], "b2bvh_cost_lbvh": [vp, u32, u32, u32],
         "b2bvh_tree_cost": [vp, C.POINTER(Tree), fp], "b2bvh_abi_version": [], "b2bvh_last_error": [],
-        "b2bvh_synth_uniform": [vp, C.c_uint64, u32, u32, C.c_float, vp], "b2bvh_profile_enable": [vp, C.c_int],
+        "b2bvh_synth_uniform": [vp, C.c_uint64, u32, u32, C.c_float, vp], "b2bvh_synth_clustered": [vp, C.c_uint64, u32, u32, C.c_float, vp], "b2bvh_profile_enable": [vp, C.c_int],
         "b2bvh_profile_count": [vp, C.POINTER(C.c_int)], "b2bvh_profile_entry": [vp, C.c_int, C.c_char_p, sz, fp],
     }
     for name, args in sig.items():
@@ -264,12 +264,13 @@ class Context:
                 if p:
                     self.free(p)
 
-    def synth_uniform(self, n_total, seed, first=0, count=None, half=None):
-        """synth_uniform_v1 triangles [first, first+count) generated on the device; returns the device pointer."""
+    def synth_uniform(self, n_total, seed, first=0, count=None, half=None, clustered=False):
+        """synth_uniform_v1 (or synth_clustered_v1) triangles [first, first+count) generated on the device; returns the device pointer."""
         count = n_total if count is None else count
         h = np.float32(1000.0 * float(n_total) ** (-1.0 / 3.0)) if half is None else np.float32(half)
         d = self.alloc(count * 64)
-        check(self.lib.b2bvh_synth_uniform(self.h, int(first), int(count), int(seed), C.c_float(float(h)), C.c_void_p(d)), "b2bvh_synth_uniform")
+        f = self.lib.b2bvh_synth_clustered if clustered else self.lib.b2bvh_synth_uniform
+        check(f(self.h, int(first), int(count), int(seed), C.c_float(float(h)), C.c_void_p(d)), "b2bvh_synth")
         return d
 
     def profile(self, on=True):

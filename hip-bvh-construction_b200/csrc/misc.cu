@@ -43,6 +43,30 @@ __global__ void __launch_bounds__(256) synth_uniform_kernel(u64 first, u32 count
   q[3] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
+/* synth_clustered_v1 (second distribution: many primitives per Morton cell): triangle i draws a cluster
+ * j = floor(r0 * 4096); the cluster's centre comes from its own stream tea16(j, seed ^ 0xC1) (three draws, the uniform map); the
+ * triangle's centre is that + 20 * (r - 0.5) per axis; vertices as in synth_uniform_v1.  16 draws: r0, three for the centre, nine. */
+__global__ void __launch_bounds__(256) synth_clustered_kernel(u64 first, u32 count, u32 seed, float half, b2bvh_triangle* __restrict__ out) {
+  const u32 k = blockIdx.x * 256 + threadIdx.x;
+  if (k >= count) return;
+  u32 s = tea16((u32)(first + k), seed);
+  const u32 j = (u32)__fmul_rn(rand01(s), 4096.0f);
+  u32 sj = tea16(j, seed ^ 0xC1u);
+  float c[3], v[9];
+  const float twoH = __fmul_rn(2.0f, half);
+#pragma unroll
+  for (int a = 0; a < 3; a++) c[a] = __fadd_rn(-1000.0f, __fmul_rn(2000.0f, rand01(sj)));
+#pragma unroll
+  for (int a = 0; a < 3; a++) c[a] = __fadd_rn(c[a], __fmul_rn(20.0f, __fsub_rn(rand01(s), 0.5f)));
+#pragma unroll
+  for (int a = 0; a < 9; a++) v[a] = __fadd_rn(c[a % 3], __fmul_rn(__fsub_rn(rand01(s), 0.5f), twoH));
+  float4* q = reinterpret_cast<float4*>(out + k);
+  q[0] = make_float4(v[0], v[1], v[2], v[3]);
+  q[1] = make_float4(v[4], v[5], v[6], v[7]);
+  q[2] = make_float4(v[8], 0.f, 0.f, 0.f);
+  q[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
 int b2_prof_begin(b2bvh_ctx* ctx, const char* name) {
   if (ctx->prof_n >= 512) return 0;
   b2bvh_ctx::Prof& p = ctx->prof[ctx->prof_n];
@@ -68,6 +92,14 @@ int b2bvh_synth_uniform(b2bvh_ctx* ctx, uint64_t first, uint32_t count, uint32_t
   if (!ctx || !d_tris || count == 0) return b2_fail(B2BVH_ERR_INVALID, "synth_uniform: bad argument");
   B2_KERNEL(ctx, "synth_uniform");
   synth_uniform_kernel<<<(count + 255) / 256, 256, 0, ctx->stream>>>(first, count, seed, half, d_tris);
+  B2_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+int b2bvh_synth_clustered(b2bvh_ctx* ctx, uint64_t first, uint32_t count, uint32_t seed, float half, b2bvh_triangle* d_tris) {
+  if (!ctx || !d_tris || count == 0) return b2_fail(B2BVH_ERR_INVALID, "synth_clustered: bad argument");
+  B2_KERNEL(ctx, "synth_clustered");
+  synth_clustered_kernel<<<(count + 255) / 256, 256, 0, ctx->stream>>>(first, count, seed, half, d_tris);
   B2_LAUNCH_CHECK(ctx);
   return 0;
 }

@@ -209,6 +209,9 @@ int b2bvh_tree_cost(b2bvh_ctx* ctx, const b2bvh_tree* tree, float* cost);
  * triangles [first, first+count) of the stream with `seed`, written to DEVICE memory; RNG = the reference's tea<16>/lcg/randf
  * (CommonBlocksKernel.h:401-430).  `half` = 1000 * Ntotal^(-1/3) rounded to float by the caller. ---- */
 int b2bvh_synth_uniform(b2bvh_ctx* ctx, uint64_t first, uint32_t count, uint32_t seed, float half, b2bvh_triangle* d_tris);
+/* synth_clustered_v1 (optional second distribution): the same stream, but every triangle sits within +-10 of one of 4096
+ * cluster centres (cluster = floor(first draw * 4096), centre from tea<16>(cluster, seed ^ 0xC1)): many primitives per Morton cell */
+int b2bvh_synth_clustered(b2bvh_ctx* ctx, uint64_t first, uint32_t count, uint32_t seed, float half, b2bvh_triangle* d_tris);
 
 /* ---- per-launch profiler: when enabled every kernel launch of the context is bracketed by a CUDA event pair; entries are
  * read after a sync.  Replaces Timer::measure (src/Timer.h:31-73) at kernel granularity, without its per-launch host sync. ---- */

@@ -1287,6 +1287,25 @@ void orc_synth_uniform(u64 first, u32 count, u32 seed, float half, b2bvh_triangl
   }
 }
 
+/* synth_clustered_v1: see b2bvh_synth_clustered (include/b2bvh.h) — cluster j = floor(r0 * 4096), centre from tea16(j, seed ^ 0xC1),
+ * triangle centre = that + 20 * (r - 0.5), vertices as above. */
+void orc_synth_clustered(u64 first, u32 count, u32 seed, float half, b2bvh_triangle* out) {
+  const float two_h = 2 * half;
+  for (u32 k = 0; k < count; k++) {
+    u32 s = tea16((u32)(first + k), seed);
+    float r0 = rand01(s);
+    u32 j = (u32)(r0 * 4096.0f);
+    u32 sj = tea16(j, seed ^ 0xC1u);
+    float c[3];
+    for (int a = 0; a < 3; a++) { float m = 2000.0f * rand01(sj); c[a] = -1000.0f + m; }
+    for (int a = 0; a < 3; a++) { float d = rand01(s) - 0.5f; float m = 20.0f * d; c[a] = c[a] + m; }
+    float v[9];
+    for (int a = 0; a < 9; a++) { float d = rand01(s) - 0.5f; float m = d * two_h; v[a] = c[a % 3] + m; }
+    memset(&out[k], 0, sizeof(b2bvh_triangle));
+    out[k].v1 = f3(v[0], v[1], v[2]); out[k].v2 = f3(v[3], v[4], v[5]); out[k].v3 = f3(v[6], v[7], v[8]);
+  }
+}
+
 /* ------------------------------------------------- sharded build: top-level tree over G sub-tree roots
  * (new work; no reference counterpart).  Spec: Morton-code the
  * root boxes with the same extended code in the frame of their union, stable

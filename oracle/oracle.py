@@ -303,6 +303,14 @@ def synth_uniform(n, seed, first=0, count=None, half=None):
     return out
 
 
+def synth_clustered(n, seed, first=0, count=None, half=None):
+    count = n if count is None else count
+    out = np.zeros(count, dtype=T.TRIANGLE)
+    h = synth_half(n) if half is None else np.float32(half)
+    lib().orc_synth_clustered(C.c_uint64(first), _u32(count), _u32(seed), C.c_float(float(h)), _p(out))
+    return out
+
+
 def top_level(root_boxes):
     g = root_boxes.size
     nodes = np.zeros(2 * g - 1, dtype=T.BVH2_NODE)

@@ -161,6 +161,22 @@ def test_device_synth_generator_matches_oracle(ctx, oracle):
     assert g.tobytes() == oracle.synth_uniform(n_total, 0x00B20010, first=first, count=count).tobytes()
 
 
+def test_clustered_generator_and_build(ctx, oracle):
+    """synth_clustered_v1 (many primitives per Morton cell): device stream == oracle stream bit for bit, and the builders agree with the
+    oracle on it (thousands of equal keys, ordered by index)."""
+    n = 60_000
+    d = ctx.synth_uniform(n, 0x00B20010, clustered=True)
+    dev = ctx.download(d, T.TRIANGLE, n)
+    tris = oracle.synth_clustered(n, 0x00B20010)
+    assert dev.tobytes() == tris.tobytes()
+    part = ctx.synth_uniform(n, 0x00B20010, first=1234, count=777, clustered=True)
+    assert ctx.download(part, T.TRIANGLE, 777).tobytes() == tris[1234:1234 + 777].tobytes()
+    tree, g, o = check_lbvh(ctx, oracle, tris, capi.SINGLE_PASS_LBVH)
+    assert int((g["skeys"][1:] == g["skeys"][:-1]).sum()) > 100
+    check_lbvh(ctx, oracle, tris, capi.TWO_PASS_LBVH)
+    ctx.free(d); ctx.free(part)
+
+
 def test_profiler_reports_every_launch(ctx):
     tris = random_tris(10_000, 77)
     ctx.profile(True)
