@@ -19,13 +19,20 @@
 #include "lookback.cuh"
 
 #define SPLIT_THREADS 512
+#ifndef SPLIT_MINB
+#define SPLIT_MINB 2                                    /* resident CTAs per SM (2/3/4: 115/115/122 us per generation) */
+#endif
 #ifndef SPLIT_GROUP
 #define SPLIT_GROUP 1                                   /* references per thread re-read together in pass 2 (measured 1/2/4/8: 145/148/164/176 us per generation) */
 #endif
-#define SPLIT_ITEMS 16                                  /* references per thread */
-#define SPLIT_TILE (SPLIT_THREADS * SPLIT_ITEMS)        /* 8192 references per tile: the look-back costs a few L2 round trips PER TILE, and with
+#ifndef SPLIT_ITEMS
+#define SPLIT_ITEMS 8                                   /* references per thread */
+#endif
+#define SPLIT_TILE (SPLIT_THREADS * SPLIT_ITEMS)        /* 4096 references per tile.  The look-back costs a few L2 round trips PER TILE: with
                                                            512-reference tiles those round trips were the whole run time (458 us for 10 M boxes,
-                                                           86 % of the warp stalls at the barrier behind the look-back, profiles/r01q) */
+                                                           86 % of the warp stalls at the barrier behind the look-back, profiles/r01q); per
+                                                           generation of the 10 M case: 4096 per tile 113 us, 8192: 123 us, 16384: 163 us
+                                                           (too few tiles per SM to hide the two passes behind each other) */
 
 /* 24-byte boxes are 8-byte aligned: three 8-byte accesses instead of six 4-byte ones halve the L2 requests */
 __device__ __forceinline__ Box split_load_box(const b2bvh_aabb* p) {
@@ -48,7 +55,7 @@ struct SplitCtl {
 /* warp w of a tile owns 32 x SPLIT_ITEMS consecutive references; reference (k, lane) = warpBase + 32 k + lane, so every load is
  * coalesced and the order inside the warp is k-major.  Pass 1 keeps only the two ballots per k; pass 2 reads the boxes again
  * (L2 hits: the tile was just streamed) and scatters them. */
-__global__ void __launch_bounds__(SPLIT_THREADS, 2) split_level_kernel(const b2bvh_aabb* __restrict__ inBox, const u32* __restrict__ inPrim /* NULL: identity */,
+__global__ void __launch_bounds__(SPLIT_THREADS, SPLIT_MINB) split_level_kernel(const b2bvh_aabb* __restrict__ inBox, const u32* __restrict__ inPrim /* NULL: identity */,
                                                                     u32 count, float saMax, b2bvh_aabb* outBox, u32* outPrim, u32 outBase,
                                                                     b2bvh_aabb* nextBox, u32* nextPrim, u64* status, SplitCtl* ctl) {
   __shared__ u32 sTile;
