@@ -197,10 +197,13 @@ def main():
         with torch.cuda.stream(L.stream):
             capi.check(c.lib.b2bvh_shard_extents(c.h, tris_ptr, n, 1 if on_device else 0, L.box6.data_ptr()), "b2bvh_shard_extents")
             dist.all_reduce(L.box6, op=dist.ReduceOp.MAX)
-            tree = c.build(algo, tris_ptr, n=n, tris_on_device=on_device, boxes_ready=True, d_scene_negmin_max=L.box6.data_ptr(), use_graph=True)
-            capi.check(c.lib.b2bvh_d2d(c.h, L.root_local.data_ptr(), tree.d_bvhNodes + 32 * tree.root + 8, 24), "b2bvh_d2d")
+            # the build is only ENQUEUED (defer_sync) and leaves its root box on the device, so the all-gather and the top-level tree
+            # follow it on the stream without a host round trip; build_finish is the step's single host synchronisation
+            tree = c.build(algo, tris_ptr, n=n, tris_on_device=on_device, boxes_ready=True, d_scene_negmin_max=L.box6.data_ptr(), use_graph=True,
+                           defer_sync=True, d_root_box_out=L.root_local.data_ptr())
             dist.all_gather_into_tensor(L.roots, L.root_local)
             capi.check(c.lib.b2bvh_top_level(c.h, L.roots.data_ptr(), world, L.top_nodes.data_ptr()), "b2bvh_top_level")
+            c.build_finish(tree)
         launches[0] += tree.n_launches + 2
         return tree
 

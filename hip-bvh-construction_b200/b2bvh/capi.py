@@ -25,7 +25,7 @@ class Aabb(C.Structure):
 class BuildOpts(C.Structure):
     _fields_ = [("collapse", C.c_uint32), ("tris_on_device", C.c_uint32), ("use_scene_box", C.c_uint32), ("scene_box", Aabb),
                 ("stage_timing", C.c_uint32), ("karras_two_kernel", C.c_uint32), ("boxes_ready", C.c_uint32),
-                ("d_scene_negmin_max", C.c_void_p), ("lbvh_second_level", C.c_uint32), ("merge_max_ctas", C.c_uint32), ("use_graph", C.c_uint32), ("split_sa_max", C.c_float), ("morton_bits", C.c_uint32), ("reserved3", C.c_uint32)]
+                ("d_scene_negmin_max", C.c_void_p), ("lbvh_second_level", C.c_uint32), ("merge_max_ctas", C.c_uint32), ("use_graph", C.c_uint32), ("split_sa_max", C.c_float), ("morton_bits", C.c_uint32), ("defer_sync", C.c_uint32), ("d_root_box_out", C.c_void_p)]
 
 
 class Tree(C.Structure):
@@ -51,7 +51,7 @@ class Batch(C.Structure):
 # every symbol include/b2bvh.h declares (tests check the library exports each of them)
 SYMBOLS = ["b2bvh_ctx_create", "b2bvh_ctx_destroy", "b2bvh_device_name", "b2bvh_device_sm_count", "b2bvh_alloc", "b2bvh_free",
            "b2bvh_memset", "b2bvh_h2d", "b2bvh_d2h", "b2bvh_h2d_async", "b2bvh_d2h_async", "b2bvh_d2d", "b2bvh_sync", "b2bvh_host_alloc_pinned", "b2bvh_host_free_pinned",
-           "b2bvh_last_error", "b2bvh_build", "b2bvh_build_batched", "b2bvh_scene_extents", "b2bvh_morton_codes", "b2bvh_sort_pairs", "b2bvh_generate_rays",
+           "b2bvh_last_error", "b2bvh_build", "b2bvh_build_finish", "b2bvh_build_batched", "b2bvh_scene_extents", "b2bvh_morton_codes", "b2bvh_sort_pairs", "b2bvh_generate_rays",
            "b2bvh_traverse", "b2bvh_traverse_ex", "b2bvh_heat_map", "b2bvh_shard_extents", "b2bvh_top_level", "b2bvh_cost_bvh4", "b2bvh_cost_lbvh", "b2bvh_tree_cost",
            "b2bvh_abi_version", "b2bvh_synth_uniform", "b2bvh_synth_clustered", "b2bvh_profile_enable", "b2bvh_profile_count", "b2bvh_profile_entry"]
 
@@ -78,7 +78,7 @@ def load():
         "b2bvh_memset": [vp, vp, C.c_int, sz], "b2bvh_h2d": [vp, vp, vp, sz], "b2bvh_d2h": [vp, vp, vp, sz], "b2bvh_d2d": [vp, vp, vp, sz], "b2bvh_h2d_async": [vp, vp, vp, sz], "b2bvh_d2h_async": [vp, vp, vp, sz], "b2bvh_sync": [vp],
         "b2bvh_host_alloc_pinned": [sz, C.POINTER(vp)], "b2bvh_host_free_pinned": [vp],
         "b2bvh_build": [vp, C.c_int, vp, u32, C.POINTER(BuildOpts), C.POINTER(Tree)],
-        "b2bvh_build_batched": [vp, vp, u32, vp, u32, C.POINTER(Batch)],
+        "b2bvh_build_batched": [vp, vp, u32, vp, u32, C.POINTER(Batch)], "b2bvh_build_finish": [vp, C.POINTER(Tree)],
         "b2bvh_scene_extents": [vp, vp, u32, vp, vp], "b2bvh_morton_codes": [vp, vp, vp, u32, vp, vp],
         "b2bvh_sort_pairs": [vp, vp, vp, vp, vp, u32, u32, u32],
         "b2bvh_generate_rays": [vp, vp, u32, u32, vp, fp],
@@ -173,7 +173,7 @@ class Context:
 
     # ---- stages ----
     def build(self, algo, tris, n=None, collapse=True, tris_on_device=False, scene_box=None, karras_two_kernel=False, boxes_ready=False,
-              d_scene_negmin_max=None, lbvh_second_level=0, merge_max_ctas=0, use_graph=False, split_sa_max=0.0, morton_bits=0):
+              d_scene_negmin_max=None, lbvh_second_level=0, merge_max_ctas=0, use_graph=False, split_sa_max=0.0, morton_bits=0, defer_sync=False, d_root_box_out=None):
         """tris: TRIANGLE[n] numpy array (host) or an int device/pinned-host pointer (then pass n)."""
         opts = BuildOpts()
         opts.collapse = 1 if collapse else 0
@@ -186,6 +186,9 @@ class Context:
         opts.use_graph = 1 if use_graph else 0
         opts.split_sa_max = float(split_sa_max)
         opts.morton_bits = int(morton_bits)
+        opts.defer_sync = 1 if defer_sync else 0
+        if d_root_box_out:
+            opts.d_root_box_out = int(d_root_box_out)
         if d_scene_negmin_max:
             opts.d_scene_negmin_max = int(d_scene_negmin_max)
         if scene_box is not None:
@@ -221,6 +224,11 @@ class Context:
         return dict(nodes=self.download(b.d_bvhNodes, T.BVH2_NODE, b.n_nodes_total), leaves=self.download(b.d_primRefs, T.PRIM_REF, b.n_prims_total),
                     roots=self.download(b.d_rootNodes, np.uint32, b.n_items), scenes=self.download(b.d_sceneExtents, T.AABB, b.n_items),
                     leaf_off=self.download(b.d_leafOffsets, np.uint32, b.n_items + 1), node_off=self.download(b.d_nodeOffsets, np.uint32, b.n_items + 1))
+
+    def build_finish(self, tree):
+        """Completes a build enqueued with defer_sync=True: synchronises and fills root, n_wide, times."""
+        check(self.lib.b2bvh_build_finish(self.h, C.byref(tree)), "b2bvh_build_finish")
+        return tree
 
     def tree_cost(self, tree):
         c = C.c_float()

@@ -55,6 +55,8 @@ class ShardedBuild:
         else:
             roots = mine
         top = self.engine.top_level(roots)
+        if hasattr(self.engine, "finish"):
+            self.engine.finish(tree)  # the build was only enqueued: this is the step's single host synchronisation
         return dict(scene=scene, tree=tree, roots=roots, top=top)
 
     MISS = (1 << 63) - 1
@@ -114,11 +116,14 @@ class GpuEngine:
     def build(self, tris, box6):
         """box6: the all-reduced {-min, max} tensor (device).  The primitive boxes computed by shard_extents are reused."""
         p, n, on_dev = self._ptr_n(tris)
+        # enqueued only (defer_sync): the root box lands in root6 at the end of the build, stream-ordered, so the caller's all-gather
+        # and top-level tree need no host round trip in between; finish() synchronises
         tree = self.ctx.build(self.algo, p, n=n, tris_on_device=bool(on_dev), collapse=self.collapse, boxes_ready=True,
-                              d_scene_negmin_max=box6.data_ptr())
-        # root box = bytes 8..32 of the root node, device to device (stream-ordered)
-        self.capi.check(self.ctx.lib.b2bvh_d2d(self.ctx.h, self.root6.data_ptr(), tree.d_bvhNodes + 32 * tree.root + 8, 24), "b2bvh_d2d")
+                              d_scene_negmin_max=box6.data_ptr(), defer_sync=True, d_root_box_out=self.root6.data_ptr())
         return self.root6, tree
+
+    def finish(self, tree):
+        self.ctx.build_finish(tree)
 
     def top_level(self, roots):
         g = roots.numel() // 6

@@ -58,7 +58,7 @@ enum {
 
 extern "C" {
 
-uint32_t b2bvh_abi_version(void) { return 5; }
+uint32_t b2bvh_abi_version(void) { return 6; }
 const char* b2bvh_last_error(void) { return g_err; }
 
 int b2bvh_ctx_create(int device, void* cuda_stream, b2bvh_ctx** out) {
@@ -369,6 +369,7 @@ int b2bvh_build(b2bvh_ctx* ctx, int algo, const b2bvh_triangle* tris, uint32_t n
                               (b2bvh_prim_node*)dWLeaves, dCollapse, &nWide));
   B2_CUDA(record(5));
   B2_TRY(b2_fetch_words(ctx, dRoot, 1, B2_MB_ROOT));
+  if (opts.d_root_box_out) B2_TRY(b2_launch_root_box(ctx, (const b2bvh_bvh2_node*)dNodes, dRoot, opts.d_root_box_out));
   return 0;
   };
   bool wantGraph = opts.use_graph && !split && !ctx->prof_on && !(opts.use_scene_box && !opts.d_scene_negmin_max);
@@ -400,20 +401,10 @@ int b2bvh_build(b2bvh_ctx* ctx, int algo, const b2bvh_triangle* tris, uint32_t n
   } else {
     B2_TRY(enqueue());
   }
-  B2_CUDA(cudaStreamSynchronize(s)); /* the only host synchronisation of a build */
-  const u32 root = b2_mailbox(ctx, B2_MB_ROOT)[0];
-  if (opts.collapse) nWide = b2_mailbox(ctx, B2_MB_COLLAPSE)[1];
-  if (algo == B2BVH_PLOCPP) {
-    iterations = b2_mailbox(ctx, B2_MB_PLOC)[2];
-    if (b2_mailbox(ctx, B2_MB_PLOC)[1] != 1u)
-      return b2_fail(B2BVH_ERR_INTERNAL, "ploc: %u clusters left after %u iterations", b2_mailbox(ctx, B2_MB_PLOC)[1], iterations);
-  }
-
+  /* everything that does not need the device's answer */
   out->algo = (u32)algo;
   out->n_prims = n;
   out->n_internal = n - 1;
-  out->root = root;
-  out->n_wide = nWide;
   out->leaves_separate = separate ? 1u : 0u;
   out->d_triangleBuff = dT;
   out->d_triangleAabb = (const b2bvh_aabb*)dAabb;
@@ -427,6 +418,35 @@ int b2bvh_build(b2bvh_ctx* ctx, int algo, const b2bvh_triangle* tris, uint32_t n
   out->d_leafNodes = (const b2bvh_prim_ref*)dLeaves;
   out->d_wideBvhNodes = (const b2bvh_bvh4_node*)dWide;
   out->d_wideLeafNodes = (const b2bvh_prim_node*)dWLeaves;
+  out->n_launches = ctx->launches - launches0;
+  out->n_triangles = nTris;
+  out->d_primRefIdx = dRefPrim;
+  out->morton_bits = m60 ? 60u : 30u;
+  out->d_mortonCodeKeys64 = (const uint64_t*)dKeys64;
+  out->d_sortedMortonCodeKeys64 = (const uint64_t*)dSKeys64;
+  out->n_split_levels = splitLevels;
+  ctx->pending.active = true; ctx->pending.algo = algo; ctx->pending.collapse = opts.collapse != 0; ctx->pending.host_tris = !opts.tris_on_device;
+  ctx->pending.split = split;
+  if (opts.defer_sync) return 0; /* b2bvh_build_finish synchronises and fills in the rest */
+  return b2bvh_build_finish(ctx, out);
+}
+
+/* the build's single host synchronisation and everything read after it: root index, wide-node count, iteration counts, stage times */
+int b2bvh_build_finish(b2bvh_ctx* ctx, b2bvh_tree* out) {
+  if (!ctx || !out) return b2_fail(B2BVH_ERR_INVALID, "build_finish: null argument");
+  if (!ctx->pending.active) return b2_fail(B2BVH_ERR_INVALID, "build_finish: no build is waiting on this context");
+  ctx->pending.active = false;
+  const int algo = ctx->pending.algo;
+  B2_CUDA(cudaSetDevice(ctx->device));
+  B2_CUDA(cudaStreamSynchronize(ctx->stream)); /* the only host synchronisation of a build */
+  out->root = b2_mailbox(ctx, B2_MB_ROOT)[0];
+  out->n_wide = ctx->pending.collapse ? b2_mailbox(ctx, B2_MB_COLLAPSE)[1] : 0u;
+  u32 iterations = 0;
+  if (algo == B2BVH_PLOCPP) {
+    iterations = b2_mailbox(ctx, B2_MB_PLOC)[2];
+    if (b2_mailbox(ctx, B2_MB_PLOC)[1] != 1u)
+      return b2_fail(B2BVH_ERR_INTERNAL, "ploc: %u clusters left after %u iterations", b2_mailbox(ctx, B2_MB_PLOC)[1], iterations);
+  }
   float ms = 0;
   B2_CUDA(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[5]));
   out->build_ms = ms;
@@ -435,16 +455,9 @@ int b2bvh_build(b2bvh_ctx* ctx, int algo, const b2bvh_triangle* tris, uint32_t n
   B2_CUDA(cudaEventElapsedTime(&out->stage_ms[B2BVH_T_SORT], ctx->ev[2], ctx->ev[3]));
   B2_CUDA(cudaEventElapsedTime(&out->stage_ms[B2BVH_T_BUILD], ctx->ev[3], ctx->ev[4]));
   B2_CUDA(cudaEventElapsedTime(&out->stage_ms[B2BVH_T_COLLAPSE], ctx->ev[4], ctx->ev[5]));
-  if (!opts.tris_on_device) B2_CUDA(cudaEventElapsedTime(&out->h2d_ms, ctx->ev[8], ctx->ev[9]));
+  if (ctx->pending.host_tris) B2_CUDA(cudaEventElapsedTime(&out->h2d_ms, ctx->ev[8], ctx->ev[9]));
   out->n_iterations = algo == B2BVH_HPLOC ? b2_mailbox(ctx, B2_MB_HPLOC)[0] : iterations;
-  out->n_launches = ctx->launches - launches0;
-  out->n_triangles = nTris;
-  out->d_primRefIdx = dRefPrim;
-  out->morton_bits = m60 ? 60u : 30u;
-  out->d_mortonCodeKeys64 = (const uint64_t*)dKeys64;
-  out->d_sortedMortonCodeKeys64 = (const uint64_t*)dSKeys64;
-  out->n_split_levels = splitLevels;
-  if (split) B2_CUDA(cudaEventElapsedTime(&out->split_ms, ctx->ev[10], ctx->ev[11]));
+  if (ctx->pending.split) B2_CUDA(cudaEventElapsedTime(&out->split_ms, ctx->ev[10], ctx->ev[11]));
   return 0;
 }
 

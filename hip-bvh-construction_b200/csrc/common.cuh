@@ -208,6 +208,10 @@ struct b2bvh_ctx {
     const void* tris;
     b2bvh_build_opts opts;
   } graph;
+  struct Pending { /* a build enqueued with defer_sync, waiting for b2bvh_build_finish */
+    bool active, collapse, host_tris, split;
+    int algo;
+  } pending;
   u32 alloc_epoch;       /* bumped whenever a build-owned buffer is (re)allocated: a cached graph holds the old pointers */
   u32 launches;
   u32 lbvh_second_level; /* b2bvh_build_opts.lbvh_second_level of the running build */
@@ -276,6 +280,7 @@ int b2_launch_lbvh_fused64(b2bvh_ctx* ctx, const u64* d_sortedKeys64, const u32*
 int b2_launch_morton60(b2bvh_ctx* ctx, const b2bvh_aabb* d_triAabb, const b2bvh_aabb* d_scene, u32 n, u32* d_hi, u32* d_lo, u64* d_keys64);
 int b2_launch_sort60(b2bvh_ctx* ctx, const u32* d_hi, const u32* d_lo, u32 n, u32* d_a, u32* d_aVals, u32* d_hiSorted, u32* d_valsSorted, u64* d_keys64Sorted,
                      u32* d_keysTmp, u32* d_valsTmp, void* d_sortScratch);
+int b2_launch_root_box(b2bvh_ctx* ctx, const b2bvh_bvh2_node* d_nodes, const u32* d_rootIdx, float* d_box6);
 size_t b2_collapse_scratch_bytes(u32 n);
 int b2_launch_collapse(b2bvh_ctx* ctx, const b2bvh_bvh2_node* d_nodes, const b2bvh_prim_ref* d_leaves, const u32* d_sortedVals, const u32* d_rootIdx,
                        u32 n,

@@ -124,6 +124,18 @@ int b2bvh_profile_entry(b2bvh_ctx* ctx, int index, char* name, size_t cap, float
 }
 }
 
+/* root box of the build that just ran, device to device, without the host knowing the root index (sharded build: the all-gather of
+ * the sub-tree roots can be enqueued before the build's host synchronisation) */
+__global__ void root_box_kernel(const b2bvh_bvh2_node* __restrict__ nodes, const u32* __restrict__ rootIdx, float* __restrict__ box6) {
+  if (threadIdx.x < 6) box6[threadIdx.x] = reinterpret_cast<const float*>(nodes + *rootIdx)[2 + threadIdx.x];
+}
+int b2_launch_root_box(b2bvh_ctx* ctx, const b2bvh_bvh2_node* d_nodes, const u32* d_rootIdx, float* d_box6) {
+  B2_KERNEL(ctx, "root_box");
+  root_box_kernel<<<1, 32, 0, ctx->stream>>>(d_nodes, d_rootIdx, d_box6);
+  B2_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
 /* ---- small device -> host results through mapped pinned memory (b2_fetch_words, common.cuh) ---- */
 __global__ void fetch_words_kernel(const u32* __restrict__ src, u32 words, u32* dst) {
   if (threadIdx.x < words) dst[threadIdx.x] = src[threadIdx.x];

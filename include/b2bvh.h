@@ -77,7 +77,10 @@ typedef struct b2bvh_build_opts {
                                counterpart (its codes stop at 30 bits), defined by the oracle.  All four builders (PLOC++ only needs the order,
                                the LBVH kernels and the H-PLOC walk are instantiated for 64-bit keys).  b2bvh_tree.d_mortonCodeKeys64 / d_sortedMortonCodeKeys64 hold the codes, the 32-bit key
                                arrays their upper 30 bits, d_mortonCodeValues is not written (the values are the iota) */
-  uint32_t reserved3;
+  uint32_t defer_sync;      /* 1: b2bvh_build enqueues the build and returns WITHOUT its host synchronisation; the b2bvh_tree then holds the
+                               device pointers and sizes, and b2bvh_build_finish fills in root, n_wide, iteration counts and times.  Lets a caller
+                               enqueue dependent work (the root all-gather of a sharded build) before the host waits */
+  float* d_root_box_out;    /* device, 6 floats, or NULL: the root box {min.xyz, max.xyz} is written there at the end of the build (stream-ordered) */
 } b2bvh_build_opts;
 
 /* Everything a build leaves on the device.  Pointers are DEVICE pointers owned by the context
@@ -169,6 +172,9 @@ typedef struct b2bvh_batch {
 } b2bvh_batch;
 int b2bvh_build_batched(b2bvh_ctx* ctx, const b2bvh_triangle* tris, uint32_t tris_on_device, const uint32_t* counts, uint32_t n_items,
                         b2bvh_batch* out);
+
+/* completes a build enqueued with defer_sync = 1 (the build's single host synchronisation) */
+int b2bvh_build_finish(b2bvh_ctx* ctx, b2bvh_tree* tree);
 
 /* Stages, individually callable (all pointers are device pointers).  Each names the reference kernel(s) it replaces. */
 int b2bvh_scene_extents(b2bvh_ctx* ctx, const b2bvh_triangle* d_tris, uint32_t n, b2bvh_aabb* d_triAabb,

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     assert sorted(capi.SYMBOLS) == declared
     for s in declared:
         assert hasattr(lib, s), s
-    assert lib.b2bvh_abi_version() == 5
+    assert lib.b2bvh_abi_version() == 6
 
 
 def test_struct_layouts_match_header(tmp_path):

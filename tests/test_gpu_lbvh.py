@@ -267,3 +267,26 @@ def test_baseline_config_10m_properties(ctx):
     ib = wide["aabb"][internal]
     assert (ib[:, :3] <= ib[:, 3:]).all() and (ib[:, :3] >= scene["mn"][0]).all() and (ib[:, 3:] <= scene["mx"][0]).all()
     ctx.free(d)
+
+
+@pytest.mark.parametrize("algo", [capi.TWO_PASS_LBVH, capi.SINGLE_PASS_LBVH, capi.PLOCPP, capi.HPLOC], ids=["twopass", "singlepass", "ploc", "hploc"])
+def test_deferred_synchronisation_and_root_box(ctx, oracle, algo):
+    """defer_sync: b2bvh_build returns after enqueueing; b2bvh_build_finish delivers root / wide-node count / times; the root box is left
+    on the device by the build itself.  Same bytes as the synchronous call."""
+    tris = random_tris(50_000, 121)
+    ref_tree = ctx.build(algo, tris)
+    want = ctx.fetch(ref_tree)
+    d_box = ctx.alloc(24)
+    tree = ctx.build(algo, tris, defer_sync=True, d_root_box_out=d_box)
+    assert tree.n_prims == tris.size and tree.d_bvhNodes and tree.n_wide == 0 and tree.build_ms == 0.0   # not known yet
+    ctx.build_finish(tree)
+    assert tree.root == ref_tree.root and tree.n_wide == ref_tree.n_wide and tree.build_ms > 0
+    got = ctx.fetch(tree)
+    assert got["nodes"].tobytes() == want["nodes"].tobytes() and got["wide"].tobytes() == want["wide"].tobytes()
+    box = ctx.download(d_box, np.float32, 6)
+    root = got["nodes"][tree.root]
+    assert np.array_equal(box, np.concatenate([root["mn"], root["mx"]]))
+    with pytest.raises(capi.B2bvhError, match="no build is waiting"):
+        ctx.build_finish(tree)
+    ctx.free(d_box)
+
