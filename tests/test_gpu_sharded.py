@@ -67,7 +67,8 @@ def test_sharded_trace_on_one_gpu(oracle):
             shard = np.ascontiguousarray(tris[a:b])
             eng = GpuEngine(ctxs[r], capi.SINGLE_PASS_LBVH)
             eng.shard_extents(shard)
-            _, tree = eng.build(shard, box6)
+            _, tree = eng.build(shard, box6)  # enqueued only (defer_sync) ...
+            eng.finish(tree)                  # ... the root index arrives here
             k, uv = eng.trace(tree, d_rays, 128 * 128, tr, a)
             keys.append(k); uvs.append(uv)
         best = torch.minimum(keys[0], keys[1])
