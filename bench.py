@@ -206,7 +206,8 @@ def main():
                            defer_sync=True, d_root_box_out=L.root_local.data_ptr())
             dist.all_gather_into_tensor(L.roots, L.root_local)
             capi.check(c.lib.b2bvh_top_level(c.h, L.roots.data_ptr(), world, L.top_nodes.data_ptr()), "b2bvh_top_level")
-            c.build_finish(tree)
+            if not defer:
+                c.build_finish(tree)
         launches[0] += tree.n_launches + 2
         return tree
 
