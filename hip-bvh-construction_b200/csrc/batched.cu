@@ -26,7 +26,9 @@
  */
 #include "common.cuh"
 
+#ifndef BATCH_WARPS
 #define BATCH_WARPS 8
+#endif
 #define BATCH_MAX 32u
 
 __device__ __forceinline__ u32 morton3d_10(u32 x) { /* BatchedBuildKernel.h:89-96 */

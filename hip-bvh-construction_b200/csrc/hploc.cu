@@ -24,7 +24,9 @@
  */
 #include "common.cuh"
 
+#ifndef HP_THREADS
 #define HP_THREADS 128
+#endif
 #define HP_R 8
 
 /* scratch: u32 ctrl[64] | nodeIdx[n] | freeIdx[n] | meet[n] ;  ctrl[0] = merge calls, ctrl[1] = parent of node 0, ctrl[2] = side */
