@@ -11,6 +11,7 @@ from . import types as T
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "libb2bvh.so")
 
+ABI_VERSION = 6  # B2BVH_ABI_VERSION of include/b2bvh.h: the struct layouts mirrored below
 TWO_PASS_LBVH, SINGLE_PASS_LBVH, PLOCPP, HPLOC = 0, 1, 2, 3
 TRAVERSE_WHILE, TRAVERSE_SPECULATIVE_WHILE, TRAVERSE_IFIF, TRAVERSE_RESTART_TRAIL, TRAVERSE_WIDE4 = 0, 1, 2, 3, 4
 T_EXTENTS, T_MORTON, T_SORT, T_BUILD, T_TRAVERSAL, T_COLLAPSE, T_RAYGEN, T_COUNT = range(8)
@@ -98,6 +99,9 @@ def load():
     lib.b2bvh_cost_bvh4.restype = C.c_float
     lib.b2bvh_cost_lbvh.restype = C.c_float
     lib.b2bvh_abi_version.restype = C.c_uint32
+    if lib.b2bvh_abi_version() != ABI_VERSION:
+        raise B2bvhError(f"{LIB_PATH} speaks ABI version {lib.b2bvh_abi_version()}, this mirror was written for {ABI_VERSION} "
+                         f"(struct layouts differ): rebuild the library")
     _lib = lib
     return lib
 

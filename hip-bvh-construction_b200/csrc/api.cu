@@ -58,7 +58,7 @@ enum {
 
 extern "C" {
 
-uint32_t b2bvh_abi_version(void) { return 6; }
+uint32_t b2bvh_abi_version(void) { return B2BVH_ABI_VERSION; }
 const char* b2bvh_last_error(void) { return g_err; }
 
 int b2bvh_ctx_create(int device, void* cuda_stream, b2bvh_ctx** out) {

@@ -83,6 +83,9 @@ struct Api {
     B2_SYM(b2bvh_build) B2_SYM(b2bvh_build_batched) B2_SYM(b2bvh_generate_rays) B2_SYM(b2bvh_traverse) B2_SYM(b2bvh_traverse_ex) B2_SYM(b2bvh_heat_map) B2_SYM(b2bvh_tree_cost) B2_SYM(b2bvh_cost_bvh4)
     B2_SYM(b2bvh_cost_lbvh) B2_SYM(b2bvh_synth_uniform) B2_SYM(b2bvh_abi_version)
 #undef B2_SYM
+    if (api.b2bvh_abi_version() != B2BVH_ABI_VERSION)
+      throw std::runtime_error("libb2bvh.so speaks ABI version " + std::to_string(api.b2bvh_abi_version()) + ", this header was written for " +
+                               std::to_string(B2BVH_ABI_VERSION) + " (struct layouts differ): rebuild one of them");
     return api;
   }
 };

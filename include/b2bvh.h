@@ -225,6 +225,9 @@ int b2bvh_profile_enable(b2bvh_ctx* ctx, int on);  /* also clears the recorded e
 int b2bvh_profile_count(b2bvh_ctx* ctx, int* count);
 int b2bvh_profile_entry(b2bvh_ctx* ctx, int index, char* name, size_t cap, float* ms);
 
+/* the layout of b2bvh_build_opts / b2bvh_tree / b2bvh_batch this header describes; a binding compares it with the library's answer
+ * at load time and refuses a mismatch (the host classes and the Python mirror do) */
+#define B2BVH_ABI_VERSION 6u
 uint32_t b2bvh_abi_version(void);
 
 #ifdef __cplusplus

@@ -24,7 +24,9 @@ def test_library_exports_every_declared_symbol():
     assert sorted(capi.SYMBOLS) == declared
     for s in declared:
         assert hasattr(lib, s), s
-    assert lib.b2bvh_abi_version() == 6
+    assert lib.b2bvh_abi_version() == capi.ABI_VERSION
+    hdr = open(os.path.join(ROOT, "include", "b2bvh.h")).read()
+    assert f"#define B2BVH_ABI_VERSION {capi.ABI_VERSION}u" in hdr
 
 
 def test_struct_layouts_match_header(tmp_path):
