@@ -441,3 +441,100 @@ def trace_sharded(tris, world, rays, transform, single_pass=True):
     prim = np.where(hit, best & 0xFFFFFFFF, -1)
     return t.astype(np.float32), prim.astype(np.int64), uv
 
+
+
+# ---- executable specification of the globally sorted multi-GPU build (next round's GPU work) ----
+def _boundary_depth(skeys, g):
+    """Common-prefix length of the augmented keys (key, sorted position) of the sorted leaves g and g+1; -1 outside the array.
+    32-bit keys: clz of (key xor) in 0..31, else 32 + clz32(position xor); 64-bit keys: 0..63, else 64 + clz32."""
+    n = skeys.size
+    if g < 0 or g + 1 >= n:
+        return -1
+    bits = 64 if skeys.dtype == np.uint64 else 32
+    kx = int(skeys[g]) ^ int(skeys[g + 1])
+    if kx:
+        return bits - kx.bit_length()
+    return bits + (32 - (g ^ (g + 1)).bit_length())
+
+
+def lbvh_by_ranges(refs, skeys, svals, ranges, karras):
+    """The one-GPU LBVH built the way G ranks would build it: rank r owns the sorted positions ranges[r] = [a, b) of the GLOBALLY sorted
+    sequence, knows the two keys across its edges, and merges clusters exactly as lbvh_tile_kernel does — two neighbours form a node when
+    the boundary between them is deeper than both boundaries next to it — but only inside its range; the clusters it is left with (their
+    parents straddle a rank boundary) are then concatenated in rank order and finished by the same rule (the 'all-gather + group kernel'
+    step).  Returns nodes[2n-1] (LBVH layout), root, and the number of left-over clusters per rank.  Must equal lbvh_karras / lbvh_apetrei."""
+    n = skeys.size
+    nint = n - 1
+    nodes = np.zeros(2 * n - 1, dtype=T.BVH2_NODE)
+    nodes["left"][:] = 0xFFFFFFFF; nodes["right"][:] = 0xFFFFFFFF
+    for g in range(n):
+        r = refs[svals[g]]
+        nodes[nint + g] = (r["primIdx"], 0xFFFFFFFF, r["mn"], r["mx"])
+    depth = [_boundary_depth(skeys, g) for g in range(-1, n)]  # depth[g + 1] = boundary between g and g+1
+    D = lambda g: depth[g + 1]
+    root = [None]
+
+    def merge_rounds(clusters, lo_edge, hi_edge):
+        """clusters: list of (lo, hi, node id); merges while some interior boundary is a local maximum of the depths; the boundaries
+        outside [lo_edge, hi_edge) are not available (rank edges keep their own depth as the sentinel)."""
+        while True:
+            merged = False
+            out = []
+            i = 0
+            while i < len(clusters):
+                if i + 1 < len(clusters):
+                    (lo, mid, idl), (_, hi, idr) = clusters[i], clusters[i + 1]
+                    d0, dl, dr = D(mid - 1), D(lo - 1), D(hi - 1)
+                    if d0 > dl and d0 > dr and lo >= lo_edge and hi <= hi_edge:
+                        is_root = lo == 0 and hi == n
+                        if karras:
+                            nid = 0 if is_root else (hi - 1 if dr > dl else lo)
+                        else:
+                            nid = mid - 1
+                        nodes[nid]["left"] = idl; nodes[nid]["right"] = idr
+                        nodes[nid]["mn"] = np.minimum(nodes[idl]["mn"], nodes[idr]["mn"]); nodes[nid]["mx"] = np.maximum(nodes[idl]["mx"], nodes[idr]["mx"])
+                        if is_root:
+                            root[0] = nid
+                        out.append((lo, hi, nid))
+                        i += 2
+                        merged = True
+                        continue
+                out.append(clusters[i])
+                i += 1
+            clusters = out
+            if not merged:
+                return clusters
+
+    leftovers, counts = [], []
+    for a, b in ranges:
+        left = merge_rounds([(g, g + 1, nint + g) for g in range(a, b)], a, b)
+        counts.append(len(left))
+        leftovers += left
+    final = merge_rounds(leftovers, 0, n)
+    assert len(final) == 1 and final[0][0] == 0 and final[0][1] == n
+    return nodes, (root[0] if root[0] is not None else final[0][2]), counts
+
+
+def global_sort_by_exchange(keys, world, splitters):
+    """The sort step of the globally sorted build, restated: rank r holds keys[shard r] with GLOBAL indices; every pair goes to the rank
+    whose key interval [splitters[d-1], splitters[d]) contains its key (equal keys never split), the pieces a rank receives are
+    concatenated in SOURCE-RANK order (so equal keys arrive in global-index order), and one local stable sort per rank finishes.  The
+    concatenation over ranks must equal the stable sort of the whole array.  Returns (sorted keys, sorted global indices, per-rank counts)."""
+    n = keys.size
+    splitters = np.asarray(splitters, dtype=keys.dtype)
+    assert splitters.size == world - 1 and np.all(splitters[1:] >= splitters[:-1])
+    recv_k = [[] for _ in range(world)]
+    recv_v = [[] for _ in range(world)]
+    for r in range(world):
+        a, b = (n * r) // world, (n * (r + 1)) // world
+        k = keys[a:b]
+        dest = np.searchsorted(splitters, k, side="right")
+        for d in range(world):
+            m = dest == d
+            recv_k[d].append(k[m]); recv_v[d].append(np.arange(a, b, dtype=np.uint32)[m])
+    out_k, out_v, counts = [], [], []
+    for d in range(world):
+        k = np.concatenate(recv_k[d]); v = np.concatenate(recv_v[d])
+        order = np.argsort(k, kind="stable")
+        out_k.append(k[order]); out_v.append(v[order]); counts.append(k.size)
+    return np.concatenate(out_k), np.concatenate(out_v), counts
