@@ -52,7 +52,7 @@ class Batch(C.Structure):
 # every symbol include/b2bvh.h declares (tests check the library exports each of them)
 SYMBOLS = ["b2bvh_ctx_create", "b2bvh_ctx_destroy", "b2bvh_device_name", "b2bvh_device_sm_count", "b2bvh_alloc", "b2bvh_free",
            "b2bvh_memset", "b2bvh_h2d", "b2bvh_d2h", "b2bvh_h2d_async", "b2bvh_d2h_async", "b2bvh_d2d", "b2bvh_sync", "b2bvh_host_alloc_pinned", "b2bvh_host_free_pinned",
-           "b2bvh_last_error", "b2bvh_build", "b2bvh_build_finish", "b2bvh_build_batched", "b2bvh_scene_extents", "b2bvh_morton_codes", "b2bvh_sort_pairs", "b2bvh_generate_rays",
+           "b2bvh_last_error", "b2bvh_build", "b2bvh_build_finish", "b2bvh_build_batched", "b2bvh_scene_extents", "b2bvh_morton_codes", "b2bvh_sort_pairs", "b2bvh_lbvh_from_sorted64", "b2bvh_generate_rays",
            "b2bvh_traverse", "b2bvh_traverse_ex", "b2bvh_heat_map", "b2bvh_shard_extents", "b2bvh_top_level", "b2bvh_cost_bvh4", "b2bvh_cost_lbvh", "b2bvh_tree_cost",
            "b2bvh_abi_version", "b2bvh_synth_uniform", "b2bvh_synth_clustered", "b2bvh_profile_enable", "b2bvh_profile_count", "b2bvh_profile_entry"]
 
@@ -82,6 +82,7 @@ def load():
         "b2bvh_build_batched": [vp, vp, u32, vp, u32, C.POINTER(Batch)], "b2bvh_build_finish": [vp, C.POINTER(Tree)],
         "b2bvh_scene_extents": [vp, vp, u32, vp, vp], "b2bvh_morton_codes": [vp, vp, vp, u32, vp, vp],
         "b2bvh_sort_pairs": [vp, vp, vp, vp, vp, u32, u32, u32],
+        "b2bvh_lbvh_from_sorted64": [vp, vp, vp, vp, u32, C.c_int, vp, vp, C.POINTER(u32)],
         "b2bvh_generate_rays": [vp, vp, u32, u32, vp, fp],
         "b2bvh_traverse": [vp, C.POINTER(Tree), vp, u32, vp, C.c_int, vp, vp, fp],
         "b2bvh_traverse_ex": [vp, C.POINTER(Tree), vp, u32, vp, C.c_int, vp, vp, vp, fp], "b2bvh_heat_map": [vp, u32, vp],
@@ -275,6 +276,22 @@ class Context:
             for p in (dk, dv, ko, vo):
                 if p:
                     self.free(p)
+
+    def lbvh_from_sorted64(self, keys64, vals, d_boxes, karras):
+        """The hierarchy stage over sorted 64-bit keys (host arrays; d_boxes: device AABB array indexed by vals).  Returns nodes, root."""
+        keys64 = np.ascontiguousarray(keys64, dtype=np.uint64)
+        vals = np.ascontiguousarray(vals, dtype=np.uint32)
+        n = keys64.size
+        dk, dv = self.upload(keys64), self.upload(vals)
+        dn, dp = self.alloc((2 * n - 1) * 32), self.alloc((2 * n - 1) * 4)
+        root = C.c_uint32()
+        try:
+            check(self.lib.b2bvh_lbvh_from_sorted64(self.h, C.c_void_p(dk), C.c_void_p(dv), C.c_void_p(d_boxes), n, 1 if karras else 0, C.c_void_p(dn),
+                                                    C.c_void_p(dp), C.byref(root)), "b2bvh_lbvh_from_sorted64")
+            return self.download(dn, T.BVH2_NODE, 2 * n - 1), int(root.value)
+        finally:
+            for p in (dk, dv, dn, dp):
+                self.free(p)
 
     def synth_uniform(self, n_total, seed, first=0, count=None, half=None, clustered=False):
         """synth_uniform_v1 (or synth_clustered_v1) triangles [first, first+count) generated on the device; returns the device pointer."""

@@ -205,6 +205,26 @@ int b2bvh_sort_pairs(b2bvh_ctx* ctx, const uint32_t* d_keysIn, const uint32_t* d
   return b2_launch_sort(ctx, d_keysIn, d_valsIn, d_keysOut, d_valsOut, (u32*)tk, (u32*)tv, sc, n, startBit, endBit);
 }
 
+/* the hierarchy stage alone, over caller-provided SORTED 64-bit keys: the building block of the globally sorted multi-GPU build
+ * (DESIGN.md section 9), where a rank runs it over its range of the global order with keys widened to (code << 32 | global position) */
+int b2bvh_lbvh_from_sorted64(b2bvh_ctx* ctx, const uint64_t* d_sortedKeys64, const uint32_t* d_sortedVals, const b2bvh_aabb* d_primAabb, uint32_t n,
+                             int karras, b2bvh_bvh2_node* d_nodes, uint32_t* d_parents, uint32_t* root) {
+  if (!ctx || !d_sortedKeys64 || !d_sortedVals || !d_primAabb || !d_nodes || !root) return b2_fail(B2BVH_ERR_INVALID, "lbvh_from_sorted64: null argument");
+  if (n < 2 || n > 0x3FFFFFFFu) return b2_fail(B2BVH_ERR_INVALID, "lbvh_from_sorted64: n=%u out of range", n);
+  if (karras && !d_parents) return b2_fail(B2BVH_ERR_INVALID, "lbvh_from_sorted64: the Karras numbering writes parent indices (2n-1 words)");
+  B2_CUDA(cudaSetDevice(ctx->device));
+  void* dLbvh;
+  B2_TRY(b2_reserve(ctx, SLOT_LBVH, b2_lbvh_scratch_bytes(n), &dLbvh));
+  u32* dRoot = (u32*)((unsigned char*)ctx->bufs[SLOT_CTL].p + 96);
+  ctx->ref_prim = nullptr; ctx->ref_leaf_prim = nullptr; ctx->lbvh_second_level = 0;
+  B2_TRY(b2_launch_lbvh_fused64(ctx, (const u64*)d_sortedKeys64, d_sortedVals, d_primAabb, n, d_nodes, karras ? d_parents : nullptr, (u32*)dLbvh, dRoot, karras ? 1 : 0));
+  if (karras) B2_CUDA(cudaMemsetAsync(dRoot, 0, 4, ctx->stream));
+  B2_TRY(b2_fetch_words(ctx, dRoot, 1, B2_MB_ROOT));
+  B2_CUDA(cudaStreamSynchronize(ctx->stream));
+  *root = b2_mailbox(ctx, B2_MB_ROOT)[0];
+  return 0;
+}
+
 /* ------------------------------------------------------------------ the build */
 int b2bvh_build(b2bvh_ctx* ctx, int algo, const b2bvh_triangle* tris, uint32_t n, const b2bvh_build_opts* optsIn, b2bvh_tree* out) {
   if (!ctx || !tris || !out) return b2_fail(B2BVH_ERR_INVALID, "build: null argument");

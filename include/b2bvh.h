@@ -184,6 +184,13 @@ int b2bvh_morton_codes(b2bvh_ctx* ctx, const b2bvh_aabb* d_triAabb, const b2bvh_
 int b2bvh_sort_pairs(b2bvh_ctx* ctx, const uint32_t* d_keysIn, const uint32_t* d_valsIn, uint32_t* d_keysOut, uint32_t* d_valsOut,
                      uint32_t n, uint32_t startBit, uint32_t endBit); /* Oro::RadixSort::sort(KeyValueSoA...), RadixSort.cpp:291-318   */
 
+/* The hierarchy stage alone (InitBvhNodes + BvhBuildAndFit / BvhBuild + FitBvhNodes over an already sorted sequence), with 64-bit keys:
+ * d_sortedKeys64 non-decreasing, d_sortedVals[g] indexes d_primAabb; nodes in the LBVH layout (2n-1), Karras (root 0, parents written) or
+ * Apetrei numbering (root returned).  Building block of the globally sorted multi-GPU build: a rank runs it over its range of the global
+ * order with keys widened to (code << 32 | global sorted position), see DESIGN.md section 9. */
+int b2bvh_lbvh_from_sorted64(b2bvh_ctx* ctx, const uint64_t* d_sortedKeys64, const uint32_t* d_sortedVals, const b2bvh_aabb* d_primAabb, uint32_t n,
+                             int karras, b2bvh_bvh2_node* d_nodes, uint32_t* d_parents /* 2n-1 words, Karras only */, uint32_t* root);
+
 /* ---- traversal: replaces the body of TwoPassLbvh::traverseBvh (src/TwoPassLbvh.cpp:199-311). ---- */
 int b2bvh_generate_rays(b2bvh_ctx* ctx, const b2bvh_camera* cam, uint32_t width, uint32_t height, b2bvh_ray* d_rays,
                         float* ms);                       /* GenerateRays, CommonBlocksKernel.h:432-463 */

@@ -538,3 +538,118 @@ def global_sort_by_exchange(keys, world, splitters):
         order = np.argsort(k, kind="stable")
         out_k.append(k[order]); out_v.append(v[order]); counts.append(k.size)
     return np.concatenate(out_k), np.concatenate(out_v), counts
+
+
+def lbvh_by_ranges_with_unchanged_builder(tris, refs, skeys, svals, ranges, karras, builder=None):
+    """The same range-wise build, but every rank runs an UNCHANGED single-range LBVH builder (here the oracle's; on the device the
+    64-bit-key instantiation of the tile / group / climb kernels), which makes the next round's work orchestration only:
+      * the rank's keys are widened to (key << 32 | GLOBAL sorted position): they are unique, so the builder's own tie-break on LOCAL
+        positions never decides, and the common prefix of two neighbours is exactly the augmented-key depth of the one-GPU build;
+      * the range is extended by ONE ghost leaf on each inner side (the neighbour's edge key), so every boundary of a ghost-free node —
+        including the two at the rank's edges — is seen with its true depth;
+      * of the local tree, the nodes that contain no ghost ARE nodes of the one-GPU tree (local index + offset = global index); the
+        nodes containing a ghost (the two spines) are artefacts, and the ghost-free children hanging off them are the rank's left-over
+        clusters, finished after the gather as in lbvh_by_ranges.
+    skeys: uint32 sorted keys (30-bit codes).  builder(keys64, vals) -> (nodes[2m-1], root): the single-range builder under test
+    (default: the oracle's; tests pass the device's b2bvh_lbvh_from_sorted64)."""
+    n = skeys.size
+    nint = n - 1
+    nodes = np.zeros(2 * n - 1, dtype=T.BVH2_NODE)
+    nodes["left"][:] = 0xFFFFFFFF; nodes["right"][:] = 0xFFFFFFFF
+    for g in range(n):
+        r = refs[svals[g]]
+        nodes[nint + g] = (r["primIdx"], 0xFFFFFFFF, r["mn"], r["mx"])
+    leftovers, counts = [], []
+    for a, b in ranges:
+        a2, b2 = max(a - 1, 0), min(b + 1, n)
+        m = b2 - a2
+        k64 = (skeys[a2:b2].astype(np.uint64) << np.uint64(32)) | np.arange(a2, b2, dtype=np.uint64)
+        v = np.ascontiguousarray(svals[a2:b2])
+        if m == 1:
+            leftovers.append((a, b, nint + a)); counts.append(1)
+            continue
+        if builder is not None:
+            loc, lroot = builder(k64, v)
+        elif karras:
+            loc, _ = lbvh_karras(refs, k64, v)
+            lroot = 0
+        else:
+            loc, lroot = lbvh_apetrei(tris, k64, v)
+        ghostL, ghostR = a > 0, b < n
+        mine = []
+
+        def to_global(idx):
+            return (nint + a2 + (idx - (m - 1))) if idx >= m - 1 else a2 + idx
+
+        def walk(idx, lo, hi):
+            """returns after classifying the subtree rooted at local node idx covering local leaves [lo, hi)"""
+            has_ghost = (ghostL and lo == 0) or (ghostR and hi == m)
+            if idx >= m - 1:                      # a leaf
+                if not has_ghost:
+                    mine.append((a2 + lo, a2 + hi, to_global(idx)))
+                return
+            l, r = int(loc[idx]["left"]), int(loc[idx]["right"])
+            split = _subtree_size(loc, l, m) + lo
+            if not has_ghost:
+                g = to_global(idx)
+                nodes[g]["left"] = to_global(l); nodes[g]["right"] = to_global(r)
+                nodes[g]["mn"] = loc[idx]["mn"]; nodes[g]["mx"] = loc[idx]["mx"]
+                _emit_subtree(loc, l, m, to_global, nodes); _emit_subtree(loc, r, m, to_global, nodes)
+                mine.append((a2 + lo, a2 + hi, g))
+                return
+            walk(l, lo, split); walk(r, split, hi)
+
+        walk(lroot, 0, m)
+        mine.sort()
+        counts.append(len(mine))
+        leftovers += mine
+    # the gather + final rounds, as in lbvh_by_ranges
+    depth = [_boundary_depth(skeys, g) for g in range(-1, n)]
+    D = lambda g: depth[g + 1]
+    root = None
+    clusters = leftovers
+    while len(clusters) > 1:
+        out, i, merged = [], 0, False
+        while i < len(clusters):
+            if i + 1 < len(clusters):
+                (lo, mid, idl), (_, hi, idr) = clusters[i], clusters[i + 1]
+                d0, dl, dr = D(mid - 1), D(lo - 1), D(hi - 1)
+                if d0 > dl and d0 > dr:
+                    is_root = lo == 0 and hi == n
+                    nid = (0 if is_root else (hi - 1 if dr > dl else lo)) if karras else mid - 1
+                    nodes[nid]["left"] = idl; nodes[nid]["right"] = idr
+                    nodes[nid]["mn"] = np.minimum(nodes[idl]["mn"], nodes[idr]["mn"]); nodes[nid]["mx"] = np.maximum(nodes[idl]["mx"], nodes[idr]["mx"])
+                    if is_root:
+                        root = nid
+                    out.append((lo, hi, nid)); i += 2; merged = True
+                    continue
+            out.append(clusters[i]); i += 1
+        assert merged
+        clusters = out
+    return nodes, (root if root is not None else clusters[0][2]), counts
+
+
+def _subtree_size(loc, idx, m):
+    """number of leaves under local node idx (iterative)"""
+    size, stack = 0, [idx]
+    while stack:
+        i = stack.pop()
+        if i >= m - 1:
+            size += 1
+        else:
+            stack.append(int(loc[i]["left"])); stack.append(int(loc[i]["right"]))
+    return size
+
+
+def _emit_subtree(loc, idx, m, to_global, nodes):
+    """copies the internal nodes under local node idx into the global array with renumbered children"""
+    stack = [idx]
+    while stack:
+        i = stack.pop()
+        if i >= m - 1:
+            continue
+        l, r = int(loc[i]["left"]), int(loc[i]["right"])
+        g = to_global(i)
+        nodes[g]["left"] = to_global(l); nodes[g]["right"] = to_global(r)
+        nodes[g]["mn"] = loc[i]["mn"]; nodes[g]["mx"] = loc[i]["mx"]
+        stack.append(l); stack.append(r)

@@ -290,3 +290,22 @@ def test_deferred_synchronisation_and_root_box(ctx, oracle, algo):
         ctx.build_finish(tree)
     ctx.free(d_box)
 
+
+@pytest.mark.parametrize("kind,n,seed", [("uniform", 12_000, 161), ("clustered", 8000, 162), ("duplicate", 1500, 163)])
+def test_hierarchy_stage_per_range_reproduces_the_one_gpu_tree(ctx, oracle, kind, n, seed):
+    """b2bvh_lbvh_from_sorted64 — the device's tile / group / climb kernels over 64-bit keys — used the way a rank of the globally sorted
+    build would use it (oracle.lbvh_by_ranges_with_unchanged_builder: range + ghost leaves, keys = code << 32 | global position): after
+    the host-side stitching of the few left-over clusters the nodes equal the one-GPU build byte for byte, for both numberings."""
+    tris = random_tris(n, seed, kind)
+    refs, boxes, _ = oracle.primrefs(tris)
+    d_boxes = ctx.upload(boxes)
+    rng = np.random.default_rng(seed)
+    cuts = sorted(rng.choice(np.arange(1, n), size=3, replace=False).tolist())
+    ranges = list(zip([0] + cuts, cuts + [n]))
+    for karras in (True, False):
+        want = ctx.fetch(ctx.build(capi.TWO_PASS_LBVH if karras else capi.SINGLE_PASS_LBVH, tris, collapse=False))
+        nodes, root, leftovers = oracle.lbvh_by_ranges_with_unchanged_builder(
+            tris, refs, want["skeys"], want["svals"], ranges, karras, builder=lambda k64, v: ctx.lbvh_from_sorted64(k64, v, d_boxes, karras))
+        assert nodes.tobytes() == want["nodes"].tobytes() and root == want["root"], (karras, leftovers)
+    ctx.free(d_boxes)
+

@@ -37,3 +37,18 @@ def test_rangewise_merging_builds_the_one_gpu_tree(oracle, kind, n, seed, bits):
         assert nodes.tobytes() == o["nodes"].tobytes() and root == o["root"]
         # what crosses the wire in the gather: a few dozen 48-byte records per rank, independent of n
         assert max(leftovers) <= 2 * (96 if bits == 60 else 64)
+
+
+@pytest.mark.parametrize("kind,n,seed", [("uniform", 2000, 151), ("clustered", 1500, 152), ("duplicate", 300, 153), ("anisotropic", 1800, 154)])
+def test_rangewise_build_with_an_unchanged_single_range_builder(oracle, kind, n, seed):
+    """The variant that needs no new hierarchy kernel: every rank runs the ordinary 64-bit-key builder over its range + one ghost leaf
+    per inner edge, with keys widened to (code << 32 | global position); ghost-free nodes are the one-GPU tree's nodes."""
+    tris = random_tris(n, seed, kind)
+    rng = np.random.default_rng(seed)
+    cuts = sorted(rng.choice(np.arange(1, n), size=int(rng.integers(1, 8)), replace=False).tolist())
+    ranges = list(zip([0] + cuts, cuts + [n]))
+    for karras in (True, False):
+        o = oracle.build_lbvh(tris, single_pass=not karras)
+        nodes, root, leftovers = oracle.lbvh_by_ranges_with_unchanged_builder(tris, o["refs"], o["skeys"], o["svals"], ranges, karras)
+        assert nodes.tobytes() == o["nodes"].tobytes() and root == o["root"] and max(leftovers) <= 128
+
