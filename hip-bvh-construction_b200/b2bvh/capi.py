@@ -52,7 +52,7 @@ class Batch(C.Structure):
 # every symbol include/b2bvh.h declares (tests check the library exports each of them)
 SYMBOLS = ["b2bvh_ctx_create", "b2bvh_ctx_destroy", "b2bvh_device_name", "b2bvh_device_sm_count", "b2bvh_alloc", "b2bvh_free",
            "b2bvh_memset", "b2bvh_h2d", "b2bvh_d2h", "b2bvh_h2d_async", "b2bvh_d2h_async", "b2bvh_d2d", "b2bvh_sync", "b2bvh_host_alloc_pinned", "b2bvh_host_free_pinned",
-           "b2bvh_last_error", "b2bvh_build", "b2bvh_build_finish", "b2bvh_build_batched", "b2bvh_scene_extents", "b2bvh_morton_codes", "b2bvh_sort_pairs", "b2bvh_lbvh_from_sorted64", "b2bvh_generate_rays",
+           "b2bvh_last_error", "b2bvh_build", "b2bvh_build_finish", "b2bvh_build_batched", "b2bvh_scene_extents", "b2bvh_morton_codes", "b2bvh_sort_pairs", "b2bvh_lbvh_from_sorted64", "b2bvh_range_extract", "b2bvh_generate_rays",
            "b2bvh_traverse", "b2bvh_traverse_ex", "b2bvh_heat_map", "b2bvh_shard_extents", "b2bvh_top_level", "b2bvh_cost_bvh4", "b2bvh_cost_lbvh", "b2bvh_tree_cost",
            "b2bvh_abi_version", "b2bvh_synth_uniform", "b2bvh_synth_clustered", "b2bvh_profile_enable", "b2bvh_profile_count", "b2bvh_profile_entry"]
 
@@ -83,6 +83,7 @@ def load():
         "b2bvh_scene_extents": [vp, vp, u32, vp, vp], "b2bvh_morton_codes": [vp, vp, vp, u32, vp, vp],
         "b2bvh_sort_pairs": [vp, vp, vp, vp, vp, u32, u32, u32],
         "b2bvh_lbvh_from_sorted64": [vp, vp, vp, vp, u32, C.c_int, vp, vp, C.POINTER(u32)],
+        "b2bvh_range_extract": [vp, vp, u32, u32, C.c_int, u32, u32, u32, u32, vp, vp, C.POINTER(u32)],
         "b2bvh_generate_rays": [vp, vp, u32, u32, vp, fp],
         "b2bvh_traverse": [vp, C.POINTER(Tree), vp, u32, vp, C.c_int, vp, vp, fp],
         "b2bvh_traverse_ex": [vp, C.POINTER(Tree), vp, u32, vp, C.c_int, vp, vp, vp, fp], "b2bvh_heat_map": [vp, u32, vp],
@@ -291,6 +292,25 @@ class Context:
             return self.download(dn, T.BVH2_NODE, 2 * n - 1), int(root.value)
         finally:
             for p in (dk, dv, dn, dp):
+                self.free(p)
+
+    def range_tree(self, keys64, vals, d_boxes, karras, ghost_left, ghost_right, first_pos, n_global):
+        """One rank of the globally sorted build on the device: hierarchy stage over the (ghost-extended) range, then extraction.
+        Returns (nodes[2m-1] with global child indices, artefacts invalid; left-over clusters as a CLUSTER array)."""
+        keys64 = np.ascontiguousarray(keys64, dtype=np.uint64)
+        vals = np.ascontiguousarray(vals, dtype=np.uint32)
+        m = keys64.size
+        dk, dv = self.upload(keys64), self.upload(vals)
+        dn, dp, do, dc = self.alloc((2 * m - 1) * 32), self.alloc((2 * m - 1) * 4), self.alloc((2 * m - 1) * 32), self.alloc(256 * 48)
+        root, cnt = C.c_uint32(), C.c_uint32()
+        try:
+            check(self.lib.b2bvh_lbvh_from_sorted64(self.h, C.c_void_p(dk), C.c_void_p(dv), C.c_void_p(d_boxes), m, 1 if karras else 0, C.c_void_p(dn),
+                                                    C.c_void_p(dp), C.byref(root)), "b2bvh_lbvh_from_sorted64")
+            check(self.lib.b2bvh_range_extract(self.h, C.c_void_p(dn), m, root.value, 1 if karras else 0, 1 if ghost_left else 0, 1 if ghost_right else 0,
+                                               int(first_pos), int(n_global), C.c_void_p(do), C.c_void_p(dc), C.byref(cnt)), "b2bvh_range_extract")
+            return self.download(do, T.BVH2_NODE, 2 * m - 1), self.download(dc, T.CLUSTER, cnt.value)
+        finally:
+            for p in (dk, dv, dn, dp, do, dc):
                 self.free(p)
 
     def synth_uniform(self, n_total, seed, first=0, count=None, half=None, clustered=False):

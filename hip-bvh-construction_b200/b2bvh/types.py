@@ -24,6 +24,9 @@ TRANSFORM = np.dtype({"names": ["translation", "scale", "quat"], "formats": [("<
 CAMERA = np.dtype({"names": ["eye", "quat", "fov", "near", "far"], "formats": [("<f4", (4,)), ("<f4", (4,)), "<f4", "<f4", "<f4"],
                    "offsets": [0, 16, 32, 36, 40], "itemsize": 64})
 
+CLUSTER = np.dtype({"names": ["lo", "hi", "node", "mn", "mx"], "formats": ["<u4", "<u4", "<u4", ("<f4", (3,)), ("<f4", (3,))],
+                    "offsets": [0, 4, 8, 16, 28], "itemsize": 48})
+
 assert TRIANGLE.itemsize == 64 and AABB.itemsize == 24 and BVH2_NODE.itemsize == 32 and BVH4_NODE.itemsize == 128
 assert PRIM_REF.itemsize == 28 and PRIM_NODE.itemsize == 8 and RAY.itemsize == 32 and HIT.itemsize == 32
 

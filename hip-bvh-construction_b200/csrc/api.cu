@@ -225,6 +225,22 @@ int b2bvh_lbvh_from_sorted64(b2bvh_ctx* ctx, const uint64_t* d_sortedKeys64, con
   return 0;
 }
 
+int b2bvh_range_extract(b2bvh_ctx* ctx, const b2bvh_bvh2_node* d_local, uint32_t m, uint32_t local_root, int karras, uint32_t ghost_left,
+                        uint32_t ghost_right, uint32_t first_pos, uint32_t n_global, b2bvh_bvh2_node* d_out, b2bvh_cluster* d_clusters, uint32_t* count) {
+  if (!ctx || !d_local || !d_out || !d_clusters || !count) return b2_fail(B2BVH_ERR_INVALID, "range_extract: null argument");
+  if (m < 2 || (uint64_t)first_pos + m > n_global) return b2_fail(B2BVH_ERR_INVALID, "range_extract: range [%u, %u + %u) does not fit %u positions", first_pos, first_pos, m, n_global);
+  B2_CUDA(cudaSetDevice(ctx->device));
+  void* dFlags;
+  B2_TRY(b2_reserve(ctx, SLOT_MISC, (size_t)m + 64, &dFlags));
+  u32* dCount = (u32*)((unsigned char*)ctx->bufs[SLOT_CTL].p + 128);
+  B2_TRY(b2_launch_range_extract(ctx, d_local, m, local_root, karras, ghost_left, ghost_right, first_pos, n_global, (unsigned char*)dFlags, d_out, d_clusters, dCount));
+  B2_TRY(b2_fetch_words(ctx, dCount, 1, B2_MB_RANGE));
+  B2_CUDA(cudaStreamSynchronize(ctx->stream));
+  *count = b2_mailbox(ctx, B2_MB_RANGE)[0];
+  if (*count > 256u) return b2_fail(B2BVH_ERR_INTERNAL, "range_extract: %u left-over clusters (at most 256 expected)", *count);
+  return 0;
+}
+
 /* ------------------------------------------------------------------ the build */
 int b2bvh_build(b2bvh_ctx* ctx, int algo, const b2bvh_triangle* tris, uint32_t n, const b2bvh_build_opts* optsIn, b2bvh_tree* out) {
   if (!ctx || !tris || !out) return b2_fail(B2BVH_ERR_INVALID, "build: null argument");

@@ -257,7 +257,7 @@ int b2_prof_end(b2bvh_ctx* ctx);
 int b2_reserve(b2bvh_ctx* ctx, int slot, size_t bytes, void** out);
 /* words <= 16 from device memory into mailbox slot `slot`; readable at b2_mailbox(ctx, slot) after the next stream synchronisation */
 #define B2_MAILBOX_SLOTS 6
-enum { B2_MB_COLLAPSE = 0, B2_MB_PLOC = 1, B2_MB_HPLOC = 2, B2_MB_ROOT = 3, B2_MB_SPLIT = 4, B2_MB_BATCH = 5 };
+enum { B2_MB_COLLAPSE = 0, B2_MB_PLOC = 1, B2_MB_HPLOC = 2, B2_MB_ROOT = 3, B2_MB_SPLIT = 4, B2_MB_RANGE = 5 };
 int b2_fetch_words(b2bvh_ctx* ctx, const void* d_src, u32 words, int slot);
 static inline const u32* b2_mailbox(const b2bvh_ctx* ctx, int slot) { return ctx->mailbox + slot * 16; }
 
@@ -281,6 +281,8 @@ int b2_launch_morton60(b2bvh_ctx* ctx, const b2bvh_aabb* d_triAabb, const b2bvh_
 int b2_launch_sort60(b2bvh_ctx* ctx, const u32* d_hi, const u32* d_lo, u32 n, u32* d_a, u32* d_aVals, u32* d_hiSorted, u32* d_valsSorted, u64* d_keys64Sorted,
                      u32* d_keysTmp, u32* d_valsTmp, void* d_sortScratch);
 int b2_launch_root_box(b2bvh_ctx* ctx, const b2bvh_bvh2_node* d_nodes, const u32* d_rootIdx, float* d_box6);
+int b2_launch_range_extract(b2bvh_ctx* ctx, const b2bvh_bvh2_node* d_local, u32 m, u32 root, int karras, u32 ghostL, u32 ghostR, u32 firstPos, u32 nGlobal,
+                            unsigned char* d_flags, b2bvh_bvh2_node* d_out, b2bvh_cluster* d_clusters, u32* d_count);
 size_t b2_collapse_scratch_bytes(u32 n);
 int b2_launch_collapse(b2bvh_ctx* ctx, const b2bvh_bvh2_node* d_nodes, const b2bvh_prim_ref* d_leaves, const u32* d_sortedVals, const u32* d_rootIdx,
                        u32 n,

@@ -191,6 +191,21 @@ int b2bvh_sort_pairs(b2bvh_ctx* ctx, const uint32_t* d_keysIn, const uint32_t* d
 int b2bvh_lbvh_from_sorted64(b2bvh_ctx* ctx, const uint64_t* d_sortedKeys64, const uint32_t* d_sortedVals, const b2bvh_aabb* d_primAabb, uint32_t n,
                              int karras, b2bvh_bvh2_node* d_nodes, uint32_t* d_parents /* 2n-1 words, Karras only */, uint32_t* root);
 
+/* A finished sub-tree of a rank whose parent straddles a rank boundary (globally sorted multi-GPU build): global sorted positions
+ * [lo, hi), global node index, box.  48 bytes. */
+typedef struct b2bvh_cluster {
+  uint32_t lo, hi, node, pad;
+  b2bvh_aabb box;
+  uint32_t pad2[2];
+} b2bvh_cluster;
+/* Second building block of the globally sorted build: d_local = the tree b2bvh_lbvh_from_sorted64 built over the
+ * rank's range of the global order extended by a ghost leaf on the left (ghost_left) and / or right (ghost_right) edge, local leaf 0 at
+ * global sorted position first_pos.  d_out (2m-1 nodes) receives the ghost-free nodes with GLOBAL child indices (internal i -> first_pos
+ * + i, leaf slot g -> (n_global - 1) + first_pos + g), artefact nodes as {INVALID, INVALID, empty box}, leaves unchanged; d_clusters
+ * (room for 256) the left-over clusters in position order, *count their number. */
+int b2bvh_range_extract(b2bvh_ctx* ctx, const b2bvh_bvh2_node* d_local, uint32_t m, uint32_t local_root, int karras, uint32_t ghost_left,
+                        uint32_t ghost_right, uint32_t first_pos, uint32_t n_global, b2bvh_bvh2_node* d_out, b2bvh_cluster* d_clusters, uint32_t* count);
+
 /* ---- traversal: replaces the body of TwoPassLbvh::traverseBvh (src/TwoPassLbvh.cpp:199-311). ---- */
 int b2bvh_generate_rays(b2bvh_ctx* ctx, const b2bvh_camera* cam, uint32_t width, uint32_t height, b2bvh_ray* d_rays,
                         float* ms);                       /* GenerateRays, CommonBlocksKernel.h:432-463 */

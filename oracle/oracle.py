@@ -653,3 +653,33 @@ def _emit_subtree(loc, idx, m, to_global, nodes):
         nodes[g]["left"] = to_global(l); nodes[g]["right"] = to_global(r)
         nodes[g]["mn"] = loc[i]["mn"]; nodes[g]["mx"] = loc[i]["mx"]
         stack.append(l); stack.append(r)
+
+
+def stitch_leftovers(nodes, clusters, skeys, karras):
+    """The last step of the globally sorted build: the left-over clusters of all ranks, in position order ((lo, hi, node id) with boxes
+    already in nodes[node id]), merged by the usual rule — two neighbours form a node when the boundary between them is deeper than both
+    boundaries next to it — until one cluster spans everything.  Writes the new nodes into `nodes`; returns the root index."""
+    n = skeys.size
+    depth = [_boundary_depth(skeys, g) for g in range(-1, n)]
+    D = lambda g: depth[g + 1]
+    root = None
+    clusters = list(clusters)
+    while len(clusters) > 1:
+        out, i, merged = [], 0, False
+        while i < len(clusters):
+            if i + 1 < len(clusters):
+                (lo, mid, idl), (_, hi, idr) = clusters[i], clusters[i + 1]
+                d0, dl, dr = D(mid - 1), D(lo - 1), D(hi - 1)
+                if d0 > dl and d0 > dr:
+                    is_root = lo == 0 and hi == n
+                    nid = (0 if is_root else (hi - 1 if dr > dl else lo)) if karras else mid - 1
+                    nodes[nid]["left"] = idl; nodes[nid]["right"] = idr
+                    nodes[nid]["mn"] = np.minimum(nodes[idl]["mn"], nodes[idr]["mn"]); nodes[nid]["mx"] = np.maximum(nodes[idl]["mx"], nodes[idr]["mx"])
+                    if is_root:
+                        root = nid
+                    out.append((lo, hi, nid)); i += 2; merged = True
+                    continue
+            out.append(clusters[i]); i += 1
+        assert merged
+        clusters = out
+    return root if root is not None else clusters[0][2]

@@ -309,3 +309,41 @@ def test_hierarchy_stage_per_range_reproduces_the_one_gpu_tree(ctx, oracle, kind
         assert nodes.tobytes() == want["nodes"].tobytes() and root == want["root"], (karras, leftovers)
     ctx.free(d_boxes)
 
+
+@pytest.mark.parametrize("kind,n,seed", [("uniform", 12_000, 171), ("clustered", 8000, 172), ("duplicate", 1500, 173), ("uniform", 40, 174)])
+def test_range_trees_extracted_on_the_device(ctx, oracle, kind, n, seed):
+    """Both device building blocks of the globally sorted build together (b2bvh_lbvh_from_sorted64 + b2bvh_range_extract), rank by rank
+    on one GPU: the ghost-free nodes come back with global indices, the spine artefacts are dropped, the left-over clusters (a handful per
+    rank) carry position range, node and box; after stitching them the node array equals the one-GPU build byte for byte."""
+    tris = random_tris(n, seed, kind)
+    refs, boxes, _ = oracle.primrefs(tris)
+    d_boxes = ctx.upload(boxes)
+    rng = np.random.default_rng(seed)
+    cuts = sorted(rng.choice(np.arange(2, n - 1), size=3, replace=False).tolist())
+    ranges = [(a, b) for a, b in zip([0] + cuts, cuts + [n]) if b - a >= 1]
+    nint = n - 1
+    for karras in (True, False):
+        want = ctx.fetch(ctx.build(capi.TWO_PASS_LBVH if karras else capi.SINGLE_PASS_LBVH, tris, collapse=False))
+        sk, sv = want["skeys"], want["svals"]
+        nodes = np.zeros(2 * n - 1, dtype=T.BVH2_NODE)
+        nodes["left"][:] = 0xFFFFFFFF; nodes["right"][:] = 0xFFFFFFFF
+        clusters, per_rank = [], []
+        for a, b in ranges:
+            a2, b2 = max(a - 1, 0), min(b + 1, n)
+            m = b2 - a2
+            k64 = (sk[a2:b2].astype(np.uint64) << np.uint64(32)) | np.arange(a2, b2, dtype=np.uint64)
+            out, cl = ctx.range_tree(k64, sv[a2:b2], d_boxes, karras, a > 0, b < n, a2, n)
+            inner = out[:m - 1]
+            ok = inner["left"] != 0xFFFFFFFF
+            nodes[a2:a2 + m - 1][ok] = inner[ok]                       # internal node i of the range is global node a2 + i
+            nodes[nint + a:nint + b] = out[m - 1 + (a - a2):m - 1 + (a - a2) + (b - a)]   # the rank's own leaves (ghosts dropped)
+            assert (cl["lo"][1:] == cl["hi"][:-1]).all() and cl["lo"][0] == a and cl["hi"][-1] == b   # the left-overs tile the range
+            for c in cl:
+                assert np.array_equal(nodes[c["node"]]["mn"], c["mn"]) and np.array_equal(nodes[c["node"]]["mx"], c["mx"])
+            clusters += [(int(c["lo"]), int(c["hi"]), int(c["node"])) for c in cl]
+            per_rank.append(cl.size)
+        root = oracle.stitch_leftovers(nodes, clusters, sk, karras)
+        assert nodes.tobytes() == want["nodes"].tobytes() and root == want["root"], (karras, per_rank)
+        assert max(per_rank) <= 128
+    ctx.free(d_boxes)
+
