@@ -143,3 +143,140 @@ class GpuEngine:
                                                     self.capi.C.byref(ms)), "b2bvh_traverse")
         key = pack_hits(torch, hits[:, 0], hits[:, 1].view(torch.float32), prim_offset)
         return key, hits[:, 2:4].view(torch.float32).contiguous()
+
+
+class GlobalBuild:
+    """The globally sorted multi-GPU build: G ranks produce the nodes of the ONE-GPU LBVH over all triangles,
+    distributed by sorted position.  Per build:
+      1. local boxes, ONE all-reduce(MAX) of {-min, max}, Morton codes in the global frame                      (as ShardedBuild)
+      2. splitters from an all-gathered sample; every (code, global id, box) goes to the rank whose code interval holds it —
+         ONE all-to-all of counts + three all-to-alls of payload; pieces arrive in source-rank order, so equal codes keep index order
+      3. local stable sort; global position of the rank's first leaf from an all-gather of counts and edge codes
+      4. the ordinary hierarchy stage over [left ghost] + range + [right ghost] with keys (code << 32 | global position), then the
+         extraction: ghost-free nodes with global indices + the rank's left-over clusters                        (engine.range_tree)
+      5. ONE all-gather of the left-over clusters (<= 256 x 48 bytes per rank); every rank finishes the same top nodes.
+    engine: tensor(np) / boxes_and_scene(tris) -> (boxes [n,6] float32, {-min,max} [6]) / morton(boxes, scene6_minmax) -> int64 codes /
+            sort(codes int64) -> (sorted codes int64, permutation int64) / range_tree(k64 int64, vals int64, boxes [k,6], karras, ghostL,
+            ghostR, first_pos, n_global) -> (nodes uint8 [(2m-1), 32], clusters int32 [c, 12]).  All tensors live on the collective's device."""
+
+    def __init__(self, engine, dist=None, rank=0, world=1, sample=256):
+        self.engine, self.dist, self.rank, self.world, self.sample = engine, dist, rank, world, sample
+
+    def _all_gather(self, t):
+        import torch
+        if self.world == 1:
+            return t.unsqueeze(0)
+        flat = t.contiguous().reshape(-1)
+        out = torch.empty(self.world * flat.numel(), dtype=t.dtype, device=t.device)
+        self.dist.all_gather_into_tensor(out, flat)
+        return out.reshape((self.world,) + tuple(t.shape))
+
+    def _all_to_all(self, t, send_counts, recv_counts):
+        import torch
+        if self.world == 1:
+            return t
+        out = torch.empty((int(sum(recv_counts)),) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        self.dist.all_to_all_single(out, t.contiguous(), output_split_sizes=list(recv_counts), input_split_sizes=list(send_counts))
+        return out
+
+    def build(self, tris, first_global, n_total, karras=False):
+        import torch
+        eng, W = self.engine, self.world
+        boxes, box6 = eng.boxes_and_scene(tris)
+        if W > 1:
+            self.dist.all_reduce(box6, op=self.dist.ReduceOp.MAX)
+        scene = torch.cat([-box6[:3], box6[3:]])
+        codes = eng.morton(boxes, scene)                                           # int64, < 2^30
+        n_local = codes.numel()
+        gids = torch.arange(first_global, first_global + n_local, dtype=torch.int64, device=codes.device)
+        # 2. splitters from a sample (any non-decreasing choice is correct; a sample balances the ranks)
+        S = self.sample
+        pick = torch.linspace(0, max(n_local - 1, 0), S, device=codes.device).long() if n_local else torch.zeros(S, dtype=torch.int64, device=codes.device)
+        samp = codes[pick] if n_local else torch.full((S,), (1 << 62), dtype=torch.int64, device=codes.device)
+        allsamp = torch.sort(self._all_gather(samp).reshape(-1)).values
+        splitters = allsamp[(torch.arange(1, W, device=codes.device) * allsamp.numel()) // W] if W > 1 else allsamp[:0]
+        dest = torch.bucketize(codes, splitters, right=True)                        # equal codes never split
+        order = torch.sort(dest, stable=True).indices                               # by destination, local order kept
+        send_counts = torch.bincount(dest, minlength=W)
+        recv_counts = send_counts.clone()
+        if W > 1:
+            self.dist.all_to_all_single(recv_counts, send_counts)
+        sc, rc = send_counts.tolist(), recv_counts.tolist()
+        r_codes = self._all_to_all(codes[order], sc, rc)
+        r_gids = self._all_to_all(gids[order], sc, rc)
+        r_boxes = self._all_to_all(boxes[order], sc, rc)
+        cnt = r_codes.numel()
+        # 3. local stable sort + where the rank sits in the global order
+        s_codes, perm = eng.sort(r_codes) if cnt else (r_codes, r_codes)
+        edge = torch.tensor([cnt, int(s_codes[0]) if cnt else 0, int(s_codes[-1]) if cnt else 0], dtype=torch.int64, device=codes.device)
+        edges = self._all_gather(edge).cpu().tolist()
+        a = sum(e[0] for e in edges[:self.rank])
+        b = a + cnt
+        prev = [e for e in edges[:self.rank] if e[0]]
+        nxt = [e for e in edges[self.rank + 1:] if e[0]]
+        res = dict(first=a, last=b, n_total=n_total, karras=karras, nodes=None, leaves=None, clusters=None)
+        my = torch.zeros((256, 13), dtype=torch.int64, device=codes.device)      # lo, hi, node, box bits x6 (as int64), depthRight, valid, pad
+        if cnt:
+            ghostL, ghostR = bool(prev), bool(nxt)
+            a2 = a - (1 if ghostL else 0)
+            parts_k, parts_v = [], []
+            if ghostL:
+                parts_k.append(torch.tensor([prev[-1][2]], dtype=torch.int64, device=codes.device)); parts_v.append(torch.zeros(1, dtype=torch.int64, device=codes.device))
+            parts_k.append(s_codes); parts_v.append(perm)
+            if ghostR:
+                parts_k.append(torch.tensor([nxt[0][1]], dtype=torch.int64, device=codes.device)); parts_v.append(torch.zeros(1, dtype=torch.int64, device=codes.device))
+            kk, vv = torch.cat(parts_k), torch.cat(parts_v)
+            m = kk.numel()
+            k64 = (kk << 32) | torch.arange(a2, a2 + m, dtype=torch.int64, device=codes.device)
+            if m >= 2:
+                nodes_u8, cl = eng.range_tree(k64, vv, r_boxes, karras, ghostL, ghostR, a2, n_total)
+                nodes_i32 = nodes_u8.view(torch.int32).reshape(2 * m - 1, 8)
+                # leaves name the GLOBAL primitive (the local builder wrote the index into the received arrays)
+                own = nodes_i32[m - 1 + (a - a2):m - 1 + (a - a2) + cnt]
+                own[:, 0] = r_gids[own[:, 0].long()].to(torch.int32)
+                res.update(nodes=nodes_i32[:m - 1], node_first=a2, leaves=own)
+                c = cl.shape[0]
+                cl64 = cl.to(torch.int64) & 0xFFFFFFFF
+                hi_local = (cl64[:, 1] - a2)
+                kx = torch.where(hi_local < m, k64[(hi_local - 1).clamp(0, m - 1)] ^ k64[hi_local.clamp(0, m - 1)], torch.zeros_like(hi_local))
+                depth = torch.tensor([(64 - int(x).bit_length()) if (h < m) else -1 for x, h in zip(kx.cpu().tolist(), hi_local.cpu().tolist())], dtype=torch.int64,
+                                     device=codes.device)
+                my[:c, 0:3] = cl64[:, 0:3]; my[:c, 3:9] = cl64[:, 4:10]; my[:c, 9] = depth; my[:c, 10] = 1
+            else:  # a single leaf and no neighbour at all: the whole input is one primitive
+                raise ValueError("GlobalBuild needs at least two primitives in total")
+        # 5. gather the left-overs; every rank finishes the same top of the tree
+        allc = self._all_gather(my).reshape(-1, 13).cpu().numpy()
+        allc = allc[allc[:, 10] == 1]
+        res["top"], res["root"] = _finish_top(allc, n_total, karras)
+        return res
+
+
+def _finish_top(clusters, n_total, karras):
+    """clusters: rows (lo, hi, node, box bits x6, depth of the boundary right of the cluster, valid).  The usual rule — two neighbours form a
+    node when the boundary between them is deeper than both boundaries next to it.  Returns ({global node index: (left, right, box6 float32)}, root)."""
+    cur = [(int(r[0]), int(r[1]), int(r[2]), np.array(r[3:9], dtype=np.uint32).view(np.float32).copy(), int(r[9])) for r in clusters]
+    top = {}
+    root = cur[0][2] if len(cur) == 1 else None
+    while len(cur) > 1:
+        out, i, merged = [], 0, False
+        while i < len(cur):
+            if i + 1 < len(cur):
+                (lo, mid, idl, bl, d0), (_, hi, idr, br, dr) = cur[i], cur[i + 1]
+                dl = cur[i - 1][4] if i > 0 else -1
+                # dl: depth of the boundary left of cluster i == the right depth of its left neighbour IN THE CURRENT LIST
+                if out and out[-1][1] == lo:
+                    dl = out[-1][4]
+                if d0 > dl and d0 > dr:
+                    is_root = lo == 0 and hi == n_total
+                    nid = (0 if is_root else (hi - 1 if dr > dl else lo)) if karras else mid - 1
+                    box = np.concatenate([np.minimum(bl[:3], br[:3]), np.maximum(bl[3:], br[3:])]).astype(np.float32)
+                    top[nid] = (idl, idr, box)
+                    if is_root:
+                        root = nid
+                    out.append((lo, hi, nid, box, dr)); i += 2; merged = True
+                    continue
+            out.append(cur[i]); i += 1
+        if not merged:
+            raise RuntimeError("left-over clusters do not merge: inconsistent boundary depths")
+        cur = out
+    return top, root

@@ -683,3 +683,44 @@ def stitch_leftovers(nodes, clusters, skeys, karras):
         assert merged
         clusters = out
     return root if root is not None else clusters[0][2]
+
+
+def range_tree_reference(tris, refs, k64, vals, karras, ghost_left, ghost_right, first_pos, n_global):
+    """CPU twin of capi.Context.range_tree (b2bvh_lbvh_from_sorted64 + b2bvh_range_extract): local tree over the ghost-extended range,
+    ghost-free nodes renumbered to global indices, artefacts invalidated, left-over clusters in position order."""
+    m = k64.size
+    v = np.ascontiguousarray(vals, dtype=np.uint32)
+    if karras:
+        loc, _ = lbvh_karras(refs, np.ascontiguousarray(k64), v)
+        lroot = 0
+    else:
+        loc, lroot = lbvh_apetrei(tris, np.ascontiguousarray(k64), v)
+    out = loc.copy()
+    nint = n_global - 1
+    art = np.zeros(m - 1, dtype=bool)
+    cl = []
+    stack = [(lroot, 0, m)]
+    while stack:
+        idx, lo, hi = stack.pop()
+        has_ghost = (ghost_left and lo == 0) or (ghost_right and hi == m)
+        leaf = idx >= m - 1
+        if not has_ghost:
+            cl.append((first_pos + lo, first_pos + hi, (nint + first_pos + idx - (m - 1)) if leaf else first_pos + idx, loc[idx]["mn"].copy(), loc[idx]["mx"].copy()))
+            continue
+        if leaf:
+            continue
+        art[idx] = True
+        l, r = int(loc[idx]["left"]), int(loc[idx]["right"])
+        split = idx + 1 if not karras else ((l - (m - 1)) if l >= m - 1 else l) + 1
+        stack.append((r, split, hi)); stack.append((l, lo, split))
+    for i in range(m - 1):
+        if art[i]:
+            out[i]["left"] = 0xFFFFFFFF; out[i]["right"] = 0xFFFFFFFF
+        else:
+            for f in ("left", "right"):
+                c = int(loc[i][f])
+                out[i][f] = (nint + first_pos + c - (m - 1)) if c >= m - 1 else first_pos + c
+    c = np.zeros(len(cl), dtype=T.CLUSTER)
+    for j, x in enumerate(cl):
+        c[j] = (x[0], x[1], x[2], x[3], x[4])
+    return out, c
