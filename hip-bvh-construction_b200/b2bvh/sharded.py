@@ -280,3 +280,66 @@ def _finish_top(clusters, n_total, karras):
             raise RuntimeError("left-over clusters do not merge: inconsistent boundary depths")
         cur = out
     return top, root
+
+
+class GpuGlobalEngine:
+    """The device engine of GlobalBuild: every step is a call into libb2bvh.so on torch-owned buffers (the context shares torch's stream,
+    so the NCCL collectives and the kernels are ordered)."""
+
+    def __init__(self, ctx):
+        import torch
+        from . import capi
+        self.ctx, self.capi, self.torch, self.C = ctx, capi, torch, capi.C
+
+    def _p(self, t):
+        return self.C.c_void_p(t.data_ptr())
+
+    def boxes_and_scene(self, tris):
+        """tris: (device pointer, n) or a TRIANGLE numpy array."""
+        torch = self.torch
+        if isinstance(tris, tuple):
+            d, n = tris
+        else:
+            n = tris.size
+            self._tris = torch.from_numpy(tris.view(np.uint8).reshape(n, 64)).cuda()
+            d = self._tris.data_ptr()
+        boxes = torch.empty((n, 6), dtype=torch.float32, device="cuda")
+        scene = torch.empty(6, dtype=torch.float32, device="cuda")
+        self.capi.check(self.ctx.lib.b2bvh_scene_extents(self.ctx.h, self.C.c_void_p(int(d)), n, self._p(boxes), self._p(scene)), "b2bvh_scene_extents")
+        return boxes, torch.cat([-scene[:3], scene[3:]])
+
+    def morton(self, boxes, scene):
+        torch = self.torch
+        n = boxes.shape[0]
+        keys = torch.empty(n, dtype=torch.int32, device="cuda")
+        vals = torch.empty(n, dtype=torch.int32, device="cuda")
+        sc = scene.contiguous()
+        self.capi.check(self.ctx.lib.b2bvh_morton_codes(self.ctx.h, self._p(boxes), self._p(sc), n, self._p(keys), self._p(vals)), "b2bvh_morton_codes")
+        return keys.to(torch.int64)
+
+    def sort(self, codes):
+        torch = self.torch
+        n = codes.numel()
+        kin = codes.to(torch.int32).contiguous()
+        kout = torch.empty(n, dtype=torch.int32, device="cuda")
+        vout = torch.empty(n, dtype=torch.int32, device="cuda")
+        self.capi.check(self.ctx.lib.b2bvh_sort_pairs(self.ctx.h, self._p(kin), None, self._p(kout), self._p(vout), n, 0, 32), "b2bvh_sort_pairs")
+        return kout.to(torch.int64), vout.to(torch.int64)
+
+    def range_tree(self, k64, vals, boxes, karras, ghost_left, ghost_right, first_pos, n_global):
+        torch, C = self.torch, self.C
+        m = k64.numel()
+        k = k64.contiguous()
+        v = vals.to(torch.int32).contiguous()
+        bx = boxes.contiguous()
+        nodes = torch.empty((2 * m - 1, 32), dtype=torch.uint8, device="cuda")
+        parents = torch.empty(2 * m - 1, dtype=torch.int32, device="cuda")
+        out = torch.empty((2 * m - 1, 32), dtype=torch.uint8, device="cuda")
+        clusters = torch.zeros((256, 12), dtype=torch.int32, device="cuda")
+        root, cnt = C.c_uint32(), C.c_uint32()
+        self.capi.check(self.ctx.lib.b2bvh_lbvh_from_sorted64(self.ctx.h, self._p(k), self._p(v), self._p(bx), m, 1 if karras else 0, self._p(nodes), self._p(parents),
+                                                              C.byref(root)), "b2bvh_lbvh_from_sorted64")
+        self.capi.check(self.ctx.lib.b2bvh_range_extract(self.ctx.h, self._p(nodes), m, root.value, 1 if karras else 0, 1 if ghost_left else 0,
+                                                         1 if ghost_right else 0, int(first_pos), int(n_global), self._p(out), self._p(clusters), C.byref(cnt)),
+                        "b2bvh_range_extract")
+        return out, clusters[:cnt.value]
