@@ -94,3 +94,25 @@ def test_sharded_trace_on_one_gpu(oracle):
         ctxs[0].free(d_rays)
         for c in ctxs:
             c.close()
+
+
+@pytest.mark.parametrize("karras", [False, True], ids=["apetrei", "karras"])
+def test_global_build_engine_on_one_gpu(oracle, karras):
+    """GlobalBuild with the device engine at world size 1 (the exchange and the gathers are covered with gloo on 2-3 ranks in
+    tests/test_sharded_gloo.py and over NCCL by tools/global_build_check.py): codes, sort, hierarchy stage over widened keys and the
+    extraction run on the device and give the nodes of the ordinary build, which equal the oracle's."""
+    import torch
+    from b2bvh import types as T
+    from b2bvh.sharded import GlobalBuild, GpuGlobalEngine
+    n = 30_000
+    tris = random_tris(n, 79)
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        c = capi.Context(0, stream=stream.cuda_stream)
+        res = GlobalBuild(GpuGlobalEngine(c)).build(tris, 0, n, karras=karras)
+        stream.synchronize()
+        o = oracle.build_lbvh(tris, single_pass=not karras)
+        want = o["nodes"].view(np.int32).reshape(-1, 8)
+        assert res["root"] == o["root"] and res["first"] == 0 and res["last"] == n and res["top"] == {}
+        assert np.array_equal(res["nodes"].cpu().numpy(), want[:n - 1]) and np.array_equal(res["leaves"].cpu().numpy(), want[n - 1:])
+        c.close()
