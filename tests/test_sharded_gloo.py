@@ -149,13 +149,13 @@ class OracleGlobalEngine:
         return torch.from_numpy(out.view(np.uint8).reshape(-1, 32).copy()), torch.from_numpy(cl.view(np.int32).reshape(-1, 12).copy())
 
 
-def _global_worker(rank, world, port, n, karras, out_dir):
+def _global_worker(rank, world, port, n, karras, out_dir, kind=None):
     sys.path.insert(0, os.path.join(ROOT, "hip-bvh-construction_b200")); sys.path.insert(0, os.path.join(ROOT, "oracle")); sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle as orc
     from b2bvh.sharded import GlobalBuild, shard_range
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    tris = random_tris(n, 97, "clustered" if karras else "uniform")
+    tris = random_tris(n, 97, kind or ("clustered" if karras else "uniform"))
     a, b = shard_range(n, rank, world)
     res = GlobalBuild(OracleGlobalEngine(orc), dist, rank, world, sample=32).build(np.ascontiguousarray(tris[a:b]), a, n, karras=karras)
     np.save(os.path.join(out_dir, f"g_nodes{rank}.npy"), res["nodes"].numpy() if res["nodes"] is not None else np.zeros((0, 8), np.int32))
@@ -167,16 +167,16 @@ def _global_worker(rank, world, port, n, karras, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,karras", [(2, False), (3, True), (3, False)])
-def test_global_build_yields_the_one_gpu_tree(oracle, tmp_path, world, karras):
+@pytest.mark.parametrize("world,karras,kind,n", [(2, False, None, 3001), (3, True, None, 3001), (3, False, None, 3001), (3, False, "duplicate", 301), (4, True, "duplicate", 302),
+                                                 (4, False, "flat", 7)])
+def test_global_build_yields_the_one_gpu_tree(oracle, tmp_path, world, karras, kind, n):
     """G ranks, gloo, oracle-backed engine: exchange by code interval, local stable sorts, range trees with ghosts, gathered left-overs —
     the assembled node array equals the single build over all triangles byte for byte."""
-    from b2bvh import types as T
-    n = 3001
+    """(duplicate: all codes but one are equal, so whole ranks receive nothing; flat / 7: fewer primitives than sample slots)"""
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]
-    mp.spawn(_global_worker, args=(world, port, n, karras, str(tmp_path)), nprocs=world, join=True)
-    tris = random_tris(n, 97, "clustered" if karras else "uniform")
+    mp.spawn(_global_worker, args=(world, port, n, karras, str(tmp_path), kind), nprocs=world, join=True)
+    tris = random_tris(n, 97, kind or ("clustered" if karras else "uniform"))
     want = oracle.build_lbvh(tris, single_pass=not karras)
     nodes = np.zeros((2 * n - 1, 8), dtype=np.int32)
     nint = n - 1
