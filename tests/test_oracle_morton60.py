@@ -1,7 +1,27 @@
 """60-bit Morton variant, CPU side: known answers of the code definition and its relation to the pinned 10-bit interleave."""
-import numpy as np
+import json
+import os
 
-from conftest import random_tris
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, load_mesh, random_tris
+
+KA = json.load(open(os.path.join(GOLDEN, "morton60_known_answers.json")))
+
+
+@pytest.mark.parametrize("key", [k for k in KA if not k.startswith("_")])
+def test_morton60_definition_is_frozen(oracle, key):
+    """The committed known answers of the 60-bit variant (tests/golden/make_golden_morton60.py): the definition has no reference to
+    be pinned to, so it is frozen instead."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("mk60", os.path.join(GOLDEN, "make_golden_morton60.py"))
+    mk = importlib.util.module_from_spec(spec); spec.loader.exec_module(mk)
+    kind, n, seed = key.rsplit("_", 2)
+    tris = load_mesh(kind) if n == "None" else random_tris(int(n), int(seed), kind)
+    got = mk.summarize(tris)
+    for f, v in KA[key].items():
+        assert got[f] == (pytest.approx(v, rel=0, abs=0) if isinstance(v, float) else v), f
 
 
 def test_morton60_known_answers(oracle):
