@@ -182,6 +182,9 @@ class GlobalBuild:
     def build(self, tris, first_global, n_total, karras=False):
         import torch
         eng, W = self.engine, self.world
+        # checked on EVERY rank before the first collective: a rank that raised later would leave the others waiting in the next one
+        if n_total < 2:
+            raise ValueError("GlobalBuild needs at least two primitives in total")
         boxes, box6 = eng.boxes_and_scene(tris)
         if W > 1:
             self.dist.all_reduce(box6, op=self.dist.ReduceOp.MAX)
@@ -191,7 +194,8 @@ class GlobalBuild:
         gids = torch.arange(first_global, first_global + n_local, dtype=torch.int64, device=codes.device)
         # 2. splitters from a sample (any non-decreasing choice is correct; a sample balances the ranks)
         S = self.sample
-        pick = torch.linspace(0, max(n_local - 1, 0), S, device=codes.device).long() if n_local else torch.zeros(S, dtype=torch.int64, device=codes.device)
+        # integer arithmetic: float32 linspace rounds its end value up to n_local for shards beyond 2^24 primitives (out-of-bounds read)
+        pick = (torch.arange(S, dtype=torch.int64, device=codes.device) * max(n_local - 1, 0)) // max(S - 1, 1)
         samp = codes[pick] if n_local else torch.full((S,), (1 << 62), dtype=torch.int64, device=codes.device)
         allsamp = torch.sort(self._all_gather(samp).reshape(-1)).values
         splitters = allsamp[(torch.arange(1, W, device=codes.device) * allsamp.numel()) // W] if W > 1 else allsamp[:0]
@@ -242,8 +246,7 @@ class GlobalBuild:
                 depth = torch.tensor([(64 - int(x).bit_length()) if (h < m) else -1 for x, h in zip(kx.cpu().tolist(), hi_local.cpu().tolist())], dtype=torch.int64,
                                      device=codes.device)
                 my[:c, 0:3] = cl64[:, 0:3]; my[:c, 3:9] = cl64[:, 4:10]; my[:c, 9] = depth; my[:c, 10] = 1
-            else:  # a single leaf and no neighbour at all: the whole input is one primitive
-                raise ValueError("GlobalBuild needs at least two primitives in total")
+            # m < 2 cannot happen here: n_total >= 2 was checked up front, so a rank that holds a leaf also has a neighbour (a ghost)
         # 5. gather the left-overs; every rank finishes the same top of the tree
         allc = self._all_gather(my).reshape(-1, 13).cpu().numpy()
         allc = allc[allc[:, 10] == 1]

@@ -47,20 +47,13 @@ int b2_reserve(b2bvh_ctx* ctx, int slot, size_t bytes, void** out) {
   return 0;
 }
 
-enum {
-  SLOT_TRIS = 0, SLOT_AABB, SLOT_CTL, SLOT_KEYS, SLOT_VALS, SLOT_SKEYS, SLOT_SVALS, SLOT_TKEYS, SLOT_TVALS, SLOT_SORT, SLOT_NODES,
-  SLOT_PARENTS, SLOT_LBVH, SLOT_WIDE, SLOT_WLEAVES, SLOT_COLLAPSE, SLOT_LEAVES, SLOT_PLOC, SLOT_HPLOC, SLOT_MISC,
-  SLOT_SPLIT_BOX, SLOT_SPLIT_PRIM, SLOT_SPLIT_LIST_A, SLOT_SPLIT_LIST_B, SLOT_SPLIT_STATUS, SLOT_SPLIT_LEAFPRIM,
-  SLOT_BATCH_NODES, SLOT_BATCH_LEAVES, SLOT_BATCH_ROOTS, SLOT_BATCH_SCENES, SLOT_BATCH_OFFSETS,
-  SLOT_KEYS_LO, SLOT_KEYS64, SLOT_SKEYS64, SLOT_M60_KEYS, SLOT_M60_VALS, SLOT_COUNT
-};
-/* SLOT_CTL (256 B): [0..23] scene box, [32..63] extents scratch8, [64..87] {-min,max}, [96] root index, [128..] misc */
 
 extern "C" {
 
 uint32_t b2bvh_abi_version(void) { return B2BVH_ABI_VERSION; }
 const char* b2bvh_last_error(void) { return g_err; }
 
+int b2bvh_ctx_destroy(b2bvh_ctx* ctx);
 int b2bvh_ctx_create(int device, void* cuda_stream, b2bvh_ctx** out) {
   if (!out) return b2_fail(B2BVH_ERR_INVALID, "ctx_create: out is null");
   int count = 0;
@@ -71,39 +64,52 @@ int b2bvh_ctx_create(int device, void* cuda_stream, b2bvh_ctx** out) {
   B2_CUDA(cudaSetDevice(device));
   cudaDeviceProp prop;
   B2_CUDA(cudaGetDeviceProperties(&prop, device));
-  if (prop.major < 10) return b2_fail(B2BVH_ERR_CUDA, "ctx_create: device '%s' is sm_%d%d; libb2bvh is built for sm_100a only", prop.name, prop.major, prop.minor);
+  if (prop.major != 10 || prop.minor != 0)
+    return b2_fail(B2BVH_ERR_CUDA, "ctx_create: device '%s' is sm_%d%d; libb2bvh is built for sm_100a only", prop.name, prop.major, prop.minor);
   b2bvh_ctx* c = new b2bvh_ctx();
   memset(c, 0, sizeof(*c));
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
   snprintf(c->name, sizeof(c->name), "%s", prop.name);
+  /* a failure half way must not leak what was created so far: everything below goes through `st` and one exit */
+  int st = 0;
+  auto cu = [&](cudaError_t e, const char* what) { if (!st) st = b2_check(e, what); };
   if (cuda_stream) { c->stream = (cudaStream_t)cuda_stream; c->own_stream = false; }
-  else { B2_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
-  for (int i = 0; i < 16; i++) B2_CUDA(cudaEventCreate(&c->ev[i]));
-  B2_CUDA(cudaStreamCreateWithFlags(&c->dl_stream, cudaStreamNonBlocking));
-  B2_CUDA(cudaEventCreateWithFlags(&c->dl_event, cudaEventDisableTiming));
-  B2_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&c->mailbox), B2_MAILBOX_SLOTS * 16 * sizeof(u32), cudaHostAllocMapped));
-  B2_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&c->mailbox_dev), c->mailbox, 0));
-  void* ctl;
-  B2_TRY(b2_reserve(c, SLOT_CTL, 256, &ctl));
-  B2_CUDA(cudaMemsetAsync(ctl, 0, 256, c->stream));
-  B2_CUDA(cudaStreamSynchronize(c->stream));
+  else { cu(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate"); c->own_stream = st == 0; }
+  for (int i = 0; i < 16 && !st; i++) cu(cudaEventCreate(&c->ev[i]), "cudaEventCreate");
+  if (!st) cu(cudaStreamCreateWithFlags(&c->dl_stream, cudaStreamNonBlocking), "cudaStreamCreate (download)");
+  if (!st) cu(cudaEventCreateWithFlags(&c->dl_event, cudaEventDisableTiming), "cudaEventCreate (download)");
+  if (!st) cu(cudaHostAlloc(reinterpret_cast<void**>(&c->mailbox), B2_MAILBOX_SLOTS * 16 * sizeof(u32), cudaHostAllocMapped), "cudaHostAlloc (mailbox)");
+  if (!st) cu(cudaHostGetDevicePointer(reinterpret_cast<void**>(&c->mailbox_dev), c->mailbox, 0), "cudaHostGetDevicePointer");
+  void* ctl = nullptr;
+  if (!st) st = b2_reserve(c, SLOT_CTL, 256, &ctl);
+  if (!st) cu(cudaMemsetAsync(ctl, 0, 256, c->stream), "cudaMemsetAsync");
+  if (!st) cu(cudaStreamSynchronize(c->stream), "cudaStreamSynchronize");
+  if (st) {
+    char keep[sizeof(g_err)];
+    memcpy(keep, g_err, sizeof(keep)); /* the message of the first failure, not of the clean-up */
+    b2bvh_ctx_destroy(c);
+    memcpy(g_err, keep, sizeof(keep));
+    return st;
+  }
   *out = c;
   return 0;
 }
 
 int b2bvh_ctx_destroy(b2bvh_ctx* ctx) {
   if (!ctx) return 0;
+  /* also the clean-up path of a context that b2bvh_ctx_create could not finish: every member may still be null */
   cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   for (int i = 0; i < 48; i++) if (ctx->bufs[i].p) cudaFree(ctx->bufs[i].p);
-  for (int i = 0; i < 16; i++) cudaEventDestroy(ctx->ev[i]);
+  for (int i = 0; i < 16; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  for (int i = 0; i < ctx->prof_events; i++) { cudaEventDestroy(ctx->prof[i].a); cudaEventDestroy(ctx->prof[i].b); }
   if (ctx->graph.exec) cudaGraphExecDestroy(ctx->graph.exec);
   if (ctx->mailbox) cudaFreeHost(ctx->mailbox);
-  cudaStreamSynchronize(ctx->dl_stream);
-  cudaStreamDestroy(ctx->dl_stream);
-  cudaEventDestroy(ctx->dl_event);
-  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->dl_stream) { cudaStreamSynchronize(ctx->dl_stream); cudaStreamDestroy(ctx->dl_stream); }
+  if (ctx->dl_event) cudaEventDestroy(ctx->dl_event);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  cudaGetLastError();
   delete ctx;
   return 0;
 }
@@ -197,7 +203,10 @@ int b2bvh_morton_codes(b2bvh_ctx* ctx, const b2bvh_aabb* d_triAabb, const b2bvh_
 int b2bvh_sort_pairs(b2bvh_ctx* ctx, const uint32_t* d_keysIn, const uint32_t* d_valsIn, uint32_t* d_keysOut, uint32_t* d_valsOut, uint32_t n,
                      uint32_t startBit, uint32_t endBit) {
   if (!ctx || !d_keysIn || !d_keysOut || !d_valsOut) return b2_fail(B2BVH_ERR_INVALID, "sort_pairs: bad argument");
-  if (((uintptr_t)d_keysIn | (uintptr_t)d_valsIn) & 15) return b2_fail(B2BVH_ERR_INVALID, "sort_pairs: inputs must be 16-byte aligned");
+  /* the passes ping-pong between the context's temporaries and the caller's OUTPUT arrays, so the outputs are read back with 16-byte
+   * vector loads and bulk copies as well */
+  if (((uintptr_t)d_keysIn | (uintptr_t)d_valsIn | (uintptr_t)d_keysOut | (uintptr_t)d_valsOut) & 15)
+    return b2_fail(B2BVH_ERR_INVALID, "sort_pairs: inputs and outputs must be 16-byte aligned");
   void *tk, *tv, *sc;
   B2_TRY(b2_reserve(ctx, SLOT_TKEYS, (size_t)n * 4, &tk));
   B2_TRY(b2_reserve(ctx, SLOT_TVALS, (size_t)n * 4, &tv));

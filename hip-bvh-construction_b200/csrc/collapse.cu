@@ -339,14 +339,15 @@ int b2_launch_collapse(b2bvh_ctx* ctx, const b2bvh_bvh2_node* d_nodes, const b2b
                        b2bvh_bvh4_node* d_wide, b2bvh_prim_node* d_wideLeaves, void* d_scratch, u32* h_nWide) {
   (void)d_leaves; /* both layouts name leaves by slot; the primitive index comes from the sorted value array */
   if (n < 2) return b2_fail(B2BVH_ERR_INVALID, "collapse needs at least 2 primitives");
-  static int occLarge = 0, occSmall = 0;
+  int &occLarge = ctx->occ[B2_OCC_COLLAPSE_LARGE], &occSmall = ctx->occ[B2_OCC_COLLAPSE_SMALL];
   const size_t emitSmem = sizeof(EmitSmem);
-  if (!occLarge) {
+  if (!(ctx->once_mask & B2_ONCE_COLLAPSE)) {
     B2_CUDA(cudaFuncSetAttribute(collapse_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emitSmem));
     B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occLarge, collapse_number_kernel<NUM_THREADS_LARGE>, NUM_THREADS_LARGE, 0));
     B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occSmall, collapse_number_kernel<NUM_THREADS_SMALL>, NUM_THREADS_SMALL, 0));
     if (occLarge < 1 || occSmall < 1) return b2_fail(B2BVH_ERR_INTERNAL, "collapse: kernel does not fit on an SM");
     if (occLarge > 2) occLarge = 2; /* fewer arrivals per grid-wide step beat more warps (see NUM_THREADS_LARGE) */
+    ctx->once_mask |= B2_ONCE_COLLAPSE;
   }
   const bool large = n >= (1u << 20);
   /* every CTA must be resident (grid barrier): at most SMs x occupancy; small inputs use fewer CTAs (cheaper barriers) */

@@ -212,6 +212,10 @@ struct b2bvh_ctx {
     bool active, collapse, host_tris, split;
     int algo;
   } pending;
+  /* one-time per-context (= per-device) kernel setup: cudaFuncSetAttribute applies to the CURRENT device only, so the opt-ins and the
+   * occupancy answers live here and not in process-wide statics (a second context on another device needs its own) */
+  u32 once_mask;         /* B2_ONCE_* bits already done on this context's device */
+  int occ[8];            /* B2_OCC_* occupancy answers */
   u32 alloc_epoch;       /* bumped whenever a build-owned buffer is (re)allocated: a cached graph holds the old pointers */
   u32 launches;
   u32 lbvh_second_level; /* b2bvh_build_opts.lbvh_second_level of the running build */
@@ -227,6 +231,10 @@ struct b2bvh_ctx {
   } prof[512];
   int prof_events; /* number of event pairs created so far */
 };
+
+enum { B2_ONCE_SORT4 = 1u << 0, B2_ONCE_SORT15 = 1u << 1, B2_ONCE_LBVH32 = 1u << 2, B2_ONCE_LBVH64 = 1u << 3, B2_ONCE_COLLAPSE = 1u << 4, B2_ONCE_PLOC = 1u << 5,
+       B2_ONCE_SORT3 = 1u << 6, B2_ONCE_MISC = 1u << 7 };
+enum { B2_OCC_COLLAPSE_LARGE = 0, B2_OCC_COLLAPSE_SMALL = 1, B2_OCC_PLOC = 2 };
 
 int b2_fail(int code, const char* fmt, ...);
 int b2_check(cudaError_t e, const char* what);
@@ -254,10 +262,19 @@ int b2_prof_end(b2bvh_ctx* ctx);
     if ((ctx)->prof_on) B2_TRY(b2_prof_end((ctx)));   \
   } while (0)
 
+/* context-owned device buffers (b2bvh_ctx::bufs) */
+enum {
+  SLOT_TRIS = 0, SLOT_AABB, SLOT_CTL, SLOT_KEYS, SLOT_VALS, SLOT_SKEYS, SLOT_SVALS, SLOT_TKEYS, SLOT_TVALS, SLOT_SORT, SLOT_NODES,
+  SLOT_PARENTS, SLOT_LBVH, SLOT_WIDE, SLOT_WLEAVES, SLOT_COLLAPSE, SLOT_LEAVES, SLOT_PLOC, SLOT_HPLOC, SLOT_MISC,
+  SLOT_SPLIT_BOX, SLOT_SPLIT_PRIM, SLOT_SPLIT_LIST_A, SLOT_SPLIT_LIST_B, SLOT_SPLIT_STATUS, SLOT_SPLIT_LEAFPRIM,
+  SLOT_BATCH_NODES, SLOT_BATCH_LEAVES, SLOT_BATCH_ROOTS, SLOT_BATCH_SCENES, SLOT_BATCH_OFFSETS,
+  SLOT_KEYS_LO, SLOT_KEYS64, SLOT_SKEYS64, SLOT_M60_KEYS, SLOT_M60_VALS, SLOT_COUNT
+};
+/* SLOT_CTL (256 B): [0..23] scene box, [32..63] extents scratch8, [64..87] {-min,max}, [96] root index, [128] range-extract count, [160] traversal overflow flag, [192..] misc */
 int b2_reserve(b2bvh_ctx* ctx, int slot, size_t bytes, void** out);
 /* words <= 16 from device memory into mailbox slot `slot`; readable at b2_mailbox(ctx, slot) after the next stream synchronisation */
-#define B2_MAILBOX_SLOTS 6
-enum { B2_MB_COLLAPSE = 0, B2_MB_PLOC = 1, B2_MB_HPLOC = 2, B2_MB_ROOT = 3, B2_MB_SPLIT = 4, B2_MB_RANGE = 5 };
+#define B2_MAILBOX_SLOTS 8
+enum { B2_MB_COLLAPSE = 0, B2_MB_PLOC = 1, B2_MB_HPLOC = 2, B2_MB_ROOT = 3, B2_MB_SPLIT = 4, B2_MB_RANGE = 5, B2_MB_TRAVERSE = 6, B2_MB_GLOBAL = 7 };
 int b2_fetch_words(b2bvh_ctx* ctx, const void* d_src, u32 words, int slot);
 static inline const u32* b2_mailbox(const b2bvh_ctx* ctx, int slot) { return ctx->mailbox + slot * 16; }
 

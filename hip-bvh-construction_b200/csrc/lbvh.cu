@@ -615,13 +615,13 @@ static int launch_lbvh_fused_t(b2bvh_ctx* ctx, const K* d_sortedKeys, const u32*
     const bool useGroups = ctx->lbvh_second_level == 1 ? true : (ctx->lbvh_second_level == 2 ? false : n >= (1u << 23));
     uint2* tileInfo = reinterpret_cast<uint2*>(pending + cap);
     LbvhPending* tileBuf = useGroups ? reinterpret_cast<LbvhPending*>(reinterpret_cast<unsigned char*>(tileInfo) + (((size_t)grid * sizeof(uint2) + 15) & ~(size_t)15)) : nullptr;
-    static bool attrSet = false;
-    if (!attrSet) {
+    const u32 onceBit = sizeof(K) == 8 ? B2_ONCE_LBVH64 : B2_ONCE_LBVH32;
+    if (!(ctx->once_mask & onceBit)) {
       B2_CUDA(cudaFuncSetAttribute(lbvh_group_kernel<true, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LbvhGroupSmem)));
       B2_CUDA(cudaFuncSetAttribute(lbvh_group_kernel<false, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LbvhGroupSmem)));
       B2_CUDA(cudaFuncSetAttribute(lbvh_tile_kernel<true, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LbvhTileSmem<true>)));
       B2_CUDA(cudaFuncSetAttribute(lbvh_tile_kernel<false, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LbvhTileSmem<false>)));
-      attrSet = true;
+      ctx->once_mask |= onceBit;
     }
     if (karrasNumbering)
       lbvh_tile_kernel<true, K><<<grid, LBVH_TILE_THREADS, sizeof(LbvhTileSmem<true>), ctx->stream>>>(d_sortedKeys, d_sortedVals, d_triAabb, n, d_nodes, d_parents, d_scratch, d_root, pendingCount, pending, cap, tileInfo, tileBuf, ctx->ref_prim, ctx->ref_leaf_prim);

@@ -459,11 +459,12 @@ int b2_launch_ploc(b2bvh_ctx* ctx, const b2bvh_aabb* d_triAabb, const u32* d_sor
   boxes[1] = boxes[0] + np;
   unsigned char* dec = p + 256 + 2 * np * 4 + 2 * np * sizeof(b2bvh_aabb);
   u64* counts = reinterpret_cast<u64*>(dec + np);
-  static int occ = 0;
-  if (!occ) {
+  int& occ = ctx->occ[B2_OCC_PLOC];
+  if (!(ctx->once_mask & B2_ONCE_PLOC)) {
     B2_CUDA(cudaFuncSetAttribute(ploc_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PlocTailSmem)));
     B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ploc_merge_kernel, PLOC_THREADS, 0));
     if (occ < 1) return b2_fail(B2BVH_ERR_INTERNAL, "ploc: kernel does not fit on an SM");
+    ctx->once_mask |= B2_ONCE_PLOC;
   }
   B2_KERNEL(ctx, "ploc_setup");
   ploc_setup_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_triAabb, d_sortedVals, n, d_leaves, ids[0], boxes[0], ctrl);

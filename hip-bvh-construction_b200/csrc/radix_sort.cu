@@ -302,11 +302,11 @@ template <int ITEMS>
 static int launch_scatter(b2bvh_ctx* ctx, u32 grid, const u32* kin, const u32* vin, u32* kout, u32* vout, const u32* counts, const u32* totals, u32 n,
                           u32 chunk, u32 shift, u32 mask, u32 gpad) {
   const size_t smem = sizeof(ScatterSmem<ITEMS>);
-  static bool attrSet = false;
-  if (!attrSet) {
+  const u32 onceBit = ITEMS == 4 ? B2_ONCE_SORT4 : B2_ONCE_SORT15;
+  if (!(ctx->once_mask & onceBit)) {
     B2_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<ITEMS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     B2_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<ITEMS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attrSet = true;
+    ctx->once_mask |= onceBit;
   }
   B2_KERNEL(ctx, "radix_scatter");
   if (vin == nullptr)

@@ -72,6 +72,7 @@ struct TravArgs {
   u32* counter;                 /* leaf (triangle) tests per ray, or null */
   const b2bvh_bvh4_node* wide;  /* 4-wide traversal only */
   u32 root, nInt, width, height;
+  u32* overflow;                /* set to 1 by a ray whose stack (or 64-bit trail) is too short for the tree: the call then fails, a subtree is never dropped silently */
 };
 
 __device__ __forceinline__ void slab(const Box& b, F3 o, F3 inv, float maxt, float& tn, float& tf) {
@@ -157,7 +158,7 @@ __global__ void __launch_bounds__(64) traverse_kernel(TravArgs A) {
       if (hl && hr) {
         const bool leftFirst = n0 < n1;
         node = leftFirst ? ch.x : ch.y;
-        if (top < 64) stack[top++] = leftFirst ? ch.y : ch.x;
+        if (top < 64) stack[top++] = leftFirst ? ch.y : ch.x; else *A.overflow = 1u;
       } else if (hl || hr) {
         node = hl ? ch.x : ch.y;
       } else {
@@ -229,7 +230,7 @@ __global__ void __launch_bounds__(64) traverse_step_kernel(TravArgs A) {
           if (hl && hr) {
             const bool leftFirst = n0 < n1;
             node = leftFirst ? ch.x : ch.y;
-            if (top < 64) stack[top++] = leftFirst ? ch.y : ch.x;
+            if (top < 64) stack[top++] = leftFirst ? ch.y : ch.x; else *A.overflow = 1u;
           } else {
             node = hl ? ch.x : ch.y;
           }
@@ -269,9 +270,11 @@ __global__ void __launch_bounds__(64) traverse_step_kernel(TravArgs A) {
           const bool swap = n0 > n1;
           const u32 nearC = swap ? ch.y : ch.x, farC = swap ? ch.x : ch.y;
           level >>= 1;
+          if (level == 0) { *A.overflow = 1u; break; } /* deeper than the 64-bit trail can record */
           node = (trail & level) ? farC : nearC;
         } else if (hl || hr) {
           level >>= 1;
+          if (level == 0) { *A.overflow = 1u; break; }
           if (level != popLevel) { trail |= level; node = hr ? ch.y : ch.x; }
           else done = pop();
         } else {
@@ -347,7 +350,7 @@ __global__ void __launch_bounds__(64) traverse_wide4_kernel(TravArgs A) {
     for (int r = 3; r >= 1; r--)
 #pragma unroll
       for (int k = 0; k < 4; k++)
-        if (hitK[k] && rank[k] == (u32)r && top < 128) stack[top++] = ch[k];
+        if (hitK[k] && rank[k] == (u32)r) { if (top < 128) stack[top++] = ch[k]; else *A.overflow = 1u; }
 #pragma unroll
     for (int k = 0; k < 4; k++)
       if (hitK[k] && rank[k] == 0) node = ch[k];
@@ -447,6 +450,8 @@ int b2bvh_traverse_ex(b2bvh_ctx* ctx, const b2bvh_tree* tree, const b2bvh_ray* d
   A.rays = d_rays; A.nodes = tree->d_bvhNodes; A.leaves = tree->leaves_separate ? tree->d_leafNodes : nullptr; A.tris = tree->d_triangleBuff;
   A.tr = *xform; A.hits = d_hits; A.rgba = d_rgba; A.counter = d_rayCounter; A.wide = tree->d_wideBvhNodes;
   A.root = tree->root; A.nInt = tree->n_internal; A.width = side; A.height = side;
+  A.overflow = reinterpret_cast<u32*>(reinterpret_cast<unsigned char*>(ctx->bufs[SLOT_CTL].p) + 160);
+  B2_CUDA(cudaMemsetAsync(A.overflow, 0, 4, ctx->stream));
   if (d_rgba) B2_CUDA(cudaMemsetAsync(d_rgba, 0, (size_t)n_rays * 4, ctx->stream));
   const dim3 grid((side + 7) / 8, (side + 7) / 8);
   static const char* const names[] = {"traverse_while", "traverse_speculative_while", "traverse_ifif", "traverse_restart_trail", "traverse_wide4"};
@@ -472,8 +477,12 @@ int b2bvh_traverse_ex(b2bvh_ctx* ctx, const b2bvh_tree* tree, const b2bvh_ray* d
   }
   B2_LAUNCH_CHECK(ctx);
   B2_CUDA(cudaEventRecord(ctx->ev[11], ctx->stream));
-  B2_CUDA(cudaEventSynchronize(ctx->ev[11]));
+  B2_TRY(b2_fetch_words(ctx, A.overflow, 1, B2_MB_TRAVERSE));
+  B2_CUDA(cudaStreamSynchronize(ctx->stream));
   if (ms) B2_CUDA(cudaEventElapsedTime(ms, ctx->ev[10], ctx->ev[11]));
+  if (b2_mailbox(ctx, B2_MB_TRAVERSE)[0] != 0u)
+    return b2_fail(B2BVH_ERR_INTERNAL, "traverse: the tree is deeper than the %s of kernel %d holds; hits are incomplete",
+                   kernel == B2BVH_TRAVERSE_RESTART_TRAIL ? "64-bit trail" : (kernel == B2BVH_TRAVERSE_WIDE4 ? "128-entry stack" : "64-entry stack"), kernel);
   return 0;
 }
 
