@@ -228,10 +228,10 @@ __global__ void __launch_bounds__(NUM_THREADS, NUM_THREADS == NUM_THREADS_LARGE 
           st_relaxed64(counts + c, (u64)chunkTotal);
           __threadfence();
           atomicAdd(&ctrl->arrive, 1u);
-          u32 polls = 0;
+          SpinGuard guard;
           while (ld_acquire(&ctrl->arrive) < arriveTarget) {
             __nanosleep(32);
-            if (++polls > (1u << 22)) __trap(); /* a chunk never posted: fail, never hang the device */
+            guard.tick();
           }
         }
         __syncthreads();

@@ -142,6 +142,23 @@ __device__ __forceinline__ void st_relaxed(u32* p, u32 v) { asm volatile("st.rel
 /* Barrier among the first `threads` threads of the CTA (a multiple of 32; whole warps arrive). */
 __device__ __forceinline__ void named_barrier(u32 id, u32 threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
+/* Watchdog of every spin loop in the library: a wait that lasts longer than 20 s of wall clock (%globaltimer) traps — a CTA is missing
+ * (not a cooperative launch?) or a chunk never posted; fail, never hang the device.  Time based, not a poll count: under compute-sanitizer
+ * the CTAs being waited for run two orders of magnitude slower while a poll costs the same. */
+struct SpinGuard {
+  u64 t0;
+  u32 polls;
+  __device__ __forceinline__ SpinGuard() : t0(0), polls(0) {}
+  __device__ __forceinline__ void tick() {
+    if ((++polls & 0xFFFu) == 0) {
+      u64 now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 20000000000ull) __trap();
+    }
+  }
+};
+
 /* Grid-wide barrier of a cooperative launch (every CTA resident): `target` = arrivals expected so far (the counter is never
  * reset: barrier number b of a launch of G CTAs waits for b * G). */
 __device__ __forceinline__ void grid_barrier(u32* bar, u32 target) {
@@ -149,9 +166,8 @@ __device__ __forceinline__ void grid_barrier(u32* bar, u32 target) {
   if (threadIdx.x == 0) {
     __threadfence();
     atomicAdd(bar, 1u);
-    u32 polls = 0;
-    while (ld_acquire(bar) < target)
-      if (++polls > (1u << 22)) __trap(); /* seconds: a CTA is missing (not a cooperative launch?) — fail, never hang the device */
+    SpinGuard guard;
+    while (ld_acquire(bar) < target) guard.tick();
   }
   __syncthreads();
 }

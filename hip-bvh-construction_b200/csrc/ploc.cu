@@ -132,8 +132,10 @@ __device__ __forceinline__ int pl_nearest(u32 (*dist)[SLOTS + PLOC_R], short* nn
   u32 d[PLOC_R];
 #pragma unroll
   for (int r = 1; r <= PLOC_R; r++) {
-    const int t = s + r;
-    bool ok = true; /* unchecked windows: slots >= SLOTS - R read a few records past the buffer (still inside the CTA's shared memory) and nobody reads their answers */
+    /* unchecked windows: nobody reads the answers of the slots >= SLOTS - R; they re-read the last record instead of running past the
+     * buffer (the next buffer may be the destination of a bulk copy in flight: compute-sanitizer racecheck, profiles/r02_sanitizer.txt) */
+    const int t = CHECK ? s + r : min(s + r, SLOTS - 1);
+    bool ok = true;
     if (CHECK) ok = t < SLOTS && vs && winBase + t >= 0 && winBase + t < (int)count;
     u32 v = 0xFFFFFFFFu;
     if (ok) v = __float_as_uint(box_area(box_union(pl_slot_box(raw, t), me)));
@@ -283,10 +285,10 @@ __global__ void __launch_bounds__(PLOC_THREADS, 4) ploc_merge_kernel(u32* ids0, 
         __threadfence();
         atomicAdd(&ctrl->arrive, 1u);
         PL_TRACE(2);
-        u32 polls = 0;
+        SpinGuard guard;
         while (ld_acquire(&ctrl->arrive) < arriveTarget) {
           __nanosleep(32);
-          if (++polls > (1u << 22)) __trap(); /* a chunk never posted: fail, never hang the device */
+          guard.tick();
         }
       }
       __syncthreads();
