@@ -372,7 +372,7 @@ int b2bvh_build(b2bvh_ctx* ctx, int algo, const b2bvh_triangle* tris, uint32_t n
     B2_TRY(b2_launch_sort60(ctx, (const u32*)dKeys, (const u32*)dKeysLo, n, (u32*)dM60K, (u32*)dM60V, (u32*)dSKeys, (u32*)dSVals, (u64*)dSKeys64, (u32*)dTKeys,
                             (u32*)dTVals, dSort));
   else
-    B2_TRY(b2_launch_sort(ctx, (const u32*)dKeys, nullptr, (u32*)dSKeys, (u32*)dSVals, (u32*)dTKeys, (u32*)dTVals, dSort, n, 0, 32));
+    B2_TRY(b2_launch_sort(ctx, (const u32*)dKeys, nullptr, (u32*)dSKeys, (u32*)dSVals, (u32*)dTKeys, (u32*)dTVals, dSort, n, 0, 32)); /* as the reference: bits 0..32; three 10-bit passes + a conditional one for bits 30-31 (radix_sort.cu) */
   B2_CUDA(record(3));
   /* ---- S4 / S6 / S7 hierarchy ---- */
   switch (algo) {
@@ -486,6 +486,10 @@ int b2bvh_build_finish(b2bvh_ctx* ctx, b2bvh_tree* out) {
   B2_CUDA(cudaStreamSynchronize(ctx->stream)); /* the only host synchronisation of a build */
   out->root = b2_mailbox(ctx, B2_MB_ROOT)[0];
   out->n_wide = ctx->pending.collapse ? b2_mailbox(ctx, B2_MB_COLLAPSE)[1] : 0u;
+  if (out->n_wide == B2BVH_INVALID) {
+    out->n_wide = 0;
+    return b2_fail(B2BVH_ERR_INTERNAL, "collapse: the Bvh2 nodes do not form a tree (more wide-node tasks than internal nodes)");
+  }
   u32 iterations = 0;
   if (algo == B2BVH_PLOCPP) {
     iterations = b2_mailbox(ctx, B2_MB_PLOC)[2];

@@ -47,7 +47,8 @@ struct CollapseCtrl {
   u32 bar;        /* grid barrier: arrivals so far */
   u32 nWide;      /* result: number of wide nodes */
   u32 arrive;     /* chunks that have posted their count, all levels so far */
-  u32 pad;
+  u32 error;      /* set when a level would hold more tasks than there are internal nodes: the input is not a tree (cannot happen after a correct
+                     hierarchy stage; the numbering stops and the build fails instead of running away over a cyclic input) */
   uint4 next[2];  /* {level, start, end, -}: the level to process after barrier b is published in next[b & 1] (a CTA that
                      leaves barrier b early may publish the level after it before a late CTA has read this one) */
 };
@@ -172,8 +173,7 @@ __device__ __forceinline__ u32 number_tile(u32 nInt, u32* taskNode, const uint4*
 #pragma unroll
   for (int k = 0; k < 4; k++)
     if (ch[k] < nInt) {
-      taskNode[nextId] = ch[k];
-      taskParent[nextId] = g;
+      if (nextId < nInt) { taskNode[nextId] = ch[k]; taskParent[nextId] = g; } /* never past the arrays, whatever the input */
       nextId++;
     }
   __syncthreads(); /* warpSum is reused by the next tile */
@@ -202,6 +202,7 @@ __global__ void __launch_bounds__(NUM_THREADS, NUM_THREADS == NUM_THREADS_LARGE 
           for (u32 tileStart = start; tileStart < end; tileStart += NUM_THREADS)
             running += number_tile<NUM_THREADS>(nInt, taskNode, taskCh, taskParent, firstChild, S, tileStart, end, running);
           start = end; end = running; level++;
+          if (end > nInt) { if (tid == 0) st_relaxed(&ctrl->error, 1u); end = start; } /* not a tree: stop */
         } while (end - start <= NUM_SOLO && end != start);
         if (tid == 0) publish_level(ctrl, barriers + 1u, level, start, end);
       }
@@ -244,7 +245,11 @@ __global__ void __launch_bounds__(NUM_THREADS, NUM_THREADS == NUM_THREADS_LARGE 
         u32 running = end;
 #pragma unroll
         for (int q = 0; q < NUM_THREADS / 32; q++) running += S.warpSum[2][q];
-        if (c == nActive - 1 && tid == 0) publish_level(ctrl, barriers + 1u, level + 1u, end, running + chunkTotal); /* last chunk of the level */
+        if (c == nActive - 1 && tid == 0) { /* last chunk of the level */
+          u32 nextEnd = running + chunkTotal;
+          if (nextEnd > nInt) { st_relaxed(&ctrl->error, 1u); nextEnd = end; } /* not a tree: publish an empty level, everybody stops */
+          publish_level(ctrl, barriers + 1u, level + 1u, end, nextEnd);
+        }
         /* C. the chunk tile by tile: no CTA waits for another one here */
         for (u32 tileStart = cStart; tileStart < cEnd; tileStart += NUM_THREADS)
           running += number_tile<NUM_THREADS>(nInt, taskNode, taskCh, taskParent, firstChild, S, tileStart, cEnd, running);
@@ -257,7 +262,7 @@ __global__ void __launch_bounds__(NUM_THREADS, NUM_THREADS == NUM_THREADS_LARGE 
       level = ld_relaxed(nx); start = ld_relaxed(nx + 1); end = ld_relaxed(nx + 2);
     }
   }
-  if (c == 0 && tid == 0) ctrl->nWide = end;
+  if (c == 0 && tid == 0) ctrl->nWide = ld_relaxed(&ctrl->error) ? B2_INVALID : end;
 }
 
 /* ---- 3. wide nodes + leaf records: one thread per wide node, no synchronisation between CTAs.  Boxes of the internal
@@ -275,6 +280,7 @@ __global__ void __launch_bounds__(COL_THREADS, 5) collapse_emit_kernel(const b2b
   extern __shared__ __align__(16) unsigned char smemRaw[];
   EmitSmem& S = *reinterpret_cast<EmitSmem*>(smemRaw);
   const u32 nWide = ctrl->nWide, tid = threadIdx.x;
+  if (nWide > nInt) return; /* the numbering gave up (CollapseCtrl::error) */
   for (u32 tileStart = blockIdx.x * COL_THREADS; tileStart < nWide; tileStart += gridDim.x * COL_THREADS) {
     const u32 g = tileStart + tid;
     u32 ch[4] = {B2_INVALID, B2_INVALID, B2_INVALID, B2_INVALID};

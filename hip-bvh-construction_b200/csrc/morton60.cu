@@ -66,12 +66,12 @@ int b2_launch_morton60(b2bvh_ctx* ctx, const b2bvh_aabb* d_triAabb, const b2bvh_
 int b2_launch_sort60(b2bvh_ctx* ctx, const u32* d_hi, const u32* d_lo, u32 n, u32* d_a, u32* d_aVals, u32* d_hiSorted, u32* d_valsSorted, u64* d_keys64Sorted,
                      u32* d_keysTmp, u32* d_valsTmp, void* d_sortScratch) {
   /* digit 0: LO, values = iota (not read) */
-  B2_TRY(b2_launch_sort(ctx, d_lo, nullptr, d_a, d_aVals, d_keysTmp, d_valsTmp, d_sortScratch, n, 0, 32));
+  B2_TRY(b2_launch_sort(ctx, d_lo, nullptr, d_a, d_aVals, d_keysTmp, d_valsTmp, d_sortScratch, n, 0, 30)); /* both words of the code have 30 bits */
   B2_KERNEL(ctx, "morton60_gather_hi");
   gather_u32_kernel<<<m60_grid(ctx, n), M60_THREADS, 0, ctx->stream>>>(d_hi, d_aVals, n, d_a); /* the sorted LO words are not needed again */
   B2_LAUNCH_CHECK(ctx);
   /* digit 1: HI in LO order, stable */
-  B2_TRY(b2_launch_sort(ctx, d_a, d_aVals, d_hiSorted, d_valsSorted, d_keysTmp, d_valsTmp, d_sortScratch, n, 0, 32));
+  B2_TRY(b2_launch_sort(ctx, d_a, d_aVals, d_hiSorted, d_valsSorted, d_keysTmp, d_valsTmp, d_sortScratch, n, 0, 30)); /* both words of the code have 30 bits */
   B2_KERNEL(ctx, "morton60_combine");
   combine60_kernel<<<m60_grid(ctx, n), M60_THREADS, 0, ctx->stream>>>(d_hiSorted, d_lo, d_valsSorted, n, d_keys64Sorted);
   B2_LAUNCH_CHECK(ctx);

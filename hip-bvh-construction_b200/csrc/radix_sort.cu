@@ -23,6 +23,15 @@
  * than the chains did.  The reference uses the same count/scan/scatter split per digit, but with spinning scan CTAs
  * (RadixSortKernels.h:606-637), LDS-atomic ranking and no vectorised or bulk loads.
  * Algorithmic traffic per pair: 4 passes x (4 count + 8 in + 8 out) = 80 B (the iota values of pass 0 are not read: 76 B).
+ *
+ * Same-box yardsticks (baseline/sort_compare.cu, profiles/r02a_sort_compare.json; 10 M / 100 M pairs, 30-bit keys): this sort 0.33 / 2.40 ms,
+ * cub::DeviceRadixSort::SortPairs (onesweep, CUDA 12.9) 0.43 / 3.55 ms, the reference's own Orochi kernels compiled unmodified 1.12 / 7.42 ms.
+ * Round-2 experiments that did NOT pay and were taken out again (profiles/r02_sort_experiments.txt):
+ *   - three passes over 10-bit digits for the 30-bit Morton codes (+ a conditional pass for bits 30-31, which flat scenes use): 1024 bins cut
+ *     the run a tile sends to one bin to 6 keys, every output sector becomes a partial write: 0.40 ms at 10 M, 5.1 ms at 100 M;
+ *   - (key, value) pairs reordered in shared memory with one 8-byte store each instead of key + origin tag + value gather: 66.8 us per pass
+ *     against 68.0 at 10 M and 2.7 ms against 2.4 at 100 M — the scatter kernel is not bound by shared-memory wavefronts but by its five
+ *     barrier-separated phases per tile at two CTAs per SM.
  */
 #include "common.cuh"
 
