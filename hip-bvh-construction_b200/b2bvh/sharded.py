@@ -346,3 +346,155 @@ class GpuGlobalEngine:
                                                          1 if ghost_right else 0, int(first_pos), int(n_global), self._p(out), self._p(clusters), C.byref(cnt)),
                         "b2bvh_range_extract")
         return out, clusters[:cnt.value]
+
+
+class GlobalBuildDevice:
+    """The globally sorted multi-GPU build with every data-path step on the device behind the C ABI (b2bvh_global_*, csrc/global_build.cu):
+    G ranks produce the nodes of the ONE-GPU LBVH over all triangles, distributed by sorted position.  What is left to
+    this class is the sequence and the collectives between the steps:
+      boxes + local scene box  -> all-reduce(MAX) of {-min,max}  -> Morton codes in the global frame
+      256 sampled codes        -> all-gather, sorted             -> G-1 splitters                                        (2 KB: control plane)
+      b2bvh_global_partition   -> all-gather of the G send counts -> the G x G count matrix goes to the host (the build's ONE synchronisation:
+                                  NCCL takes send / receive sizes from the host) -> three all-to-alls: code, global id, 24-byte box = 32 B/primitive;
+                                  the local sort starts as soon as the codes have landed, ids and boxes are still on the wire then
+      b2bvh_global_sort        -> all-gather of the ranks' edge codes (8 B each)
+      b2bvh_global_tree        -> all-gather of the left-over clusters (<= 256 x 48 B per rank) -> b2bvh_global_top on every rank
+    Results stay on the device (torch tensors); nothing is read back here.
+    dist: torch.distributed (or an object with all_reduce / all_gather_into_tensor / all_to_all_single and ReduceOp), None for world == 1."""
+
+    def __init__(self, ctx, dist=None, rank=0, world=1, sample=256):
+        import torch
+        from . import capi
+        self.ctx, self.dist, self.rank, self.world, self.sample = ctx, dist, rank, world, sample
+        self.torch, self.capi, self.C = torch, capi, capi.C
+        self.timing = {}
+
+    def _p(self, t):
+        return self.C.c_void_p(t.data_ptr())
+
+    def _all_gather(self, t):
+        if self.world == 1:
+            return t.reshape(1, -1)
+        flat = t.contiguous().reshape(-1)
+        out = self.torch.empty(self.world * flat.numel(), dtype=t.dtype, device=t.device)
+        self.dist.all_gather_into_tensor(out, flat)
+        return out.reshape(self.world, -1)
+
+    def build(self, tris, first_global, n_total, karras=False):
+        """tris: (device pointer, n) or a TRIANGLE numpy array (this rank's primitives, global indices first_global + i)."""
+        torch, capi, C, W = self.torch, self.capi, self.C, self.world
+        lib, h = self.ctx.lib, self.ctx.h
+        if n_total < 2:  # on every rank, before the first collective
+            raise ValueError("GlobalBuildDevice needs at least two primitives in total")
+        dev = torch.device("cuda", torch.cuda.current_device())
+        i32 = dict(dtype=torch.int32, device=dev)
+        if isinstance(tris, tuple):
+            d, n = tris
+        else:
+            n = tris.size
+            self._tris = torch.from_numpy(tris.view(np.uint8).reshape(n, 64)).to(dev)
+            d = self._tris.data_ptr()
+        # ---- boxes, global scene box, codes ----
+        boxes = torch.empty((max(n, 1), 6), dtype=torch.float32, device=dev)
+        scene = torch.empty(6, dtype=torch.float32, device=dev)
+        if n:
+            capi.check(lib.b2bvh_scene_extents(h, C.c_void_p(int(d)), n, self._p(boxes), self._p(scene)), "b2bvh_scene_extents")
+            box6 = torch.cat([-scene[:3], scene[3:]])
+        else:
+            box6 = torch.full((6,), -3.0e38, dtype=torch.float32, device=dev)
+        if W > 1:
+            self.dist.all_reduce(box6, op=self.dist.ReduceOp.MAX)
+        scene = torch.cat([-box6[:3], box6[3:]]).contiguous()
+        codes = torch.empty(max(n, 1), **i32)
+        iota = torch.empty(max(n, 1), **i32)
+        if n:
+            capi.check(lib.b2bvh_morton_codes(h, self._p(boxes), self._p(scene), n, self._p(codes), self._p(iota)), "b2bvh_morton_codes")
+        # ---- splitters from a sample (any non-decreasing choice is correct; a sample balances the ranks) ----
+        S = self.sample
+        if n:
+            pick = (torch.arange(S, dtype=torch.int64, device=dev) * (n - 1)) // max(S - 1, 1)
+            samp = codes[pick].to(torch.int64) & 0xFFFFFFFF
+        else:
+            samp = torch.full((S,), 1 << 62, dtype=torch.int64, device=dev)
+        allsamp = torch.sort(self._all_gather(samp).reshape(-1)).values
+        if W > 1:
+            spl = allsamp[(torch.arange(1, W, device=dev) * allsamp.numel()) // W].clamp(max=0xFFFFFFFF)
+            splitters = torch.where(spl >= (1 << 31), spl - (1 << 32), spl).to(torch.int32).contiguous()  # u32 bit patterns in an int32 tensor
+        else:
+            splitters = torch.zeros(1, **i32)
+        # ---- destination, stable partition, payload in send order ----
+        s_codes, s_gids = torch.empty(max(n, 1), **i32), torch.empty(max(n, 1), **i32)
+        s_boxes = torch.empty((max(n, 1), 6), dtype=torch.float32, device=dev)
+        s_counts = torch.zeros(W, **i32)
+        capi.check(lib.b2bvh_global_partition(h, self._p(codes), self._p(boxes), n, int(first_global), self._p(splitters), W, self._p(s_codes), self._p(s_gids),
+                                              self._p(s_boxes), self._p(s_counts)), "b2bvh_global_partition")
+        M = self._all_gather(s_counts).cpu().tolist()  # the build's one host synchronisation: M[src][dst]
+        sc = M[self.rank]
+        rc = [M[src][self.rank] for src in range(W)]
+        cnts = [sum(M[src][r] for src in range(W)) for r in range(W)]
+        cnt, a = cnts[self.rank], sum(cnts[:self.rank])
+        prev = max((r for r in range(self.rank) if cnts[r]), default=-1)
+        nxt = min((r for r in range(self.rank + 1, W) if cnts[r]), default=-1)
+        # ---- the exchange: the sort starts when the codes are here ----
+        r_codes, r_gids = torch.empty(max(cnt, 1), **i32), torch.empty(max(cnt, 1), **i32)
+        r_boxes = torch.empty((max(cnt, 1), 6), dtype=torch.float32, device=dev)
+        works = []
+        if W > 1:
+            for out, src in ((r_codes, s_codes), (r_gids, s_gids), (r_boxes, s_boxes)):
+                works.append(self.dist.all_to_all_single(out[:cnt], src[:n], output_split_sizes=rc, input_split_sizes=sc, async_op=True))
+            works[0].wait()
+        else:
+            r_codes, r_gids, r_boxes = s_codes, s_gids, s_boxes
+        sorted_codes, perm = torch.empty(max(cnt, 1), **i32), torch.empty(max(cnt, 1), **i32)
+        edge2 = torch.zeros(2, **i32)
+        capi.check(lib.b2bvh_global_sort(h, self._p(r_codes), cnt, self._p(sorted_codes), self._p(perm), self._p(edge2)), "b2bvh_global_sort")
+        all_edges = self._all_gather(edge2).reshape(-1).contiguous()
+        for wk in works[1:]:
+            wk.wait()
+        # ---- the rank's part of the tree ----
+        gl, gr = (1 if prev >= 0 else 0), (1 if nxt >= 0 else 0)
+        m = cnt + gl + gr if cnt else 0
+        nodes = torch.empty((max(2 * m - 1, 1), 8), **i32)
+        clusters = torch.zeros(256 * 12, **i32)
+        ccount = torch.zeros(1, **i32)
+        capi.check(lib.b2bvh_global_tree(h, self._p(sorted_codes), self._p(perm), self._p(r_gids), self._p(r_boxes), cnt, self._p(all_edges), prev, nxt, a, int(n_total),
+                                         1 if karras else 0, self._p(nodes), self._p(clusters), self._p(ccount)), "b2bvh_global_tree")
+        # ---- the nodes above the ranks ----
+        all_clusters = self._all_gather(clusters).reshape(-1).contiguous()
+        all_counts = self._all_gather(ccount).reshape(-1).contiguous()
+        top = torch.zeros(W * 256 * 12, **i32)
+        res3 = torch.zeros(3, **i32)
+        capi.check(lib.b2bvh_global_top(h, self._p(all_clusters), self._p(all_counts), W, int(n_total), 1 if karras else 0, self._p(top), self._p(res3)), "b2bvh_global_top")
+        self._keep = (boxes, codes, iota, s_codes, s_gids, s_boxes, r_codes, r_gids, r_boxes, sorted_codes, perm, all_edges, all_clusters, all_counts)
+        a2 = a - gl
+        return dict(first=a, last=a + cnt, n_total=n_total, karras=karras, m=m, node_first=a2, nodes=nodes[:max(m - 1, 0)] if cnt else nodes[:0],
+                    leaves=nodes[m - 1 + gl:m - 1 + gl + cnt] if cnt else nodes[:0], top=top.reshape(-1, 12), top_result=res3, sorted_codes=sorted_codes[:cnt],
+                    wire_bytes_sent=32 * (n - sc[self.rank]), counts=cnts)
+
+
+def assemble_global_tree(parts, n_total):
+    """Host-side check helper: the full node array (2n-1, LBVH layout) of the one-GPU tree from every rank's GlobalBuildDevice result
+    (nodes / leaves / top as numpy int32 arrays).  Returns (nodes int32 [(2n-1), 8], root)."""
+    out = np.zeros((2 * n_total - 1, 8), dtype=np.int32)
+    written = np.zeros(2 * n_total - 1, dtype=bool)
+    root = None
+    for p in parts:
+        nd = p["nodes"]
+        if nd.shape[0]:
+            keep = nd[:, 0] != -1  # artefacts are {INVALID, INVALID, empty}
+            idx = p["node_first"] + np.nonzero(keep)[0]
+            out[idx] = nd[keep]
+            written[idx] = True
+        lv = p["leaves"]
+        out[n_total - 1 + p["first"]:n_total - 1 + p["first"] + lv.shape[0]] = lv
+        written[n_total - 1 + p["first"]:n_total - 1 + p["first"] + lv.shape[0]] = True
+    p = parts[0]
+    ntop, root, status = [int(x) & 0xFFFFFFFF for x in p["top_result"]]
+    if status != 0:
+        raise RuntimeError(f"b2bvh_global_top reported status {status}")
+    for t in p["top"][:ntop]:
+        i = int(t[0])
+        out[i, 0], out[i, 1] = t[1], t[2]
+        out[i, 2:8] = t[4:10]
+        written[i] = True
+    return out, root, written

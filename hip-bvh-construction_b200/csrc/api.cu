@@ -242,7 +242,9 @@ int b2bvh_range_extract(b2bvh_ctx* ctx, const b2bvh_bvh2_node* d_local, uint32_t
   void* dFlags;
   B2_TRY(b2_reserve(ctx, SLOT_MISC, (size_t)m + 64, &dFlags));
   u32* dCount = (u32*)((unsigned char*)ctx->bufs[SLOT_CTL].p + 128);
-  B2_TRY(b2_launch_range_extract(ctx, d_local, m, local_root, karras, ghost_left, ghost_right, first_pos, n_global, (unsigned char*)dFlags, d_out, d_clusters, dCount));
+  u32* dRootIn = (u32*)((unsigned char*)ctx->bufs[SLOT_CTL].p + 192);
+  B2_CUDA(cudaMemcpyAsync(dRootIn, &local_root, sizeof(u32), cudaMemcpyHostToDevice, ctx->stream)); /* pageable source: staged before the call returns */
+  B2_TRY(b2_launch_range_extract(ctx, d_local, m, dRootIn, karras, ghost_left, ghost_right, first_pos, n_global, (unsigned char*)dFlags, d_out, d_clusters, dCount));
   B2_TRY(b2_fetch_words(ctx, dCount, 1, B2_MB_RANGE));
   B2_CUDA(cudaStreamSynchronize(ctx->stream));
   *count = b2_mailbox(ctx, B2_MB_RANGE)[0];

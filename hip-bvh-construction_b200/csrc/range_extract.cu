@@ -24,9 +24,10 @@ __device__ __forceinline__ u32 rx_split(u32 idx, u32 l, u32 m) {
 }
 
 template <bool KARRAS>
-__global__ void range_spine_kernel(const b2bvh_bvh2_node* __restrict__ loc, u32 m, u32 root, u32 ghostL, u32 ghostR, u32 firstPos, u32 nGlobal,
-                                   unsigned char* __restrict__ artefact, b2bvh_cluster* __restrict__ out, u32* __restrict__ count) {
+__global__ void range_spine_kernel(const b2bvh_bvh2_node* __restrict__ loc, u32 m, const u32* __restrict__ rootPtr, u32 ghostL, u32 ghostR, u32 firstPos,
+                                   u32 nGlobal, unsigned char* __restrict__ artefact, b2bvh_cluster* __restrict__ out, u32* __restrict__ count) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const u32 root = *rootPtr; /* left on the device by the hierarchy stage: no host round trip between the two */
   const u32 nIntG = nGlobal - 1u;
   u32 n = 0;
   /* iterative in-order walk over the ghost-containing nodes only; everything else is emitted whole */
@@ -78,12 +79,12 @@ __global__ void __launch_bounds__(256) range_renumber_kernel(const b2bvh_bvh2_no
   store_node2(out + i, nd.left, nd.right, nd.box); /* leaves: unchanged (m_leftChildIdx is the primitive) */
 }
 
-int b2_launch_range_extract(b2bvh_ctx* ctx, const b2bvh_bvh2_node* d_local, u32 m, u32 root, int karras, u32 ghostL, u32 ghostR, u32 firstPos, u32 nGlobal,
+int b2_launch_range_extract(b2bvh_ctx* ctx, const b2bvh_bvh2_node* d_local, u32 m, const u32* d_root, int karras, u32 ghostL, u32 ghostR, u32 firstPos, u32 nGlobal,
                             unsigned char* d_flags, b2bvh_bvh2_node* d_out, b2bvh_cluster* d_clusters, u32* d_count) {
   B2_CUDA(cudaMemsetAsync(d_flags, 0, m, ctx->stream));
   B2_KERNEL(ctx, "range_spine");
-  if (karras) range_spine_kernel<true><<<1, 32, 0, ctx->stream>>>(d_local, m, root, ghostL, ghostR, firstPos, nGlobal, d_flags, d_clusters, d_count);
-  else range_spine_kernel<false><<<1, 32, 0, ctx->stream>>>(d_local, m, root, ghostL, ghostR, firstPos, nGlobal, d_flags, d_clusters, d_count);
+  if (karras) range_spine_kernel<true><<<1, 32, 0, ctx->stream>>>(d_local, m, d_root, ghostL, ghostR, firstPos, nGlobal, d_flags, d_clusters, d_count);
+  else range_spine_kernel<false><<<1, 32, 0, ctx->stream>>>(d_local, m, d_root, ghostL, ghostR, firstPos, nGlobal, d_flags, d_clusters, d_count);
   B2_LAUNCH_CHECK(ctx);
   B2_KERNEL(ctx, "range_renumber");
   range_renumber_kernel<<<(2 * m - 1 + 255) / 256, 256, 0, ctx->stream>>>(d_local, m, firstPos, nGlobal, d_flags, d_out);

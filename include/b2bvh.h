@@ -206,6 +206,36 @@ typedef struct b2bvh_cluster {
 int b2bvh_range_extract(b2bvh_ctx* ctx, const b2bvh_bvh2_node* d_local, uint32_t m, uint32_t local_root, int karras, uint32_t ghost_left,
                         uint32_t ghost_right, uint32_t first_pos, uint32_t n_global, b2bvh_bvh2_node* d_out, b2bvh_cluster* d_clusters, uint32_t* count);
 
+/* ---- The globally sorted multi-GPU build as device steps: G ranks produce the nodes of the ONE-GPU LBVH over all
+ * triangles, distributed by sorted position.  Rank-local kernels only, all asynchronous on the context's stream; the collectives between
+ * them (scene box all-reduce, sample all-gather, all-to-all of counts and payload, all-gather of edge codes and clusters) belong to the
+ * caller's communicator (b2bvh/sharded.py GlobalBuildDevice).  New work specified by the north star; no reference counterpart. ---- */
+/* A node of the top of the tree, whose range straddles rank borders: global node index, global child indices, box.  48 bytes. */
+typedef struct b2bvh_top_node {
+  uint32_t index, left, right, pad;
+  b2bvh_aabb box;
+  uint32_t pad2[2];
+} b2bvh_top_node;
+/* destination rank of every primitive = number of splitters <= its code (equal codes never split); stable partition into send order:
+ * d_sendCodes / d_sendGids (= first_gid + local index) / d_sendBoxes hold destination 0's primitives first, then 1's, ...; d_sendCounts[world] */
+int b2bvh_global_partition(b2bvh_ctx* ctx, const uint32_t* d_codes, const b2bvh_aabb* d_boxes, uint32_t n, uint32_t first_gid,
+                           const uint32_t* d_splitters /* world - 1, non-decreasing */, uint32_t world, uint32_t* d_sendCodes, uint32_t* d_sendGids,
+                           b2bvh_aabb* d_sendBoxes, uint32_t* d_sendCounts);
+/* stable sort of the received codes (pieces in source-rank order); d_perm[g] = received position of sorted leaf g; d_edge2 = {first, last} code */
+int b2bvh_global_sort(b2bvh_ctx* ctx, const uint32_t* d_codes, uint32_t cnt, uint32_t* d_sortedCodes, uint32_t* d_perm, uint32_t* d_edge2);
+/* hierarchy over the rank's range [first_pos, first_pos + cnt) of the global order, one ghost leaf per inner edge (prev_rank / next_rank: the
+ * nearest non-empty neighbour whose edge code in d_allEdges[2 * rank + {0,1}] supplies it, or -1): d_nodesOut (2m-1 nodes, m = cnt + ghosts) =
+ * ghost-free nodes with GLOBAL indices (internal i -> first_pos - ghostL + i; leaves name the global primitive d_gids[...]), artefacts as
+ * {INVALID, INVALID, empty}; d_clusters (256) = left-over clusters in position order, pad = depth + 1 of the boundary on the right (0: none),
+ * pad2[0] = 1 where valid; *d_clusterCount their number */
+int b2bvh_global_tree(b2bvh_ctx* ctx, const uint32_t* d_sortedCodes, const uint32_t* d_perm, const uint32_t* d_gids, const b2bvh_aabb* d_boxes,
+                      uint32_t cnt, const uint32_t* d_allEdges, int prev_rank, int next_rank, uint32_t first_pos, uint32_t n_total, int karras,
+                      b2bvh_bvh2_node* d_nodesOut, b2bvh_cluster* d_clusters, uint32_t* d_clusterCount);
+/* the nodes above the ranks from the all-gathered clusters (world x 256 records, world counts): d_topNodes (room for world * 256),
+ * d_result3 = {number of top nodes, root node index, status (0 ok, 1 inconsistent depths, 2 a rank reported more than 256 clusters)} */
+int b2bvh_global_top(b2bvh_ctx* ctx, const b2bvh_cluster* d_allClusters, const uint32_t* d_allCounts, uint32_t world, uint32_t n_total,
+                     int karras, b2bvh_top_node* d_topNodes, uint32_t* d_result3);
+
 /* ---- traversal: replaces the body of TwoPassLbvh::traverseBvh (src/TwoPassLbvh.cpp:199-311). ---- */
 int b2bvh_generate_rays(b2bvh_ctx* ctx, const b2bvh_camera* cam, uint32_t width, uint32_t height, b2bvh_ray* d_rays,
                         float* ms);                       /* GenerateRays, CommonBlocksKernel.h:432-463 */
