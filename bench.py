@@ -308,6 +308,56 @@ def strong_100m(orc, np, torch, T, capi, dist, L, step, timed, args, rank, world
         c.free(d)
 
 
+def global_100m(orc, np, torch, capi, dist, L, args, rank, world):
+    """The globally sorted multi-GPU build at BASELINE configs[4]'s size: rank r contributes triangles [r*N/G, (r+1)*N/G),
+    the ranks exchange 32 B per primitive over NVLink and end up with the nodes of the ONE-GPU single-pass LBVH, distributed by sorted position
+    (Bvh2 only: the 4-wide collapse is not distributed).  Parity: every rank compares its slice and the nodes above the ranks with the tree it
+    builds alone over all 100 M triangles; rank 0 also hashes that tree against the frozen oracle answer."""
+    from b2bvh.sharded import GlobalBuildDevice, check_against_one_tree
+    n = TOTAL_100M
+    a, b = (n * rank) // world, (n * (rank + 1)) // world
+    c = L.ctx
+    d = c.synth_uniform(n, SEED_100M, first=a, count=b - a)
+    gb = GlobalBuildDevice(c, dist, rank, world)
+    try:
+        for _ in range(max(2, args.warmup // 2)):
+            res = gb.build((d, b - a), a, n)
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        steps = max(3, args.steps // 4)
+        e0.record(L.stream)
+        for _ in range(steps):
+            res = gb.build((d, b - a), a, n)
+        e1.record(L.stream)
+        dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / steps], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        wire = torch.tensor([float(res["wire_bytes_sent"])], device="cuda", dtype=torch.float64)
+        dist.all_reduce(wire, op=dist.ReduceOp.SUM)
+        t0 = time.perf_counter()
+        d_all = c.synth_uniform(n, SEED_100M)
+        gp = os.path.join(ROOT, "tests", "golden", "sharded_100m_known_answers.json")
+        ka = json.load(open(gp)).get("world1") if os.path.exists(gp) else None
+        hasher = (lambda want: orc.fnv1a(np.ascontiguousarray(want).view(np.uint32).reshape(-1))) if (rank == 0 and ka) else None
+        ok, mine, ntop, hv = check_against_one_tree(c, res, d_all, n, False, want_hash=hasher)
+        c.free(d_all)
+        checks = {"slice_and_top_equal_the_one_gpu_tree": ok}
+        if hasher:
+            checks["one_gpu_tree_has_the_frozen_oracle_hash"] = hv == ka["shards"][0]["nodes_fnv"]
+        allok, ranks_ok = _all_ok(torch, dist, all(checks.values()))
+        return {"workload": f"synth_uniform_v1 {n // 1_000_000}M triangles, ONE globally sorted single-pass LBVH (Bvh2) across {world} GPUs", "total_prims": n, "n_gpus": world,
+                "steps": steps, "ms_per_build": ms, "value": n / (ms * 1e-3) / 1e6, "unit": "Mprims/s", "wire_bytes_per_build_all_ranks": float(wire.item()),
+                "wire_GBs_aggregate_over_the_whole_build": float(wire.item()) / (ms * 1e-3) / 1e9, "positions_per_rank": res["counts"], "nodes_above_the_ranks": ntop,
+                "status": "ok" if allok else "FAILED", "ranks_ok": ranks_ok, "rank0_checks": checks, "parity_seconds": time.perf_counter() - t0,
+                "how": "every rank: its ghost-free nodes, its leaves and the nodes above the ranks == the tree ONE context builds over all triangles (memcmp); rank 0: "
+                       "FNV-1a of that tree == the oracle's frozen answer (tests/golden/sharded_100m_known_answers.json world1)"}
+    finally:
+        c.free(d)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -476,7 +526,11 @@ def main():
         line["parity"] = parity_weak(orc, np, torch, T, capi, dist, lane0, step, d_tris, n, n_total, rank, world)
         # ---- BASELINE configs[4]: 100 M triangles in total, split by primitive range over the ranks (strong scaling) ----
         line["strong_100M"] = strong_100m(orc, np, torch, T, capi, dist, lane0, step, timed, args, rank, world, peak)
-        failed = [k for k in ("parity", "strong_100M") if line[k].get("status", line[k].get("parity", {}).get("status")) == "FAILED"]
+        if world > 1:
+            # ---- the same 100 M triangles as ONE globally sorted tree across the ranks (b2bvh_global_*), checked node for node
+            # against the tree one GPU builds over all of them, which in turn carries the frozen oracle hash ----
+            line["global_100M"] = global_100m(orc, np, torch, capi, dist, lane0, args, rank, world)
+        failed = [k for k in ("parity", "strong_100M", "global_100M") if k in line and line[k].get("status", line[k].get("parity", {}).get("status")) == "FAILED"]
         if failed:
             if rank == 0:
                 print(json.dumps(line))

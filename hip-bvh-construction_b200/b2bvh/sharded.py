@@ -498,3 +498,24 @@ def assemble_global_tree(parts, n_total):
         out[i, 2:8] = t[4:10]
         written[i] = True
     return out, root, written
+
+
+def check_against_one_tree(ctx, res, d_all, n, karras, want_hash=None):
+    """Check helper (tools/global_build_check.py, bench.py).  res: GlobalBuildDevice.build result of this rank; d_all: ALL triangles on this GPU.  True when this rank's ghost-free nodes, its leaves
+    and the nodes above the ranks equal the corresponding nodes of the tree one context builds over all triangles."""
+    from . import capi, types as T
+    whole = ctx.build(capi.TWO_PASS_LBVH if karras else capi.SINGLE_PASS_LBVH, d_all, n=n, tris_on_device=True, collapse=False)
+    want = ctx.download(whole.d_bvhNodes, T.BVH2_NODE, 2 * n - 1).view(np.int32).reshape(-1, 8)
+    ntop, root, status = [int(x) & 0xFFFFFFFF for x in res["top_result"].cpu().numpy()]
+    ok = status == 0 and root == whole.root
+    mine = res["nodes"].cpu().numpy()
+    valid = mine[:, 0] != -1
+    idx = res["node_first"] + np.nonzero(valid)[0]
+    ok = ok and np.array_equal(mine[valid], want[idx])
+    ok = ok and np.array_equal(res["leaves"].cpu().numpy(), want[n - 1 + res["first"]:n - 1 + res["last"]])
+    top = res["top"].cpu().numpy()[:ntop]
+    ok = ok and np.array_equal(top[:, 1:3], want[top[:, 0], 0:2]) and np.array_equal(top[:, 4:10], want[top[:, 0], 2:8])
+    # want_hash: callable(node array) -> value, e.g. the FNV-1a the frozen oracle answers use: ties the one-GPU tree itself to the oracle
+    return bool(ok), int(valid.sum()), ntop, (want_hash(want) if want_hash else None)
+
+

@@ -595,6 +595,65 @@ static inline float h_area(const b2bvh_aabb& b) {
 static inline float h_min(float a, float b) { return (b < a) ? b : a; }
 static inline float h_max(float a, float b) { return (b > a) ? b : a; }
 
+/* The whole primitive-range sharded build from ONE host thread over G contexts (SURVEY.md §8(b) proposal; the reference is single-device,
+ * Context.cpp:11): local boxes on every device -> the 6-float {-min,max} vectors meet on the host (24 bytes per device: the exchange is
+ * latency, not bandwidth; ranks in separate processes use NCCL for it, b2bvh/sharded.py) -> every device builds its shard in the global
+ * frame, all enqueued before the first is waited for -> root boxes -> top-level tree on the first context.  Contexts may share a device. */
+int b2bvh_build_sharded(b2bvh_ctx* const* ctxs, uint32_t n_gpus, int algo, const b2bvh_triangle* const* tris, const uint32_t* counts,
+                        const b2bvh_build_opts* optsIn, b2bvh_tree* trees, b2bvh_aabb* h_scene, b2bvh_bvh2_node* h_topNodes) {
+  if (!ctxs || !tris || !counts || !trees || !h_topNodes || n_gpus == 0 || n_gpus > 256u) return b2_fail(B2BVH_ERR_INVALID, "build_sharded: bad argument (1 <= n_gpus <= 256)");
+  for (u32 g = 0; g < n_gpus; g++)
+    if (!ctxs[g] || !tris[g] || counts[g] < 2) return b2_fail(B2BVH_ERR_INVALID, "build_sharded: shard %u needs a context and at least 2 primitives", g);
+  b2bvh_build_opts base;
+  memset(&base, 0, sizeof(base));
+  if (optsIn) base = *optsIn; else base.collapse = 1;
+  if (base.split_sa_max > 0.0f || base.use_scene_box || base.d_scene_negmin_max || base.boxes_ready || base.d_root_box_out)
+    return b2_fail(B2BVH_ERR_INVALID, "build_sharded: the scene-box, boxes_ready, root-box and split options are set by the sharded build itself");
+  std::vector<float> local(6 * (size_t)n_gpus);
+  auto ctl = [&](u32 g, size_t off) { return (float*)((unsigned char*)ctxs[g]->bufs[SLOT_CTL].p + off); };
+  for (u32 g = 0; g < n_gpus; g++) B2_TRY(b2bvh_shard_extents(ctxs[g], tris[g], counts[g], base.tris_on_device, ctl(g, 64)));
+  for (u32 g = 0; g < n_gpus; g++) {
+    B2_CUDA(cudaSetDevice(ctxs[g]->device));
+    B2_CUDA(cudaMemcpyAsync(&local[6 * g], ctl(g, 64), 24, cudaMemcpyDeviceToHost, ctxs[g]->stream));
+  }
+  float global6[6] = {-B2BVH_FLT_MAX, -B2BVH_FLT_MAX, -B2BVH_FLT_MAX, -B2BVH_FLT_MAX, -B2BVH_FLT_MAX, -B2BVH_FLT_MAX};
+  for (u32 g = 0; g < n_gpus; g++) {
+    B2_CUDA(cudaSetDevice(ctxs[g]->device));
+    B2_CUDA(cudaStreamSynchronize(ctxs[g]->stream));
+    for (int k = 0; k < 6; k++) global6[k] = h_max(global6[k], local[6 * g + k]); /* the all-reduce(MAX) of {-min, max} */
+  }
+  if (h_scene) { h_scene->m_min = {-global6[0], -global6[1], -global6[2]}; h_scene->m_max = {global6[3], global6[4], global6[5]}; }
+  for (u32 g = 0; g < n_gpus; g++) {
+    B2_CUDA(cudaSetDevice(ctxs[g]->device));
+    B2_CUDA(cudaMemcpyAsync(ctl(g, 64), global6, 24, cudaMemcpyHostToDevice, ctxs[g]->stream));
+    b2bvh_build_opts o = base;
+    o.boxes_ready = 1;
+    o.d_scene_negmin_max = ctl(g, 64);
+    o.d_root_box_out = ctl(g, 224);
+    o.defer_sync = 1; /* every shard is enqueued before the first one is waited for */
+    B2_TRY(b2bvh_build(ctxs[g], algo, tris[g], counts[g], &o, &trees[g]));
+  }
+  std::vector<b2bvh_aabb> roots(n_gpus);
+  for (u32 g = 0; g < n_gpus; g++) {
+    B2_TRY(b2bvh_build_finish(ctxs[g], &trees[g]));
+    B2_CUDA(cudaSetDevice(ctxs[g]->device));
+    B2_CUDA(cudaMemcpyAsync(&roots[g], ctl(g, 224), sizeof(b2bvh_aabb), cudaMemcpyDeviceToHost, ctxs[g]->stream));
+    B2_CUDA(cudaStreamSynchronize(ctxs[g]->stream));
+  }
+  b2bvh_ctx* c0 = ctxs[0];
+  B2_CUDA(cudaSetDevice(c0->device));
+  void* dTop;
+  const size_t rootBytes = ((size_t)n_gpus * sizeof(b2bvh_aabb) + 255) & ~(size_t)255;
+  B2_TRY(b2_reserve(c0, SLOT_MISC, rootBytes + (2 * (size_t)n_gpus - 1) * sizeof(b2bvh_bvh2_node), &dTop));
+  B2_CUDA(cudaMemcpyAsync(dTop, roots.data(), n_gpus * sizeof(b2bvh_aabb), cudaMemcpyHostToDevice, c0->stream));
+  b2bvh_bvh2_node* dNodes = (b2bvh_bvh2_node*)((unsigned char*)dTop + rootBytes);
+  B2_TRY(b2bvh_top_level(c0, (const b2bvh_aabb*)dTop, n_gpus, dNodes));
+  B2_CUDA(cudaMemcpyAsync(h_topNodes, dNodes, (2 * (size_t)n_gpus - 1) * sizeof(b2bvh_bvh2_node), cudaMemcpyDeviceToHost, c0->stream));
+  B2_CUDA(cudaStreamSynchronize(c0->stream));
+  return 0;
+}
+
+
 /* Utility::calculatebvh4Cost (Utility.cpp:351-396): root box = union of the root's child boxes, then a float
  * running sum in index order: 1 + sum over wide nodes of internal-child areas / rootArea + sum over leaf slots of
  * primitive areas / rootArea. */

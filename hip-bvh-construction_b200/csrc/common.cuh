@@ -286,7 +286,7 @@ enum {
   SLOT_BATCH_NODES, SLOT_BATCH_LEAVES, SLOT_BATCH_ROOTS, SLOT_BATCH_SCENES, SLOT_BATCH_OFFSETS,
   SLOT_KEYS_LO, SLOT_KEYS64, SLOT_SKEYS64, SLOT_M60_KEYS, SLOT_M60_VALS, SLOT_COUNT
 };
-/* SLOT_CTL (256 B): [0..23] scene box, [32..63] extents scratch8, [64..87] {-min,max}, [96] root index, [128] range-extract count, [160] traversal overflow flag, [192..] misc */
+/* SLOT_CTL (256 B): [0..23] scene box, [32..63] extents scratch8, [64..87] {-min,max}, [96] root index, [128] range-extract count, [160] traversal overflow flag, [192] range-extract root, [224..247] root box of a sharded build */
 int b2_reserve(b2bvh_ctx* ctx, int slot, size_t bytes, void** out);
 /* words <= 16 from device memory into mailbox slot `slot`; readable at b2_mailbox(ctx, slot) after the next stream synchronisation */
 #define B2_MAILBOX_SLOTS 8

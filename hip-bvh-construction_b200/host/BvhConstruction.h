@@ -65,7 +65,7 @@ struct Api {
   B2_SYM(b2bvh_ctx_create) B2_SYM(b2bvh_ctx_destroy) B2_SYM(b2bvh_device_name) B2_SYM(b2bvh_device_sm_count) B2_SYM(b2bvh_alloc)
   B2_SYM(b2bvh_free) B2_SYM(b2bvh_memset) B2_SYM(b2bvh_h2d) B2_SYM(b2bvh_d2h) B2_SYM(b2bvh_sync) B2_SYM(b2bvh_last_error)
   B2_SYM(b2bvh_build) B2_SYM(b2bvh_build_batched) B2_SYM(b2bvh_generate_rays) B2_SYM(b2bvh_traverse) B2_SYM(b2bvh_traverse_ex) B2_SYM(b2bvh_heat_map) B2_SYM(b2bvh_tree_cost) B2_SYM(b2bvh_cost_bvh4)
-  B2_SYM(b2bvh_cost_lbvh) B2_SYM(b2bvh_synth_uniform) B2_SYM(b2bvh_abi_version)
+  B2_SYM(b2bvh_cost_lbvh) B2_SYM(b2bvh_synth_uniform) B2_SYM(b2bvh_abi_version) B2_SYM(b2bvh_build_sharded)
 #undef B2_SYM
   void* handle = nullptr;
   static Api& get(const char* path = nullptr) {
@@ -81,7 +81,7 @@ struct Api {
     B2_SYM(b2bvh_ctx_create) B2_SYM(b2bvh_ctx_destroy) B2_SYM(b2bvh_device_name) B2_SYM(b2bvh_device_sm_count) B2_SYM(b2bvh_alloc)
     B2_SYM(b2bvh_free) B2_SYM(b2bvh_memset) B2_SYM(b2bvh_h2d) B2_SYM(b2bvh_d2h) B2_SYM(b2bvh_sync) B2_SYM(b2bvh_last_error)
     B2_SYM(b2bvh_build) B2_SYM(b2bvh_build_batched) B2_SYM(b2bvh_generate_rays) B2_SYM(b2bvh_traverse) B2_SYM(b2bvh_traverse_ex) B2_SYM(b2bvh_heat_map) B2_SYM(b2bvh_tree_cost) B2_SYM(b2bvh_cost_bvh4)
-    B2_SYM(b2bvh_cost_lbvh) B2_SYM(b2bvh_synth_uniform) B2_SYM(b2bvh_abi_version)
+    B2_SYM(b2bvh_cost_lbvh) B2_SYM(b2bvh_synth_uniform) B2_SYM(b2bvh_abi_version) B2_SYM(b2bvh_build_sharded)
 #undef B2_SYM
     if (api.b2bvh_abi_version() != B2BVH_ABI_VERSION)
       throw std::runtime_error("libb2bvh.so speaks ABI version " + std::to_string(api.b2bvh_abi_version()) + ", this header was written for " +
@@ -95,8 +95,8 @@ inline void checkStatus(int status, const char* what) {
 
 class Context {
  public:
-  Context() {
-    checkStatus(Api::get().b2bvh_ctx_create(0, nullptr, &m_ctx), "b2bvh_ctx_create"); /* device 0, as Context.cpp:11 */
+  explicit Context(int device = 0) { /* device 0 by default, as Context.cpp:11; the sharded build makes one per device */
+    checkStatus(Api::get().b2bvh_ctx_create(device, nullptr, &m_ctx), "b2bvh_ctx_create");
     char name[256];
     Api::get().b2bvh_device_name(m_ctx, name, sizeof(name));
     std::cout << "Executing on '" << name << "'" << std::endl; /* Context.cpp:14 */
@@ -345,6 +345,40 @@ class BatchedBvhBuilder {
   u32 m_nInternalNodes = 0;
   float m_cost = 0.0f;
   b2bvh_batch m_batch{};
+};
+
+/* Primitive-range sharded build over several contexts, one per GPU (north star: large meshes shard by primitive range across the GPUs
+ * of a node; the reference is single-device, Context.cpp:11 — no counterpart).  Shard g = primitives [g*N/G, (g+1)*N/G), built by the
+ * chosen LBVH builder in the frame of the global scene box; m_topNodes = the top-level tree over the shard roots (leaf m_leftChildIdx =
+ * shard).  One host thread: b2bvh_build_sharded enqueues every shard before it waits for the first. */
+class ShardedLbvh {
+ public:
+  void build(std::vector<Context*>& contexts, std::vector<Triangle>& primitives, int algo = B2BVH_SINGLE_PASS_LBVH) {
+    const u32 G = (u32)contexts.size();
+    const size_t N = primitives.size();
+    std::vector<b2bvh_ctx*> ctxs(G);
+    std::vector<const Triangle*> ptrs(G);
+    std::vector<u32> counts(G);
+    m_firstPrim.assign(G + 1, 0);
+    for (u32 g = 0; g <= G; g++) m_firstPrim[g] = (u32)((N * g) / G);
+    for (u32 g = 0; g < G; g++) { ctxs[g] = contexts[g]->m_ctx; ptrs[g] = primitives.data() + m_firstPrim[g]; counts[g] = m_firstPrim[g + 1] - m_firstPrim[g]; }
+    m_trees.assign(G, b2bvh_tree{});
+    m_topNodes.assign(2 * (size_t)G - 1, Bvh2Node{});
+    checkStatus(Api::get().b2bvh_build_sharded(ctxs.data(), G, algo, ptrs.data(), counts.data(), nullptr, m_trees.data(), &m_sceneExtents, m_topNodes.data()),
+                "b2bvh_build_sharded");
+    float slowest = 0.0f;
+    std::cout << "==========================Perf Times==========================" << std::endl;
+    for (u32 g = 0; g < G; g++) {
+      std::cout << "Shard " << g << " : " << counts[g] << " primitives, BuildTime " << m_trees[g].build_ms << "ms, wide nodes " << m_trees[g].n_wide << std::endl;
+      slowest = m_trees[g].build_ms > slowest ? m_trees[g].build_ms : slowest;
+    }
+    std::cout << "Total Time (slowest shard) : " << slowest << "ms" << std::endl;
+    std::cout << "==============================================================" << std::endl;
+  }
+  std::vector<b2bvh_tree> m_trees;   /* device buffers of shard g live in contexts[g] */
+  std::vector<Bvh2Node> m_topNodes;  /* host copy: 2G-1 nodes, root 0 */
+  std::vector<u32> m_firstPrim;      /* shard g holds primitives [m_firstPrim[g], m_firstPrim[g+1]) */
+  Aabb m_sceneExtents{};
 };
 
 }  // namespace BvhConstruction

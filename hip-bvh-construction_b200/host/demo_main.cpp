@@ -9,12 +9,15 @@
  *   b2bvh_demo batched <mesh.tri | synth:N>      the USE_BATCHED_BUILDER branch (main.cpp:38-52): 4096 items; a mesh of <= 32
  *                                                 triangles is one item repeated (the reference's cornell box), a larger one is cut
  *                                                 into items of 32 consecutive triangles
+ *   b2bvh_demo sharded:<G> <mesh.tri | synth:N>  primitive-range sharded single-pass LBVH over G contexts (device g % device count): prints the
+ *                                                 per-shard table, checks that the top-level root box is the global scene box
  * exits 0 when the build succeeded (and the cost matches expected_cost to 1e-5 relative, when given).
  */
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <memory>
 
 #include "BvhConstruction.h"
 
@@ -94,6 +97,22 @@ int main(int argc, char* argv[]) {
         if (memcmp(&r.m_aabb, &scenes[i], sizeof(Aabb)) != 0) { fprintf(stderr, "item %u: root box differs from the item's scene box\n", i); return 1; }
       }
       std::cout << "items : " << batchSize << "  nodes : " << nodes.size() << "  root of item 0 : " << roots[0] << std::endl;
+      return 0;
+    }
+    if (which.rfind("sharded:", 0) == 0) {
+      const int G = atoi(which.c_str() + 8);
+      if (G < 1 || G > 64) throw std::runtime_error("sharded:<G> needs 1 <= G <= 64");
+      int devices = 1;
+      if (const char* e = getenv("B2BVH_DEVICES")) devices = atoi(e) > 0 ? atoi(e) : 1;
+      std::vector<std::unique_ptr<Context>> owned;
+      std::vector<Context*> ctxs;
+      for (int g = 0; g < G; g++) { owned.emplace_back(new Context(g % devices)); ctxs.push_back(owned.back().get()); }
+      ShardedLbvh bvh;
+      bvh.build(ctxs, triangles);
+      const Bvh2Node& root = bvh.m_topNodes[0];
+      if (memcmp(&root.m_aabb, &bvh.m_sceneExtents, sizeof(Aabb)) != 0) { fprintf(stderr, "top-level root box differs from the global scene box\n"); return 1; }
+      std::cout << "shards : " << G << "  top-level nodes : " << bvh.m_topNodes.size() << "  scene min : " << bvh.m_sceneExtents.m_min.x << " " << bvh.m_sceneExtents.m_min.y
+                << " " << bvh.m_sceneExtents.m_min.z << std::endl;
       return 0;
     }
     if (which == "twopass") cost = run<TwoPassLbvh>(context, triangles);

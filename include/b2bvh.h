@@ -255,6 +255,13 @@ int b2bvh_heat_map(const uint32_t* rayCounter, uint32_t count, uint8_t* rgba);
 int b2bvh_shard_extents(b2bvh_ctx* ctx, const b2bvh_triangle* tris, uint32_t n, uint32_t tris_on_device,
                         float* d_negmin_max6 /* device, 6 floats: {-min.xyz, max.xyz}, ready for one all-reduce(MAX) */);
 int b2bvh_top_level(b2bvh_ctx* ctx, const b2bvh_aabb* d_rootBoxes, uint32_t g, b2bvh_bvh2_node* d_topNodes /* 2g-1 */);
+/* The whole sharded build from ONE host thread over n_gpus contexts (one per device; contexts may also share a device): shard g =
+ * tris[g][0 .. counts[g]) (host or device pointers per opts->tris_on_device), built in the frame of the union of all shards' boxes;
+ * trees[g] = shard g's tree (as b2bvh_build fills it), *h_scene = the global scene box (may be NULL), h_topNodes (host, 2*n_gpus-1 nodes) =
+ * the top-level tree over the shard roots (leaf m_leftChildIdx = shard).  The 24-byte exchanges go through the host; ranks in separate
+ * processes use b2bvh_shard_extents / b2bvh_build / b2bvh_top_level with their own communicator instead (b2bvh/sharded.py). */
+int b2bvh_build_sharded(b2bvh_ctx* const* ctxs, uint32_t n_gpus, int algo, const b2bvh_triangle* const* tris, const uint32_t* counts,
+                        const b2bvh_build_opts* opts, b2bvh_tree* trees, b2bvh_aabb* h_scene, b2bvh_bvh2_node* h_topNodes);
 
 /* ---- SAH-cost reporting on the host (pure functions on host copies; Utility.cpp:317-396). ---- */
 float b2bvh_cost_bvh4(const b2bvh_bvh4_node* wide, const b2bvh_prim_node* wideLeaves, const b2bvh_aabb* primAabbs, uint32_t root,

@@ -116,3 +116,35 @@ def test_global_build_engine_on_one_gpu(oracle, karras):
         assert res["root"] == o["root"] and res["first"] == 0 and res["last"] == n and res["top"] == {}
         assert np.array_equal(res["nodes"].cpu().numpy(), want[:n - 1]) and np.array_equal(res["leaves"].cpu().numpy(), want[n - 1:])
         c.close()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_build_sharded_c_abi(ctx, oracle, world):
+    """b2bvh_build_sharded: ONE host thread over `world` contexts (here all on the box's one GPU): every shard's tree and the top-level tree
+    equal the oracle's sharded procedure byte for byte."""
+    from b2bvh import types as T
+    tris = random_tris(60_001, 91)
+    n = tris.size
+    ctxs = [capi.Context(0) for _ in range(world)]
+    try:
+        ranges = [((n * r) // world, (n * (r + 1)) // world) for r in range(world)]
+        shards = [np.ascontiguousarray(tris[a:b]) for a, b in ranges]
+        handles = (C.c_void_p * world)(*[c.h for c in ctxs])
+        ptrs = (C.c_void_p * world)(*[s.ctypes.data for s in shards])
+        counts = (C.c_uint32 * world)(*[s.size for s in shards])
+        trees = (capi.Tree * world)()
+        scene = np.zeros(1, dtype=T.AABB)
+        top = np.zeros(2 * world - 1, dtype=T.BVH2_NODE)
+        capi.check(ctx.lib.b2bvh_build_sharded(handles, world, capi.SINGLE_PASS_LBVH, ptrs, counts, None, trees, scene.ctypes.data_as(C.c_void_p),
+                                               top.ctypes.data_as(C.c_void_p)), "b2bvh_build_sharded")
+        o_scene, o_shards, o_top = oracle.build_sharded(tris, world, single_pass=True)
+        assert scene.tobytes() == o_scene.tobytes()
+        assert top.tobytes() == o_top.tobytes()
+        for r in range(world):
+            g = ctxs[r].fetch(trees[r])
+            for k in ("skeys", "svals", "nodes", "wide", "wide_leaves"):
+                assert g[k].tobytes() == o_shards[r][k].tobytes(), (r, k)
+            assert g["root"] == o_shards[r]["root"]
+    finally:
+        for c in ctxs:
+            c.close()
