@@ -9,7 +9,8 @@ import numpy as np
 from . import types as T
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "libb2bvh.so")
+# B2BVH_LIB: the same override the C++ host layer honours (host/BvhConstruction.h) — development builds of the library, never a fallback
+LIB_PATH = os.environ.get("B2BVH_LIB") or os.path.join(os.path.dirname(_HERE), "libb2bvh.so")
 
 ABI_VERSION = 6  # B2BVH_ABI_VERSION of include/b2bvh.h: the struct layouts mirrored below
 TWO_PASS_LBVH, SINGLE_PASS_LBVH, PLOCPP, HPLOC = 0, 1, 2, 3

@@ -185,16 +185,27 @@ __global__ void __launch_bounds__(HP_THREADS) hploc_kernel(const K* __restrict__
       }
     }
     u32 todo = __ballot_sync(B2_FULL, wantMerge);
+    const bool merged = todo != 0u;
     while (todo) {
       const int src = __ffs(todo) - 1;
       todo &= todo - 1;
       const u32 mL = __shfl_sync(B2_FULL, L, src), mR = __shfl_sync(B2_FULL, R, src), mS = __shfl_sync(B2_FULL, split, src);
       const bool mF = __shfl_sync(B2_FULL, fin ? 1 : 0, src) != 0;
       hploc_merge_warp(mL, mR, mS, mF, n, nodes, leaves, nodeIdx, freeIdx, ctrl);
+#ifndef HP_FENCE_ONCE
       /* make this call's stores (done by all lanes) visible before lane `src` publishes the range further up */
       __threadfence();
+#endif
       __syncwarp();
     }
+#ifdef HP_FENCE_ONCE
+    /* the merge calls of one round work on disjoint ranges and nothing is published before the next exchange: ONE fence makes the stores of
+     * all of them (done by all lanes) visible before the lanes hand their ranges further up */
+    if (merged) __threadfence();
+    __syncwarp();
+#else
+    (void)merged;
+#endif
     if (fin) active = false;
   }
 }

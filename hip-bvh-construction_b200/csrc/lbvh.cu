@@ -612,6 +612,9 @@ static int launch_lbvh_fused_t(b2bvh_ctx* ctx, const K* d_sortedKeys, const u32*
     const u32 grid = (n + LBVH_TILE - 1) / LBVH_TILE;
     /* second level only where it pays (build stage in us without / with it: 1 M 104 / 119, 3 M 203 / 217, 7 M 379 / 399, 10 M 551 / 533,
      * tools/micro/lbvh_level_sweep.py): below ~8 M primitives the extra launch costs more than the shorter climb saves */
+    /* (Round 2 tried more merge levels above the groups — 16 groups per CTA, repeated until one CTA finishes the root — in place of the climb:
+     * three launches of 23 us each against 67 us of climbing at 10 M, no gain.  The left-over clusters are the two monotone depth runs of
+     * every group, and a monotone run merges one pair per round, so a level costs ~40 dependent rounds whatever its size; gpurun r2h.) */
     const bool useGroups = ctx->lbvh_second_level == 1 ? true : (ctx->lbvh_second_level == 2 ? false : n >= (1u << 23));
     uint2* tileInfo = reinterpret_cast<uint2*>(pending + cap);
     LbvhPending* tileBuf = useGroups ? reinterpret_cast<LbvhPending*>(reinterpret_cast<unsigned char*>(tileInfo) + (((size_t)grid * sizeof(uint2) + 15) & ~(size_t)15)) : nullptr;
