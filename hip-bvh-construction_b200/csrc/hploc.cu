@@ -25,7 +25,10 @@
 #include "common.cuh"
 
 #ifndef HP_THREADS
-#define HP_THREADS 128
+#define HP_THREADS 32  /* one warp per CTA: a CTA's slot is free again as soon as its warp has handed over its last range.  10 M uniform, merge stage in ms
+                          (tools/variant_bench.py, gpurun r2i): 32 threads 2.28, 64 2.37, 128 2.40, 256 2.44; one fence per round instead of one per merge
+                          call (HP_FENCE_ONCE) changes nothing (2.40 / 2.38 / 2.44): the kernel is bound by the ~7 us dependent chain of a merge call
+                          (ids -> boxes -> 2-3 search rounds -> stores -> fence -> exchange) at ~24 resident warps per SM, not by the fences */
 #endif
 #define HP_R 8
 
