@@ -13,6 +13,10 @@
  * LBVH layout or in the separate-leaf layout of PLOC++/H-PLOC (the reference never traverses those); a HitInfo buffer can
  * be returned (parity is checked on hits, not pixels); the Bvh4 of the build can be traced (traverse_wide4_kernel; the
  * reference builds it and only reports its cost).  Arithmetic is evaluated without FMA, in the reference's order.
+ * Round-2 experiment, taken out again: carrying the child indices of the node the ray descends into (they sit in the 32-byte record that
+ * was just fetched for its box) instead of re-reading them at the visit — same Mray/s for while-while (sponza 981 vs 1003), 12 % less for
+ * if-if: the re-read hits L1, there was no second memory round trip to save (gpurun r2j).  512 x 512 rays are one partial wave of a B200
+ * (4096 CTAs of 64 threads, all resident): the time is the longest ray's path; at 4096 x 4096 the same kernels reach 4.0-4.3 Gray/s.
  */
 #include <math.h>
 
