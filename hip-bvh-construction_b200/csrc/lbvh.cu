@@ -123,6 +123,9 @@ __global__ void __launch_bounds__(LBVH_THREADS) lbvh_fused_kernel(const K* __res
  * lbvh_climb_kernel, which finishes the top of the tree with the global exchange protocol above. */
 #define LBVH_TILE 256
 #define LBVH_TILE_THREADS 256
+#ifndef LBVH_EARLY_STOP
+#define LBVH_EARLY_STOP 16   /* > 0: a tile whose list fits its slot stops merging once a round makes at most this many merges (second merge level only) */
+#endif
 #define LBVH_GROUP 32        /* tiles whose left-over clusters are merged further by one CTA of lbvh_group_kernel */
 #define LBVH_TILE_CAP 32     /* left-over clusters a tile may park in its slot (typically ~14; at most 124: two monotone depth runs) */
 #define LBVH_GROUP_CAP (LBVH_GROUP * LBVH_TILE_CAP)
@@ -279,6 +282,13 @@ __global__ void __launch_bounds__(LBVH_TILE_THREADS, 8) lbvh_tile_kernel(const K
     named_barrier(1, nW * 32u);
     cur ^= 1u;
     count -= total;
+#if LBVH_EARLY_STOP > 0
+    /* the tail of a tile is two monotone depth runs that merge one or two pairs per round with ONE warp at work while the other seven wait
+     * at the barrier below (35 % of the kernel's stall samples, profiles/r02k_ncu_source_hotspots.txt).  With a second merge level the rest is
+     * cheaper there: 32 tiles' left-overs merge side by side in one CTA of lbvh_group_kernel.  (count and total are the same in every
+     * participating warp.) */
+    if (tileBuf != nullptr && count <= LBVH_TILE_CAP && total <= LBVH_EARLY_STOP) break;
+#endif
   }
   if (tid == 0) { S.finalCur = cur; S.finalCount = count; } /* warp 0 takes part in every round */
   rootDone = __syncthreads_or(rootDone);
