@@ -121,6 +121,30 @@ def batched_build_mt(tris, n_items, prim_count):
     return nodes, leaves, roots, scenes
 
 
+def hploc_build_mt(boxes, skeys, svals):
+    """Runs the reference's HPloc kernel (HplocKernel.h:257-315) wavefront by wavefront under the block emulator, after its SetupClusters
+    semantics (leaf g = {svals[g], boxes[svals[g]]}, nodeIdx[g] = g + n-1, parentIdx = INVALID; the kernel itself is shared with Ploc++'s
+    setup in the single-thread emulator).  One statement is added to the compiled copy of the header (a barrier where a lock-step wavefront
+    is converged anyway; oracle/Makefile, ref_shim/ref_emul_ploc_mt.cpp).  Returns (nodes, leaves, merged) — numbering follows the atomicAdd order."""
+    global _emul_mt
+    if _emul_mt is None:
+        _emul_mt = C.CDLL(os.path.join(_HERE, "_ref", "libref_emul_mt.so"))
+        _emul_mt.ref_ploc_build_mt.restype = C.c_uint32
+    _emul_mt.ref_hploc_mt.restype = C.c_uint32
+    n = svals.size
+    assert (n - 1) % 32 != 0, "the reference launches n-1 threads rounded up to 32: leaf n-1 has no thread when (n-1) % 32 == 0"
+    nodes = np.zeros(n - 1, dtype=T.BVH2_NODE)
+    nodes["left"] = 0xFFFFFFFF; nodes["right"] = 0xFFFFFFFF
+    leaves = np.zeros(n, dtype=T.PRIM_REF)
+    leaves["primIdx"] = svals
+    leaves["mn"] = boxes["mn"][svals]; leaves["mx"] = boxes["mx"][svals]
+    idx = (np.arange(n, dtype=np.uint32) + np.uint32(n - 1)).copy()
+    parent = np.full(n, 0xFFFFFFFF, dtype=np.uint32)
+    keys = np.ascontiguousarray(skeys, dtype=np.uint32).copy()
+    merged = _emul_mt.ref_hploc_mt(_p(nodes), _p(leaves), _p(keys), _p(idx), _p(parent), _u32(n))
+    return nodes, leaves, int(merged)
+
+
 def collapse(nodes, leaves, root, n):
     """Runs the reference CollapseToWide4Bvh (LBVH variant when leaves is None, PLOC variant otherwise)."""
     wide = np.zeros(2 * n, dtype=T.BVH4_NODE); wl = np.zeros(n, dtype=T.PRIM_NODE)

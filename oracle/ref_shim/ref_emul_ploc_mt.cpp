@@ -16,6 +16,7 @@ Block g_blk;
 void yield_to_scheduler() { swapcontext(&g_blk.fibers[g_blk.current].ctx, &g_blk.main); }
 }
 static std::function<void()>* g_kernel;
+static bool g_lowestFirst = false; /* order of the runnable fibers between two synchronisation points (see ref_hploc_mt) */
 static void fiber_entry() {
   (*g_kernel)();
   b2emul::g_blk.fibers[b2emul::g_blk.current].state = b2emul::EXITED;
@@ -43,7 +44,8 @@ static void run_block(uint32_t block, uint32_t nThreads, uint32_t nBlocks, std::
   while (true) {
     /* run every READY fiber once, highest index first */
     bool ran = false;
-    for (int t = (int)nThreads - 1; t >= 0; t--) {
+    for (int k = 0; k < (int)nThreads; k++) {
+      const int t = g_lowestFirst ? k : (int)nThreads - 1 - k;
       if (fibers[t].state != READY) continue;
       g_blk.current = t;
       threadIdx = {(uint32_t)t, 0, 0};
@@ -123,3 +125,35 @@ extern "C" void ref_batched_build_mt(const Triangle* tris, uint32_t nItems, uint
 }
 #endif
 
+
+/* ---- the reference's H-PLOC kernel (HplocKernel.h:257-315 with findParent, plocMerge, loadIndices, findNearestNeighbours, mergeClusters,
+ * storeIndices) under the block emulator: one 32-thread block = one wavefront (HPlocBlockSize = 32, Common.h:594), blocks one after the
+ * other (siblings meet through atomicExch on parentIdx and the first arriver leaves: nobody ever waits for another block, so any block
+ * order is a schedule the GPU could have produced).  The kernel relies on LOCK-STEP execution of the wavefront in two places, and the
+ * emulation reproduces exactly that:
+ *   1. mergeClusters reads nearestNeighbours[] of OTHER lanes right after findNearestNeighbours' atomicMin, with no barrier in between
+ *      (HplocKernel.h:117 -> :137-142): a lock-step wavefront has finished every lane's atomicMin before any lane reads.  The header is
+ *      compiled from a temporary copy with ONE statement added — `__syncthreads();` as the first statement of mergeClusters (oracle/Makefile
+ *      makes and deletes the copy) — a no-op on lock-step hardware, the reconvergence point for the fibers here.
+ *   2. the compaction at the end of mergeClusters (:183-185) lets the lanes WITHOUT a surviving cluster write to the slot of the next
+ *      surviving lane; the surviving lane is the highest lane writing that slot and must win.  Between two synchronisation points the
+ *      fibers run one at a time in ASCENDING lane order: the highest lane writes last (and a merging lane reads its partner's slot, which
+ *      belongs to a higher lane, before the partner invalidates it, :139-141).
+ * Launch as Hploc.cpp:120: nInternalNodes threads rounded up to whole blocks — leaf n-1 gets no thread when (n-1) % 32 == 0 (a defect of the
+ * reference; callers use other sizes).  Node numbering follows the order of the atomicAdd on nMergedClusters (timing dependent on a GPU):
+ * callers compare trees up to numbering. ---- */
+#ifdef B2_HPLOC_KERNEL
+namespace refhploc {
+#include B2_HPLOC_KERNEL
+}
+extern "C" uint32_t ref_hploc_mt(Bvh2Node* bvhNodes, PrimRef* primRefs, uint32_t* sortedKeys, uint32_t* nodeIdx0, uint32_t* parentIdx, uint32_t n) {
+  uint32_t nMerged = 0;
+  const uint32_t nInternalNodes = n - 1;
+  const uint32_t nBlocks = (nInternalNodes + HPlocBlockSize - 1) / HPlocBlockSize;
+  g_lowestFirst = true;
+  for (uint32_t b = 0; b < nBlocks; b++)
+    run_block(b, HPlocBlockSize, nBlocks, [&] { refhploc::HPloc(bvhNodes, primRefs, sortedKeys, nodeIdx0, parentIdx, &nMerged, n, nInternalNodes); });
+  g_lowestFirst = false;
+  return nMerged;
+}
+#endif

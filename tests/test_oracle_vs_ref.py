@@ -117,6 +117,32 @@ def test_ploc_matches_reference_kernels_run_blockwise(oracle, kind, arg):
     assert nodes_ref[0]["mn"].tobytes() == pn[0]["mn"].tobytes() and nodes_ref[0]["mx"].tobytes() == pn[0]["mx"].tobytes()
 
 
+HPLOC_INPUTS = [("cornellbox", None), ("uniform", (100, 41)), ("uniform", (1000, 42)), ("uniform", (4098, 43)), ("clustered", (5000, 44)), ("duplicate", (700, 45)),
+                ("flat", (3000, 46)), ("anisotropic", (20_002, 47)), ("bunny", None), ("sponza", None)]
+
+
+@pytest.mark.parametrize("kind,arg", HPLOC_INPUTS, ids=[f"{k}-{a[0] if a else 'mesh'}" for k, a in HPLOC_INPUTS])
+def test_hploc_matches_reference_kernel_run_lockstep(oracle, kind, arg):
+    """H-PLOC: the reference's own HPloc kernel (HplocKernel.h:257-315 with findParent / plocMerge / loadIndices / findNearestNeighbours /
+    mergeClusters / storeIndices), executed wavefront by wavefront under the block emulator in the way a lock-step wavefront executes it
+    (ascending lane order between synchronisation points, one barrier added where the hardware is converged anyway: ref_shim/ref_emul_ploc_mt.cpp),
+    against the oracle's restatement — same tree (topology and box bits of every node) up to node numbering, which follows the atomicAdd order
+    in the reference and the free-index scheme in the oracle.  Round 1 pinned H-PLOC by the README costs only."""
+    tris = load_mesh(kind) if arg is None else random_tris(arg[0], arg[1], kind)
+    if tris is None:
+        pytest.skip(f"{kind} not staged")
+    n = tris.size
+    assert (n - 1) % 32 != 0
+    refs, boxes, scene = oracle.primrefs(tris)
+    k, v = oracle.morton_codes(refs, scene)
+    sk, sv = oracle.sort_kv(k, v)
+    on, ol, stats = oracle.hploc(boxes, sk, sv)
+    rn, rl, merged = ref.hploc_build_mt(boxes, sk, sv)
+    assert merged == n - 1 and rl.tobytes() == ol.tobytes()
+    assert tree_signature(rn, rl, n) == tree_signature(on, ol, n)
+    assert rn[0]["mn"].tobytes() == on[0]["mn"].tobytes() and rn[0]["mx"].tobytes() == on[0]["mx"].tobytes()  # root 0 in both
+
+
 def test_morton_function_matches_reference_on_random_extents(oracle):
     rng = np.random.default_rng(7)
     for _ in range(300):
