@@ -31,7 +31,7 @@ SEED = 0x00B20010
 TOTAL_100M = 100_000_000   # BASELINE configs[4]: the fixed-size (strong scaling) block, split by primitive range over the ranks
 SEED_100M = 0x00B20100
 REF_SAMPLE = 262_144       # --impl reference: triangles per step
-CPU_BASELINE_SAMPLE = 1_000_000
+CPU_BASELINE_SAMPLE = 3_000_000  # ~11 s of the single-threaded CPU builder
 
 # algorithmic bytes per primitive of the five stages of a single-pass LBVH + collapse build (the survey's own figures;
 # ALGO_BYTES below are this repo's per-kernel denominators, lower for S1/S2/S4, higher for the sort and the collapse — both are reported)
