@@ -347,8 +347,38 @@ def global_100m(orc, np, torch, capi, dist, L, args, rank, world):
         checks = {"slice_and_top_equal_the_one_gpu_tree": ok}
         if hasher:
             checks["one_gpu_tree_has_the_frozen_oracle_hash"] = hv == ka["shards"][0]["nodes_fnv"]
+        # ---- the 4-wide tree of the same build, replicated: all-gather of the pieces, assembly and the ordinary collapse on every rank ----
+        bvh4 = None
+        try:
+            w4 = gb.collapse_replicated(res)
+            dist.barrier()
+            torch.cuda.synchronize()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record(L.stream)
+            for _ in range(3):
+                w4 = gb.collapse_replicated(res)
+            f1.record(L.stream)
+            torch.cuda.synchronize()
+            tw = torch.tensor([f0.elapsed_time(f1) / 3], device="cuda")
+            dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+            nw = torch.tensor([w4["n_wide"]], device="cuda", dtype=torch.int64)
+            nws = torch.zeros(world, device="cuda", dtype=torch.int64)
+            dist.all_gather_into_tensor(nws, nw)
+            checks["bvh4_same_count_on_all_ranks"] = bool((nws == nws[0]).all().item())
+            if rank == 0 and ka:
+                k0 = ka["shards"][0]
+                checks["bvh4_has_the_frozen_oracle_hashes"] = bool(
+                    w4["n_wide"] == k0["wide_count"] and orc.fnv1a(w4["wide"].cpu().numpy().reshape(-1).view(np.uint32)) == k0["wide_fnv"]
+                    and orc.fnv1a(w4["wide_leaves"].cpu().numpy().reshape(-1).view(np.uint32)) == k0["wide_leaves_fnv"])
+            bvh4 = {"ms_gather_assemble_collapse": float(tw.item()), "n_wide": int(w4["n_wide"]), "wire_bytes_sent_per_rank": int(w4["wire_bytes_sent"]),
+                    "what": "every rank all-gathers the pieces (64 B per primitive), assembles the one-GPU node array and runs the ordinary collapse: the Bvh4 is REPLICATED, "
+                            "not distributed (its breadth-first numbering is a property of the whole tree)"}
+            del w4
+        except capi.B2bvhError as e:
+            bvh4 = {"error": str(e)[:160]}
+            checks["bvh4"] = False
         allok, ranks_ok = _all_ok(torch, dist, all(checks.values()))
-        return {"workload": f"synth_uniform_v1 {n // 1_000_000}M triangles, ONE globally sorted single-pass LBVH (Bvh2) across {world} GPUs", "total_prims": n, "n_gpus": world,
+        return {"workload": f"synth_uniform_v1 {n // 1_000_000}M triangles, ONE globally sorted single-pass LBVH (Bvh2) across {world} GPUs", "total_prims": n, "n_gpus": world, "bvh4_replicated": bvh4,
                 "steps": steps, "ms_per_build": ms, "value": n / (ms * 1e-3) / 1e6, "unit": "Mprims/s", "wire_bytes_per_build_all_ranks": float(wire.item()),
                 "wire_GBs_aggregate_over_the_whole_build": float(wire.item()) / (ms * 1e-3) / 1e9, "positions_per_rank": res["counts"], "nodes_above_the_ranks": ntop,
                 "status": "ok" if allok else "FAILED", "ranks_ok": ranks_ok, "rank0_checks": checks, "parity_seconds": time.perf_counter() - t0,

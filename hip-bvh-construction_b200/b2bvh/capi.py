@@ -56,7 +56,7 @@ SYMBOLS = ["b2bvh_ctx_create", "b2bvh_ctx_destroy", "b2bvh_device_name", "b2bvh_
            "b2bvh_last_error", "b2bvh_build", "b2bvh_build_finish", "b2bvh_build_batched", "b2bvh_scene_extents", "b2bvh_morton_codes", "b2bvh_sort_pairs", "b2bvh_lbvh_from_sorted64", "b2bvh_range_extract", "b2bvh_generate_rays",
            "b2bvh_traverse", "b2bvh_traverse_ex", "b2bvh_heat_map", "b2bvh_shard_extents", "b2bvh_top_level", "b2bvh_cost_bvh4", "b2bvh_cost_lbvh", "b2bvh_tree_cost",
            "b2bvh_abi_version", "b2bvh_synth_uniform", "b2bvh_synth_clustered", "b2bvh_profile_enable", "b2bvh_profile_count", "b2bvh_profile_entry",
-           "b2bvh_global_partition", "b2bvh_global_sort", "b2bvh_global_tree", "b2bvh_global_top", "b2bvh_build_sharded"]
+           "b2bvh_global_partition", "b2bvh_global_sort", "b2bvh_global_tree", "b2bvh_global_top", "b2bvh_build_sharded", "b2bvh_global_assemble", "b2bvh_collapse_bvh2"]
 
 _lib = None
 
@@ -90,6 +90,7 @@ def load():
         "b2bvh_global_tree": [vp, vp, vp, vp, vp, u32, vp, C.c_int, C.c_int, u32, u32, C.c_int, vp, vp, vp],
         "b2bvh_global_top": [vp, vp, vp, u32, u32, C.c_int, vp, vp],
         "b2bvh_build_sharded": [vp, u32, C.c_int, vp, vp, C.POINTER(BuildOpts), vp, vp, vp],
+        "b2bvh_global_assemble": [vp, vp, vp, u32, u32, u32, vp, vp, vp, u32, vp, vp], "b2bvh_collapse_bvh2": [vp, vp, vp, vp, u32, vp, vp, C.POINTER(u32)],
         "b2bvh_generate_rays": [vp, vp, u32, u32, vp, fp],
         "b2bvh_traverse": [vp, C.POINTER(Tree), vp, u32, vp, C.c_int, vp, vp, fp],
         "b2bvh_traverse_ex": [vp, C.POINTER(Tree), vp, u32, vp, C.c_int, vp, vp, vp, fp], "b2bvh_heat_map": [vp, u32, vp],

@@ -472,6 +472,51 @@ class GlobalBuildDevice:
                     wire_bytes_sent=32 * (n - sc[self.rank]), counts=cnts)
 
 
+def _collapse_replicated(self, res):
+    """The 4-wide tree of the globally sorted build, REPLICATED: the breadth-first wide-node numbering is a property of the whole tree, so every
+    rank all-gathers the pieces (64 B per primitive over NVLink, padded to the longest piece), assembles the one-GPU node array on its device
+    (b2bvh_global_assemble) and runs the ordinary collapse over it (b2bvh_collapse_bvh2).  Every rank ends up with the Bvh4 ONE GPU would build
+    over all triangles — byte-identical nodes, leaves and count.  Returns dict(full_nodes, wide, wide_leaves, n_wide)."""
+    torch, capi, C, W = self.torch, self.capi, self.C, self.world
+    lib, h = self.ctx.lib, self.ctx.h
+    n_total, cnts = res["n_total"], res["counts"]
+    dev = res["top"].device
+    firsts = [sum(cnts[:r]) for r in range(W)]
+    prevs = [max((q for q in range(r) if cnts[q]), default=-1) for r in range(W)]
+    nexts = [min((q for q in range(r + 1, W) if cnts[q]), default=-1) for r in range(W)]
+    ms = [(cnts[r] + (1 if prevs[r] >= 0 else 0) + (1 if nexts[r] >= 0 else 0)) if cnts[r] else 0 for r in range(W)]
+    node_counts = [max(m - 1, 0) for m in ms]
+    node_firsts = [firsts[r] - (1 if prevs[r] >= 0 else 0) for r in range(W)]
+    max_nodes, max_leaves = max(max(node_counts), 1), max(max(cnts), 1)
+    pn = torch.zeros((max_nodes, 8), dtype=torch.int32, device=dev)
+    pl = torch.zeros((max_leaves, 8), dtype=torch.int32, device=dev)
+    pn[:res["nodes"].shape[0]] = res["nodes"]
+    pl[:res["leaves"].shape[0]] = res["leaves"]
+    if W > 1:
+        all_n = torch.empty((W * max_nodes, 8), dtype=torch.int32, device=dev)
+        all_l = torch.empty((W * max_leaves, 8), dtype=torch.int32, device=dev)
+        self.dist.all_gather_into_tensor(all_n, pn)
+        self.dist.all_gather_into_tensor(all_l, pl)
+    else:
+        all_n, all_l = pn, pl
+    layout = np.array([[node_firsts[r], node_counts[r], firsts[r], cnts[r]] for r in range(W)], dtype=np.uint32)
+    full = torch.empty((2 * n_total - 1, 8), dtype=torch.int32, device=dev)
+    leaf_prim = torch.empty(n_total, dtype=torch.int32, device=dev)
+    top = res["top"].contiguous()
+    capi.check(lib.b2bvh_global_assemble(h, self._p(all_n), self._p(all_l), W, max_nodes, max_leaves, layout.ctypes.data_as(C.c_void_p), self._p(top), self._p(res["top_result"]),
+                                         int(n_total), self._p(full), self._p(leaf_prim)), "b2bvh_global_assemble")
+    wide = torch.empty((n_total, 32), dtype=torch.int32, device=dev)       # Bvh4Node: 128 B
+    wide_leaves = torch.empty((n_total, 2), dtype=torch.int32, device=dev)  # PrimNode: 8 B
+    n_wide = C.c_uint32()
+    d_root = self.C.c_void_p(res["top_result"].data_ptr() + 4)  # result3[1] = root node index, on the device
+    capi.check(lib.b2bvh_collapse_bvh2(h, self._p(full), self._p(leaf_prim), d_root, int(n_total), self._p(wide), self._p(wide_leaves), C.byref(n_wide)), "b2bvh_collapse_bvh2")
+    self._keep2 = (all_n, all_l, pn, pl, top)
+    return dict(full_nodes=full, wide=wide[:n_wide.value], wide_leaves=wide_leaves, n_wide=int(n_wide.value), wire_bytes_sent=(W - 1) * 32 * (max_nodes + max_leaves))
+
+
+GlobalBuildDevice.collapse_replicated = _collapse_replicated
+
+
 def assemble_global_tree(parts, n_total):
     """Host-side check helper: the full node array (2n-1, LBVH layout) of the one-GPU tree from every rank's GlobalBuildDevice result
     (nodes / leaves / top as numpy int32 arrays).  Returns (nodes int32 [(2n-1), 8], root)."""

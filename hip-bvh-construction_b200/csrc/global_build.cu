@@ -262,3 +262,76 @@ int b2bvh_global_top(b2bvh_ctx* ctx, const b2bvh_cluster* d_allClusters, const u
 }
 
 } /* extern "C" */
+
+/* ---- 5. the whole tree on every rank (for the 4-wide collapse, whose breadth-first numbering is a property of the WHOLE tree): the ranks
+ * all-gather their pieces (padded to the longest) and every rank assembles the one-GPU node array, then runs the ordinary collapse over it ---- */
+__global__ void __launch_bounds__(GB_THREADS) gb_assemble_kernel(const b2bvh_bvh2_node* __restrict__ pieceNodes, const b2bvh_bvh2_node* __restrict__ pieceLeaves,
+                                                                 u32 world, u32 maxNodes, u32 maxLeaves, const u32* __restrict__ layout /* world x 4: nodeFirst,
+                                                                 nodeCount, leafFirst, leafCount */, u32 nTotal, b2bvh_bvh2_node* __restrict__ full,
+                                                                 u32* __restrict__ leafPrim) {
+  const u32 r = blockIdx.y;
+  const u32 nodeFirst = layout[4 * r], nodeCount = layout[4 * r + 1], leafFirst = layout[4 * r + 2], leafCount = layout[4 * r + 3];
+  const u32 nInt = nTotal - 1u;
+  for (u32 i = blockIdx.x * GB_THREADS + threadIdx.x; i < nodeCount + leafCount; i += gridDim.x * GB_THREADS) {
+    if (i < nodeCount) {
+      const Node2 nd = load_node2_ro(pieceNodes + (size_t)r * maxNodes + i);
+      if (nd.left != B2_INVALID) store_node2(full + nodeFirst + i, nd.left, nd.right, nd.box); /* artefact (ghost spine) nodes are skipped */
+    } else {
+      const u32 j = i - nodeCount;
+      const Node2 nd = load_node2_ro(pieceLeaves + (size_t)r * maxLeaves + j);
+      store_node2(full + nInt + leafFirst + j, nd.left, nd.right, nd.box);
+      leafPrim[leafFirst + j] = nd.left; /* leaf slot -> (global) primitive: what the collapse's PrimNode records name */
+    }
+  }
+}
+__global__ void gb_assemble_top_kernel(const b2bvh_top_node* __restrict__ top, const u32* __restrict__ result3, b2bvh_bvh2_node* __restrict__ full) {
+  const u32 nTop = result3[0];
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < nTop; i += gridDim.x * blockDim.x) {
+    const b2bvh_top_node t = top[i];
+    const Box b = Box{t.box.m_min.x, t.box.m_min.y, t.box.m_min.z, t.box.m_max.x, t.box.m_max.y, t.box.m_max.z};
+    store_node2(full + t.index, t.left, t.right, b);
+  }
+}
+
+extern "C" {
+
+int b2bvh_global_assemble(b2bvh_ctx* ctx, const b2bvh_bvh2_node* d_pieceNodes, const b2bvh_bvh2_node* d_pieceLeaves, uint32_t world, uint32_t max_nodes,
+                          uint32_t max_leaves, const uint32_t* h_layout4, const b2bvh_top_node* d_top, const uint32_t* d_result3, uint32_t n_total,
+                          b2bvh_bvh2_node* d_fullNodes, uint32_t* d_leafPrim) {
+  if (!ctx || !d_pieceNodes || !d_pieceLeaves || !h_layout4 || !d_top || !d_result3 || !d_fullNodes || !d_leafPrim || world == 0 || world > 256u || n_total < 2)
+    return b2_fail(B2BVH_ERR_INVALID, "global_assemble: bad argument");
+  B2_CUDA(cudaSetDevice(ctx->device));
+  void* dLayout;
+  B2_TRY(b2_reserve(ctx, SLOT_MISC, 4096 + 64, &dLayout));
+  B2_CUDA(cudaMemcpyAsync(dLayout, h_layout4, (size_t)world * 16, cudaMemcpyHostToDevice, ctx->stream)); /* pageable source: staged before the call returns */
+  u32 gx = (max_nodes + max_leaves + GB_THREADS - 1) / GB_THREADS;
+  const u32 cap = (u32)ctx->sm_count * 8u;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  B2_KERNEL(ctx, "global_assemble");
+  gb_assemble_kernel<<<dim3(gx, world), GB_THREADS, 0, ctx->stream>>>(d_pieceNodes, d_pieceLeaves, world, max_nodes, max_leaves, (const u32*)dLayout, n_total, d_fullNodes,
+                                                                      d_leafPrim);
+  B2_LAUNCH_CHECK(ctx);
+  B2_KERNEL(ctx, "global_assemble_top");
+  gb_assemble_top_kernel<<<8, 256, 0, ctx->stream>>>(d_top, d_result3, d_fullNodes);
+  B2_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+/* The collapse stage alone over a Bvh2 in the LBVH layout (2n-1 nodes, leaves at n-1 + slot): CollapseToWide4Bvh (TwoPassLbvhKernel.h:237-337) as an
+ * individually callable stage.  d_root: DEVICE pointer of the root index (the globally sorted build leaves it in d_result3[1]); d_leafPrim[slot] =
+ * primitive of leaf slot.  Synchronises once, for *n_wide. */
+int b2bvh_collapse_bvh2(b2bvh_ctx* ctx, const b2bvh_bvh2_node* d_nodes, const uint32_t* d_leafPrim, const uint32_t* d_root, uint32_t n, b2bvh_bvh4_node* d_wide,
+                        b2bvh_prim_node* d_wideLeaves, uint32_t* n_wide) {
+  if (!ctx || !d_nodes || !d_leafPrim || !d_root || !d_wide || !d_wideLeaves || !n_wide || n < 2 || n > 0x3FFFFFFFu) return b2_fail(B2BVH_ERR_INVALID, "collapse_bvh2: bad argument");
+  B2_CUDA(cudaSetDevice(ctx->device));
+  void* scratch;
+  B2_TRY(b2_reserve(ctx, SLOT_COLLAPSE, b2_collapse_scratch_bytes(n), &scratch));
+  B2_TRY(b2_launch_collapse(ctx, d_nodes, nullptr, d_leafPrim, d_root, n, d_wide, d_wideLeaves, scratch, nullptr));
+  B2_CUDA(cudaStreamSynchronize(ctx->stream));
+  *n_wide = b2_mailbox(ctx, B2_MB_COLLAPSE)[1];
+  if (*n_wide == B2_INVALID) { *n_wide = 0; return b2_fail(B2BVH_ERR_INTERNAL, "collapse_bvh2: the nodes do not form a tree"); }
+  return 0;
+}
+
+} /* extern "C" */

@@ -236,6 +236,17 @@ int b2bvh_global_tree(b2bvh_ctx* ctx, const uint32_t* d_sortedCodes, const uint3
 int b2bvh_global_top(b2bvh_ctx* ctx, const b2bvh_cluster* d_allClusters, const uint32_t* d_allCounts, uint32_t world, uint32_t n_total,
                      int karras, b2bvh_top_node* d_topNodes, uint32_t* d_result3);
 
+/* the WHOLE tree on every rank: d_pieceNodes / d_pieceLeaves = every rank's b2bvh_global_tree output all-gathered, padded to max_nodes / max_leaves
+ * records per rank; h_layout4 (HOST, world x 4) = {first global node index, node count, first global leaf position, leaf count} per rank; writes the
+ * one-GPU node array d_fullNodes (2 n_total - 1, LBVH layout; artefact nodes skipped, the nodes above the ranks from d_top) and d_leafPrim (n_total) */
+int b2bvh_global_assemble(b2bvh_ctx* ctx, const b2bvh_bvh2_node* d_pieceNodes, const b2bvh_bvh2_node* d_pieceLeaves, uint32_t world,
+                          uint32_t max_nodes, uint32_t max_leaves, const uint32_t* h_layout4, const b2bvh_top_node* d_top, const uint32_t* d_result3,
+                          uint32_t n_total, b2bvh_bvh2_node* d_fullNodes, uint32_t* d_leafPrim);
+/* CollapseToWide4Bvh (TwoPassLbvhKernel.h:237-337) as an individually callable stage over a Bvh2 in the LBVH layout (2n-1 nodes): d_root = DEVICE
+ * pointer of the root index, d_leafPrim[slot] = primitive of leaf slot; d_wide / d_wideLeaves have room for n records; synchronises once */
+int b2bvh_collapse_bvh2(b2bvh_ctx* ctx, const b2bvh_bvh2_node* d_nodes, const uint32_t* d_leafPrim, const uint32_t* d_root, uint32_t n,
+                        b2bvh_bvh4_node* d_wide, b2bvh_prim_node* d_wideLeaves, uint32_t* n_wide);
+
 /* ---- traversal: replaces the body of TwoPassLbvh::traverseBvh (src/TwoPassLbvh.cpp:199-311). ---- */
 int b2bvh_generate_rays(b2bvh_ctx* ctx, const b2bvh_camera* cam, uint32_t width, uint32_t height, b2bvh_ray* d_rays,
                         float* ms);                       /* GenerateRays, CommonBlocksKernel.h:432-463 */

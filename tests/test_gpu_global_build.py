@@ -43,7 +43,7 @@ class ThreadDist:
 
     def all_gather_into_tensor(self, out, t):
         got = self._exchange(t.clone())
-        out.copy_(self.torch.cat([g.reshape(-1) for g in got]))
+        out.view(-1).copy_(self.torch.cat([g.reshape(-1) for g in got]))
 
     def all_to_all_single(self, out, inp, output_split_sizes=None, input_split_sizes=None, async_op=False):
         offs = np.concatenate([[0], np.cumsum(input_split_sizes)]).astype(int)
@@ -55,7 +55,7 @@ class ThreadDist:
         return self._Done()
 
 
-def run_global(tris, world, karras, cuts=None):
+def run_global(tris, world, karras, cuts=None, collapse=False):
     import torch
     from b2bvh.sharded import GlobalBuildDevice, assemble_global_tree
     n = tris.size
@@ -73,6 +73,10 @@ def run_global(tris, world, karras, cuts=None):
                 res = gb.build(np.ascontiguousarray(tris[cuts[r]:cuts[r + 1]]), cuts[r], n, karras=karras)
                 stream.synchronize()
                 parts[r] = {k: (v.cpu().numpy() if hasattr(v, "cpu") else v) for k, v in res.items()}
+                if collapse:
+                    w4 = gb.collapse_replicated(res)
+                    stream.synchronize()
+                    parts[r]["bvh4"] = {k: (v.cpu().numpy() if hasattr(v, "cpu") else v) for k, v in w4.items()}
                 ctx.close()
         except Exception as e:  # a dead thread would leave the others in the barrier
             errs.append(e)
@@ -111,3 +115,20 @@ def test_world_size_one_is_the_plain_build(ctx):
     (nodes, root, written), _ = run_global(tris, 1, False)
     one = ctx.fetch(ctx.build(capi.SINGLE_PASS_LBVH, tris, collapse=False))
     assert written.all() and root == one["root"] and nodes.tobytes() == one["nodes"].tobytes()
+
+
+@pytest.mark.parametrize("karras", [False, True], ids=["apetrei", "karras"])
+@pytest.mark.parametrize("kind,n,world,cuts", [("uniform", 50_001, 3, None), ("clustered", 30_000, 4, None), ("uniform", 9000, 3, [0, 100, 100, 9000]), ("uniform", 12_345, 1, None)],
+                         ids=["uniform-w3", "clustered-w4", "ragged-w3", "w1"])
+def test_replicated_collapse_is_the_one_gpu_bvh4(ctx, kind, n, world, cuts, karras):
+    """collapse_replicated: every rank assembles the whole node array from the all-gathered pieces and collapses it — Bvh4 nodes, leaves and count
+    equal the one-GPU build's byte for byte, on every rank."""
+    tris = random_tris(n, 1200 + n % 89, kind)
+    (_, root, _), parts = run_global(tris, world, karras, cuts, collapse=True)
+    one = ctx.fetch(ctx.build(capi.TWO_PASS_LBVH if karras else capi.SINGLE_PASS_LBVH, tris))
+    for r, p in enumerate(parts):
+        b = p["bvh4"]
+        assert b["n_wide"] == one["n_wide"], r
+        assert b["full_nodes"].tobytes() == one["nodes"].tobytes(), r
+        assert b["wide"].tobytes() == one["wide"].tobytes(), r
+        assert b["wide_leaves"].tobytes() == one["wide_leaves"].tobytes(), r
