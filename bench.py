@@ -13,6 +13,14 @@ ONE all-gather for the top-level tree (weak scaling: 10 M per GPU).
   roofline = dominant kernel: algorithmic bytes per launch / CUDA-event time per launch vs MEASURED_PEAKS.json hbm_gbs
   cpu_baseline = the reference's CPU builder (BinnedSahBvh, restated in oracle/) on a bounded sample, 1 thread
 
+  stage_roofline = per stage, GB/s and fraction with SURVEY.md §8(d)'s own bytes per primitive (kernels.* uses this repo's per-kernel bytes)
+  parity   = outside the timed regions: every rank's device buffers memcmp'ed with the CPU oracle's build of its shard (rc != 0 on mismatch)
+  strong_100M = BASELINE configs[4]: 100 M triangles IN TOTAL split by primitive range over the ranks, own timed region, parity against the
+           frozen oracle hashes (tests/golden/sharded_100m_known_answers.json)
+  global_100M = (N > 1) the same triangles as ONE globally sorted tree across the ranks (b2bvh_global_*), checked against the one-GPU tree;
+           bvh4_replicated: its 4-wide collapse on every rank against the frozen oracle hashes
+  sort_comparators = same-box yardsticks of the sort stage: the reference's Orochi kernels (unmodified) and cub::DeviceRadixSort
+
 `--impl reference` times that CPU builder alone (rank 0 only)."""
 import argparse
 import json
