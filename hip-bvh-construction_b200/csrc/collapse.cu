@@ -70,7 +70,10 @@ __device__ __forceinline__ void publish_level(CollapseCtrl* ctrl, u32 barrier, u
 
 /* ---- 1. expansion of every internal node: CollapseToWide4Bvh, TwoPassLbvhKernel.h:262-296 — two rounds of "replace the
  * internal child with the largest area by its two children" (the new right child is appended) ---- */
-__global__ void __launch_bounds__(COL_THREADS) collapse_expand_kernel(const b2bvh_bvh2_node* __restrict__ nodes, u32 nInt, uint4* __restrict__ expansion) {
+#ifndef COL_EXPAND_MINB
+#define COL_EXPAND_MINB 1
+#endif
+__global__ void __launch_bounds__(COL_THREADS, COL_EXPAND_MINB) collapse_expand_kernel(const b2bvh_bvh2_node* __restrict__ nodes, u32 nInt, uint4* __restrict__ expansion) {
   const u32 i = blockIdx.x * COL_THREADS + threadIdx.x;
   if (i >= nInt) return;
   const uint2 top = __ldg(reinterpret_cast<const uint2*>(nodes + i));
@@ -269,14 +272,17 @@ __global__ void __launch_bounds__(NUM_THREADS, NUM_THREADS == NUM_THREADS_LARGE 
  * children are gathered (leaf slots keep the empty box, TwoPassLbvhKernel.h:320-325); the 128-byte node goes out through a
  * swizzled shared-memory transpose as full, contiguous lines (eight 16-byte stores per thread at a 128-byte stride run at a
  * third of the speed, tools/micro/mem_micro.cu). ---- */
+#ifndef COL_EMIT_THREADS
+#define COL_EMIT_THREADS 256
+#endif
 struct EmitSmem {
-  uint4 stage[COL_THREADS * 8]; /* 256 wide nodes, 16-byte pieces, piece p of node t at t*8 + (p ^ (t & 7)) */
+  uint4 stage[COL_EMIT_THREADS * 8]; /* 256 wide nodes, 16-byte pieces, piece p of node t at t*8 + (p ^ (t & 7)) */
 };
 
 #ifndef COL_EMIT_MINB
 #define COL_EMIT_MINB 5
 #endif
-__global__ void __launch_bounds__(COL_THREADS, COL_EMIT_MINB) collapse_emit_kernel(const b2bvh_bvh2_node* __restrict__ nodes, const u32* __restrict__ sortedVals, u32 nInt,
+__global__ void __launch_bounds__(COL_EMIT_THREADS, COL_EMIT_MINB) collapse_emit_kernel(const b2bvh_bvh2_node* __restrict__ nodes, const u32* __restrict__ sortedVals, u32 nInt,
                                                                       const uint4* __restrict__ taskCh, const u32* __restrict__ taskParent,
                                                                       const u32* __restrict__ firstChild, const CollapseCtrl* __restrict__ ctrl,
                                                                       b2bvh_bvh4_node* __restrict__ wide, b2bvh_prim_node* __restrict__ wideLeaves) {
@@ -284,7 +290,7 @@ __global__ void __launch_bounds__(COL_THREADS, COL_EMIT_MINB) collapse_emit_kern
   EmitSmem& S = *reinterpret_cast<EmitSmem*>(smemRaw);
   const u32 nWide = ctrl->nWide, tid = threadIdx.x;
   if (nWide > nInt) return; /* the numbering gave up (CollapseCtrl::error) */
-  for (u32 tileStart = blockIdx.x * COL_THREADS; tileStart < nWide; tileStart += gridDim.x * COL_THREADS) {
+  for (u32 tileStart = blockIdx.x * COL_EMIT_THREADS; tileStart < nWide; tileStart += gridDim.x * COL_EMIT_THREADS) {
     const u32 g = tileStart + tid;
     u32 ch[4] = {B2_INVALID, B2_INVALID, B2_INVALID, B2_INVALID};
     u32 parent = B2_INVALID, nextId = 0;
@@ -333,11 +339,11 @@ __global__ void __launch_bounds__(COL_THREADS, COL_EMIT_MINB) collapse_emit_kern
      * 1-2 % slower: 0.610 vs 0.602 ms for the stage at 10 M, 5.40 vs 5.30 ms at 100 M, gpurun r2m) */
     __syncthreads();
     {
-      const u32 valid = min((u32)COL_THREADS, nWide - tileStart) * 8u;
+      const u32 valid = min((u32)COL_EMIT_THREADS, nWide - tileStart) * 8u;
       uint4* out = reinterpret_cast<uint4*>(wide + tileStart);
 #pragma unroll
       for (int i = 0; i < 8; i++) {
-        const u32 q = (u32)i * COL_THREADS + tid;
+        const u32 q = (u32)i * COL_EMIT_THREADS + tid;
         const u32 node = q >> 3, part = q & 7u;
         if (q < valid) out[q] = S.stage[node * 8 + (part ^ (node & 7u))];
       }
@@ -386,11 +392,11 @@ int b2_launch_collapse(b2bvh_ctx* ctx, const b2bvh_bvh2_node* d_nodes, const b2b
   else B2_CUDA(cudaLaunchCooperativeKernel((const void*)collapse_number_kernel<NUM_THREADS_SMALL>, dim3(grid), dim3(NUM_THREADS_SMALL), args, 0, ctx->stream));
   B2_LAUNCH_CHECK(ctx);
   /* the number of wide nodes stays on the device: the emit grid is sized for the worst case and strides over ctrl->nWide */
-  u32 egrid = (nInt + COL_THREADS - 1) / COL_THREADS;
-  const u32 ecap = (u32)ctx->sm_count * 2u * COL_EMIT_MINB;
+  u32 egrid = (nInt + COL_EMIT_THREADS - 1) / COL_EMIT_THREADS;
+  const u32 ecap = (u32)ctx->sm_count * 2u * COL_EMIT_MINB * (256 / COL_EMIT_THREADS);
   if (egrid > ecap) egrid = ecap;
   B2_KERNEL(ctx, "collapse_emit");
-  collapse_emit_kernel<<<egrid, COL_THREADS, emitSmem, ctx->stream>>>(d_nodes, d_sortedVals, nInt, taskCh, taskParent, firstChild, ctrl, d_wide, d_wideLeaves);
+  collapse_emit_kernel<<<egrid, COL_EMIT_THREADS, emitSmem, ctx->stream>>>(d_nodes, d_sortedVals, nInt, taskCh, taskParent, firstChild, ctrl, d_wide, d_wideLeaves);
   B2_LAUNCH_CHECK(ctx);
   /* CollapseCtrl::nWide comes back through the mailbox: b2_mailbox(ctx, B2_MB_COLLAPSE)[1] after the build's final synchronisation
    * (no host round trip in the middle of a build) */
