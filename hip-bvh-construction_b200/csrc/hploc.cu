@@ -22,6 +22,8 @@
  *   - launched with one lane per LEAF (the reference launches N-1 threads and loses leaf N-1 when (N-1) % 32 == 0).
  * Traffic per primitive: key 4 + (id, free index) 8 read/written ~2x + leaf box 28 + node written 32 + node box re-read ~32.
  */
+#include <stdlib.h>
+
 #include "common.cuh"
 
 #ifndef HP_THREADS
@@ -65,30 +67,41 @@ __device__ __forceinline__ Box shfl_down_box(const Box& b, int d) {
              __shfl_down_sync(B2_FULL, b.hx, d), __shfl_down_sync(B2_FULL, b.hy, d), __shfl_down_sync(B2_FULL, b.hz, d)};
 }
 
-/* One plocMerge call, executed by a full warp; lane == list slot. */
+/* One plocMerge call, executed by a full warp; lane == list slot.  SMEM: the lists (cluster id, free index, box per list position) live in the
+ * CTA's shared memory — the tile phase of hploc_tile_kernel, L / R / split are then positions inside the tile — instead of in global memory. */
+template <bool SMEM>
 __device__ void hploc_merge_warp(u32 L, u32 R, u32 split, bool fin, u32 n, b2bvh_bvh2_node* nodes, const b2bvh_prim_ref* __restrict__ leaves,
-                                 u32* nodeIdx, u32* freeIdx, u32* ctrl) {
+                                 u32* nodeIdx, u32* freeIdx, u32* ctrl, float (*sBox)[6] = nullptr) {
   const u32 lane = lane_id();
   const u32 nInt = n - 1;
   /* ---- loadIndices: <=16 raw entries of the left part, then <=16 of the right part behind the left part's valid ones ---- */
   const u32 cL = min(split - L, 16u), cR = min(R + 1 - split, 16u);
   u32 a = B2_INVALID, af = B2_INVALID;
-  if (lane < cL) { a = __ldcg(nodeIdx + L + lane); af = __ldcg(freeIdx + L + lane); }
+  if (lane < cL) { a = SMEM ? nodeIdx[L + lane] : __ldcg(nodeIdx + L + lane); af = SMEM ? freeIdx[L + lane] : __ldcg(freeIdx + L + lane); }
   const u32 nLeft = __popc(__ballot_sync(B2_FULL, a != B2_INVALID));
   u32 cl = (lane < nLeft) ? a : B2_INVALID, fr = (lane < nLeft) ? af : B2_INVALID;
-  if (lane >= nLeft && lane < nLeft + cR) { cl = __ldcg(nodeIdx + split + (lane - nLeft)); fr = __ldcg(freeIdx + split + (lane - nLeft)); }
+  u32 src = L + lane; /* list position this lane's cluster came from (SMEM: where its box sits) */
+  if (lane >= nLeft && lane < nLeft + cR) {
+    src = split + (lane - nLeft);
+    cl = SMEM ? nodeIdx[src] : __ldcg(nodeIdx + src);
+    fr = SMEM ? freeIdx[src] : __ldcg(freeIdx + src);
+  }
   u32 np = __popc(__ballot_sync(B2_FULL, cl != B2_INVALID));
   const u32 stored = np;
   const u32 threshold = fin ? 1u : 16u;
   Box box = box_empty();
   if (cl != B2_INVALID) {
-    if (cl >= nInt) {
+    if (SMEM) {
+      const float* f = sBox[src];
+      box = Box{f[0], f[1], f[2], f[3], f[4], f[5]};
+    } else if (cl >= nInt) {
       const float* f = reinterpret_cast<const float*>(leaves + (cl - nInt)) + 1;
       box = Box{__ldg(f), __ldg(f + 1), __ldg(f + 2), __ldg(f + 3), __ldg(f + 4), __ldg(f + 5)};
     } else {
       box = load_node2_cg(nodes + cl).box;
     }
   }
+  if (SMEM) __syncwarp(); /* every lane has read its slot before the compacted list is written back over the same positions */
   while (np > threshold) {
     /* ---- nearest neighbour inside the list: pairs (l, l+r), r = 1..8, evaluated once and offered to both lanes ---- */
     u64 nn = ~0ull;
@@ -125,6 +138,14 @@ __device__ void hploc_merge_warp(u32 L, u32 R, u32 split, bool fin, u32 n, b2bvh
     np = cnt;
   }
   /* ---- storeIndices ---- */
+  if (SMEM) {
+    if (lane < stored) {
+      nodeIdx[L + lane] = cl; freeIdx[L + lane] = fr;
+      float* f = sBox[L + lane];
+      f[0] = box.lx; f[1] = box.ly; f[2] = box.lz; f[3] = box.hx; f[4] = box.hy; f[5] = box.hz;
+    }
+    return; /* the tile counts its merge calls itself; the root is never finished inside a tile */
+  }
   if (lane < stored) { __stcg(nodeIdx + L + lane, cl); __stcg(freeIdx + L + lane, fr); }
   if (lane == 0) atomicAdd(ctrl, 1u);
   if (fin) {
@@ -157,12 +178,11 @@ __device__ __forceinline__ bool hp_right_deeper(const u64* __restrict__ keys, u3
   return (R ^ (R + 1)) < ((L - 1) ^ L);
 }
 
+/* The walk up the hierarchy through global memory from the range [L, R] this lane holds (active) — whole warps call it; a lane leaves when it is
+ * the first to arrive at a parent. */
 template <typename K>
-__global__ void __launch_bounds__(HP_THREADS) hploc_kernel(const K* __restrict__ keys, u32 n, b2bvh_bvh2_node* nodes,
-                                                          const b2bvh_prim_ref* __restrict__ leaves, u32* nodeIdx, u32* freeIdx, u32* meet, u32* ctrl) {
-  const u32 i = blockIdx.x * HP_THREADS + threadIdx.x;
-  bool active = i < n;
-  u32 L = i, R = i;
+__device__ __forceinline__ void hploc_walk(const K* __restrict__ keys, u32 n, b2bvh_bvh2_node* nodes, const b2bvh_prim_ref* __restrict__ leaves, u32* nodeIdx,
+                                           u32* freeIdx, u32* meet, u32* ctrl, bool active, u32 L, u32 R) {
   while (__any_sync(B2_FULL, active)) {
     u32 split = 0;
     bool fin = false, wantMerge = false;
@@ -188,29 +208,149 @@ __global__ void __launch_bounds__(HP_THREADS) hploc_kernel(const K* __restrict__
       }
     }
     u32 todo = __ballot_sync(B2_FULL, wantMerge);
-    const bool merged = todo != 0u;
     while (todo) {
       const int src = __ffs(todo) - 1;
       todo &= todo - 1;
       const u32 mL = __shfl_sync(B2_FULL, L, src), mR = __shfl_sync(B2_FULL, R, src), mS = __shfl_sync(B2_FULL, split, src);
       const bool mF = __shfl_sync(B2_FULL, fin ? 1 : 0, src) != 0;
-      hploc_merge_warp(mL, mR, mS, mF, n, nodes, leaves, nodeIdx, freeIdx, ctrl);
-#ifndef HP_FENCE_ONCE
+      hploc_merge_warp<false>(mL, mR, mS, mF, n, nodes, leaves, nodeIdx, freeIdx, ctrl);
       /* make this call's stores (done by all lanes) visible before lane `src` publishes the range further up */
       __threadfence();
-#endif
       __syncwarp();
     }
-#ifdef HP_FENCE_ONCE
-    /* the merge calls of one round work on disjoint ranges and nothing is published before the next exchange: ONE fence makes the stores of
-     * all of them (done by all lanes) visible before the lanes hand their ranges further up */
-    if (merged) __threadfence();
-    __syncwarp();
-#else
-    (void)merged;
-#endif
     if (fin) active = false;
   }
+}
+
+template <typename K>
+__global__ void __launch_bounds__(HP_THREADS) hploc_kernel(const K* __restrict__ keys, u32 n, b2bvh_bvh2_node* nodes,
+                                                          const b2bvh_prim_ref* __restrict__ leaves, u32* nodeIdx, u32* freeIdx, u32* meet, u32* ctrl) {
+  const u32 i = blockIdx.x * HP_THREADS + threadIdx.x;
+  hploc_walk(keys, n, nodes, leaves, nodeIdx, freeIdx, meet, ctrl, i < n, i, i);
+}
+
+/* ---------------------------------------------------------------- tile phase (round 2)
+ * hploc_kernel sends every range of the hierarchy through global memory: an atomic exchange per node, and for every range with more than 16
+ * leaves a merge call that loads its lists and boxes from global memory, stores them back and fences — a ~7 us dependent chain per call at
+ * ~24 resident warps per SM (2.0 ms for 10 M primitives, 0.10 of the roofline).  Most of those ranges lie inside a few hundred consecutive leaves.
+ * hploc_tile_kernel gives a CTA HT_TILE consecutive leaves and finds the ranges of the hierarchy inside them the way lbvh_tile_kernel does —
+ * an ordered list of finished ranges, two neighbours form their parent exactly when the boundary between them is deeper than both
+ * boundaries next to it, all such pairs in one ROUND — with the cluster lists (id, free index, box per list position) in shared memory.
+ * The merge calls of a round work on disjoint positions: the warps of the CTA take them in turn, no atomics, no fences, no global loads.
+ * What is left when no boundary inside the tile is a maximum (the ranges whose parents straddle tiles, ~15 per tile) is written back and
+ * continues through hploc_walk.  Same merge calls on the same lists in an order the dependencies allow: identical output.
+ * Measured (10 M uniform, merge stage): walk only 2.01 ms; tiles of 512 leaves 2.99 ms, 256 2.0 ms, 128 1.76 ms, 64 3.4 ms — a merge call is ~1000
+ * dependent warp instructions (48 shuffles per search round) whether its operands come from shared or global memory, so what the tile saves is the
+ * global round trips, and what it costs is the idle warps of a CTA whose upper rounds hold one or two calls: small tiles, many CTAs per SM. */
+#ifndef HT_TILE
+#define HT_TILE 128
+#endif
+#ifndef HT_MINB
+#define HT_MINB 12
+#endif
+#define HT_D_SHIFT 16
+struct HpTileSmem {
+  u32 w[2][HT_TILE + 4];       /* range j of the ordered list = w[b][j + 2]: [22:16] depth + 1 of the boundary on its right, [9:0] first leaf - b0; sentinels as in lbvh_tile_kernel */
+  u32 nodeIdx[HT_TILE], freeIdx[HT_TILE];
+  float box[HT_TILE][6];       /* box of the cluster at list position p */
+  uint4 tasks[HT_TILE / 2];    /* merge calls of the round: {L, R, split} (positions inside the tile) */
+  u32 warpCount[2][HT_TILE / 32];
+  u32 nTasks, finalCur, finalCount, calls;
+};
+
+__device__ __forceinline__ int hp_boundary_depth(u32 keyA, u32 keyB, u32 a /* b = a + 1 */) {
+  return __clzll((long long)(((u64)(keyA ^ keyB) << 32) | (u64)(a ^ (a + 1u))));
+}
+__device__ __forceinline__ int hp_boundary_depth(u64 keyA, u64 keyB, u32 a) {
+  const u64 kx = keyA ^ keyB;
+  return kx ? __clzll((long long)kx) : 64 + __clz((int)(a ^ (a + 1u)));
+}
+
+template <typename K>
+__global__ void __launch_bounds__(HT_TILE, HT_MINB) hploc_tile_kernel(const K* __restrict__ keys, u32 n, b2bvh_bvh2_node* nodes, const b2bvh_prim_ref* __restrict__ leaves,
+                                                                u32* nodeIdx, u32* freeIdx, u32* meet, u32* ctrl) {
+  extern __shared__ __align__(16) unsigned char hpRaw[];
+  HpTileSmem& S = *reinterpret_cast<HpTileSmem*>(hpRaw);
+  constexpr u32 T = HT_TILE, NW = HT_TILE / 32;
+  const u32 tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+  const u32 b0 = blockIdx.x * T, b1 = min(n, b0 + T), cnt0 = b1 - b0, nInt = n - 1;
+  /* ---- leaves: initial lists (every leaf is a cluster with free index g - 1), boxes, boundary depths ---- */
+  if (tid < cnt0) {
+    const u32 g = b0 + tid;
+    const K k0 = __ldg(keys + g);
+    int d = -1;
+    if (g + 1 < n) d = hp_boundary_depth(k0, __ldg(keys + g + 1), g);
+    const float* f = reinterpret_cast<const float*>(leaves + g) + 1;
+    float* bx = S.box[tid];
+#pragma unroll
+    for (int k = 0; k < 6; k++) bx[k] = __ldg(f + k);
+    S.nodeIdx[tid] = nInt + g;
+    S.freeIdx[tid] = g ? g - 1u : B2_INVALID;
+    S.w[0][tid + 2] = ((u32)(d + 1) << HT_D_SHIFT) | tid;
+  }
+  if (tid == 0) {
+    const int dl = b0 > 0 ? hp_boundary_depth(__ldg(keys + b0 - 1), __ldg(keys + b0), b0 - 1) : -1;
+    S.w[0][1] = (u32)(dl + 1) << HT_D_SHIFT;
+    S.w[0][cnt0 + 2] = cnt0;
+    S.calls = 0;
+  }
+  __syncthreads();
+  /* ---- rounds ---- */
+  u32 cur = 0, count = cnt0;
+  while (true) {
+    const u32* W = S.w[cur];
+    u32 x0 = 0, xp1 = 0;
+    bool mrg = false, absorbed = false, task = false;
+    u32 tL = 0, tS = 0, tE = 0;
+    if (tid < count) {
+      const u32 xm2 = W[tid], xm1 = W[tid + 1];
+      x0 = W[tid + 2]; xp1 = W[tid + 3];
+      const u32 dLL = xm2 >> HT_D_SHIFT, dL = xm1 >> HT_D_SHIFT, d0 = x0 >> HT_D_SHIFT, dR = xp1 >> HT_D_SHIFT;
+      mrg = (tid + 1 < count) && d0 > dL && d0 > dR;
+      absorbed = (tid >= 1) && dL > dLL && dL > d0;
+      if (mrg) {
+        tL = x0 & 0xFFFFu; tS = xp1 & 0xFFFFu; tE = W[tid + 4] & 0xFFFFu; /* the parent covers leaves [tL, tE), its right child starts at tS */
+        task = tE - tL > 16u;
+      }
+    }
+    const u32 balM = __ballot_sync(B2_FULL, mrg), balT = __ballot_sync(B2_FULL, task);
+    if (lane == 0) { S.warpCount[0][warp] = __popc(balM); S.warpCount[1][warp] = __popc(balT); }
+    __syncthreads();
+    u32 beforeM = 0, totalM = 0, beforeT = 0, totalT = 0;
+#pragma unroll
+    for (u32 k = 0; k < NW; k++) {
+      const u32 cm = S.warpCount[0][k], ct = S.warpCount[1][k];
+      if (k < warp) { beforeM += cm; beforeT += ct; }
+      totalM += cm; totalT += ct;
+    }
+    if (totalM == 0) break;
+    u32* Wn = S.w[cur ^ 1u];
+    if (tid < count && !absorbed) {
+      const u32 k = tid - beforeM - __popc(balM & lanemask_lt());
+      Wn[k + 2] = mrg ? ((xp1 & ~0xFFFFu) | (x0 & 0xFFFFu)) : x0;
+    }
+    if (task) S.tasks[beforeT + __popc(balT & lanemask_lt())] = make_uint4(tL, tE - 1u, tS, 0u);
+    if (tid == 0) { Wn[1] = W[1]; Wn[count - totalM + 2] = W[count + 2]; S.calls += totalT; }
+    __syncthreads();
+    /* the merge calls of this round: disjoint positions, one warp each */
+    for (u32 t = warp; t < totalT; t += NW) {
+      const uint4 q = S.tasks[t];
+      hploc_merge_warp<true>(q.x, q.y, q.z, false, n, nodes, leaves, S.nodeIdx, S.freeIdx, ctrl, S.box);
+    }
+    __syncthreads();
+    cur ^= 1u;
+    count -= totalM;
+  }
+  /* ---- lists back to global memory; the ranges that are left continue through the hierarchy above the tile ---- */
+  if (tid < cnt0) { __stcg(nodeIdx + b0 + tid, S.nodeIdx[tid]); __stcg(freeIdx + b0 + tid, S.freeIdx[tid]); }
+  if (tid == 0 && S.calls) atomicAdd(ctrl, S.calls);
+  __threadfence(); /* lists and the nodes written by the merge calls, before any lane publishes a range */
+  __syncthreads();
+  if (warp * 32u >= count) return; /* whole warps without a range leave */
+  const u32* W = S.w[cur];
+  const bool active = tid < count;
+  const u32 L = active ? b0 + (W[tid + 2] & 0xFFFFu) : 0u, R = active ? b0 + (W[tid + 3] & 0xFFFFu) - 1u : 0u;
+  hploc_walk(keys, n, nodes, leaves, nodeIdx, freeIdx, meet, ctrl, active, L, R);
 }
 
 int b2_launch_hploc(b2bvh_ctx* ctx, const b2bvh_aabb* d_triAabb, const u32* d_sortedKeys, const u32* d_sortedVals, u32 n,
@@ -229,7 +369,21 @@ int b2_launch_hploc_keys(b2bvh_ctx* ctx, const b2bvh_aabb* d_triAabb, const u32*
   hploc_setup_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_triAabb, d_sortedVals, n, d_leaves, nodeIdx, freeIdx, meet, ctrl);
   B2_LAUNCH_CHECK(ctx);
   B2_KERNEL(ctx, "hploc");
-  if (d_sortedKeys64)
+  static const bool walkOnly = getenv("B2BVH_HPLOC_WALK_ONLY") != nullptr; /* development switch: the all-global-memory kernel of round 1, identical output */
+  /* tile phase from 2^20 primitives (merge stage in ms, tile / walk only, tools/hploc_ab.py: 10 M 1.76 / 2.01, 1 M 0.289 / 0.305, sponza 0.164 / 0.154,
+   * bunny 0.138 / 0.117 — a small scene does not fill the machine and pays the tile's barriers); b2bvh_build_opts.lbvh_second_level = 1 / 2 forces it
+   * on / off (tests).  Two tiles or more: the root is never finished inside a tile. */
+  const bool wantTile = ctx->lbvh_second_level == 1 ? true : (ctx->lbvh_second_level == 2 ? false : n >= (1u << 20));
+  if (n > HT_TILE && wantTile && !walkOnly) {
+    if (!(ctx->once_mask & B2_ONCE_MISC)) {
+      B2_CUDA(cudaFuncSetAttribute(hploc_tile_kernel<u32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HpTileSmem)));
+      B2_CUDA(cudaFuncSetAttribute(hploc_tile_kernel<u64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HpTileSmem)));
+      ctx->once_mask |= B2_ONCE_MISC;
+    }
+    const u32 grid = (n + HT_TILE - 1) / HT_TILE;
+    if (d_sortedKeys64) hploc_tile_kernel<u64><<<grid, HT_TILE, sizeof(HpTileSmem), ctx->stream>>>(d_sortedKeys64, n, d_nodes, d_leaves, nodeIdx, freeIdx, meet, ctrl);
+    else hploc_tile_kernel<u32><<<grid, HT_TILE, sizeof(HpTileSmem), ctx->stream>>>(d_sortedKeys, n, d_nodes, d_leaves, nodeIdx, freeIdx, meet, ctrl);
+  } else if (d_sortedKeys64)
     hploc_kernel<u64><<<(n + HP_THREADS - 1) / HP_THREADS, HP_THREADS, 0, ctx->stream>>>(d_sortedKeys64, n, d_nodes, d_leaves, nodeIdx, freeIdx, meet, ctrl);
   else
     hploc_kernel<u32><<<(n + HP_THREADS - 1) / HP_THREADS, HP_THREADS, 0, ctx->stream>>>(d_sortedKeys, n, d_nodes, d_leaves, nodeIdx, freeIdx, meet, ctrl);

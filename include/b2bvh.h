@@ -60,7 +60,8 @@ typedef struct b2bvh_build_opts {
   uint32_t boxes_ready;     /* 1: b2bvh_shard_extents ran on the same context and triangles: primitive boxes are in place, skip S1 */
   const float* d_scene_negmin_max; /* device, 6 floats {-min.xyz, max.xyz} (the all-reduced output of b2bvh_shard_extents): the
                                       global scene box without a host round trip; overrides scene_box when not NULL     */
-  uint32_t lbvh_second_level; /* LBVH builders: 0 = automatic (second merge level from 2^23 primitives), 1 = always, 2 = never; same output */
+  uint32_t lbvh_second_level; /* LBVH builders: 0 = automatic (second merge level from 2^23 primitives), 1 = always, 2 = never; same output.
+                                 H-PLOC: the same switch for its tile phase (automatic from 2^20 primitives) */
   uint32_t merge_max_ctas;  /* PLOC++: cap on the CTAs of the cooperative merge launch, 0 = every resident CTA; same output (tests use it to
                                reach many-tile chunks with small inputs) */
   uint32_t use_graph;       /* 1: capture the launch sequence of this build in a CUDA graph and REPLAY it when the next build on the context

@@ -81,3 +81,22 @@ def test_large_synthetic_properties(ctx, oracle, algo):
     assert ctx.tree_cost(tree) > 1.0
     g2 = ctx.fetch(ctx.build(algo, tris))
     assert g2["nodes"].tobytes() == nodes.tobytes() and g2["wide"].tobytes() == g["wide"].tobytes()
+
+
+HPLOC_TILE = [("uniform", 129, 51), ("uniform", 257, 52), ("uniform", 1025, 53), ("uniform", 5000, 54), ("uniform", 100_003, 55), ("clustered", 30_000, 56),
+              ("flat", 4000, 57), ("duplicate", 900, 58), ("anisotropic", 20_000, 59)]
+
+
+@pytest.mark.parametrize("kind,n,seed", HPLOC_TILE, ids=[f"{k}-{n}" for k, n, _ in HPLOC_TILE])
+def test_hploc_tile_phase_forced(ctx, oracle, kind, n, seed):
+    """hploc_tile_kernel (automatic only from 2^20 primitives) forced on small inputs: same bytes and the same number of merge calls as the oracle."""
+    check_ploc(ctx, oracle, random_tris(n, seed, kind), capi.HPLOC, lbvh_second_level=1)
+
+
+@pytest.mark.parametrize("mesh", ["bunny", "sponza"])
+def test_hploc_tile_phase_forced_on_meshes(ctx, oracle, mesh):
+    tris = load_mesh(mesh)
+    if tris is None:
+        pytest.skip(f"{mesh} not staged")
+    check_ploc(ctx, oracle, tris, capi.HPLOC, lbvh_second_level=1)
+    check_ploc(ctx, oracle, tris, capi.HPLOC, lbvh_second_level=2)

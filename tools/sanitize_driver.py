@@ -36,6 +36,7 @@ if "ploc" in what:
     done.append("ploc")
 if "hploc" in what:
     build(capi.HPLOC); build(capi.HPLOC, tris=dc)
+    build(capi.HPLOC, lbvh_second_level=1); build(capi.HPLOC, tris=dc, lbvh_second_level=1)  # the tile phase (automatic from 2^20 primitives)
     done.append("hploc")
 if "sizes" in what:  # sizes around the tile boundaries of the hierarchy, sort and collapse kernels
     for n in (2, 3, 33, 511, 512, 513, 1025, 7681, 15361):
