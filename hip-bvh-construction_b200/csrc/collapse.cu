@@ -31,6 +31,9 @@
  * + 4 sorted value ~ 180 B, of which ~133 B are compulsory; a gather moves 64 B of DRAM whatever it asks for.
  */
 #include "common.cuh"
+#ifdef COL_TRACE
+#include <stdio.h>
+#endif
 
 #define COL_THREADS 256
 #ifndef NUM_SOLO
@@ -39,6 +42,12 @@
 /* numbering kernel: CTA size by input size (measured, 10 M / bunny / sponza in us: 128 threads x 12 CTAs per SM 325 / 52 / 78,
  * 256 x 6 247 / 50 / 89, 512 x 2 210 / 60 / 121, 1024 x 1 234 / 85 / 129): large levels want few arrivals per grid-wide step,
  * the deep thin trees of small scenes want a short tile loop */
+#ifndef NUM_OWN_SLACK_DIV
+#define NUM_OWN_SLACK_DIV 4   /* a CTA keeps its own children while the largest part is below mean x (1 + 1/4) + 2 tiles */
+#endif
+#ifndef NUM_OWN_SLACK
+#define NUM_OWN_SLACK 2
+#endif
 #define NUM_THREADS_LARGE 512
 #define NUM_THREADS_SMALL 128
 
@@ -61,6 +70,8 @@ size_t b2_collapse_scratch_bytes(u32 n) {
 template <int NUM_THREADS>
 struct ColSmem {
   u32 warpSum[3][NUM_THREADS / 32];
+  u32 warpMax[NUM_THREADS / 32];
+  u32 tileSum[4][NUM_THREADS / 32];
 };
 
 __device__ __forceinline__ void publish_level(CollapseCtrl* ctrl, u32 barrier, u32 level, u32 start, u32 end) {
@@ -147,44 +158,71 @@ __device__ __forceinline__ u32 number_fetch(const uint4* __restrict__ expansion,
   return cnt;
 }
 
-/* C. one tile of NUM_THREADS tasks [tileStart, min(tileStart + NUM_THREADS, end)): number the internal children from
- * childBase + (exclusive count inside the tile) in (task, slot) order and append their tasks.  The records were written by
- * the same threads in number_fetch.  Returns the tile's number of internal children (same value in every thread). */
-template <int NUM_THREADS>
-__device__ __forceinline__ u32 number_tile(u32 nInt, u32* taskNode, const uint4* taskCh, u32* taskParent, u32* firstChild, ColSmem<NUM_THREADS>& S, u32 tileStart,
-                                           u32 end, u32 childBase) {
+/* C. B consecutive tiles of NUM_THREADS tasks, [tileStart, min(tileStart + B * NUM_THREADS, end)): number the internal children from
+ * childBase + (exclusive count before the task) in (task, slot) order and append their tasks.  The records were written by the same CTA in
+ * number_fetch.  B tiles share one pair of barriers and have their record loads in flight together: tile by tile, a CTA's part of a large
+ * level was a chain of ~1.5 us steps (25 of the 58 us of the largest level at 10 M primitives).  Returns the number of internal children
+ * of the B tiles (same value in every thread). */
+template <int NUM_THREADS, int B>
+__device__ __forceinline__ u32 number_tiles(u32 nInt, u32* taskNode, const uint4* taskCh, u32* taskParent, u32* firstChild, ColSmem<NUM_THREADS>& S, u32 tileStart,
+                                            u32 end, u32 childBase) {
   const u32 tid = threadIdx.x, w = tid >> 5, l = tid & 31u;
-  const u32 g = tileStart + tid;
-  const bool active = g < end;
-  uint4 t = make_uint4(B2_INVALID, B2_INVALID, B2_INVALID, B2_INVALID);
-  if (active) t = taskCh[g];
-  const u32 nInternal = count_internal(t, nInt);
-  u32 incl = nInternal;
+  uint4 t[B];
+  u32 nInternal[B], incl[B];
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const u32 v = __shfl_up_sync(B2_FULL, incl, o);
-    if ((int)l >= o) incl += v;
+  for (int k = 0; k < B; k++) {
+    const u32 g = tileStart + (u32)k * NUM_THREADS + tid;
+    t[k] = make_uint4(B2_INVALID, B2_INVALID, B2_INVALID, B2_INVALID);
+    if (g < end) t[k] = __ldcg(taskCh + g); /* own part: written by this CTA, possibly by another thread (a part does not start on a tile boundary) */
   }
-  if (l == 31) S.warpSum[0][w] = incl;
-  __syncthreads();
-  u32 warpBase = 0, tileTotal = 0;
 #pragma unroll
-  for (int k = 0; k < NUM_THREADS / 32; k++) { const u32 v = S.warpSum[0][k]; if (k < (int)w) warpBase += v; tileTotal += v; }
-  u32 nextId = childBase + warpBase + incl - nInternal;
-  if (active) firstChild[g] = nextId;
-  const u32 ch[4] = {t.x, t.y, t.z, t.w};
+  for (int k = 0; k < B; k++) {
+    nInternal[k] = count_internal(t[k], nInt);
+    incl[k] = nInternal[k];
 #pragma unroll
-  for (int k = 0; k < 4; k++)
-    if (ch[k] < nInt) {
-      if (nextId < nInt) { taskNode[nextId] = ch[k]; taskParent[nextId] = g; } /* never past the arrays, whatever the input */
-      nextId++;
+    for (int o = 1; o < 32; o <<= 1) {
+      const u32 v = __shfl_up_sync(B2_FULL, incl[k], o);
+      if ((int)l >= o) incl[k] += v;
     }
-  __syncthreads(); /* warpSum is reused by the next tile */
-  return tileTotal;
+    if (l == 31) S.tileSum[k][w] = incl[k];
+  }
+  __syncthreads();
+  u32 running = childBase;
+#pragma unroll
+  for (int k = 0; k < B; k++) {
+    u32 warpBase = 0, tileTotal = 0;
+#pragma unroll
+    for (int q = 0; q < NUM_THREADS / 32; q++) { const u32 v = S.tileSum[k][q]; if (q < (int)w) warpBase += v; tileTotal += v; }
+    const u32 g = tileStart + (u32)k * NUM_THREADS + tid;
+    u32 nextId = running + warpBase + incl[k] - nInternal[k];
+    if (g < end) firstChild[g] = nextId;
+    const u32 ch[4] = {t[k].x, t[k].y, t[k].z, t[k].w};
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      if (ch[j] < nInt) {
+        if (nextId < nInt) { taskNode[nextId] = ch[j]; taskParent[nextId] = g; } /* never past the arrays, whatever the input */
+        nextId++;
+      }
+    running += tileTotal;
+  }
+  __syncthreads(); /* tileSum is reused by the next call */
+  return running - childBase;
+}
+
+/* tasks [a, b) of one CTA, numbered from childBase: batches of four tiles, then single tiles */
+template <int NUM_THREADS>
+__device__ __forceinline__ u32 number_range(u32 nInt, u32* taskNode, const uint4* taskCh, u32* taskParent, u32* firstChild, ColSmem<NUM_THREADS>& S, u32 a, u32 b,
+                                            u32 childBase) {
+  u32 running = childBase, tileStart = a;
+  for (; tileStart + 2 * NUM_THREADS < b; tileStart += 4 * NUM_THREADS)
+    running += number_tiles<NUM_THREADS, 4>(nInt, taskNode, taskCh, taskParent, firstChild, S, tileStart, b, running);
+  for (; tileStart < b; tileStart += NUM_THREADS)
+    running += number_tiles<NUM_THREADS, 1>(nInt, taskNode, taskCh, taskParent, firstChild, S, tileStart, b, running);
+  return running - childBase;
 }
 
 template <int NUM_THREADS>
-__global__ void __launch_bounds__(NUM_THREADS, NUM_THREADS == NUM_THREADS_LARGE ? 2 : 12) collapse_number_kernel(const uint4* __restrict__ expansion, u32 nInt, const u32* __restrict__ rootIdx,
+__global__ void __launch_bounds__(NUM_THREADS, NUM_THREADS == NUM_THREADS_LARGE ? 2 : 4) collapse_number_kernel(const uint4* __restrict__ expansion, u32 nInt, const u32* __restrict__ rootIdx,
                                                                         u32* taskNode, uint4* taskCh, u32* taskParent, u32* firstChild,
                                                                         CollapseCtrl* ctrl, u64* counts) {
   __shared__ ColSmem<NUM_THREADS> S;
@@ -193,78 +231,116 @@ __global__ void __launch_bounds__(NUM_THREADS, NUM_THREADS == NUM_THREADS_LARGE 
   if (c == 0 && tid == 0) { taskNode[0] = *rootIdx; taskParent[0] = B2_INVALID; }
   __syncthreads();
 
+  bool own = false;   /* this CTA's part of the level is [oa, ob): the children it numbered itself one level earlier */
+  u32 oa = 0, ob = 0;
+#ifdef COL_TRACE
+  __shared__ unsigned long long trT[256], trP[256][3]; __shared__ u32 trS[256], trM[256]; u32 trN = 0;
+#define TR_STAMP(k) if (c == 0 && tid == 0 && trN - 1 < 256) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); trP[trN - 1][k] = t; }
+#else
+#define TR_STAMP(k)
+#endif
   while (true) {
     const u32 size = end - start;
+#ifdef COL_TRACE
+    if (c == 0 && tid == 0 && trN < 256) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); trT[trN] = t; trS[trN] = size; trM[trN] = (own ? 1u : 0u) | (level << 8); trN++; }
+#endif
     if (size == 0) break;
     if (size <= NUM_SOLO) {
       /* ---- a run of small levels (the top of the tree, the tail of a deep one): CTA 0 alone, no grid-wide step in between ---- */
       if (c == 0) {
         do {
           number_fetch<NUM_THREADS>(expansion, nInt, taskNode, taskCh, start, end);
-          u32 running = end;
-          for (u32 tileStart = start; tileStart < end; tileStart += NUM_THREADS)
-            running += number_tile<NUM_THREADS>(nInt, taskNode, taskCh, taskParent, firstChild, S, tileStart, end, running);
+          const u32 running = end + number_range<NUM_THREADS>(nInt, taskNode, taskCh, taskParent, firstChild, S, start, end, end);
           start = end; end = running; level++;
           if (end > nInt) { if (tid == 0) st_relaxed(&ctrl->error, 1u); end = start; } /* not a tree: stop */
         } while (end - start <= NUM_SOLO && end != start);
         if (tid == 0) publish_level(ctrl, barriers + 1u, level, start, end);
       }
-    } else {
-      /* ---- a level of many tiles: CTA c owns the contiguous chunk c of the level ---- */
-      const u32 chunk = ((size + G - 1) / G + NUM_THREADS - 1) / NUM_THREADS * NUM_THREADS;
-      const u32 nActive = (size + chunk - 1) / chunk;
-      arriveTarget += nActive;
-      if (c < nActive) {
-        const u32 cStart = start + c * chunk, cEnd = min(end, cStart + chunk);
-        /* A. records + internal children of the whole chunk */
-        u32 cnt = number_fetch<NUM_THREADS>(expansion, nInt, taskNode, taskCh, cStart, cEnd);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(B2_FULL, cnt, o);
-        if (l == 0) S.warpSum[1][w] = cnt;
-        __syncthreads();
-        u32 chunkTotal = 0;
-#pragma unroll
-        for (int q = 0; q < NUM_THREADS / 32; q++) chunkTotal += S.warpSum[1][q];
-        /* B. children of the chunks before this one: every CTA posts after the same pass and counts itself in on an arrival
-         * counter that ONE thread per CTA watches (every thread spinning on the posted words — 227 K pollers — starves the
-         * CTAs still at work, as measured for the PLOC++ merge kernel, profiles/r01m) */
-        if (tid == 0) {
-          st_relaxed64(counts + c, (u64)chunkTotal);
-          __threadfence();
-          atomicAdd(&ctrl->arrive, 1u);
-          SpinGuard guard;
-          while (ld_acquire(&ctrl->arrive) < arriveTarget) {
-            __nanosleep(32);
-            guard.tick();
-          }
-        }
-        __syncthreads();
-        u32 before = 0;
-        for (u32 i = tid; i < c; i += NUM_THREADS) before += (u32)ld_relaxed64(counts + i);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(B2_FULL, before, o);
-        if (l == 0) S.warpSum[2][w] = before;
-        __syncthreads();
-        u32 running = end;
-#pragma unroll
-        for (int q = 0; q < NUM_THREADS / 32; q++) running += S.warpSum[2][q];
-        if (c == nActive - 1 && tid == 0) { /* last chunk of the level */
-          u32 nextEnd = running + chunkTotal;
-          if (nextEnd > nInt) { st_relaxed(&ctrl->error, 1u); nextEnd = end; } /* not a tree: publish an empty level, everybody stops */
-          publish_level(ctrl, barriers + 1u, level + 1u, end, nextEnd);
-        }
-        /* C. the chunk tile by tile: no CTA waits for another one here */
-        for (u32 tileStart = cStart; tileStart < cEnd; tileStart += NUM_THREADS)
-          running += number_tile<NUM_THREADS>(nInt, taskNode, taskCh, taskParent, firstChild, S, tileStart, cEnd, running);
-      }
-    }
-    barriers++;
-    grid_barrier(&ctrl->bar, barriers * G);
-    {
+      barriers++;
+      grid_barrier(&ctrl->bar, barriers * G);
       const u32* nx = reinterpret_cast<const u32*>(&ctrl->next[barriers & 1u]);
       level = ld_relaxed(nx); start = ld_relaxed(nx + 1); end = ld_relaxed(nx + 2);
+      own = false;
+      continue;
     }
+    /* ---- a level of many tiles.  After a grid barrier CTA c takes the contiguous chunk c of the level; from then on it keeps the
+     * children it numbered itself (its part of the next level is contiguous and in chunk order, so the numbering is the same) and the
+     * levels follow each other with ONE grid-wide step — the exchange of counts — instead of two, until the parts drift apart ---- */
+    if (!own) {
+      const u32 chunk = ((size + G - 1) / G + NUM_THREADS - 1) / NUM_THREADS * NUM_THREADS;
+      oa = min(end, start + c * chunk);
+      ob = min(end, oa + chunk);
+    }
+    arriveTarget += G;
+    /* A. records + internal children of the whole part */
+    u32 cnt = number_fetch<NUM_THREADS>(expansion, nInt, taskNode, taskCh, oa, ob);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(B2_FULL, cnt, o);
+    if (l == 0) S.warpSum[1][w] = cnt;
+    __syncthreads();
+    u32 partTotal = 0;
+#pragma unroll
+    for (int q = 0; q < NUM_THREADS / 32; q++) partTotal += S.warpSum[1][q];
+    /* B. children of the parts before this one: every CTA posts after the same pass and counts itself in on an arrival
+     * counter that ONE thread per CTA watches (every thread spinning on the posted words — 227 K pollers — starves the
+     * CTAs still at work, as measured for the PLOC++ merge kernel, profiles/r01m).  The words of two consecutive levels live in two
+     * buffers: nobody posts level L+2 before everybody has posted L+1, that is, after everybody has read the words of level L. */
+    u64* lvlCounts = counts + (size_t)(level & 1u) * G;
+    TR_STAMP(0)
+    if (tid == 0) {
+      st_relaxed64(lvlCounts + c, (u64)partTotal);
+      __threadfence();
+      atomicAdd(&ctrl->arrive, 1u);
+      SpinGuard guard;
+      while (ld_acquire(&ctrl->arrive) < arriveTarget) {
+        __nanosleep(32);
+        guard.tick();
+      }
+    }
+    __syncthreads();
+    TR_STAMP(1)
+    u32 before = 0, total = 0, most = 0;
+    for (u32 i = tid; i < G; i += NUM_THREADS) {
+      const u32 v = (u32)ld_relaxed64(lvlCounts + i);
+      if (i < c) before += v;
+      total += v;
+      most = max(most, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      before += __shfl_xor_sync(B2_FULL, before, o);
+      total += __shfl_xor_sync(B2_FULL, total, o);
+      most = max(most, __shfl_xor_sync(B2_FULL, most, o));
+    }
+    if (l == 0) { S.warpSum[2][w] = before; S.warpSum[0][w] = total; S.warpMax[w] = most; }
+    __syncthreads();
+    before = 0; total = 0; most = 0;
+#pragma unroll
+    for (int q = 0; q < NUM_THREADS / 32; q++) { before += S.warpSum[2][q]; total += S.warpSum[0][q]; most = max(most, S.warpMax[q]); }
+    __syncthreads(); /* warpSum is rewritten in the next level */
+    if (total > nInt - end) { /* more tasks than internal nodes: not a tree — every CTA sees the same counts and stops here */
+      if (c == 0 && tid == 0) st_relaxed(&ctrl->error, 1u);
+      break;
+    }
+    /* C. the part tile by tile: no CTA waits for another one here */
+    const u32 childBase = end + before;
+    number_range<NUM_THREADS>(nInt, taskNode, taskCh, taskParent, firstChild, S, oa, ob, childBase);
+    TR_STAMP(2)
+    oa = childBase; ob = childBase + partTotal;
+    level++; start = end; end += total;
+    if (total == 0) break;
+    /* keep the parts while the largest is within reach of the mean (all CTAs decide alike, from the same words); otherwise — and before a
+     * run of small levels, which CTA 0 must see complete — one grid barrier and equal chunks again */
+    const u32 mean = total / G;
+    if (total <= NUM_SOLO || most > mean + mean / NUM_OWN_SLACK_DIV + NUM_OWN_SLACK * NUM_THREADS) {
+      barriers++;
+      grid_barrier(&ctrl->bar, barriers * G);
+      own = false;
+    } else own = true;
   }
+#ifdef COL_TRACE
+  if (c == 0 && tid == 0) for (u32 i = 0; i + 1 < trN; i++) printf("TRACE lvl %u own %u size %u us %.2f  A %.2f wait %.2f C %.2f rest %.2f\n", trM[i] >> 8, trM[i] & 1u, trS[i], (double)(trT[i + 1] - trT[i]) * 1e-3, (double)(trP[i][0] - trT[i]) * 1e-3, (double)(trP[i][1] - trP[i][0]) * 1e-3, (double)(trP[i][2] - trP[i][1]) * 1e-3, (double)(trT[i + 1] - trP[i][2]) * 1e-3);
+#endif
   if (c == 0 && tid == 0) ctrl->nWide = ld_relaxed(&ctrl->error) ? B2_INVALID : end;
 }
 
