@@ -232,6 +232,7 @@ struct b2bvh_ctx {
    * occupancy answers live here and not in process-wide statics (a second context on another device needs its own) */
   u32 once_mask;         /* B2_ONCE_* bits already done on this context's device */
   int occ[8];            /* B2_OCC_* occupancy answers */
+  u32 meet_clean;        /* leading words of SLOT_MEET known to hold 0xFFFFFFFF (b2_meet_acquire): the LBVH climb leaves its exchange words as it found them */
   u32 alloc_epoch;       /* bumped whenever a build-owned buffer is (re)allocated: a cached graph holds the old pointers */
   u32 launches;
   u32 lbvh_second_level; /* b2bvh_build_opts.lbvh_second_level of the running build */
@@ -284,10 +285,13 @@ enum {
   SLOT_PARENTS, SLOT_LBVH, SLOT_WIDE, SLOT_WLEAVES, SLOT_COLLAPSE, SLOT_LEAVES, SLOT_PLOC, SLOT_HPLOC, SLOT_MISC,
   SLOT_SPLIT_BOX, SLOT_SPLIT_PRIM, SLOT_SPLIT_LIST_A, SLOT_SPLIT_LIST_B, SLOT_SPLIT_STATUS, SLOT_SPLIT_LEAFPRIM,
   SLOT_BATCH_NODES, SLOT_BATCH_LEAVES, SLOT_BATCH_ROOTS, SLOT_BATCH_SCENES, SLOT_BATCH_OFFSETS,
-  SLOT_KEYS_LO, SLOT_KEYS64, SLOT_SKEYS64, SLOT_M60_KEYS, SLOT_M60_VALS, SLOT_COUNT
+  SLOT_KEYS_LO, SLOT_KEYS64, SLOT_SKEYS64, SLOT_M60_KEYS, SLOT_M60_VALS, SLOT_MEET, SLOT_COUNT
 };
 /* SLOT_CTL (256 B): [0..23] scene box, [32..63] extents scratch8, [64..87] {-min,max}, [96] root index, [128] range-extract count, [160] traversal overflow flag, [192] range-extract root, [224..247] root box of a sharded build */
 int b2_reserve(b2bvh_ctx* ctx, int slot, size_t bytes, void** out);
+/* the n-1 exchange words of the LBVH climb (SLOT_MEET), all 0xFFFFFFFF: filled when the buffer is new or grew, never again (lbvh.cu).  Allocates:
+ * call it before a stream capture begins; the launchers call it again, which is then free. */
+int b2_meet_acquire(b2bvh_ctx* ctx, u32 n, u32** out);
 /* words <= 16 from device memory into mailbox slot `slot`; readable at b2_mailbox(ctx, slot) after the next stream synchronisation */
 #define B2_MAILBOX_SLOTS 8
 enum { B2_MB_COLLAPSE = 0, B2_MB_PLOC = 1, B2_MB_HPLOC = 2, B2_MB_ROOT = 3, B2_MB_SPLIT = 4, B2_MB_RANGE = 5, B2_MB_TRAVERSE = 6, B2_MB_GLOBAL = 7 };

@@ -64,6 +64,7 @@ __device__ __forceinline__ void climb_global(const K* __restrict__ keys, u32 n, 
     }
     const u32 other = atom_exch_acq_rel(meet + p, isLeft ? lo : hi);
     if (other == B2_INVALID) return; /* first arriver: the sibling's thread finishes this node */
+    st_relaxed(meet + p, B2_INVALID); /* both children have been here: the word is as the next build expects it (b2_meet_acquire) */
     /* second arriver: the node with split p now has its full range */
     if (isLeft) hi = other; else lo = other;
     u32 sib;
@@ -591,6 +592,22 @@ __global__ void __launch_bounds__(LBVH_THREADS) lbvh_refit_kernel(b2bvh_bvh2_nod
   }
 }
 
+int b2_meet_acquire(b2bvh_ctx* ctx, u32 n, u32** out) {
+  const size_t words = n > 1 ? (size_t)n - 1 : 1;
+  b2bvh_ctx::Buf& b = ctx->bufs[SLOT_MEET];
+  const void* pBefore = b.p;
+  const size_t capBefore = b.cap;
+  void* p = nullptr;
+  B2_TRY(b2_reserve(ctx, SLOT_MEET, words * sizeof(u32), &p));
+  if (p != pBefore || b.cap != capBefore) ctx->meet_clean = 0;
+  if ((size_t)ctx->meet_clean < words) {
+    B2_CUDA(cudaMemsetAsync(p, 0xFF, b.cap, ctx->stream));
+    ctx->meet_clean = (u32)(b.cap / sizeof(u32) > 0xFFFFFFFFull ? 0xFFFFFFFFull : b.cap / sizeof(u32));
+  }
+  *out = reinterpret_cast<u32*>(p);
+  return 0;
+}
+
 size_t b2_lbvh_scratch_bytes(u32 n) {
   /* the larger of: fused path (meet words + hand-over list) and two-kernel path (2n-1 flags) */
   const size_t tiles = ((size_t)n + LBVH_TILE - 1) / LBVH_TILE;
@@ -603,15 +620,18 @@ size_t b2_lbvh_scratch_bytes(u32 n) {
 template <typename K>
 static int launch_lbvh_fused_t(b2bvh_ctx* ctx, const K* d_sortedKeys, const u32* d_sortedVals, const b2bvh_aabb* d_triAabb, u32 n,
                          b2bvh_bvh2_node* d_nodes, u32* d_parents, u32* d_scratch, u32* d_root, int karrasNumbering) {
-  if (n > 1) B2_CUDA(cudaMemsetAsync(d_scratch, 0xFF, (size_t)(n - 1) * sizeof(u32), ctx->stream));
+  /* the exchange words are NOT cleared per build (40 MB of writes at 10 M primitives): every word the climb uses sees exactly two arrivals and
+   * the second one puts 0xFFFFFFFF back */
+  u32* meet = nullptr;
+  B2_TRY(b2_meet_acquire(ctx, n, &meet));
   B2_KERNEL(ctx, sizeof(K) == 8 ? (karrasNumbering ? "lbvh_fused64_karras" : "lbvh_fused64_apetrei") : (karrasNumbering ? "lbvh_fused_karras" : "lbvh_fused_apetrei"));
   static const bool globalOnly = getenv("B2BVH_LBVH_GLOBAL_ONLY") != nullptr; /* development switch: the all-global-memory variant */
   if (globalOnly) {
     const u32 grid = (n + LBVH_THREADS - 1) / LBVH_THREADS;
     if (karrasNumbering)
-      lbvh_fused_kernel<true, K><<<grid, LBVH_THREADS, 0, ctx->stream>>>(d_sortedKeys, d_sortedVals, d_triAabb, n, d_nodes, d_parents, d_scratch, d_root, ctx->ref_prim, ctx->ref_leaf_prim);
+      lbvh_fused_kernel<true, K><<<grid, LBVH_THREADS, 0, ctx->stream>>>(d_sortedKeys, d_sortedVals, d_triAabb, n, d_nodes, d_parents, meet, d_root, ctx->ref_prim, ctx->ref_leaf_prim);
     else
-      lbvh_fused_kernel<false, K><<<grid, LBVH_THREADS, 0, ctx->stream>>>(d_sortedKeys, d_sortedVals, d_triAabb, n, d_nodes, d_parents, d_scratch, d_root, ctx->ref_prim, ctx->ref_leaf_prim);
+      lbvh_fused_kernel<false, K><<<grid, LBVH_THREADS, 0, ctx->stream>>>(d_sortedKeys, d_sortedVals, d_triAabb, n, d_nodes, d_parents, meet, d_root, ctx->ref_prim, ctx->ref_leaf_prim);
   } else {
     /* scratch: meet[n-1] | (16-byte aligned) pendingCount | pending[cap] | tileInfo[tiles] | tileBuf[tiles][LBVH_TILE_CAP] */
     const size_t off = (((size_t)n * 4 + 15) & ~(size_t)15);
@@ -637,17 +657,17 @@ static int launch_lbvh_fused_t(b2bvh_ctx* ctx, const K* d_sortedKeys, const u32*
       ctx->once_mask |= onceBit;
     }
     if (karrasNumbering)
-      lbvh_tile_kernel<true, K><<<grid, LBVH_TILE_THREADS, sizeof(LbvhTileSmem<true>), ctx->stream>>>(d_sortedKeys, d_sortedVals, d_triAabb, n, d_nodes, d_parents, d_scratch, d_root, pendingCount, pending, cap, tileInfo, tileBuf, ctx->ref_prim, ctx->ref_leaf_prim);
+      lbvh_tile_kernel<true, K><<<grid, LBVH_TILE_THREADS, sizeof(LbvhTileSmem<true>), ctx->stream>>>(d_sortedKeys, d_sortedVals, d_triAabb, n, d_nodes, d_parents, meet, d_root, pendingCount, pending, cap, tileInfo, tileBuf, ctx->ref_prim, ctx->ref_leaf_prim);
     else
-      lbvh_tile_kernel<false, K><<<grid, LBVH_TILE_THREADS, sizeof(LbvhTileSmem<false>), ctx->stream>>>(d_sortedKeys, d_sortedVals, d_triAabb, n, d_nodes, d_parents, d_scratch, d_root, pendingCount, pending, cap, tileInfo, tileBuf, ctx->ref_prim, ctx->ref_leaf_prim);
+      lbvh_tile_kernel<false, K><<<grid, LBVH_TILE_THREADS, sizeof(LbvhTileSmem<false>), ctx->stream>>>(d_sortedKeys, d_sortedVals, d_triAabb, n, d_nodes, d_parents, meet, d_root, pendingCount, pending, cap, tileInfo, tileBuf, ctx->ref_prim, ctx->ref_leaf_prim);
     B2_LAUNCH_CHECK(ctx);
     if (useGroups) {
       const u32 groups = (grid + LBVH_GROUP - 1) / LBVH_GROUP;
       B2_KERNEL(ctx, "lbvh_group");
       if (karrasNumbering)
-        lbvh_group_kernel<true, K><<<groups, 256, sizeof(LbvhGroupSmem), ctx->stream>>>(d_sortedKeys, n, d_nodes, d_parents, d_scratch, d_root, pendingCount, pending, cap, tileInfo, tileBuf, grid);
+        lbvh_group_kernel<true, K><<<groups, 256, sizeof(LbvhGroupSmem), ctx->stream>>>(d_sortedKeys, n, d_nodes, d_parents, meet, d_root, pendingCount, pending, cap, tileInfo, tileBuf, grid);
       else
-        lbvh_group_kernel<false, K><<<groups, 256, sizeof(LbvhGroupSmem), ctx->stream>>>(d_sortedKeys, n, d_nodes, d_parents, d_scratch, d_root, pendingCount, pending, cap, tileInfo, tileBuf, grid);
+        lbvh_group_kernel<false, K><<<groups, 256, sizeof(LbvhGroupSmem), ctx->stream>>>(d_sortedKeys, n, d_nodes, d_parents, meet, d_root, pendingCount, pending, cap, tileInfo, tileBuf, grid);
       B2_LAUNCH_CHECK(ctx);
     }
     u32 grid2 = (cap + LBVH_THREADS - 1) / LBVH_THREADS;
@@ -655,9 +675,9 @@ static int launch_lbvh_fused_t(b2bvh_ctx* ctx, const K* d_sortedKeys, const u32*
     if (grid2 > cap2) grid2 = cap2;
     B2_KERNEL(ctx, "lbvh_climb");
     if (karrasNumbering)
-      lbvh_climb_kernel<true, K><<<grid2, LBVH_THREADS, 0, ctx->stream>>>(d_sortedKeys, n, d_nodes, d_parents, d_scratch, d_root, pendingCount, pending, cap);
+      lbvh_climb_kernel<true, K><<<grid2, LBVH_THREADS, 0, ctx->stream>>>(d_sortedKeys, n, d_nodes, d_parents, meet, d_root, pendingCount, pending, cap);
     else
-      lbvh_climb_kernel<false, K><<<grid2, LBVH_THREADS, 0, ctx->stream>>>(d_sortedKeys, n, d_nodes, d_parents, d_scratch, d_root, pendingCount, pending, cap);
+      lbvh_climb_kernel<false, K><<<grid2, LBVH_THREADS, 0, ctx->stream>>>(d_sortedKeys, n, d_nodes, d_parents, meet, d_root, pendingCount, pending, cap);
   }
   B2_LAUNCH_CHECK(ctx);
   return 0;

@@ -83,6 +83,21 @@ def test_twopass_two_kernel_variant(ctx, oracle, kind, n, seed):
     check_lbvh(ctx, oracle, random_tris(n, seed, kind), capi.TWO_PASS_LBVH, karras_two_kernel=True)
 
 
+def test_exchange_words_are_left_clean_between_builds(oracle):
+    """The climb's exchange words (SLOT_MEET) are filled once and every build leaves them as it found them: sizes going up and down, both numberings,
+    the all-global variant's neighbours (two-kernel Karras, second merge level) in between, graph replays — every tree against the oracle."""
+    own = capi.Context(0)
+    try:
+        seq = [(30_000, capi.SINGLE_PASS_LBVH, {}), (700, capi.TWO_PASS_LBVH, {}), (30_000, capi.TWO_PASS_LBVH, {}), (2, capi.SINGLE_PASS_LBVH, {}),
+               (90_001, capi.SINGLE_PASS_LBVH, {"lbvh_second_level": 1}), (5000, capi.TWO_PASS_LBVH, {"karras_two_kernel": True}),
+               (90_001, capi.TWO_PASS_LBVH, {"lbvh_second_level": 2}), (257, capi.SINGLE_PASS_LBVH, {"use_graph": True}), (257, capi.SINGLE_PASS_LBVH, {"use_graph": True}),
+               (120_000, capi.SINGLE_PASS_LBVH, {}), (30_000, capi.SINGLE_PASS_LBVH, {})]
+        for i, (n, algo, kw) in enumerate(seq):
+            check_lbvh(own, oracle, random_tris(n, 300 + i, "clustered" if i % 3 == 1 else "uniform"), algo, **kw)
+    finally:
+        own.close()
+
+
 @pytest.mark.parametrize("algo", [capi.TWO_PASS_LBVH, capi.SINGLE_PASS_LBVH], ids=["twopass", "singlepass"])
 @pytest.mark.parametrize("mesh", ["cornellbox", "bunny", "sponza"])
 def test_reference_meshes(ctx, oracle, algo, mesh):
