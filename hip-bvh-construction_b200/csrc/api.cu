@@ -350,6 +350,7 @@ int b2bvh_build(b2bvh_ctx* ctx, int algo, const b2bvh_triangle* tris, uint32_t n
   u32 iterations = 0, nWide = 0;
   bool capturing = false;
   /* stage events: inside a capture they must become event-record NODES (cudaEventRecordExternal), or they cannot be timed */
+  /* (the four event nodes between the stages cost 7-8 us of a 1.6 ms replay at 10 M primitives: measured with them left out, gpurun r2y) */
   auto record = [&](int i) { return capturing ? cudaEventRecordWithFlags(ctx->ev[i], s, cudaEventRecordExternal) : cudaEventRecord(ctx->ev[i], s); };
   auto enqueue = [&]() -> int {
   /* ---- upload (TwoPassLbvh.cpp:19-20) ---- */

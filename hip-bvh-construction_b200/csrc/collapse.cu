@@ -84,8 +84,10 @@ __device__ __forceinline__ void publish_level(CollapseCtrl* ctrl, u32 barrier, u
 #ifndef COL_EXPAND_MINB
 #define COL_EXPAND_MINB 1
 #endif
-__global__ void __launch_bounds__(COL_THREADS, COL_EXPAND_MINB) collapse_expand_kernel(const b2bvh_bvh2_node* __restrict__ nodes, u32 nInt, uint4* __restrict__ expansion) {
+__global__ void __launch_bounds__(COL_THREADS, COL_EXPAND_MINB) collapse_expand_kernel(const b2bvh_bvh2_node* __restrict__ nodes, u32 nInt, uint4* __restrict__ expansion,
+                                                                                         uint4* __restrict__ ctrlWords) {
   const u32 i = blockIdx.x * COL_THREADS + threadIdx.x;
+  if (blockIdx.x == 0 && threadIdx.x < 256 / 16) ctrlWords[threadIdx.x] = make_uint4(0u, 0u, 0u, 0u); /* CollapseCtrl of the numbering kernel that follows (a memset node costs ~2 us of the stream) */
   if (i >= nInt) return;
   const uint2 top = __ldg(reinterpret_cast<const uint2*>(nodes + i));
   u32 ch[4] = {top.x, top.y, B2_INVALID, B2_INVALID};
@@ -457,10 +459,9 @@ int b2_launch_collapse(b2bvh_ctx* ctx, const b2bvh_bvh2_node* d_nodes, const b2b
   u32* taskNode = firstChild + n;
   u64* counts = reinterpret_cast<u64*>(taskNode + n + (n & 1u)); /* one tagged word per CTA; 3n (+1) words after a 16-byte aligned start */
   u32 nInt = n - 1;
-  B2_CUDA(cudaMemsetAsync(ctrl, 0, 256, ctx->stream));
-  B2_CUDA(cudaMemsetAsync(counts, 0, (size_t)grid * sizeof(u64), ctx->stream));
+  /* no memsets: the expansion kernel clears CollapseCtrl, and every count word is posted before it is read */
   B2_KERNEL(ctx, "collapse_expand");
-  collapse_expand_kernel<<<(nInt + COL_THREADS - 1) / COL_THREADS, COL_THREADS, 0, ctx->stream>>>(d_nodes, nInt, expansion);
+  collapse_expand_kernel<<<(nInt + COL_THREADS - 1) / COL_THREADS, COL_THREADS, 0, ctx->stream>>>(d_nodes, nInt, expansion, reinterpret_cast<uint4*>(ctrl));
   B2_LAUNCH_CHECK(ctx);
   B2_KERNEL(ctx, "collapse_number");
   void* args[] = {(void*)&expansion, (void*)&nInt, (void*)&d_rootIdx, (void*)&taskNode, (void*)&taskCh, (void*)&taskParent, (void*)&firstChild, (void*)&ctrl, (void*)&counts};
