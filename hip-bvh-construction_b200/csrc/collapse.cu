@@ -366,6 +366,7 @@ __global__ void __launch_bounds__(COL_EMIT_THREADS, COL_EMIT_MINB) collapse_emit
                                                                       b2bvh_bvh4_node* __restrict__ wide, b2bvh_prim_node* __restrict__ wideLeaves) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
   EmitSmem& S = *reinterpret_cast<EmitSmem*>(smemRaw);
+  pdl_wait(); /* launched programmatically behind the numbering kernel */
   const u32 nWide = ctrl->nWide, tid = threadIdx.x;
   if (nWide > nInt) return; /* the numbering gave up (CollapseCtrl::error) */
   for (u32 tileStart = blockIdx.x * COL_EMIT_THREADS; tileStart < nWide; tileStart += gridDim.x * COL_EMIT_THREADS) {
@@ -473,7 +474,7 @@ int b2_launch_collapse(b2bvh_ctx* ctx, const b2bvh_bvh2_node* d_nodes, const b2b
   const u32 ecap = (u32)ctx->sm_count * 2u * COL_EMIT_MINB * (256 / COL_EMIT_THREADS);
   if (egrid > ecap) egrid = ecap;
   B2_KERNEL(ctx, "collapse_emit");
-  collapse_emit_kernel<<<egrid, COL_EMIT_THREADS, emitSmem, ctx->stream>>>(d_nodes, d_sortedVals, nInt, taskCh, taskParent, firstChild, ctrl, d_wide, d_wideLeaves);
+  B2_LAUNCH_PDL(collapse_emit_kernel, egrid, COL_EMIT_THREADS, emitSmem, ctx->stream, d_nodes, d_sortedVals, nInt, taskCh, taskParent, firstChild, ctrl, d_wide, d_wideLeaves);
   B2_LAUNCH_CHECK(ctx);
   /* CollapseCtrl::nWide comes back through the mailbox: b2_mailbox(ctx, B2_MB_COLLAPSE)[1] after the build's final synchronisation
    * (no host round trip in the middle of a build) */

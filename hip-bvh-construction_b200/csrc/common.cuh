@@ -267,6 +267,27 @@ int b2_check(cudaError_t e, const char* what);
   } while (0)
 int b2_prof_begin(b2bvh_ctx* ctx, const char* name);
 int b2_prof_end(b2bvh_ctx* ctx);
+/* Programmatic dependent launch (sm_90+): a kernel launched through b2_launch_pdl may be made resident while its predecessor in the stream is
+ * still running; it must not touch global memory before pdl_wait() (which returns once the predecessor has completed and its writes are
+ * visible).  Without an explicit pdl_launch_dependents() in the predecessor the successor comes in as the predecessor's CTAs exit: what
+ * overlaps is the launch latency, the prologue (shared-memory clearing, barrier initialisation) and the drain of the short kernels of a
+ * chain.  (Letting the successor in from the START of the predecessor made the 10 M sort 9 % slower: resident, waiting CTAs of the next
+ * kernel get in the way of the tail of this one; profiles/r02_experiments.txt.)  Launched the ordinary way, both instructions do nothing. */
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+static inline cudaError_t b2_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+#define B2_LAUNCH_PDL(kernel, grid, block, smem, stream, ...) B2_CUDA(b2_launch_pdl(kernel, dim3(grid), dim3(block), smem, stream, __VA_ARGS__))
+
 /* bracket of every kernel launch: B2_KERNEL(ctx, "name"); kernel<<<...>>>(...); B2_LAUNCH_CHECK(ctx); */
 #define B2_KERNEL(ctx, name)                          \
   do {                                                \

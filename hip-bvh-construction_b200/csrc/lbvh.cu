@@ -365,6 +365,7 @@ __global__ void __launch_bounds__(256) lbvh_group_kernel(const K* __restrict__ k
   constexpr u32 SLOT_MASK = 0x7FFu, P = LBVH_GROUP_CAP / 256;
   const u32 tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
   const u32 t0 = blockIdx.x * LBVH_GROUP, t1 = min(nTiles, t0 + LBVH_GROUP);
+  pdl_wait(); /* launched programmatically behind the tile kernel */
   if (warp == 0) {
     const u32 t = t0 + lane;
     const u32 c = t < t1 ? __ldg(&tileInfo[t].x) : 0u;
@@ -515,6 +516,7 @@ template <bool KARRAS, typename K>
 __global__ void __launch_bounds__(LBVH_THREADS) lbvh_climb_kernel(const K* __restrict__ keys, u32 n, b2bvh_bvh2_node* nodes, u32* parents, u32* meet,
                                                                   u32* rootOut, const u32* __restrict__ pendingCount,
                                                                   const LbvhPending* __restrict__ pending, u32 pendingCap) {
+  pdl_wait(); /* launched programmatically behind the tile / group kernel */
   const u32 count = min(*pendingCount, pendingCap);
   for (u32 i = blockIdx.x * LBVH_THREADS + threadIdx.x; i < count; i += gridDim.x * LBVH_THREADS) {
     const uint4* q = reinterpret_cast<const uint4*>(pending + i);
@@ -665,9 +667,9 @@ static int launch_lbvh_fused_t(b2bvh_ctx* ctx, const K* d_sortedKeys, const u32*
       const u32 groups = (grid + LBVH_GROUP - 1) / LBVH_GROUP;
       B2_KERNEL(ctx, "lbvh_group");
       if (karrasNumbering)
-        lbvh_group_kernel<true, K><<<groups, 256, sizeof(LbvhGroupSmem), ctx->stream>>>(d_sortedKeys, n, d_nodes, d_parents, meet, d_root, pendingCount, pending, cap, tileInfo, tileBuf, grid);
+        B2_LAUNCH_PDL((lbvh_group_kernel<true, K>), groups, 256, sizeof(LbvhGroupSmem), ctx->stream, d_sortedKeys, n, d_nodes, d_parents, meet, d_root, pendingCount, pending, cap, tileInfo, tileBuf, grid);
       else
-        lbvh_group_kernel<false, K><<<groups, 256, sizeof(LbvhGroupSmem), ctx->stream>>>(d_sortedKeys, n, d_nodes, d_parents, meet, d_root, pendingCount, pending, cap, tileInfo, tileBuf, grid);
+        B2_LAUNCH_PDL((lbvh_group_kernel<false, K>), groups, 256, sizeof(LbvhGroupSmem), ctx->stream, d_sortedKeys, n, d_nodes, d_parents, meet, d_root, pendingCount, pending, cap, tileInfo, tileBuf, grid);
       B2_LAUNCH_CHECK(ctx);
     }
     u32 grid2 = (cap + LBVH_THREADS - 1) / LBVH_THREADS;
@@ -675,9 +677,9 @@ static int launch_lbvh_fused_t(b2bvh_ctx* ctx, const K* d_sortedKeys, const u32*
     if (grid2 > cap2) grid2 = cap2;
     B2_KERNEL(ctx, "lbvh_climb");
     if (karrasNumbering)
-      lbvh_climb_kernel<true, K><<<grid2, LBVH_THREADS, 0, ctx->stream>>>(d_sortedKeys, n, d_nodes, d_parents, meet, d_root, pendingCount, pending, cap);
+      B2_LAUNCH_PDL((lbvh_climb_kernel<true, K>), grid2, LBVH_THREADS, 0, ctx->stream, d_sortedKeys, n, d_nodes, d_parents, meet, d_root, pendingCount, pending, cap);
     else
-      lbvh_climb_kernel<false, K><<<grid2, LBVH_THREADS, 0, ctx->stream>>>(d_sortedKeys, n, d_nodes, d_parents, meet, d_root, pendingCount, pending, cap);
+      B2_LAUNCH_PDL((lbvh_climb_kernel<false, K>), grid2, LBVH_THREADS, 0, ctx->stream, d_sortedKeys, n, d_nodes, d_parents, meet, d_root, pendingCount, pending, cap);
   }
   B2_LAUNCH_CHECK(ctx);
   return 0;

@@ -58,12 +58,19 @@ size_t b2_sort_scratch_bytes(u32 n) {
   return ((size_t)RS_RADIX * rs_gpad(1024) + RS_RADIX) * sizeof(u32); /* G <= 2 * SMs <= 1024 */
 }
 
+/* The twelve launches of a sort are one dependent chain of short kernels: each is launched programmatically (common.cuh), clears its shared
+ * memory / initialises its barriers while its predecessor drains, and only then waits for it.  Sort stage, us, without / with: 10 M 303 / 297
+ * (replayed graph) and 323 / 300 (stream launches); 1 M 71.6 / 67.5 and 93 / 73; 144 K 45.0 / 40.9 and 66.7 / 43.9. */
+#define RS_PDL_PROLOGUE() pdl_wait()
+#define RS_LAUNCH(kernel, grid, block, smem, stream, ...) B2_LAUNCH_PDL(kernel, grid, block, smem, stream, __VA_ARGS__)
+
 /* ------------------------------------------------------------------------------------------------ count */
 __global__ void __launch_bounds__(RS_THREADS) radix_count_kernel(const u32* __restrict__ keys, u32 n, u32 chunk, u32 shift, u32 mask,
                                                                  u32* __restrict__ counts, u32 gpad) {
   __shared__ u32 h[RS_WARPS][RS_RADIX];
   const u32 tid = threadIdx.x, w = tid >> 5;
   for (u32 k = tid; k < RS_WARPS * RS_RADIX; k += RS_THREADS) (&h[0][0])[k] = 0;
+  RS_PDL_PROLOGUE();
   __syncthreads();
   const u32 begin = blockIdx.x * chunk, end = min(n, begin + chunk); /* chunk is a multiple of 4: 16-byte aligned loads */
   auto add4 = [&](const uint4& q) {
@@ -100,6 +107,7 @@ __global__ void __launch_bounds__(RS_SCAN_WARPS * 32) radix_scan_kernel(u32* __r
   /* one warp per digit walks its row 32 words at a time (a variant with one contiguous segment per lane and all loads
    * independent was slower: 12.5 vs 8.6 us, the strided accesses cost more than the dependent steps) */
   const u32 d = blockIdx.x * RS_SCAN_WARPS + (threadIdx.x >> 5), l = lane_id();
+  RS_PDL_PROLOGUE();
   u32* row = counts + (size_t)d * gpad;
   u32 carry = 0;
   for (u32 base = 0; base < g; base += 32) {
@@ -182,6 +190,7 @@ __global__ void __launch_bounds__(RS_THREADS, ITEMS == RS_ITEMS ? RS_MINB : 2) r
     mbar_init(&S.bar[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  RS_PDL_PROLOGUE();
   /* global start of every digit for this chunk = exclusive scan of the digit totals + this chunk's offset inside the digit */
   if (tid < RS_RADIX) {
     const u32 tot = __ldg(totals + tid);
@@ -319,9 +328,9 @@ static int launch_scatter(b2bvh_ctx* ctx, u32 grid, const u32* kin, const u32* v
   }
   B2_KERNEL(ctx, "radix_scatter");
   if (vin == nullptr)
-    radix_scatter_kernel<ITEMS, true><<<grid, RS_THREADS, smem, ctx->stream>>>(kin, nullptr, kout, vout, counts, totals, n, chunk, shift, mask, gpad);
+    RS_LAUNCH((radix_scatter_kernel<ITEMS, true>), grid, RS_THREADS, smem, ctx->stream, kin, (const u32*)nullptr, kout, vout, counts, totals, n, chunk, shift, mask, gpad);
   else
-    radix_scatter_kernel<ITEMS, false><<<grid, RS_THREADS, smem, ctx->stream>>>(kin, vin, kout, vout, counts, totals, n, chunk, shift, mask, gpad);
+    RS_LAUNCH((radix_scatter_kernel<ITEMS, false>), grid, RS_THREADS, smem, ctx->stream, kin, vin, kout, vout, counts, totals, n, chunk, shift, mask, gpad);
   B2_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -351,10 +360,10 @@ int b2_launch_sort(b2bvh_ctx* ctx, const u32* d_keysIn, const u32* d_valsIn, u32
     const u32 bits = (endBit - shift) < RS_RADIX_BITS ? (endBit - shift) : RS_RADIX_BITS;
     const u32 mask = (1u << bits) - 1u;
     B2_KERNEL(ctx, "radix_count");
-    radix_count_kernel<<<grid, RS_THREADS, 0, ctx->stream>>>(kin, n, chunk, shift, mask, counts, gpad);
+    RS_LAUNCH(radix_count_kernel, grid, RS_THREADS, 0, ctx->stream, kin, n, chunk, shift, mask, counts, gpad);
     B2_LAUNCH_CHECK(ctx);
     B2_KERNEL(ctx, "radix_scan");
-    radix_scan_kernel<<<RS_RADIX / RS_SCAN_WARPS, RS_SCAN_WARPS * 32, 0, ctx->stream>>>(counts, totals, grid, gpad);
+    RS_LAUNCH(radix_scan_kernel, RS_RADIX / RS_SCAN_WARPS, RS_SCAN_WARPS * 32, 0, ctx->stream, counts, totals, grid, gpad);
     B2_LAUNCH_CHECK(ctx);
     if (small) B2_TRY(launch_scatter<4>(ctx, grid, kin, vin, kout, vout, counts, totals, n, chunk, shift, mask, gpad));
     else B2_TRY(launch_scatter<RS_ITEMS>(ctx, grid, kin, vin, kout, vout, counts, totals, n, chunk, shift, mask, gpad));
