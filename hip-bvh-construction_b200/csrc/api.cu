@@ -336,7 +336,7 @@ int b2bvh_build(b2bvh_ctx* ctx, int algo, const b2bvh_triangle* tris, uint32_t n
   B2_TRY(b2_reserve(ctx, SLOT_NODES, (size_t)(separate ? n - 1 : 2 * (size_t)n - 1) * sizeof(b2bvh_bvh2_node), &dNodes));
   if (algo == B2BVH_TWO_PASS_LBVH) B2_TRY(b2_reserve(ctx, SLOT_PARENTS, (2 * (size_t)n - 1) * 4, &dParents));
   if (!separate) B2_TRY(b2_reserve(ctx, SLOT_LBVH, b2_lbvh_scratch_bytes(n), &dLbvh));
-  if (!separate) { u32* dMeet = nullptr; B2_TRY(b2_meet_acquire(ctx, n, &dMeet)); } /* allocates and fills on first use: not inside a capture */
+  if (!separate) { u64* dMeet = nullptr; B2_TRY(b2_meet_acquire(ctx, n, &dMeet)); } /* allocates and fills on first use: not inside a capture */
   if (separate) B2_TRY(b2_reserve(ctx, SLOT_LEAVES, (size_t)n * sizeof(b2bvh_prim_ref), &dLeaves));
   if (algo == B2BVH_PLOCPP) B2_TRY(b2_reserve(ctx, SLOT_PLOC, b2_ploc_scratch_bytes(n), &dMerge));
   if (algo == B2BVH_HPLOC) B2_TRY(b2_reserve(ctx, SLOT_HPLOC, b2_hploc_scratch_bytes(n), &dMerge));

@@ -109,6 +109,11 @@ __device__ __forceinline__ u32 atom_exch_acq_rel(u32* p, u32 v) {
   asm volatile("atom.exch.acq_rel.gpu.global.b32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
   return old;
 }
+__device__ __forceinline__ u64 atom_exch_acq_rel64(u64* p, u64 v) {
+  u64 old;
+  asm volatile("atom.exch.acq_rel.gpu.global.b64 %0, [%1], %2;" : "=l"(old) : "l"(p), "l"(v) : "memory");
+  return old;
+}
 __device__ __forceinline__ u32 atom_exch_relaxed(u32* p, u32 v) {
   u32 old;
   asm volatile("atom.exch.relaxed.gpu.global.b32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
@@ -232,7 +237,7 @@ struct b2bvh_ctx {
    * occupancy answers live here and not in process-wide statics (a second context on another device needs its own) */
   u32 once_mask;         /* B2_ONCE_* bits already done on this context's device */
   int occ[8];            /* B2_OCC_* occupancy answers */
-  u32 meet_clean;        /* leading words of SLOT_MEET known to hold 0xFFFFFFFF (b2_meet_acquire): the LBVH climb leaves its exchange words as it found them */
+  u32 meet_clean;        /* leading 64-bit words of SLOT_MEET known to hold all ones (b2_meet_acquire): the LBVH climb leaves its exchange words as it found them */
   u32 alloc_epoch;       /* bumped whenever a build-owned buffer is (re)allocated: a cached graph holds the old pointers */
   u32 launches;
   u32 lbvh_second_level; /* b2bvh_build_opts.lbvh_second_level of the running build */
@@ -310,9 +315,9 @@ enum {
 };
 /* SLOT_CTL (256 B): [0..23] scene box, [32..63] extents scratch8, [64..87] {-min,max}, [96] root index, [128] range-extract count, [160] traversal overflow flag, [192] range-extract root, [224..247] root box of a sharded build */
 int b2_reserve(b2bvh_ctx* ctx, int slot, size_t bytes, void** out);
-/* the n-1 exchange words of the LBVH climb (SLOT_MEET), all 0xFFFFFFFF: filled when the buffer is new or grew, never again (lbvh.cu).  Allocates:
+/* the n-1 64-bit exchange words of the LBVH climb (SLOT_MEET), all ones: filled when the buffer is new or grew, never again (lbvh.cu).  Allocates:
  * call it before a stream capture begins; the launchers call it again, which is then free. */
-int b2_meet_acquire(b2bvh_ctx* ctx, u32 n, u32** out);
+int b2_meet_acquire(b2bvh_ctx* ctx, u32 n, u64** out);
 /* words <= 16 from device memory into mailbox slot `slot`; readable at b2_mailbox(ctx, slot) after the next stream synchronisation */
 #define B2_MAILBOX_SLOTS 8
 enum { B2_MB_COLLAPSE = 0, B2_MB_PLOC = 1, B2_MB_HPLOC = 2, B2_MB_ROOT = 3, B2_MB_SPLIT = 4, B2_MB_RANGE = 5, B2_MB_TRAVERSE = 6, B2_MB_GLOBAL = 7 };

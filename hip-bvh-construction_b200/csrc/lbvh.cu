@@ -54,26 +54,23 @@ __device__ __forceinline__ u32 choose_parent(const K* __restrict__ keys, u32 n, 
  * split `p` (this node being its left child iff isLeft).  Returns when the node is the first to arrive at some parent
  * (the sibling's thread takes over) or when the root has been written. */
 template <bool KARRAS, typename K>
-__device__ __forceinline__ void climb_global(const K* __restrict__ keys, u32 n, b2bvh_bvh2_node* nodes, u32* parents, u32* meet, u32* rootOut,
+__device__ __forceinline__ void climb_global(const K* __restrict__ keys, u32 n, b2bvh_bvh2_node* nodes, u32* parents, u64* meet, u32* rootOut,
                                              u32 self, u32 lo, u32 hi, Box box, u32 p, bool isLeft) {
   const u32 nInt = n - 1;
   while (true) {
-    if (!KARRAS) {
-      /* Apetrei numbering: hand our index to the parent slot (the sibling cannot derive it) */
-      st_relaxed(reinterpret_cast<u32*>(nodes + p) + (isLeft ? 0 : 1), self);
-    }
-    const u32 other = atom_exch_acq_rel(meet + p, isLeft ? lo : hi);
-    if (other == B2_INVALID) return; /* first arriver: the sibling's thread finishes this node */
-    st_relaxed(meet + p, B2_INVALID); /* both children have been here: the word is as the next build expects it (b2_meet_acquire) */
+    /* one 64-bit exchange hands the sibling both what it cannot derive: the range bound and (Apetrei numbering) this node's index */
+    const u64 other = atom_exch_acq_rel64(meet + p, ((u64)self << 32) | (u64)(isLeft ? lo : hi));
+    if (other == ~0ull) return; /* first arriver: the sibling's thread finishes this node */
+    st_relaxed64(meet + p, ~0ull); /* both children have been here: the word is as the next build expects it (b2_meet_acquire) */
     /* second arriver: the node with split p now has its full range */
-    if (isLeft) hi = other; else lo = other;
+    if (isLeft) hi = (u32)other; else lo = (u32)other;
     u32 sib;
     if (KARRAS) {
       /* derivable: left child = p (leaf: p + nInt), right child = p + 1 (leaf: p + 1 + nInt) */
       if (isLeft) sib = (p + 2 == hi) ? p + 1 + nInt : p + 1;
       else sib = (p == lo) ? p + nInt : p;
     } else {
-      sib = ld_relaxed(reinterpret_cast<const u32*>(nodes + p) + (isLeft ? 1 : 0));
+      sib = (u32)(other >> 32);
     }
     box = box_union(box, load_node2_cg(nodes + sib).box);
     const u32 left = isLeft ? self : sib, right = isLeft ? sib : self;
@@ -91,7 +88,7 @@ __device__ __forceinline__ void climb_global(const K* __restrict__ keys, u32 n, 
 template <bool KARRAS, typename K>
 __global__ void __launch_bounds__(LBVH_THREADS) lbvh_fused_kernel(const K* __restrict__ keys, const u32* __restrict__ vals,
                                                                   const b2bvh_aabb* __restrict__ triAabb, u32 n, b2bvh_bvh2_node* nodes,
-                                                                  u32* parents, u32* meet /* n-1 words, 0xFFFFFFFF */, u32* rootOut,
+                                                                  u32* parents, u64* meet /* n-1 words, all ones */, u32* rootOut,
                                                                   const u32* __restrict__ refPrim /* early split: triangle of each reference, else NULL */,
                                                                   u32* __restrict__ leafPrim /* early split: triangle of leaf g, dense (for the collapse) */) {
   const u32 g = blockIdx.x * LBVH_THREADS + threadIdx.x;
@@ -170,7 +167,7 @@ __device__ __forceinline__ int boundary_depth(u64 keyA, u64 keyB, u32 a) {
 template <bool KARRAS, typename K>
 __global__ void __launch_bounds__(LBVH_TILE_THREADS, 8) lbvh_tile_kernel(const K* __restrict__ keys, const u32* __restrict__ vals,
                                                                       const b2bvh_aabb* __restrict__ triAabb, u32 n, b2bvh_bvh2_node* nodes, u32* parents,
-                                                                      u32* meet, u32* rootOut, u32* pendingCount, LbvhPending* pending, u32 pendingCap,
+                                                                      u64* meet, u32* rootOut, u32* pendingCount, LbvhPending* pending, u32 pendingCap,
                                                                       uint2* tileInfo, LbvhPending* tileBuf, const u32* __restrict__ refPrim, u32* __restrict__ leafPrim) {
   constexpr bool PARENTS = KARRAS; /* only TwoPassLbvh publishes d_parentIdxs */
   constexpr u32 T = LBVH_TILE;
@@ -357,7 +354,7 @@ struct LbvhGroupSmem {
 };
 
 template <bool KARRAS, typename K>
-__global__ void __launch_bounds__(256) lbvh_group_kernel(const K* __restrict__ keys, u32 n, b2bvh_bvh2_node* nodes, u32* parents, u32* meet, u32* rootOut,
+__global__ void __launch_bounds__(256) lbvh_group_kernel(const K* __restrict__ keys, u32 n, b2bvh_bvh2_node* nodes, u32* parents, u64* meet, u32* rootOut,
                                                          u32* pendingCount, LbvhPending* pending, u32 pendingCap, const uint2* __restrict__ tileInfo,
                                                          const LbvhPending* __restrict__ tileBuf, u32 nTiles) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
@@ -513,7 +510,7 @@ __global__ void __launch_bounds__(256) lbvh_group_kernel(const K* __restrict__ k
 }
 
 template <bool KARRAS, typename K>
-__global__ void __launch_bounds__(LBVH_THREADS) lbvh_climb_kernel(const K* __restrict__ keys, u32 n, b2bvh_bvh2_node* nodes, u32* parents, u32* meet,
+__global__ void __launch_bounds__(LBVH_THREADS) lbvh_climb_kernel(const K* __restrict__ keys, u32 n, b2bvh_bvh2_node* nodes, u32* parents, u64* meet,
                                                                   u32* rootOut, const u32* __restrict__ pendingCount,
                                                                   const LbvhPending* __restrict__ pending, u32 pendingCap) {
   pdl_wait(); /* launched programmatically behind the tile / group kernel */
@@ -594,19 +591,19 @@ __global__ void __launch_bounds__(LBVH_THREADS) lbvh_refit_kernel(b2bvh_bvh2_nod
   }
 }
 
-int b2_meet_acquire(b2bvh_ctx* ctx, u32 n, u32** out) {
+int b2_meet_acquire(b2bvh_ctx* ctx, u32 n, u64** out) {
   const size_t words = n > 1 ? (size_t)n - 1 : 1;
   b2bvh_ctx::Buf& b = ctx->bufs[SLOT_MEET];
   const void* pBefore = b.p;
   const size_t capBefore = b.cap;
   void* p = nullptr;
-  B2_TRY(b2_reserve(ctx, SLOT_MEET, words * sizeof(u32), &p));
+  B2_TRY(b2_reserve(ctx, SLOT_MEET, words * sizeof(u64), &p));
   if (p != pBefore || b.cap != capBefore) ctx->meet_clean = 0;
   if ((size_t)ctx->meet_clean < words) {
     B2_CUDA(cudaMemsetAsync(p, 0xFF, b.cap, ctx->stream));
-    ctx->meet_clean = (u32)(b.cap / sizeof(u32) > 0xFFFFFFFFull ? 0xFFFFFFFFull : b.cap / sizeof(u32));
+    ctx->meet_clean = (u32)(b.cap / sizeof(u64)); /* n <= 2^30: fits */
   }
-  *out = reinterpret_cast<u32*>(p);
+  *out = reinterpret_cast<u64*>(p);
   return 0;
 }
 
@@ -624,7 +621,7 @@ static int launch_lbvh_fused_t(b2bvh_ctx* ctx, const K* d_sortedKeys, const u32*
                          b2bvh_bvh2_node* d_nodes, u32* d_parents, u32* d_scratch, u32* d_root, int karrasNumbering) {
   /* the exchange words are NOT cleared per build (40 MB of writes at 10 M primitives): every word the climb uses sees exactly two arrivals and
    * the second one puts 0xFFFFFFFF back */
-  u32* meet = nullptr;
+  u64* meet = nullptr;
   B2_TRY(b2_meet_acquire(ctx, n, &meet));
   B2_KERNEL(ctx, sizeof(K) == 8 ? (karrasNumbering ? "lbvh_fused64_karras" : "lbvh_fused64_apetrei") : (karrasNumbering ? "lbvh_fused_karras" : "lbvh_fused_apetrei"));
   static const bool globalOnly = getenv("B2BVH_LBVH_GLOBAL_ONLY") != nullptr; /* development switch: the all-global-memory variant */
