@@ -8,7 +8,7 @@ NCU="ncu --set full --clock-control none --import-source on"
 for K in "$@"; do
   case $K in
     ploc_iter|ploc_setup|ploc_tail|ploc_merge) ALGO=ploc;;
-    hploc|hploc_setup|hploc_kernel) ALGO=hploc;;
+    hploc|hploc_setup|hploc_kernel|hploc_tile) ALGO=hploc;;
     lbvh_karras_emit|lbvh_refit) ALGO="twopass --two-kernel";;
     lbvh_fused_karras) ALGO=twopass;;
     split_level|split_remap) ALGO=split;;
@@ -22,6 +22,6 @@ for K in "$@"; do
     onesweep_pass) CNT="-c 4";;
     *) CNT="-c 1";;
   esac
-  $NCU -k regex:$K $CNT -f -o gpurun_out/${TAG}_$K python tools/kernel_bench.py --algo $ALGO --reps 1 --warmup 0 > gpurun_out/${TAG}_$K.log 2>&1
+  timeout 240 $NCU -k regex:$K $CNT -f -o gpurun_out/${TAG}_$K python tools/kernel_bench.py --algo $ALGO --reps 1 --warmup 0 > gpurun_out/${TAG}_$K.log 2>&1
   tail -2 gpurun_out/${TAG}_$K.log
 done
