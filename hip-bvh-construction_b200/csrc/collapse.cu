@@ -11,17 +11,19 @@
  *                                  the internal child with the largest area is replaced by its two children (strict '>' so
  *                                  the first of equals wins, areas without FMA).  One thread per node, no synchronisation,
  *                                  16 B out.  Keeps the dependent node reads out of the level-synchronous part.
- *   2. collapse_number_kernel      one cooperative launch, every CTA resident, levels separated by a grid barrier (one atomic
- *                                  counter).  One task = one wide node = one thread; a task is (Bvh2 node, wide parent).
- *                                  The tasks of a level are a contiguous index range; CTA c owns chunk c of it.  Pass A
- *                                  copies the expansion of every task's node into the task's record (the gathers of the
- *                                  whole chunk are independent and overlap) and counts the internal children; the CTA posts
- *                                  the count in counts[c], counts itself in on an arrival counter (one polling thread per
- *                                  CTA) and sums the counts of the chunks before it — all due at the same moment: no
- *                                  chain of dependent look-backs.  Pass C
- *                                  numbers the children consecutively in (task, slot) order, appends their tasks and notes
- *                                  each task's first child index.  Runs of levels that fit one tile (the top of the tree,
- *                                  the tail of a deep one) are processed by CTA 0 alone between two barriers.
+ *   2. collapse_number_kernel      one cooperative launch, every CTA resident.  One task = one wide node = one thread; a task is
+ *                                  (Bvh2 node, wide parent).  The tasks of a level are a contiguous index range.  After a grid barrier
+ *                                  CTA c takes chunk c of it; from then on a CTA keeps the children it numbered itself (its part of
+ *                                  the next level is contiguous and in chunk order: same numbering) until the parts drift apart.
+ *                                  Pass A copies the expansion of every task's node into the task's record (independent gathers, four
+ *                                  tiles in flight) and counts the internal children; the CTA posts the count, counts itself in on an
+ *                                  arrival counter (one polling thread per CTA) and sums the counts of all parts — all due at the
+ *                                  same moment: no chain of dependent look-backs, ONE grid-wide step per level.  Pass C numbers the
+ *                                  children consecutively in (task, slot) order, four tiles per barrier pair, appends their tasks
+ *                                  and notes each task's first child index.  Every CTA sees the same counts, so all decide alike
+ *                                  when to re-cut the level into equal chunks (one grid barrier).  Runs of levels of at most 1024
+ *                                  tasks (the top of the tree, the tail of a deep one) are processed by CTA 0 alone between two
+ *                                  barriers; the very first levels hand their nodes from level to level through shared memory.
  *   3. collapse_emit_kernel        one thread per wide node, no synchronisation: boxes of the internal children gathered
  *                                  with L2::64B loads, the 128-byte node written through a swizzled shared-memory transpose
  *                                  as full contiguous lines, PrimNode records for the leaf children.
@@ -51,7 +53,7 @@
 #define NUM_THREADS_LARGE 512
 #define NUM_THREADS_SMALL 128
 
-/* scratch layout: CollapseCtrl (256 B) | uint4 expansion[n] | uint4 taskCh[n] | u32 taskParent[n] | u32 firstChild[n] | u32 taskNode[n] | u64 counts[G] */
+/* scratch layout: CollapseCtrl (256 B) | uint4 expansion[n] | uint4 taskCh[n] | u32 taskParent[n] | u32 firstChild[n] | u32 taskNode[n] | u64 counts[2][G] */
 struct CollapseCtrl {
   u32 bar;        /* grid barrier: arrivals so far */
   u32 nWide;      /* result: number of wide nodes */
@@ -63,7 +65,7 @@ struct CollapseCtrl {
 };
 
 size_t b2_collapse_scratch_bytes(u32 n) {
-  /* one tagged count word per CTA, G <= 16 CTAs x 1024 SMs */
+  /* two buffers (consecutive levels) of one count word per CTA, G <= 8 CTAs x 1024 SMs */
   return 256 + (size_t)n * (2 * sizeof(uint4) + 3 * sizeof(u32)) + 16 + 16384 * sizeof(u64);
 }
 
@@ -505,7 +507,7 @@ int b2_launch_collapse(b2bvh_ctx* ctx, const b2bvh_bvh2_node* d_nodes, const b2b
   u32* taskParent = reinterpret_cast<u32*>(base + 256 + (size_t)n * 2 * sizeof(uint4));
   u32* firstChild = taskParent + n;
   u32* taskNode = firstChild + n;
-  u64* counts = reinterpret_cast<u64*>(taskNode + n + (n & 1u)); /* one tagged word per CTA; 3n (+1) words after a 16-byte aligned start */
+  u64* counts = reinterpret_cast<u64*>(taskNode + n + (n & 1u)); /* counts[2][G]: one word per CTA and level parity; 3n (+1) words after a 16-byte aligned start */
   u32 nInt = n - 1;
   /* no memsets: the expansion kernel clears CollapseCtrl, and every count word is posted before it is read */
   B2_KERNEL(ctx, "collapse_expand");

@@ -1,6 +1,8 @@
 /*
  * hploc.cu — stage S7: H-PLOC (Benthin et al. 2024): the whole build in ONE launch; a warp walks the LBVH hierarchy
  * bottom-up and PLOC-merges at most 32 clusters in registers whenever a hierarchy node covers more than 16 leaves.
+ * (From 2^20 primitives the launch is hploc_tile_kernel: the same walk, with the part of the hierarchy that lies inside 128
+ * consecutive leaves done in shared memory first — see the tile phase below.)
  *
  * Replaces SetupClusters (HplocKernel.h:39-56), HPloc (:257-315), findParent (:66-81), plocMerge (:220-255),
  * loadIndices / storeIndices (:192-218), findNearestNeighbours (:83-117), mergeClusters (:126-190) and the host side
