@@ -18,7 +18,7 @@ ctx = capi.Context(0)
 d = ctx.synth_uniform(n, 0x00B20010, clustered=len(sys.argv) > 3 and sys.argv[3] == "clustered")
 best = None
 for _ in range(12):
-    t = ctx.build(algo, d, n=n, tris_on_device=True, use_graph=len(sys.argv) > 4 and sys.argv[4] == "graph")
+    t = ctx.build(algo, d, n=n, tris_on_device=True, use_graph=len(sys.argv) > 4 and sys.argv[4] == "graph", lbvh_second_level=int(sys.argv[5]) if len(sys.argv) > 5 else 0)
     st = [float(x) for x in t.stage_ms[:6]]
     if best is None or st[3] < best[3]:
         best = st
@@ -28,6 +28,7 @@ which = sys.argv[1] if len(sys.argv) > 1 else "hploc"
 n = sys.argv[2] if len(sys.argv) > 2 else "10000000"
 kind = sys.argv[3] if len(sys.argv) > 3 else "uniform"
 graph = sys.argv[4] if len(sys.argv) > 4 else "stream"
+second = sys.argv[5] if len(sys.argv) > 5 else "0"
 for lib in sorted(glob.glob(os.path.join(ROOT, "hip-bvh-construction_b200", "variants", "libb2bvh_*.so"))):
-    r = subprocess.run([sys.executable, "-c", CHILD, which, n, kind, graph], env=dict(os.environ, B2BVH_LIB=lib), capture_output=True, text=True, timeout=120, cwd=ROOT)
+    r = subprocess.run([sys.executable, "-c", CHILD, which, n, kind, graph, second], env=dict(os.environ, B2BVH_LIB=lib), capture_output=True, text=True, timeout=120, cwd=ROOT)
     print(os.path.basename(lib), r.stdout.strip() or r.stderr[-300:], flush=True)
