@@ -15,10 +15,18 @@ from b2bvh import capi
 algo = {"twopass": 0, "singlepass": 1, "ploc": 2, "hploc": 3}[sys.argv[1]]
 n = int(sys.argv[2])
 ctx = capi.Context(0)
-d = ctx.synth_uniform(n, 0x00B20010, clustered=len(sys.argv) > 3 and sys.argv[3] == "clustered")
+kw = dict(n=n, tris_on_device=True)
+if len(sys.argv) > 3 and sys.argv[3].startswith("mesh:"):
+    import lzma, numpy as np
+    from b2bvh import types as T
+    d = T.triangles_from_array(np.frombuffer(lzma.open("tests/golden/" + sys.argv[3][5:] + ".tri.xz").read(), dtype=np.float32).reshape(-1, 9).copy())
+    dd = ctx.upload_triangles(d) if hasattr(ctx, "upload_triangles") else None
+    kw = {}
+else:
+    d = ctx.synth_uniform(n, 0x00B20010, clustered=len(sys.argv) > 3 and sys.argv[3] == "clustered")
 best = None
 for _ in range(12):
-    t = ctx.build(algo, d, n=n, tris_on_device=True, use_graph=len(sys.argv) > 4 and sys.argv[4] == "graph", lbvh_second_level=int(sys.argv[5]) if len(sys.argv) > 5 else 0)
+    t = ctx.build(algo, d, **kw, use_graph=len(sys.argv) > 4 and sys.argv[4] == "graph", lbvh_second_level=int(sys.argv[5]) if len(sys.argv) > 5 else 0)
     st = [float(x) for x in t.stage_ms[:6]]
     if best is None or st[5] < best[5]:
         best = st
