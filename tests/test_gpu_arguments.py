@@ -1,0 +1,72 @@
+"""GPU: what the boundary does with inputs the reference never sees in its own scenes — argument errors (status + message, nothing launched) and
+degenerate geometry (zero-area triangles, a scene on a line, every triangle the same one, a scene that is one point, huge and denormal
+coordinates) — every buffer of all four builders byte for byte against the oracle, which restates the reference's arithmetic for exactly these
+cases (division by a zero extent, saturating conversions: DESIGN.md section 4)."""
+import numpy as np
+import pytest
+
+from conftest import random_tris
+from b2bvh import capi, types as T
+from test_gpu_lbvh import check_lbvh
+from test_gpu_ploc import check_ploc
+
+pytestmark = pytest.mark.gpu
+
+
+def degenerate(kind, n, seed):
+    rng = np.random.default_rng(seed)
+    if kind == "points":        # zero-area triangles: boxes without extent
+        v = np.repeat(rng.uniform(-50, 50, size=(n, 1, 3)), 3, axis=1)
+    elif kind == "line":        # the whole scene on one axis: two flat scene extents
+        v = np.zeros((n, 3, 3))
+        v[:, :, 0] = rng.uniform(-100, 100, size=(n, 1)) + rng.uniform(-0.5, 0.5, size=(n, 3))
+        v[:, :, 1] = 2.0
+        v[:, :, 2] = -7.0
+    elif kind == "coincident":  # every triangle the same one, no outlier: all centroids equal, every key equal
+        v = np.tile(rng.uniform(-1, 1, size=(1, 3, 3)), (n, 1, 1))
+    elif kind == "one_point":   # the scene is a single point: every extent is zero
+        v = np.tile(rng.uniform(-1, 1, size=(1, 1, 3)), (n, 3, 1))
+    elif kind == "huge":        # areas near the top of the float range
+        v = rng.uniform(-1, 1, size=(n, 1, 3)) * 1e15 + rng.uniform(-1, 1, size=(n, 3, 3)) * 1e13
+    elif kind == "denormal":    # box areas are denormal numbers (no flush to zero on either side)
+        v = rng.uniform(-1, 1, size=(n, 1, 3)) * 1e-19 + rng.uniform(-1, 1, size=(n, 3, 3)) * 1e-21
+    elif kind == "mixed_scale": # one far outlier squeezes everything else into a few Morton cells
+        v = rng.uniform(-1, 1, size=(n, 1, 3)) + rng.uniform(-0.01, 0.01, size=(n, 3, 3))
+        v[n // 2] += 1e7
+    else:
+        raise ValueError(kind)
+    return T.triangles_from_array(v.astype(np.float32))
+
+
+KINDS = ["points", "line", "coincident", "one_point", "huge", "denormal", "mixed_scale"]
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("algo", [capi.TWO_PASS_LBVH, capi.SINGLE_PASS_LBVH], ids=["twopass", "singlepass"])
+def test_degenerate_geometry_lbvh(ctx, oracle, algo, kind):
+    for n, seed in ((2, 401), (97, 402), (3001, 403)):
+        check_lbvh(ctx, oracle, degenerate(kind, n, seed), algo)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("algo", [capi.PLOCPP, capi.HPLOC], ids=["ploc", "hploc"])
+def test_degenerate_geometry_ploc(ctx, oracle, algo, kind):
+    for n, seed in ((2, 411), (97, 412), (3001, 413)):
+        check_ploc(ctx, oracle, degenerate(kind, n, seed), algo)
+
+
+def test_argument_errors_are_statuses_with_messages(ctx):
+    tris = random_tris(64, 421)
+    with pytest.raises(capi.B2bvhError, match="at least 2 primitives"):
+        ctx.build(capi.SINGLE_PASS_LBVH, tris[:1])
+    with pytest.raises(capi.B2bvhError, match="at least 2 primitives"):
+        ctx.build(capi.PLOCPP, tris[:0])
+    with pytest.raises(capi.B2bvhError):
+        ctx.build(7, tris)                      # no such builder
+    with pytest.raises(capi.B2bvhError, match="morton_bits"):
+        ctx.build(capi.SINGLE_PASS_LBVH, tris, morton_bits=48)
+    with pytest.raises(capi.B2bvhError):
+        ctx.sort_pairs(np.zeros(0, dtype=np.uint32), np.zeros(0, dtype=np.uint32))
+    # the context is still usable after every refusal
+    t = ctx.build(capi.SINGLE_PASS_LBVH, tris)
+    assert t.n_prims == 64 and t.n_internal == 63

@@ -8,7 +8,7 @@ import pytest
 
 from conftest import GOLDEN, load_mesh, random_tris
 from b2bvh import capi
-from test_gpu_lbvh import assert_same_struct, h32
+from test_gpu_lbvh import assert_same_struct, h32, same_cost
 
 pytestmark = pytest.mark.gpu
 KA = json.load(open(os.path.join(GOLDEN, "known_answers.json")))
@@ -28,7 +28,7 @@ def check_ploc(ctx, oracle, tris, algo, **opts):
     assert g["n_wide"] == o["wide_count"]
     assert_same_struct(g["wide"], o["wide"], "bvh4 nodes")
     assert_same_struct(g["wide_leaves"], o["wide_leaves"], "bvh4 leaves")
-    assert np.float32(ctx.tree_cost(tree)) == np.float32(o["cost"])
+    assert same_cost(ctx.tree_cost(tree), o["cost"])
     return tree, g, o
 
 
