@@ -9,6 +9,7 @@ from conftest import random_tris
 from b2bvh import capi, types as T
 from test_gpu_lbvh import check_lbvh
 from test_gpu_ploc import check_ploc
+from test_gpu_morton60 import check60
 
 pytestmark = pytest.mark.gpu
 
@@ -53,6 +54,17 @@ def test_degenerate_geometry_lbvh(ctx, oracle, algo, kind):
 def test_degenerate_geometry_ploc(ctx, oracle, algo, kind):
     for n, seed in ((2, 411), (97, 412), (3001, 413)):
         check_ploc(ctx, oracle, degenerate(kind, n, seed), algo)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_degenerate_geometry_morton60_split_and_graph(ctx, oracle, kind):
+    """The same inputs through the 60-bit codes (all four builders), through a replayed graph, and — where triangles have area — through early split clipping."""
+    tris = degenerate(kind, 2500, 431)
+    for algo in (capi.TWO_PASS_LBVH, capi.SINGLE_PASS_LBVH, capi.PLOCPP, capi.HPLOC):
+        check60(ctx, oracle, tris, algo)
+    check_lbvh(ctx, oracle, tris, capi.SINGLE_PASS_LBVH, use_graph=True)
+    check_lbvh(ctx, oracle, tris, capi.SINGLE_PASS_LBVH, use_graph=True)
+    check_ploc(ctx, oracle, tris, capi.HPLOC, lbvh_second_level=1)  # H-PLOC's tile phase
 
 
 def test_argument_errors_are_statuses_with_messages(ctx):
