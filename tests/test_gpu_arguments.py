@@ -82,3 +82,37 @@ def test_argument_errors_are_statuses_with_messages(ctx):
     # the context is still usable after every refusal
     t = ctx.build(capi.SINGLE_PASS_LBVH, tris)
     assert t.n_prims == 64 and t.n_internal == 63
+
+
+@pytest.mark.parametrize("kind", ["coincident", "points", "line", "mixed_scale", "one_point"])
+@pytest.mark.parametrize("algo", [capi.SINGLE_PASS_LBVH, capi.PLOCPP], ids=["singlepass", "ploc"])
+def test_degenerate_geometry_traversal(ctx, oracle, algo, kind):
+    """Primary rays against the same degenerate scenes: HitInfo of the while-while kernel bit for bit against the oracle (zero-area triangles are
+    never hit; among coincident triangles the first one met in traversal order wins on both sides), the other kernels agree on t."""
+    from test_gpu_traverse import PI, compare_hits
+    tris = degenerate(kind, 1500, 441)
+    n = tris.size
+    tr = T.make_transform([0.0, 2.5, -3.0], [3.0, 3.0, 3.0], [0.0, 0.0, 0.0, 1.0])
+    cam = T.make_camera([0.0, 2.5, 5.8, 0.0], oracle.qt_rotation([0.0, 0.0, 1.0, -1.57]), np.float32(45.0) * PI / np.float32(180.0))
+    size = 96
+    tree = ctx.build(algo, tris)
+    g = ctx.fetch(tree)
+    d_rays, _ = ctx.generate_rays(cam, size, size)
+    rays = ctx.download(d_rays, T.RAY, size * size)
+    o_hits, o_cnt = oracle.traverse(rays, g["nodes"], g["leaves"], tris, tr, tree.root, n)
+    hits, _, _ = ctx.traverse(tree, d_rays, size * size, tr, capi.TRAVERSE_WHILE)
+    compare_hits(hits, o_hits)
+    assert int((hits["primIdx"] != 0xFFFFFFFF).sum()) == o_cnt
+    if kind == "coincident":
+        assert o_cnt > 0
+    if kind in ("points", "one_point"):
+        assert o_cnt == 0
+    for k in (capi.TRAVERSE_SPECULATIVE_WHILE, capi.TRAVERSE_IFIF, capi.TRAVERSE_RESTART_TRAIL, capi.TRAVERSE_WIDE4):
+        try:
+            h2, _, _ = ctx.traverse(tree, d_rays, size * size, tr, k)
+        except capi.B2bvhError as e:
+            # PLOC++ over coincident triangles builds a tree deeper than the 64-bit restart trail (or a stack) holds: refused loudly, never a wrong image
+            assert "deeper than" in str(e), e
+            continue
+        assert np.array_equal(h2["t"].view(np.uint32), hits["t"].view(np.uint32)), k
+    ctx.free(d_rays)
