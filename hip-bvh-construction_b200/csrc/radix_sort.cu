@@ -33,6 +33,8 @@
  *     against 68.0 at 10 M and 2.7 ms against 2.4 at 100 M — the scatter kernel is not bound by shared-memory wavefronts but by its five
  *     barrier-separated phases per tile at two CTAs per SM.
  */
+#include <stdlib.h>
+
 #include "common.cuh"
 
 #define RS_RADIX_BITS 8
@@ -41,6 +43,7 @@
 #define RS_WARPS (RS_THREADS / 32)
 #define RS_MAX_PASSES 4
 #define RS_SCAN_WARPS 32
+#define RS_SELF_MAX 136  /* chunks of 2048 pairs; sort of 144 K pairs 40.8 -> 34.8 us, 262 K (129 chunks) 40.9 -> 38.9, 390 K (191 chunks) 49.1 -> 53.2: the rows a CTA sums grow with the input */
 #ifndef RS_ITEMS
 #define RS_ITEMS 15   /* pairs per thread and tile of the scatter kernel (large inputs) */
 #define RS_MINB 2     /* resident scatter CTAs per SM: 3 x 30 KB tile buffers + counters, twice */
@@ -66,7 +69,7 @@ size_t b2_sort_scratch_bytes(u32 n) {
 
 /* ------------------------------------------------------------------------------------------------ count */
 __global__ void __launch_bounds__(RS_THREADS) radix_count_kernel(const u32* __restrict__ keys, u32 n, u32 chunk, u32 shift, u32 mask,
-                                                                 u32* __restrict__ counts, u32 gpad) {
+                                                                 u32* __restrict__ counts, u32 gpad, u32 chunkMajor) {
   __shared__ u32 h[RS_WARPS][RS_RADIX];
   const u32 tid = threadIdx.x, w = tid >> 5;
   for (u32 k = tid; k < RS_WARPS * RS_RADIX; k += RS_THREADS) (&h[0][0])[k] = 0;
@@ -98,7 +101,8 @@ __global__ void __launch_bounds__(RS_THREADS) radix_count_kernel(const u32* __re
     u32 c = 0;
 #pragma unroll
     for (int k = 0; k < RS_WARPS; k++) c += h[k][tid];
-    counts[(size_t)tid * gpad + blockIdx.x] = c;
+    if (chunkMajor) counts[(size_t)blockIdx.x * RS_RADIX + tid] = c; /* small inputs: no scan kernel, the scatter CTAs sum the rows themselves */
+    else counts[(size_t)tid * gpad + blockIdx.x] = c;
   }
 }
 
@@ -178,7 +182,7 @@ template <int ITEMS, bool IOTA_VALUES>
 __global__ void __launch_bounds__(RS_THREADS, ITEMS == RS_ITEMS ? RS_MINB : 2) radix_scatter_kernel(const u32* __restrict__ keysIn, const u32* __restrict__ valsIn,
                                                                       u32* __restrict__ keysOut, u32* __restrict__ valsOut,
                                                                       const u32* __restrict__ counts, const u32* __restrict__ totals, u32 n,
-                                                                      u32 chunk, u32 shift, u32 mask, u32 gpad) {
+                                                                      u32 chunk, u32 shift, u32 mask, u32 gpad, u32 selfG) {
   using Smem = ScatterSmem<ITEMS>;
   constexpr u32 TILE = Smem::TILE;
   extern __shared__ __align__(128) unsigned char smemRaw[];
@@ -191,9 +195,29 @@ __global__ void __launch_bounds__(RS_THREADS, ITEMS == RS_ITEMS ? RS_MINB : 2) r
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   RS_PDL_PROLOGUE();
+  /* small inputs (selfG = number of chunks, at most RS_SELF_MAX): the count kernel left its raw counts chunk-major and no scan kernel ran — every CTA sums
+   * the rows itself (coalesced 1 KB rows, two half ranges per digit): digit totals and the counts of the chunks before this one.  One launch
+   * less per pass where a launch is a third of the pass. */
+  u32 selfTot = 0, selfBefore = 0;
+  if (selfG) {
+    static_assert(RS_THREADS == 2 * RS_RADIX, "two half ranges per digit");
+    const u32 d = tid & (RS_RADIX - 1u), half = tid >> 8;
+    const u32 gh = (selfG + 1u) >> 1, c0 = half * gh, c1 = min(selfG, c0 + gh);
+    u32 tot = 0, bef = 0;
+    for (u32 c = c0; c < c1; c++) {
+      const u32 v = __ldg(counts + (size_t)c * RS_RADIX + d);
+      tot += v;
+      if (c < blockIdx.x) bef += v;
+    }
+    u32* tmp = reinterpret_cast<u32*>(S.keys); /* the key tile is not in use yet */
+    tmp[tid] = tot; tmp[RS_THREADS + tid] = bef;
+    __syncthreads();
+    if (tid < RS_RADIX) { selfTot = tmp[tid] + tmp[tid + RS_RADIX]; selfBefore = tmp[RS_THREADS + tid] + tmp[RS_THREADS + tid + RS_RADIX]; }
+    __syncthreads();
+  }
   /* global start of every digit for this chunk = exclusive scan of the digit totals + this chunk's offset inside the digit */
   if (tid < RS_RADIX) {
-    const u32 tot = __ldg(totals + tid);
+    const u32 tot = selfG ? selfTot : __ldg(totals + tid);
     u32 incl = tot;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -207,7 +231,7 @@ __global__ void __launch_bounds__(RS_THREADS, ITEMS == RS_ITEMS ? RS_MINB : 2) r
   if (tid < RS_RADIX) {
     u32 add = 0;
     for (u32 k = 0; k < w; k++) add += S.warpTotals[k];
-    S.digitBase[tid] = (u32)S.globalBase[tid] + add + __ldg(counts + (size_t)tid * gpad + blockIdx.x);
+    S.digitBase[tid] = (u32)S.globalBase[tid] + add + (selfG ? selfBefore : __ldg(counts + (size_t)tid * gpad + blockIdx.x));
   }
   const u32 begin = blockIdx.x * chunk, end = min(n, begin + chunk);
   u32 phase = 0;
@@ -318,7 +342,7 @@ __global__ void __launch_bounds__(RS_THREADS, ITEMS == RS_ITEMS ? RS_MINB : 2) r
 
 template <int ITEMS>
 static int launch_scatter(b2bvh_ctx* ctx, u32 grid, const u32* kin, const u32* vin, u32* kout, u32* vout, const u32* counts, const u32* totals, u32 n,
-                          u32 chunk, u32 shift, u32 mask, u32 gpad) {
+                          u32 chunk, u32 shift, u32 mask, u32 gpad, u32 selfG) {
   const size_t smem = sizeof(ScatterSmem<ITEMS>);
   const u32 onceBit = ITEMS == 4 ? B2_ONCE_SORT4 : B2_ONCE_SORT15;
   if (!(ctx->once_mask & onceBit)) {
@@ -328,9 +352,9 @@ static int launch_scatter(b2bvh_ctx* ctx, u32 grid, const u32* kin, const u32* v
   }
   B2_KERNEL(ctx, "radix_scatter");
   if (vin == nullptr)
-    RS_LAUNCH((radix_scatter_kernel<ITEMS, true>), grid, RS_THREADS, smem, ctx->stream, kin, (const u32*)nullptr, kout, vout, counts, totals, n, chunk, shift, mask, gpad);
+    RS_LAUNCH((radix_scatter_kernel<ITEMS, true>), grid, RS_THREADS, smem, ctx->stream, kin, (const u32*)nullptr, kout, vout, counts, totals, n, chunk, shift, mask, gpad, selfG);
   else
-    RS_LAUNCH((radix_scatter_kernel<ITEMS, false>), grid, RS_THREADS, smem, ctx->stream, kin, vin, kout, vout, counts, totals, n, chunk, shift, mask, gpad);
+    RS_LAUNCH((radix_scatter_kernel<ITEMS, false>), grid, RS_THREADS, smem, ctx->stream, kin, vin, kout, vout, counts, totals, n, chunk, shift, mask, gpad, selfG);
   B2_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -347,6 +371,9 @@ int b2_launch_sort(b2bvh_ctx* ctx, const u32* d_keysIn, const u32* d_valsIn, u32
   const u32 gpad = rs_gpad(grid);
   u32 chunk = (n + grid - 1) / grid;
   chunk = (chunk + 3u) & ~3u; /* 16-byte aligned chunk starts for the vector and bulk loads */
+  /* up to RS_SELF_MAX chunks (~278 K pairs) the scatter CTAs do the scan themselves: two launches per pass instead of three */
+  static const bool noSelf = getenv("B2BVH_SORT_NO_SELF_SCAN") != nullptr; /* development switch, identical output */
+  const u32 selfG = (small && grid <= RS_SELF_MAX && !noSelf) ? grid : 0u;
   u32* counts = reinterpret_cast<u32*>(d_scratch);
   u32* totals = counts + (size_t)RS_RADIX * gpad;
   const u32* kin = d_keysIn;
@@ -360,13 +387,15 @@ int b2_launch_sort(b2bvh_ctx* ctx, const u32* d_keysIn, const u32* d_valsIn, u32
     const u32 bits = (endBit - shift) < RS_RADIX_BITS ? (endBit - shift) : RS_RADIX_BITS;
     const u32 mask = (1u << bits) - 1u;
     B2_KERNEL(ctx, "radix_count");
-    RS_LAUNCH(radix_count_kernel, grid, RS_THREADS, 0, ctx->stream, kin, n, chunk, shift, mask, counts, gpad);
+    RS_LAUNCH(radix_count_kernel, grid, RS_THREADS, 0, ctx->stream, kin, n, chunk, shift, mask, counts, gpad, selfG ? 1u : 0u);
     B2_LAUNCH_CHECK(ctx);
-    B2_KERNEL(ctx, "radix_scan");
-    RS_LAUNCH(radix_scan_kernel, RS_RADIX / RS_SCAN_WARPS, RS_SCAN_WARPS * 32, 0, ctx->stream, counts, totals, grid, gpad);
-    B2_LAUNCH_CHECK(ctx);
-    if (small) B2_TRY(launch_scatter<4>(ctx, grid, kin, vin, kout, vout, counts, totals, n, chunk, shift, mask, gpad));
-    else B2_TRY(launch_scatter<RS_ITEMS>(ctx, grid, kin, vin, kout, vout, counts, totals, n, chunk, shift, mask, gpad));
+    if (!selfG) {
+      B2_KERNEL(ctx, "radix_scan");
+      RS_LAUNCH(radix_scan_kernel, RS_RADIX / RS_SCAN_WARPS, RS_SCAN_WARPS * 32, 0, ctx->stream, counts, totals, grid, gpad);
+      B2_LAUNCH_CHECK(ctx);
+    }
+    if (small) B2_TRY(launch_scatter<4>(ctx, grid, kin, vin, kout, vout, counts, totals, n, chunk, shift, mask, gpad, selfG));
+    else B2_TRY(launch_scatter<RS_ITEMS>(ctx, grid, kin, vin, kout, vout, counts, totals, n, chunk, shift, mask, gpad, 0u));
     kin = kout;
     vin = vout;
   }
